@@ -1,0 +1,1173 @@
+// K1: per-frame binning of index-group atom positions into the occupancy grid
+// (replaces gridcount(), g_ri3Dc.c:139-152, and the atom loop g_ri3Dc.c:425-426),
+// K2: density normalisation (g_ri3Dc.c:451-460) + file-order transpose
+//     (grid3_serialise, xdr_grid.c:113-126),
+// K4: counter-based synthetic frames, and the gcb_counter host object that
+//     stages frames through pinned buffers on CUDA streams.
+//
+// sm_100a only.  Built with -fmad=false; the float->bin conversion uses
+// explicit round-to-nearest intrinsics (__fsub_rn, __fdiv_rn) in the
+// reference's operation order so that bin indices match bit for bit.
+//
+// Data layout in HBM
+//   frames   x[frame][atom][3] f32, exactly the host rvec layout (12 B/atom)
+//   counts   u32 [mx][my][mz], z fastest (the reference's contiguous block)
+//   acc      f32 same shape, only materialised when frame weights change
+//   gindex   i32 sorted copy of the index group, rank[] = prefix count per atom
+#include "gcb_internal.h"
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <vector>
+
+namespace {
+
+struct GridParams {
+  float a[3], b[3], delta[3], fmx[3];
+  int my, mz;
+};
+
+enum { MODE_COUNT = 0, MODE_FLOAT = 1 };
+
+// ---------------------------------------------------------------------------
+// float -> bin, g_ri3Dc.c:144-147.  Returns the flat z-fastest cell, -1 when
+// the atom fails a bounds test (u < 0 or x - b >= 0, two separate f32
+// subtractions as in the reference), -2 when it passes all three but a
+// quotient is >= mx or NaN (the reference would then write out of bounds).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int cell_of(const GridParams &P, float x, float y, float z)
+{
+  const float ux = __fsub_rn(x, P.a[0]), uy = __fsub_rn(y, P.a[1]), uz = __fsub_rn(z, P.a[2]);
+  const bool outside = (ux < 0.0f) | (__fsub_rn(x, P.b[0]) >= 0.0f) |
+                       (uy < 0.0f) | (__fsub_rn(y, P.b[1]) >= 0.0f) |
+                       (uz < 0.0f) | (__fsub_rn(z, P.b[2]) >= 0.0f);
+  if (outside) return -1;
+  const float qx = __fdiv_rn(ux, P.delta[0]), qy = __fdiv_rn(uy, P.delta[1]), qz = __fdiv_rn(uz, P.delta[2]);
+  const bool bad = !(qx < P.fmx[0]) | !(qy < P.fmx[1]) | !(qz < P.fmx[2]);
+  if (bad) return -2;
+  // (int)floor((double)q) == round-down conversion for 0 <= q < 2^31
+  return (__float2int_rd(qx) * P.my + __float2int_rd(qy)) * P.mz + __float2int_rd(qz);
+}
+
+// count.c:88-92: single-image wrap, `< 0` below and `> L` above
+__device__ __forceinline__ float wrap1(float v, float L)
+{
+  if (v < 0.0f) v = __fadd_rn(v, L);
+  if (v > L) v = __fsub_rn(v, L);
+  return v;
+}
+
+template <int MODE>
+__device__ __forceinline__ void deposit(uint32_t *__restrict__ counts, float *__restrict__ acc, int cell, float w)
+{
+  if (MODE == MODE_COUNT) {
+    atomicAdd(counts + cell, 1u);            // RED.E.ADD (no return value used)
+  } else {
+    atomicAdd(acc + cell, w);                // same-weight float adds commute: exact within one weight run
+    atomicAdd(counts + cell, 1u);
+  }
+}
+
+// One atomic per (warp, frame) on the per-frame hit counters.
+__device__ __forceinline__ void count_hits(unsigned long long *__restrict__ hits, bool hit, long long f)
+{
+  unsigned todo = __ballot_sync(0xffffffffu, hit);
+  const int lane = threadIdx.x & 31;
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const long long fl = __shfl_sync(0xffffffffu, f, leader);
+    const unsigned same = __ballot_sync(0xffffffffu, hit && f == fl);
+    if (lane == leader) atomicAdd(hits + fl, (unsigned long long)__popc(same));
+    todo &= ~same;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1a  gather kernel: one lane per selected atom-frame e in [e_begin, e_end),
+// direct LDG of x[f][gindex[i]].  Used for sparse index groups, unaligned
+// inputs and the tail the streaming kernel leaves.
+// ---------------------------------------------------------------------------
+constexpr int GATHER_THREADS = 256;
+constexpr int GATHER_ITEMS = 8;
+
+template <int MODE, bool PBC>
+__global__ void __launch_bounds__(GATHER_THREADS)
+bin_gather_kernel(const float *__restrict__ x, int natoms, const int *__restrict__ gindex, unsigned gnx,
+                  long long e_begin, long long e_end, GridParams P, uint32_t *__restrict__ counts,
+                  float *__restrict__ acc, float w, const float *__restrict__ box3,
+                  unsigned long long *__restrict__ hits, unsigned long long *__restrict__ diag)
+{
+  const long long chunk = (long long)GATHER_THREADS * GATHER_ITEMS;
+  const long long nchunks = (e_end - e_begin + chunk - 1) / chunk;
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const long long e0 = e_begin + c * chunk;
+    const long long f0 = e0 / gnx;                       // one 64-bit division per chunk
+    const unsigned r0 = (unsigned)(e0 - f0 * gnx);
+#pragma unroll
+    for (int it = 0; it < GATHER_ITEMS; it++) {
+      const long long e = e0 + it * GATHER_THREADS + threadIdx.x;
+      const bool valid = e < e_end;
+      unsigned rel = r0 + it * GATHER_THREADS + threadIdx.x;
+      long long f = f0;
+      if (rel >= gnx) { const unsigned q = rel / gnx; rel -= q * gnx; f += q; }
+      int cell = -1;
+      if (valid) {
+        const int idx = __ldg(gindex + rel);
+        const float *p = x + ((size_t)f * natoms + idx) * 3;
+        float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
+        if (PBC) {
+          const float *L = box3 + 3 * f;
+          px = wrap1(px, __ldg(L)); py = wrap1(py, __ldg(L + 1)); pz = wrap1(pz, __ldg(L + 2));
+        }
+        cell = cell_of(P, px, py, pz);
+        if (cell >= 0) deposit<MODE>(counts, acc, cell, w);
+        else if (cell == -2) atomicAdd(diag, 1ull);
+      }
+      count_hits(hits, cell >= 0, f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1b  streaming kernel: persistent CTAs pull fixed-size tiles of the raw
+// frame array into shared memory with TMA bulk copies (cp.async.bulk +
+// mbarrier, a STAGES-deep ring), then each lane picks its selected atoms out
+// of the tile through the sorted index group.  HBM sees only full-line
+// streaming reads; the gather happens in shared memory (stride 3 or 9 words,
+// both conflict free).
+//
+// Tiles are TILE_ATOMS atoms of the FLAT array (frame boundaries fall inside
+// tiles); TILE_ATOMS*3 floats is a multiple of both 3 and 4, so atoms never
+// straddle tiles and every tile starts 16-byte aligned.
+// ---------------------------------------------------------------------------
+constexpr int STREAM_THREADS = 256;
+constexpr int TILE_ATOMS = 2048;
+constexpr int TILE_FLOATS = TILE_ATOMS * 3;
+constexpr int TILE_BYTES = TILE_FLOATS * 4;      // 24 KiB
+constexpr int STAGES = 3;
+
+struct TileMeta {
+  long long f0;          // frame of the tile's first atom
+  int r0;                // atom index (within frame f0) of the tile's first atom
+  unsigned rel0;         // rank[r0]: index-group position of the first selected atom, relative to frame f0
+  unsigned nsel;         // selected atom-frames inside the tile
+};
+
+struct StreamSmem {
+  alignas(128) float tile[STAGES][TILE_FLOATS];
+  alignas(8) unsigned long long full[STAGES];
+  TileMeta meta[STAGES];
+  unsigned long long hits[STAGES][2];
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// TMA 1D bulk copy global -> shared, completion signalled on the mbarrier; frames are read once: evict-first in L2
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar,
+                                            unsigned long long policy)
+{
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
+}
+
+template <int MODE, bool PBC>
+__global__ void __launch_bounds__(STREAM_THREADS)
+bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict__ gindex, unsigned gnx,
+                  const unsigned *__restrict__ rank, long long ntiles, GridParams P,
+                  uint32_t *__restrict__ counts, float *__restrict__ acc, float w,
+                  const float *__restrict__ box3, unsigned long long *__restrict__ hits,
+                  unsigned long long *__restrict__ diag)
+{
+  extern __shared__ unsigned char smem_raw[];
+  StreamSmem &S = *reinterpret_cast<StreamSmem *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  const int tid = threadIdx.x;
+  unsigned long long policy = 0;
+
+  auto issue = [&](long long t, int stage) {       // thread 0 only
+    const long long g0 = t * TILE_ATOMS;
+    const long long f0 = g0 / natoms;
+    const int r0 = (int)(g0 - f0 * natoms);
+    const long long g1 = g0 + TILE_ATOMS;
+    const long long f1 = g1 / natoms;
+    const int r1 = (int)(g1 - f1 * natoms);
+    const unsigned rel0 = __ldg(rank + r0);
+    TileMeta m;
+    m.f0 = f0; m.r0 = r0; m.rel0 = rel0;
+    m.nsel = (unsigned)((f1 - f0) * (long long)gnx + (long long)__ldg(rank + r1) - (long long)rel0);
+    S.meta[stage] = m;
+    S.hits[stage][0] = 0; S.hits[stage][1] = 0;
+    mbar_expect_tx(&S.full[stage], TILE_BYTES);
+    tma_load_1d(S.tile[stage], x + (size_t)t * TILE_FLOATS, TILE_BYTES, &S.full[stage], policy);
+  };
+
+  if (tid == 0) {
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    for (int s = 0; s < STAGES; s++) mbar_init(&S.full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+      if (t < ntiles) issue(t, s);
+    }
+  }
+  __syncthreads();   // meta of the first tiles visible
+
+  int it = 0;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int stage = it % STAGES;
+    const unsigned parity = (unsigned)(it / STAGES) & 1u;
+    mbar_wait(&S.full[stage], parity);
+    const TileMeta m = S.meta[stage];
+    const float *tile = S.tile[stage];
+    unsigned c0 = 0, c1 = 0;            // hits in frame f0 / f0+1 (later frames go straight to global)
+    for (unsigned s = tid; s < m.nsel; s += STREAM_THREADS) {
+      unsigned rel = m.rel0 + s;
+      unsigned df = 0;
+      if (rel >= gnx) { df = rel / gnx; rel -= df * gnx; }
+      const int idx = __ldg(gindex + rel);
+      const int local = (int)((long long)df * natoms + idx - m.r0);
+      float px = tile[3 * local], py = tile[3 * local + 1], pz = tile[3 * local + 2];
+      if (PBC) {
+        const float *L = box3 + 3 * (m.f0 + df);
+        px = wrap1(px, __ldg(L)); py = wrap1(py, __ldg(L + 1)); pz = wrap1(pz, __ldg(L + 2));
+      }
+      const int cell = cell_of(P, px, py, pz);
+      if (cell >= 0) {
+        deposit<MODE>(counts, acc, cell, w);
+        if (df == 0) c0++;
+        else if (df == 1) c1++;
+        else atomicAdd(hits + m.f0 + df, 1ull);
+      } else if (cell == -2) {
+        atomicAdd(diag, 1ull);
+      }
+    }
+    c0 = __reduce_add_sync(0xffffffffu, c0);
+    c1 = __reduce_add_sync(0xffffffffu, c1);
+    if ((tid & 31) == 0) {
+      if (c0) atomicAdd(&S.hits[stage][0], (unsigned long long)c0);
+      if (c1) atomicAdd(&S.hits[stage][1], (unsigned long long)c1);
+    }
+    __syncthreads();                    // everyone is done with this stage's tile and hit counters
+    if (tid == 0) {
+      if (S.hits[stage][0]) atomicAdd(hits + m.f0, S.hits[stage][0]);
+      if (S.hits[stage][1]) atomicAdd(hits + m.f0 + 1, S.hits[stage][1]);
+      const long long tn = t + (long long)STAGES * gridDim.x;
+      if (tn < ntiles) issue(tn, stage);   // its smem writes are published by the mbarrier (release/acquire)
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// n sequential f32 additions of w to v (see gcb::seq_add_f32)
+// ---------------------------------------------------------------------------
+__device__ float seq_add_dev(float v, float w, unsigned long long n)
+{
+  while (n > 0) {
+    const float v1 = __fadd_rn(v, w);
+    --n;
+    if (v1 == v || v1 != v1) return v1;
+    v = v1;
+    if (n < 2) continue;
+    const float v2 = __fadd_rn(v, w), v3 = __fadd_rn(v2, w);
+    unsigned b1 = __float_as_uint(v), b2 = __float_as_uint(v2), b3 = __float_as_uint(v3);
+    if (v > 0.0f && w > 0.0f && (b1 >> 23) == (b2 >> 23) && (b2 >> 23) == (b3 >> 23) && b3 > b2) {
+      const unsigned inc = b3 - b2, last = b2 | 0x7FFFFFu;
+      --n;
+      unsigned long long k = (unsigned long long)(last - b2) / inc;
+      if (k > n) k = n;
+      b2 += (unsigned)(k * inc);
+      n -= k;
+      v = __uint_as_float(b2);
+    }
+  }
+  return v;
+}
+
+// fold a finished weight run into the f32 accumulator: acc = acc (+)= w, runcnt times
+__global__ void fold_run_kernel(uint32_t *__restrict__ runcnt, uint32_t *__restrict__ total,
+                                float *__restrict__ acc, float w, size_t n)
+{
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t k = runcnt[c];
+    if (k) {
+      acc[c] = seq_add_dev(acc[c], w, k);
+      total[c] += k;
+      runcnt[c] = 0;
+    }
+  }
+}
+
+// K2: occupancy (the reference's f32 `grid` before normalisation) and density
+//     grid / ((double)(float)dV * T_tot), g_ri3Dc.c:451-460; denom == 0 -> occupancy only
+__global__ void density_kernel(const uint32_t *__restrict__ runcnt, const float *__restrict__ acc, float w,
+                               int have_run, double denom, float *__restrict__ out, size_t n)
+{
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x) {
+    float v = acc ? acc[c] : 0.0f;
+    if (have_run) {
+      const uint32_t k = runcnt[c];
+      if (k) v = seq_add_dev(v, w, k);
+    }
+    out[c] = denom != 0.0 ? (float)__ddiv_rn((double)v, denom) : v;
+  }
+}
+
+// z-fastest [mx][my][mz] -> x-fastest [mz][my][mx]   (grid3_serialise, xdr_grid.c:113-126)
+__global__ void zfast_to_xfast_kernel(const float *__restrict__ in, float *__restrict__ out, int mx, int my, int mz)
+{
+  __shared__ float tile[32][33];
+  const int j = blockIdx.z;
+  const int i0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r, k = k0 + threadIdx.x;
+    if (i < mx && k < mz) tile[r][threadIdx.x] = in[((size_t)i * my + j) * mz + k];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r, i = i0 + threadIdx.x;
+    if (i < mx && k < mz) out[((size_t)k * my + j) * mx + i] = tile[threadIdx.x][r];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4: counter-based synthetic frames; bit-identical to oracle/gc_oracle.c
+// ---------------------------------------------------------------------------
+__host__ __device__ inline unsigned long long splitmix64(unsigned long long z)
+{
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ unsigned gen_u24(unsigned long long seed, unsigned long long frame,
+                                            unsigned long long atom, unsigned long long lane)
+{
+  const unsigned long long key = seed ^ (frame * 0xD1342543DE82EF95ull) ^ (atom * 0xA24BAED4963EE407ull) ^
+                                 (lane * 0x9FB21C651E98DF25ull);
+  return (unsigned)(splitmix64(key) >> 40);
+}
+__device__ __forceinline__ float unit24(unsigned u) { return __fmul_rn(__uint2float_rn(u), 5.9604644775390625e-08f); }
+
+__global__ void gen_frames_kernel(gcb_gen p, long long frame0, long long nframes, int natoms, float *__restrict__ x)
+{
+  const long long total = nframes * natoms;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    const long long fl = g / natoms;
+    const unsigned long long fr = (unsigned long long)(frame0 + fl);
+    const unsigned long long i = (unsigned long long)(g - fl * natoms);
+    float L[3] = {p.L[0], p.L[1], p.L[2]};
+    if (p.box_period > 0) {
+      const long long ph = (frame0 + fl) % p.box_period, half = p.box_period / 2;
+      const float hh = __fmul_rn(0.5f, (float)half);
+      const float tri = __fdiv_rn(__fsub_rn((float)llabs(ph - half), hh), hh);
+      const float s = __fadd_rn(1.0f, __fmul_rn(p.box_amp, tri));
+      for (int d = 0; d < 3; d++) L[d] = __fmul_rn(p.L[d], s);
+    }
+    float r[3];
+    if (p.mode == GCB_GEN_CLUSTER) {
+      const unsigned site = gen_u24(p.seed, fr, i, 3) % (unsigned)p.nsites;
+      const float spread = __fmul_rn(p.sigma, 1.7320508f);
+      for (int d = 0; d < 3; d++) {
+        const float c = __fmul_rn(unit24(gen_u24(p.seed ^ 0x5151515151515151ull, 0, site, d)), L[d]);
+        const unsigned s4 = gen_u24(p.seed, fr, i, 4 + d) + gen_u24(p.seed, fr, i, 8 + d) +
+                            gen_u24(p.seed, fr, i, 12 + d) + gen_u24(p.seed, fr, i, 16 + d);
+        const float off = __fmul_rn(__fsub_rn(__fmul_rn(__uint2float_rn(s4), 5.9604644775390625e-08f), 2.0f), spread);
+        float v = __fadd_rn(c, off);
+        if (v < 0.0f) v = __fadd_rn(v, L[d]);
+        if (v >= L[d]) v = __fsub_rn(v, L[d]);
+        r[d] = v;
+      }
+    } else {
+      for (int d = 0; d < 3; d++) r[d] = __fmul_rn(unit24(gen_u24(p.seed, fr, i, d)), L[d]);
+      if (p.mode == GCB_GEN_PORE) {
+        const float dx = __fsub_rn(r[0], __fmul_rn(0.5f, L[0])), dy = __fsub_rn(r[1], __fmul_rn(0.5f, L[1]));
+        const float r2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (r[2] >= p.slab_lo && r[2] < p.slab_hi && r2 > __fmul_rn(p.pore_r, p.pore_r)) {
+          const float thick = __fsub_rn(p.slab_hi, p.slab_lo);
+          float z = __fmul_rn(unit24(gen_u24(p.seed, fr, i, 3)), __fsub_rn(L[2], thick));
+          if (z >= p.slab_lo) z = __fadd_rn(z, thick);
+          r[2] = z;
+        }
+      }
+      if (p.mode == GCB_GEN_QUANTISED)
+        for (int d = 0; d < 3; d++) r[d] = __fmul_rn(rintf(__fmul_rn(r[d], 1000.0f)), 0.001f);
+    }
+    float *o = x + (size_t)g * 3;
+    o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host object
+// ---------------------------------------------------------------------------
+struct Slot {
+  cudaStream_t copy = nullptr;
+  cudaEvent_t copied = nullptr, consumed = nullptr;
+  float *h_x = nullptr;               // pinned staging [cap][natoms][3]
+  float *d_x = nullptr;               // device staging
+  unsigned long long *d_hits = nullptr, *h_hits = nullptr;
+  float *d_box3 = nullptr, *h_box3 = nullptr;
+  long cap = 0;                       // frames
+  long pending = 0;                   // frames whose hit counts have not been collected yet
+};
+
+struct DevHits {                      // hit counters of an add_device_frames call awaiting collection
+  unsigned long long *d = nullptr;
+  float *d_box3 = nullptr;
+  long n = 0;
+};
+
+}  // namespace
+
+struct gcb_counter {
+  gcb_tgrid tg{};
+  GridParams P{};
+  gcb_counter_opts opts{};
+  int natoms = 0, gnx = 0;
+  size_t ncells = 0;
+  int sm_count = 148;
+  bool stream_ok = false;             // index group dense enough for the streaming kernel
+
+  std::vector<int> h_gindex;          // sorted copy of the index group
+  int *d_gindex = nullptr;
+  unsigned *d_rank = nullptr;         // rank[r] = number of group entries < r, r in [0, natoms]
+  uint32_t *d_runcnt = nullptr, *d_total = nullptr;
+  float *d_acc = nullptr;
+  unsigned long long *d_diag = nullptr;
+  float *d_out = nullptr, *d_out2 = nullptr;   // density / transpose outputs
+
+  bool have_run = false;              // d_runcnt holds hits of weight w_cur not yet folded into d_acc
+  float w_cur = 0;
+  bool uniform = true, any = false;
+  float w_first = 0;
+
+  cudaStream_t compute = nullptr;
+  std::vector<Slot> slots;
+  int next_slot = 0;
+  std::vector<DevHits> devhits;
+
+  std::vector<uint64_t> hits_per_frame;
+  std::vector<float> weight_per_frame;
+  double sumP = 0;
+  size_t sumP_frames = 0;
+  uint64_t hits_total = 0, edge_overflow = 0;
+  int64_t launches = 0;
+  void *nccl = nullptr;               // ncclComm_t, see nccl_reduce.cpp
+  int nranks = 1, rank = 0;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  bool reduced = false;               // statistics below are global after gcb_counter_allreduce
+  uint64_t global_frames = 0;
+};
+
+namespace {
+
+inline bool same_bits(float p, float q) { uint32_t x, y; memcpy(&x, &p, 4); memcpy(&y, &q, 4); return x == y; }
+
+unsigned rank_host(const gcb_counter *c, int r)
+{
+  return (unsigned)(std::lower_bound(c->h_gindex.begin(), c->h_gindex.end(), r) - c->h_gindex.begin());
+}
+
+int ensure_acc(gcb_counter *c)
+{
+  if (c->d_acc) return GCB_OK;
+  GCB_CUDA(cudaMalloc(&c->d_acc, c->ncells * sizeof(float)));
+  GCB_CUDA(cudaMalloc(&c->d_total, c->ncells * sizeof(uint32_t)));
+  GCB_CUDA(cudaMemsetAsync(c->d_acc, 0, c->ncells * sizeof(float), c->compute));
+  GCB_CUDA(cudaMemsetAsync(c->d_total, 0, c->ncells * sizeof(uint32_t), c->compute));
+  return GCB_OK;
+}
+
+int elementwise_grid(const gcb_counter *c, size_t n)
+{
+  const size_t b = (n + 255) / 256, cap = (size_t)c->sm_count * 8;
+  return (int)std::max<size_t>(1, std::min(b, cap));
+}
+
+int fold_pending(gcb_counter *c)
+{
+  if (!c->have_run) return GCB_OK;
+  int rc = ensure_acc(c);
+  if (rc) return rc;
+  fold_run_kernel<<<elementwise_grid(c, c->ncells), 256, 0, c->compute>>>(c->d_runcnt, c->d_total, c->d_acc,
+                                                                           c->w_cur, c->ncells);
+  c->launches++;
+  GCB_CUDA(cudaGetLastError());
+  c->have_run = false;
+  return GCB_OK;
+}
+
+size_t stream_smem_bytes() { return sizeof(StreamSmem) + 128; }
+
+template <int MODE, bool PBC>
+int launch_bin(gcb_counter *c, const float *d_x, long nframes, float w, const float *d_box3,
+               unsigned long long *d_hits)
+{
+  const long long total_e = (long long)nframes * c->gnx;
+  if (total_e == 0) return GCB_OK;
+  uint32_t *cnt = MODE == MODE_COUNT ? c->d_runcnt : c->d_total;
+  long long e_begin = 0;
+  const bool aligned = ((uintptr_t)d_x & 15u) == 0;
+  const bool use_stream = aligned && c->opts.kernel != GCB_KERNEL_GATHER &&
+                          (c->stream_ok || c->opts.kernel == GCB_KERNEL_STREAM);
+  if (use_stream) {
+    const long long total_atoms = (long long)nframes * c->natoms;
+    const long long ntiles = total_atoms / TILE_ATOMS;     // full tiles; the remainder goes to the gather kernel
+    if (ntiles > 0) {
+      static bool attr_done[4] = {false, false, false, false};
+      const int which = MODE * 2 + (PBC ? 1 : 0);
+      if (!attr_done[which]) {
+        GCB_CUDA(cudaFuncSetAttribute(bin_stream_kernel<MODE, PBC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)stream_smem_bytes()));
+        attr_done[which] = true;
+      }
+      const int per_sm = std::max(1, (int)((227 * 1024) / (stream_smem_bytes() + 1024)));
+      const long long grid = std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
+      bin_stream_kernel<MODE, PBC><<<(unsigned)grid, STREAM_THREADS, stream_smem_bytes(), c->compute>>>(
+          d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, c->P, cnt, c->d_acc, w, d_box3,
+          d_hits, c->d_diag);
+      c->launches++;
+      GCB_CUDA(cudaGetLastError());
+      const long long g1 = ntiles * TILE_ATOMS, f1 = g1 / c->natoms;
+      e_begin = f1 * c->gnx + rank_host(c, (int)(g1 - f1 * c->natoms));
+    }
+  }
+  if (e_begin < total_e) {
+    const long long chunk = (long long)GATHER_THREADS * GATHER_ITEMS;
+    const long long nchunks = (total_e - e_begin + chunk - 1) / chunk;
+    const long long grid = std::min<long long>(nchunks, (long long)c->sm_count * 8);
+    bin_gather_kernel<MODE, PBC><<<(unsigned)grid, GATHER_THREADS, 0, c->compute>>>(
+        d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, e_begin, total_e, c->P, cnt, c->d_acc, w, d_box3, d_hits,
+        c->d_diag);
+    c->launches++;
+    GCB_CUDA(cudaGetLastError());
+  }
+  return GCB_OK;
+}
+
+template <int MODE>
+int launch_bin_pbc(gcb_counter *c, const float *d_x, long nframes, float w, const float *d_box3,
+                   unsigned long long *d_hits)
+{
+  if (c->opts.pbc == GCB_PBC_RECT) return launch_bin<MODE, true>(c, d_x, nframes, w, d_box3, d_hits);
+  return launch_bin<MODE, false>(c, d_x, nframes, w, d_box3, d_hits);
+}
+
+// Bin `nframes` device-resident frames whose per-frame weights are `w[0..nframes)`
+// (host array, NULL = 1).  Frames are cut into runs of bit-identical weight.
+// Long runs (and the common uniform case) count integers and are folded into
+// the f32 accumulator when the weight changes; short runs add floats directly
+// (all additions inside one run carry the same value, so they commute, and
+// runs are ordered on the compute stream): both reproduce the reference's
+// sequential `grid += weight` exactly.
+int bin_device_batch(gcb_counter *c, const float *d_x, long nframes, const float *w, const float *d_box3,
+                     unsigned long long *d_hits)
+{
+  long f = 0;
+  while (f < nframes) {
+    const float wr = w ? w[f] : 1.0f;
+    long e = f + 1;
+    while (e < nframes && same_bits(w ? w[e] : 1.0f, wr)) e++;
+    const long n = e - f;
+    if (!c->any) { c->any = true; c->w_first = wr; }
+    else if (!same_bits(wr, c->w_first)) c->uniform = false;
+
+    const float *xs = d_x + (size_t)f * c->natoms * 3;
+    const float *bs = d_box3 ? d_box3 + 3 * f : nullptr;
+    const bool continues = c->have_run && same_bits(wr, c->w_cur);
+    const bool fresh = !c->have_run && !c->d_acc;
+    const bool long_run = (double)n * c->gnx >= (double)c->ncells / 8.0;
+    int rc;
+    if (continues || fresh || long_run) {
+      if (c->have_run && !continues) { rc = fold_pending(c); if (rc) return rc; }
+      c->have_run = true;
+      c->w_cur = wr;
+      rc = launch_bin_pbc<MODE_COUNT>(c, xs, n, wr, bs, d_hits + f);
+    } else {
+      rc = fold_pending(c);
+      if (rc) return rc;
+      rc = ensure_acc(c);
+      if (rc) return rc;
+      rc = launch_bin_pbc<MODE_FLOAT>(c, xs, n, wr, bs, d_hits + f);
+    }
+    if (rc) return rc;
+    f = e;
+  }
+  return GCB_OK;
+}
+
+// collect the hit counters of a slot whose kernels have finished
+int collect_slot(gcb_counter *c, Slot &s)
+{
+  if (s.pending == 0) return GCB_OK;
+  GCB_CUDA(cudaEventSynchronize(s.consumed));
+  for (long f = 0; f < s.pending; f++) c->hits_per_frame.push_back(s.h_hits[f]);
+  s.pending = 0;
+  return GCB_OK;
+}
+
+int alloc_slots(gcb_counter *c)
+{
+  if (!c->slots.empty()) return GCB_OK;
+  const size_t frame_bytes = (size_t)c->natoms * 12;
+  long fpb = c->opts.frames_per_batch;
+  if (fpb <= 0) fpb = (long)std::max<size_t>(1, ((size_t)32 << 20) / std::max<size_t>(frame_bytes, 1));
+  const int ns = c->opts.nslots > 0 ? c->opts.nslots : 3;
+  c->slots.resize(ns);
+  for (auto &s : c->slots) {
+    s.cap = fpb;
+    GCB_CUDA(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
+    GCB_CUDA(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    GCB_CUDA(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+    GCB_CUDA(cudaHostAlloc(&s.h_x, frame_bytes * fpb, cudaHostAllocDefault));
+    GCB_CUDA(cudaMalloc(&s.d_x, frame_bytes * fpb + 16));
+    GCB_CUDA(cudaMalloc(&s.d_hits, sizeof(unsigned long long) * (fpb + 2)));
+    GCB_CUDA(cudaHostAlloc(&s.h_hits, sizeof(unsigned long long) * (fpb + 2), cudaHostAllocDefault));
+    GCB_CUDA(cudaMalloc(&s.d_box3, sizeof(float) * 3 * fpb));
+    GCB_CUDA(cudaHostAlloc(&s.h_box3, sizeof(float) * 3 * fpb, cudaHostAllocDefault));
+  }
+  return GCB_OK;
+}
+
+// stage `n` frames that already sit in slot.h_x (or are copied there from `src`)
+int submit_slot(gcb_counter *c, Slot &s, const float *src, bool src_pinned, long n, const float *w,
+                const float *box)
+{
+  const size_t bytes = (size_t)n * c->natoms * 12;
+  const float *from = s.h_x;
+  if (src) {
+    if (src_pinned) from = src;                 // DMA straight out of the caller's pinned memory
+    else memcpy(s.h_x, src, bytes);
+  }
+  GCB_CUDA(cudaMemcpyAsync(s.d_x, from, bytes, cudaMemcpyHostToDevice, s.copy));
+  if (c->opts.pbc == GCB_PBC_RECT) {
+    if (!box) return gcb::fail(GCB_ERR_ARG, "GCB_PBC_RECT needs the per-frame box");
+    for (long f = 0; f < n; f++) { s.h_box3[3 * f] = box[9 * f]; s.h_box3[3 * f + 1] = box[9 * f + 4]; s.h_box3[3 * f + 2] = box[9 * f + 8]; }
+    GCB_CUDA(cudaMemcpyAsync(s.d_box3, s.h_box3, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, s.copy));
+  }
+  GCB_CUDA(cudaEventRecord(s.copied, s.copy));
+  GCB_CUDA(cudaStreamWaitEvent(c->compute, s.copied, 0));
+  GCB_CUDA(cudaMemsetAsync(s.d_hits, 0, sizeof(unsigned long long) * (n + 2), c->compute));
+  int rc = bin_device_batch(c, s.d_x, n, w, c->opts.pbc == GCB_PBC_RECT ? s.d_box3 : nullptr, s.d_hits);
+  if (rc) return rc;
+  GCB_CUDA(cudaMemcpyAsync(s.h_hits, s.d_hits, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, c->compute));
+  GCB_CUDA(cudaEventRecord(s.consumed, c->compute));
+  // the next copy into this slot must wait for the kernels that read it
+  GCB_CUDA(cudaStreamWaitEvent(s.copy, s.consumed, 0));
+  s.pending = n;
+  for (long f = 0; f < n; f++) c->weight_per_frame.push_back(w ? w[f] : 1.0f);
+  return GCB_OK;
+}
+
+void free_counter(gcb_counter *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->opts.device);
+  if (c->compute) cudaStreamSynchronize(c->compute);
+  for (auto &s : c->slots) {
+    if (s.copy) { cudaStreamSynchronize(s.copy); cudaStreamDestroy(s.copy); }
+    if (s.copied) cudaEventDestroy(s.copied);
+    if (s.consumed) cudaEventDestroy(s.consumed);
+    cudaFreeHost(s.h_x); cudaFree(s.d_x); cudaFree(s.d_hits); cudaFreeHost(s.h_hits);
+    cudaFree(s.d_box3); cudaFreeHost(s.h_box3);
+  }
+  for (auto &d : c->devhits) { cudaFree(d.d); cudaFree(d.d_box3); }
+  cudaFree(c->d_gindex); cudaFree(c->d_rank); cudaFree(c->d_runcnt); cudaFree(c->d_total); cudaFree(c->d_acc);
+  cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2);
+  if (c->t0) { cudaEventDestroy(c->t0); cudaEventDestroy(c->t1); }
+  if (c->compute) cudaStreamDestroy(c->compute);
+  delete c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex, int gnx, int natoms,
+                       const gcb_counter_opts *opts)
+{
+  if (!out || !tg || natoms <= 0 || gnx < 0 || (gnx > 0 && !gindex))
+    return gcb::fail(GCB_ERR_ARG, "gcb_counter_create: bad argument");
+  if (tg->mx[0] <= 0 || tg->mx[1] <= 0 || tg->mx[2] <= 0 || gcb::cells(*tg) > (size_t)INT32_MAX)
+    return gcb::fail(GCB_ERR_ARG, "gcb_counter_create: grid %d x %d x %d not supported", tg->mx[0], tg->mx[1], tg->mx[2]);
+  for (int i = 0; i < gnx; i++)
+    if (gindex[i] < 0 || gindex[i] >= natoms)
+      return gcb::fail(GCB_ERR_ARG, "index group entry %d = %d is outside [0, %d)", i, gindex[i], natoms);
+  if (gcb_device_count() <= 0) return gcb::fail(GCB_ERR_CUDA, "no CUDA device: libgridcount_b200 has no CPU fallback");
+
+  gcb_counter *c = new (std::nothrow) gcb_counter;
+  if (!c) return gcb::fail(GCB_ERR_NOMEM, "out of memory");
+  if (opts) c->opts = *opts;
+  c->tg = *tg;
+  c->natoms = natoms;
+  c->gnx = gnx;
+  c->ncells = gcb::cells(*tg);
+  for (int d = 0; d < 3; d++) {
+    c->P.a[d] = tg->a[d]; c->P.b[d] = tg->b[d]; c->P.delta[d] = tg->delta[d]; c->P.fmx[d] = (float)tg->mx[d];
+  }
+  c->P.my = tg->mx[1]; c->P.mz = tg->mx[2];
+
+#define GCB_CREATE_CUDA(call)                                                                        \
+  do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gcb::set_error("%s failed: %s", #call, cudaGetErrorString(e_)); \
+       free_counter(c); return GCB_ERR_CUDA; } } while (0)
+
+  GCB_CREATE_CUDA(cudaSetDevice(c->opts.device));
+  cudaDeviceProp prop;
+  GCB_CREATE_CUDA(cudaGetDeviceProperties(&prop, c->opts.device));
+  c->sm_count = prop.multiProcessorCount;
+  GCB_CREATE_CUDA(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+
+  // integer counts are order free, so the group may be sorted (duplicates kept)
+  c->h_gindex.assign(gindex, gindex + gnx);
+  std::sort(c->h_gindex.begin(), c->h_gindex.end());
+  std::vector<unsigned> rank((size_t)natoms + 1);
+  {
+    size_t p = 0;
+    for (int r = 0; r <= natoms; r++) {
+      while (p < c->h_gindex.size() && c->h_gindex[p] < r) p++;
+      rank[r] = (unsigned)p;
+    }
+  }
+  // streaming reads every byte of every frame: worth it while >= 1/8 of the 32-byte sectors are wanted anyway
+  c->stream_ok = (double)gnx * 8.0 >= (double)natoms && (long long)natoms * 3 >= 1;
+
+  GCB_CREATE_CUDA(cudaMalloc(&c->d_gindex, sizeof(int) * std::max(gnx, 1)));
+  GCB_CREATE_CUDA(cudaMalloc(&c->d_rank, sizeof(unsigned) * rank.size()));
+  GCB_CREATE_CUDA(cudaMalloc(&c->d_runcnt, sizeof(uint32_t) * c->ncells));
+  GCB_CREATE_CUDA(cudaMalloc(&c->d_diag, sizeof(unsigned long long) * 2));
+  if (gnx) GCB_CREATE_CUDA(cudaMemcpy(c->d_gindex, c->h_gindex.data(), sizeof(int) * gnx, cudaMemcpyHostToDevice));
+  GCB_CREATE_CUDA(cudaMemcpy(c->d_rank, rank.data(), sizeof(unsigned) * rank.size(), cudaMemcpyHostToDevice));
+  GCB_CREATE_CUDA(cudaMemset(c->d_runcnt, 0, sizeof(uint32_t) * c->ncells));
+  GCB_CREATE_CUDA(cudaMemset(c->d_diag, 0, sizeof(unsigned long long) * 2));
+#undef GCB_CREATE_CUDA
+  *out = c;
+  return GCB_OK;
+}
+
+void gcb_counter_destroy(gcb_counter *c) { free_counter(c); }
+
+int gcb_counter_reset(gcb_counter *c)
+{
+  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  int rc = gcb_counter_sync(c);
+  if (rc) return rc;
+  GCB_CUDA(cudaMemsetAsync(c->d_runcnt, 0, sizeof(uint32_t) * c->ncells, c->compute));
+  if (c->d_acc) {
+    GCB_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(float) * c->ncells, c->compute));
+    GCB_CUDA(cudaMemsetAsync(c->d_total, 0, sizeof(uint32_t) * c->ncells, c->compute));
+  }
+  GCB_CUDA(cudaMemsetAsync(c->d_diag, 0, sizeof(unsigned long long) * 2, c->compute));
+  GCB_CUDA(cudaStreamSynchronize(c->compute));
+  c->have_run = false; c->any = false; c->uniform = true; c->w_cur = 0; c->w_first = 0;
+  c->hits_per_frame.clear(); c->weight_per_frame.clear();
+  c->sumP = 0; c->sumP_frames = 0; c->hits_total = 0; c->edge_overflow = 0;
+  return GCB_OK;
+}
+
+int gcb_counter_slot(gcb_counter *c, int slot, float **x_pinned, long *capacity_frames)
+{
+  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  int rc = alloc_slots(c);
+  if (rc) return rc;
+  if (slot < 0 || slot >= (int)c->slots.size()) return gcb::fail(GCB_ERR_ARG, "slot %d out of range", slot);
+  Slot &s = c->slots[slot];
+  rc = collect_slot(c, s);              // also guarantees the previous H2D out of this slot is done
+  if (rc) return rc;
+  GCB_CUDA(cudaStreamSynchronize(s.copy));
+  if (x_pinned) *x_pinned = s.h_x;
+  if (capacity_frames) *capacity_frames = s.cap;
+  return GCB_OK;
+}
+
+int gcb_counter_submit_slot(gcb_counter *c, int slot, long nframes, const float *weight, const float *box)
+{
+  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  int rc = alloc_slots(c);
+  if (rc) return rc;
+  if (slot < 0 || slot >= (int)c->slots.size() || nframes < 0 || nframes > c->slots[slot].cap)
+    return gcb::fail(GCB_ERR_ARG, "gcb_counter_submit_slot: slot %d / %ld frames out of range", slot, nframes);
+  rc = collect_slot(c, c->slots[slot]);
+  if (rc) return rc;
+  return submit_slot(c, c->slots[slot], nullptr, false, nframes, weight, box);
+}
+
+int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes, const float *weight, const float *box)
+{
+  if (!c || (!x && nframes > 0) || nframes < 0) return gcb::fail(GCB_ERR_ARG, "gcb_counter_add_frames: bad argument");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  int rc = alloc_slots(c);
+  if (rc) return rc;
+  cudaPointerAttributes attr;
+  bool pinned = false;
+  if (cudaPointerGetAttributes(&attr, x) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+  else cudaGetLastError();
+  const size_t frame_floats = (size_t)c->natoms * 3;
+  long done = 0;
+  while (done < nframes) {
+    Slot &s = c->slots[c->next_slot];
+    c->next_slot = (c->next_slot + 1) % (int)c->slots.size();
+    rc = collect_slot(c, s);
+    if (rc) return rc;
+    if (!pinned) GCB_CUDA(cudaStreamSynchronize(s.copy));   // staging buffer free to overwrite
+    const long n = std::min(s.cap, nframes - done);
+    rc = submit_slot(c, s, x + (size_t)done * frame_floats, pinned, n, weight ? weight + done : nullptr,
+                     box ? box + 9 * (size_t)done : nullptr);
+    if (rc) return rc;
+    done += n;
+  }
+  return GCB_OK;
+}
+
+int gcb_counter_add_device_frames(gcb_counter *c, const float *x_dev, long nframes, const float *weight,
+                                  const float *box)
+{
+  if (!c || (!x_dev && nframes > 0) || nframes < 0)
+    return gcb::fail(GCB_ERR_ARG, "gcb_counter_add_device_frames: bad argument");
+  if (nframes == 0) return GCB_OK;
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  // keep submission order of the hit counters: drain staged slots first
+  for (auto &s : c->slots) { int rc = collect_slot(c, s); if (rc) return rc; }
+  DevHits h;
+  h.n = nframes;
+  GCB_CUDA(cudaMalloc(&h.d, sizeof(unsigned long long) * (nframes + 2)));
+  GCB_CUDA(cudaMemsetAsync(h.d, 0, sizeof(unsigned long long) * (nframes + 2), c->compute));
+  if (c->opts.pbc == GCB_PBC_RECT) {
+    if (!box) { cudaFree(h.d); return gcb::fail(GCB_ERR_ARG, "GCB_PBC_RECT needs the per-frame box"); }
+    std::vector<float> b3((size_t)nframes * 3);
+    for (long f = 0; f < nframes; f++) { b3[3 * f] = box[9 * f]; b3[3 * f + 1] = box[9 * f + 4]; b3[3 * f + 2] = box[9 * f + 8]; }
+    GCB_CUDA(cudaMalloc(&h.d_box3, sizeof(float) * 3 * nframes));
+    GCB_CUDA(cudaMemcpy(h.d_box3, b3.data(), sizeof(float) * 3 * nframes, cudaMemcpyHostToDevice));
+  }
+  c->devhits.push_back(h);
+  int rc = bin_device_batch(c, x_dev, nframes, weight, h.d_box3, h.d);
+  if (rc) return rc;
+  for (long f = 0; f < nframes; f++) c->weight_per_frame.push_back(weight ? weight[f] : 1.0f);
+  return GCB_OK;
+}
+
+int gcb_counter_sync(gcb_counter *c)
+{
+  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  for (auto &s : c->slots) { int rc = collect_slot(c, s); if (rc) return rc; }
+  GCB_CUDA(cudaStreamSynchronize(c->compute));
+  for (auto &h : c->devhits) {
+    std::vector<unsigned long long> tmp((size_t)h.n);
+    GCB_CUDA(cudaMemcpy(tmp.data(), h.d, sizeof(unsigned long long) * h.n, cudaMemcpyDeviceToHost));
+    for (long f = 0; f < h.n; f++) c->hits_per_frame.push_back(tmp[f]);
+    cudaFree(h.d); cudaFree(h.d_box3);
+  }
+  c->devhits.clear();
+  unsigned long long diag[2];
+  GCB_CUDA(cudaMemcpy(diag, c->d_diag, sizeof(diag), cudaMemcpyDeviceToHost));
+  c->edge_overflow = diag[0];
+  // sumP: `sumP += (double)weight` once per hit, frame by frame (g_ri3Dc.c:151,426)
+  for (; c->sumP_frames < c->hits_per_frame.size(); c->sumP_frames++) {
+    const uint64_t h = c->hits_per_frame[c->sumP_frames];
+    c->sumP = gcb::seq_add_f64(c->sumP, (double)c->weight_per_frame[c->sumP_frames], h);
+    c->hits_total += h;
+  }
+  return GCB_OK;
+}
+
+int gcb_counter_stats(gcb_counter *c, gcb_stats *out)
+{
+  if (!c || !out) return gcb::fail(GCB_ERR_ARG, "null argument");
+  int rc = gcb_counter_sync(c);
+  if (rc) return rc;
+  out->frames = c->reduced ? c->global_frames : c->hits_per_frame.size();
+  out->atom_frames = out->frames * (uint64_t)c->gnx;
+  out->hits = c->hits_total;
+  out->edge_overflow = c->edge_overflow;
+  out->sumP = c->sumP;
+  out->uniform_weight = c->uniform ? 1 : 0;
+  out->weight = c->w_first;
+  out->kernel_launches = c->launches;
+  return GCB_OK;
+}
+
+int gcb_counter_hits_per_frame(gcb_counter *c, uint64_t *hits, long capacity, long *nframes_out)
+{
+  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
+  int rc = gcb_counter_sync(c);
+  if (rc) return rc;
+  const long n = (long)c->hits_per_frame.size();
+  if (nframes_out) *nframes_out = n;
+  if (hits) memcpy(hits, c->hits_per_frame.data(), sizeof(uint64_t) * (size_t)std::min(n, capacity));
+  return GCB_OK;
+}
+
+__global__ void add_u32_kernel(const uint32_t *__restrict__ p, const uint32_t *__restrict__ q, uint32_t *__restrict__ o, size_t n)
+{
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x)
+    o[c] = p[c] + (q ? q[c] : 0u);
+}
+
+static int ensure_out(gcb_counter *c)
+{
+  if (!c->d_out) GCB_CUDA(cudaMalloc(&c->d_out, c->ncells * sizeof(float)));
+  return GCB_OK;
+}
+
+int gcb_counter_device_counts(gcb_counter *c, uint32_t **counts_dev)
+{
+  if (!c || !counts_dev) return gcb::fail(GCB_ERR_ARG, "null argument");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  if (!c->d_total) { *counts_dev = c->d_runcnt; return GCB_OK; }
+  int rc = ensure_out(c);
+  if (rc) return rc;
+  add_u32_kernel<<<elementwise_grid(c, c->ncells), 256, 0, c->compute>>>(c->d_total, c->have_run ? c->d_runcnt : nullptr,
+                                                                          (uint32_t *)c->d_out, c->ncells);
+  c->launches++;
+  GCB_CUDA(cudaGetLastError());
+  *counts_dev = (uint32_t *)c->d_out;
+  return GCB_OK;
+}
+
+int gcb_counter_counts(gcb_counter *c, uint32_t *counts_zfast)
+{
+  if (!c || !counts_zfast) return gcb::fail(GCB_ERR_ARG, "null argument");
+  uint32_t *d = nullptr;
+  int rc = gcb_counter_device_counts(c, &d);
+  if (rc) return rc;
+  GCB_CUDA(cudaMemcpyAsync(counts_zfast, d, c->ncells * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->compute));
+  GCB_CUDA(cudaStreamSynchronize(c->compute));
+  return GCB_OK;
+}
+
+static int density_to_device(gcb_counter *c, double denom)
+{
+  int rc = ensure_out(c);
+  if (rc) return rc;
+  density_kernel<<<elementwise_grid(c, c->ncells), 256, 0, c->compute>>>(c->d_runcnt, c->d_acc, c->w_cur,
+                                                                          c->have_run ? 1 : 0, denom, c->d_out, c->ncells);
+  c->launches++;
+  GCB_CUDA(cudaGetLastError());
+  return GCB_OK;
+}
+
+int gcb_counter_occupancy(gcb_counter *c, float *occ_zfast)
+{
+  if (!c || !occ_zfast) return gcb::fail(GCB_ERR_ARG, "null argument");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  int rc = density_to_device(c, 0.0);
+  if (rc) return rc;
+  GCB_CUDA(cudaMemcpyAsync(occ_zfast, c->d_out, c->ncells * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
+  GCB_CUDA(cudaStreamSynchronize(c->compute));
+  return GCB_OK;
+}
+
+int gcb_counter_density(gcb_counter *c, double T_tot, float *grid_zfast, float *grid_xfast, gcb_tgrid *tg_out)
+{
+  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  const float dV = (float)gcb_delta_v(&c->tg);            // `real dV = DeltaV(&tgrid)` (g_ri3Dc.c:453)
+  const double denom = (double)dV * T_tot;                // (dV*T_tot) with T_tot double (g_ri3Dc.c:458)
+  int rc = density_to_device(c, denom);
+  if (rc) return rc;
+  if (grid_zfast)
+    GCB_CUDA(cudaMemcpyAsync(grid_zfast, c->d_out, c->ncells * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
+  if (grid_xfast) {
+    if (!c->d_out2) GCB_CUDA(cudaMalloc(&c->d_out2, c->ncells * sizeof(float)));
+    dim3 block(32, 8), grid((c->tg.mx[2] + 31) / 32, (c->tg.mx[0] + 31) / 32, c->tg.mx[1]);
+    zfast_to_xfast_kernel<<<grid, block, 0, c->compute>>>(c->d_out, c->d_out2, c->tg.mx[0], c->tg.mx[1], c->tg.mx[2]);
+    c->launches++;
+    GCB_CUDA(cudaGetLastError());
+    GCB_CUDA(cudaMemcpyAsync(grid_xfast, c->d_out2, c->ncells * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
+  }
+  GCB_CUDA(cudaStreamSynchronize(c->compute));
+  if (tg_out) { *tg_out = c->tg; tg_out->tweight = (float)T_tot; }   // g_ri3Dc.c:460
+  return GCB_OK;
+}
+
+int gcb_counter_timer_start(gcb_counter *c)
+{
+  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  if (!c->t0) { GCB_CUDA(cudaEventCreate(&c->t0)); GCB_CUDA(cudaEventCreate(&c->t1)); }
+  GCB_CUDA(cudaEventRecord(c->t0, c->compute));
+  return GCB_OK;
+}
+
+int gcb_counter_timer_stop(gcb_counter *c, float *ms)
+{
+  if (!c || !ms || !c->t0) return gcb::fail(GCB_ERR_STATE, "gcb_counter_timer_stop without start");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  GCB_CUDA(cudaEventRecord(c->t1, c->compute));
+  GCB_CUDA(cudaEventSynchronize(c->t1));
+  GCB_CUDA(cudaEventElapsedTime(ms, c->t0, c->t1));
+  return GCB_OK;
+}
+
+int gcb_gen_device_frames(const gcb_gen *p, long frame0, long nframes, int natoms, float *x_dev, int device)
+{
+  if (!p || !x_dev || nframes < 0 || natoms <= 0) return gcb::fail(GCB_ERR_ARG, "gcb_gen_device_frames: bad argument");
+  if (p->mode == GCB_GEN_CLUSTER && p->nsites <= 0) return gcb::fail(GCB_ERR_ARG, "cluster mode needs nsites > 0");
+  GCB_CUDA(cudaSetDevice(device));
+  if (nframes == 0) return GCB_OK;
+  const long long total = (long long)nframes * natoms;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  gen_frames_kernel<<<grid, 256>>>(*p, frame0, nframes, natoms, x_dev);
+  GCB_CUDA(cudaGetLastError());
+  GCB_CUDA(cudaDeviceSynchronize());
+  return GCB_OK;
+}
+
+int gcb_device_malloc(void **p, size_t bytes, int device)
+{
+  if (!p) return gcb::fail(GCB_ERR_ARG, "null argument");
+  GCB_CUDA(cudaSetDevice(device));
+  GCB_CUDA(cudaMalloc(p, bytes));
+  return GCB_OK;
+}
+int gcb_device_free(void *p, int device)
+{
+  GCB_CUDA(cudaSetDevice(device));
+  GCB_CUDA(cudaFree(p));
+  return GCB_OK;
+}
+int gcb_host_alloc_pinned(void **p, size_t bytes)
+{
+  if (!p) return gcb::fail(GCB_ERR_ARG, "null argument");
+  GCB_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+  return GCB_OK;
+}
+int gcb_host_free_pinned(void *p)
+{
+  GCB_CUDA(cudaFreeHost(p));
+  return GCB_OK;
+}
+int gcb_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, int device)
+{
+  GCB_CUDA(cudaSetDevice(device));
+  GCB_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+  return GCB_OK;
+}
+int gcb_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, int device)
+{
+  GCB_CUDA(cudaSetDevice(device));
+  GCB_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+  return GCB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// multi-GPU reduce (the NCCL binding lives in nccl_reduce.cpp)
+// ---------------------------------------------------------------------------
+extern "C" int gcb_counter_comm_attach_(gcb_counter *c, void *comm, int rank, int nranks)
+{
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  if (comm) { c->nccl = comm; c->rank = rank; c->nranks = nranks; }
+  return GCB_OK;
+}
+
+// After this call every rank holds the global integer counts and statistics.
+// Counts are an integer sum, so the result is independent of the rank count.
+// Exact f32 occupancy needs one weight for the whole job (checked); with
+// differing weights per rank the f32 accumulators are summed instead, which is
+// no longer the reference's sequential order (documented in DESIGN.md).
+extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c,
+                                           int (*allreduce)(const void *, void *, size_t, int, void *, void *))
+{
+  enum { U32 = 3, U64 = 5, F32 = 7, F64 = 8 };
+  if (c->nranks <= 1 || !c->nccl) return gcb_counter_sync(c);
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  int rc = gcb_counter_sync(c);
+  if (rc) return rc;
+  // agree on whether a single weight run covers all ranks
+  // (an all-gather expressed as a sum of one-hot slots: one collective type for everything)
+  uint32_t wb; memcpy(&wb, &c->w_first, 4);
+  std::vector<unsigned long long> slots((size_t)c->nranks * 4, 0ull), out((size_t)c->nranks * 4, 0ull);
+  slots[(size_t)c->rank * 4 + 0] = c->any ? 1ull : 0ull;
+  slots[(size_t)c->rank * 4 + 1] = wb;
+  slots[(size_t)c->rank * 4 + 2] = c->uniform ? 1ull : 0ull;
+  slots[(size_t)c->rank * 4 + 3] = (c->d_acc != nullptr) ? 1ull : 0ull;
+  unsigned long long *d_slots = nullptr;
+  GCB_CUDA(cudaMalloc(&d_slots, sizeof(unsigned long long) * slots.size()));
+  GCB_CUDA(cudaMemcpyAsync(d_slots, slots.data(), sizeof(unsigned long long) * slots.size(), cudaMemcpyHostToDevice, c->compute));
+  rc = allreduce(d_slots, d_slots, slots.size(), U64, c->nccl, c->compute);
+  if (rc) { cudaFree(d_slots); return rc; }
+  GCB_CUDA(cudaMemcpyAsync(out.data(), d_slots, sizeof(unsigned long long) * out.size(), cudaMemcpyDeviceToHost, c->compute));
+  GCB_CUDA(cudaStreamSynchronize(c->compute));
+  cudaFree(d_slots);
+  bool global_uniform = true, any_acc = false, have_w = false;
+  uint32_t w0 = 0;
+  for (int r = 0; r < c->nranks; r++) {
+    if (!out[(size_t)r * 4 + 0]) continue;
+    if (!out[(size_t)r * 4 + 2]) global_uniform = false;
+    if (out[(size_t)r * 4 + 3]) any_acc = true;
+    if (!have_w) { w0 = (uint32_t)out[(size_t)r * 4 + 1]; have_w = true; }
+    else if (w0 != (uint32_t)out[(size_t)r * 4 + 1]) global_uniform = false;
+  }
+  if (global_uniform && !any_acc) {
+    // the common case: one integer grid per rank, one weight: sum the counts
+    rc = allreduce(c->d_runcnt, c->d_runcnt, c->ncells, U32, c->nccl, c->compute);
+    if (rc) return rc;
+    if (have_w) { memcpy(&c->w_cur, &w0, 4); c->w_first = c->w_cur; c->have_run = true; c->any = true; }
+  } else {
+    rc = fold_pending(c);
+    if (rc) return rc;
+    rc = ensure_acc(c);
+    if (rc) return rc;
+    rc = allreduce(c->d_acc, c->d_acc, c->ncells, F32, c->nccl, c->compute);
+    if (rc) return rc;
+    rc = allreduce(c->d_total, c->d_total, c->ncells, U32, c->nccl, c->compute);
+    if (rc) return rc;
+    c->uniform = false;
+  }
+  // scalars: frames, hits, overflow as u64; sumP as f64 (rank order of the sum is NCCL's)
+  unsigned long long sc[3] = {(unsigned long long)c->hits_per_frame.size(), c->hits_total, c->edge_overflow};
+  double sp = c->sumP;
+  unsigned long long *d_sc = nullptr;
+  double *d_sp = nullptr;
+  GCB_CUDA(cudaMalloc(&d_sc, sizeof(sc)));
+  GCB_CUDA(cudaMalloc(&d_sp, sizeof(double)));
+  GCB_CUDA(cudaMemcpyAsync(d_sc, sc, sizeof(sc), cudaMemcpyHostToDevice, c->compute));
+  GCB_CUDA(cudaMemcpyAsync(d_sp, &sp, sizeof(double), cudaMemcpyHostToDevice, c->compute));
+  rc = allreduce(d_sc, d_sc, 3, U64, c->nccl, c->compute);
+  if (!rc) rc = allreduce(d_sp, d_sp, 1, F64, c->nccl, c->compute);
+  if (rc) { cudaFree(d_sc); cudaFree(d_sp); return rc; }
+  GCB_CUDA(cudaMemcpyAsync(sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, c->compute));
+  GCB_CUDA(cudaMemcpyAsync(&sp, d_sp, sizeof(double), cudaMemcpyDeviceToHost, c->compute));
+  GCB_CUDA(cudaStreamSynchronize(c->compute));
+  cudaFree(d_sc); cudaFree(d_sp);
+  c->global_frames = sc[0]; c->hits_total = sc[1]; c->edge_overflow = sc[2]; c->sumP = sp;
+  c->reduced = true;
+  return GCB_OK;
+}

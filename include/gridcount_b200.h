@@ -1,0 +1,246 @@
+/*
+ * gridcount_b200.h -- C ABI of libgridcount_b200.so
+ *
+ * B200-native (sm_100a) replacement for the one data-parallel hot path of
+ * orbeckst/gridcount: g_ri3Dc's binning of index-group atom positions into a
+ * 3D occupancy grid over a trajectory, the density normalisation, the XDR grid
+ * file, and a_ri3Dc's reductions over the finished grid.
+ *
+ * The reference has no FFI: its seam is function level inside two main()s.
+ * Each entry point below names the reference code it replaces (file:line under
+ * the reference tree).  Plain C types only; every function returns 0 on
+ * success or a negative gcb_status, and gcb_last_error() gives the message.
+ * The library never calls exit(); the host tool turns errors into
+ * gmx_fatal-style exits.  There is no CPU fallback for the GPU entry points:
+ * without a CUDA device they fail with GCB_ERR_CUDA.
+ *
+ * Memory layouts (all little-endian host floats):
+ *   frames      x[frame][atom][3]             rvec arrays as read_next_x fills them
+ *                                             (g_ri3Dc.c:392,428)
+ *   grid        z fastest, cell (i,j,k) at (i*my + j)*mz + k, the contiguous block
+ *               behind t_tgrid.grid[0][0]     (utilgmx.c:57-69)
+ *   file order  x fastest, then y, then z     (xdr_grid.c:113-126, plt.c:69-75)
+ *   2D outputs  row major [n0][n1] as grid2_alloc (utilgmx.c:76-110)
+ */
+#ifndef GRIDCOUNT_B200_H
+#define GRIDCOUNT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCB_ABI_VERSION 1
+#define GCB_HEADER_MAX 256            /* HEADER_MAX, xdr_grid.h:35 */
+#define GCB_GRID_FF_VERSION 2         /* GRID_FF_VERSION, xdr_grid.h:34 */
+#define GCB_NGRID_MAX (512u * 512u * 512u)  /* NGRID_MAX, xdr_grid.h:36 */
+#define GCB_GMX_REAL_EPS 5.96046448E-08     /* GMX_REAL_EPS of single-precision Gromacs 4.5 (grid3D.c:143,146) */
+
+typedef enum {
+  GCB_OK = 0,
+  GCB_ERR_ARG = -1,        /* bad argument */
+  GCB_ERR_CUDA = -2,       /* CUDA runtime/driver failure, or no device */
+  GCB_ERR_NOMEM = -3,
+  GCB_ERR_IO = -4,         /* file open/read/write */
+  GCB_ERR_FORMAT = -5,     /* not a version-2, 3D grid file (xdr_grid.c:28-34, grid3D.c:81-83) */
+  GCB_ERR_STATE = -6,      /* call order (e.g. results requested before sync) */
+  GCB_ERR_NCCL = -7,
+  GCB_ERR_RANGE = -8       /* crop outside the grid (asserts at a_ri3Dc.c:191-192), z2 <= z1 (:163-165) */
+} gcb_status;
+
+const char *gcb_last_error(void);
+int gcb_abi_version(void);
+
+/* ------------------------------------------------------------------------
+ * Geometry (host).  Replaces t_cavity (count.h:71-77), t_tgrid without its
+ * data pointer (grid3D.h:63-71), autoset_cavity (count.c:25-64), setup_corners
+ * + setup_tgrid (grid3D.c:125-203), DeltaV (grid3D.c:108-110), update_tgrid /
+ * tgrid2cavity (a_ri3Dc.c:86-107).  Same f32/f64 operation order.
+ * ---------------------------------------------------------------------- */
+typedef struct { float axis[3], cpoint[3], radius, z1, z2, vol; } gcb_cavity;
+typedef struct { int mx[3]; float a[3], b[3], delta[3]; float tweight; } gcb_tgrid;
+
+enum { GCB_SET_CPOINT = 1, GCB_SET_R = 2, GCB_SET_Z1 = 4, GCB_SET_Z2 = 8 };   /* which options the user gave */
+
+int gcb_autoset_cavity(gcb_cavity *cav, const float box[9], int setmask);
+int gcb_setup_tgrid(gcb_tgrid *tg, gcb_cavity *cav, const float delta[3]);
+double gcb_delta_v(const gcb_tgrid *tg);
+void gcb_update_tgrid(gcb_tgrid *tg);
+void gcb_tgrid2cavity(const gcb_tgrid *tg, gcb_cavity *cav);
+/* 1 if a coordinate one ulp below b[d] would bin to mx[d] (the reference then
+ * writes out of bounds, g_ri3Dc.c:146-149); such hits are dropped and counted
+ * in gcb_stats.edge_overflow. */
+int gcb_edge_vulnerable(const gcb_tgrid *tg);
+
+/* Frame weights of the frame loop (g_ri3Dc.c:390-394, 413-416): dt = t - tlast
+ * in f32 with tlast0 = t[0] - (t[1]-t[0]); T_tot += dt in f64; weight = dt or 1.
+ * `tlast` in/out lets a caller stream frames in pieces (NULL: bootstrap from t). */
+int gcb_frame_weights(const float *t, long nframes, int dtweight, float *tlast,
+                      float *weight_out, double *T_tot_inout);
+
+/* ------------------------------------------------------------------------
+ * Binning on the GPU.  Replaces gridcount() (g_ri3Dc.c:139-152) and the atom
+ * loop g_ri3Dc.c:425-426 over many frames.
+ * ---------------------------------------------------------------------- */
+typedef struct gcb_counter gcb_counter;
+
+enum {
+  GCB_PBC_NONE = 0,        /* reference behaviour: atoms outside [a,b) are dropped (g_ri3Dc.c:145) */
+  GCB_PBC_RECT = 1         /* opt-in single-image rectangular wrap as count.c:88-92 before binning */
+};
+enum {                     /* kernel selection (GCB_KERNEL_AUTO picks by index-group density) */
+  GCB_KERNEL_AUTO = 0, GCB_KERNEL_GATHER = 1, GCB_KERNEL_STREAM = 2
+};
+
+typedef struct {
+  int device;              /* CUDA device ordinal */
+  int pbc;                 /* GCB_PBC_* */
+  int kernel;              /* GCB_KERNEL_* */
+  int nslots;              /* staging slots / copy streams for host frames (0: default 3) */
+  long frames_per_batch;   /* frames per staged batch (0: sized to ~32 MiB) */
+} gcb_counter_opts;
+
+typedef struct {
+  uint64_t frames;         /* frames binned so far */
+  uint64_t atom_frames;    /* frames * gnx */
+  uint64_t hits;           /* atom-frames that landed in the grid */
+  uint64_t edge_overflow;  /* dropped: quotient >= mx or NaN coordinate (see gcb_edge_vulnerable) */
+  double sumP;             /* Sum over hits of (double)weight in frame order (g_ri3Dc.c:151,426) */
+  int uniform_weight;      /* 1 while every frame so far had the same weight */
+  float weight;            /* that weight */
+  int64_t kernel_launches; /* CUDA kernels launched by this counter so far */
+} gcb_stats;
+
+int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex, int gnx,
+                       int natoms, const gcb_counter_opts *opts);
+void gcb_counter_destroy(gcb_counter *c);
+int gcb_counter_reset(gcb_counter *c);
+
+/* Host frames x[nframes][natoms][3]; weight[f] is the reference's per-frame
+ * `weight` (NULL: 1); box[f][9] is only read with GCB_PBC_RECT.  Frames are
+ * staged through pinned buffers in batches on CUDA streams and binned
+ * asynchronously; the call returns when all of x has been consumed. */
+int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes,
+                           const float *weight, const float *box);
+/* Same for frames already resident in device memory (16-byte aligned). */
+int gcb_counter_add_device_frames(gcb_counter *c, const float *x_dev, long nframes,
+                                  const float *weight, const float *box);
+/* Zero-copy producer interface: fill a pinned slot, then submit it. */
+int gcb_counter_slot(gcb_counter *c, int slot, float **x_pinned, long *capacity_frames);
+int gcb_counter_submit_slot(gcb_counter *c, int slot, long nframes, const float *weight, const float *box);
+int gcb_counter_sync(gcb_counter *c);
+
+int gcb_counter_stats(gcb_counter *c, gcb_stats *out);
+/* per-frame in-grid hit counts, in submission order */
+int gcb_counter_hits_per_frame(gcb_counter *c, uint64_t *hits, long capacity, long *nframes_out);
+/* raw integer hit counts per cell (z fastest) */
+int gcb_counter_counts(gcb_counter *c, uint32_t *counts_zfast);
+/* the reference's f32 accumulator grid[i][j][k] before normalisation
+ * (the value of its `+= weight` chain, g_ri3Dc.c:149), z fastest */
+int gcb_counter_occupancy(gcb_counter *c, float *occ_zfast);
+/* Normalisation g_ri3Dc.c:451-460: grid / ((double)(float)dV * T_tot); either
+ * output may be NULL.  Sets tg_out->tweight = (float)T_tot when tg_out != NULL. */
+int gcb_counter_density(gcb_counter *c, double T_tot, float *grid_zfast, float *grid_xfast,
+                        gcb_tgrid *tg_out);
+/* device pointers for callers that keep results on the GPU (valid until destroy) */
+int gcb_counter_device_counts(gcb_counter *c, uint32_t **counts_dev);
+/* CUDA-event stopwatch on the stream the binning kernels are launched on:
+ * start records an event, stop records a second one, waits for it and returns
+ * the device time between them in milliseconds. */
+int gcb_counter_timer_start(gcb_counter *c);
+int gcb_counter_timer_stop(gcb_counter *c, float *ms);
+
+/* Frame-sharded multi-GPU: one counter per rank; integer sum of the private
+ * grids and of the statistics over NCCL (the reference's manual equivalent is
+ * a_gridcalc.c:180-189).  After the call every rank holds the global result. */
+int gcb_nccl_unique_id(char id_out[128]);
+int gcb_counter_comm_init(gcb_counter *c, const char id[128], int rank, int nranks);
+int gcb_counter_allreduce(gcb_counter *c);
+
+/* ------------------------------------------------------------------------
+ * Grid files and header.  Replaces the header string (g_ri3Dc.c:462-473),
+ * grid_write / grid_read (grid3D.c:22-106), xdr_grid_v2 and the
+ * (un)serialisers (xdr_grid.c:89-158), density_write_plt / _ascii
+ * (plt.c:42-99).  Byte-exact with the reference's files.
+ * ---------------------------------------------------------------------- */
+int gcb_header(char out[GCB_HEADER_MAX], const char *subtitle, double T_tot, const char *grpname,
+               const gcb_cavity *cav, const gcb_tgrid *tg, double sumP, const char *trxname,
+               int dtweight);
+size_t gcb_xdr_size(const gcb_tgrid *tg, const char *header);
+/* grid_xfast: cells in file order (what gcb_counter_density emits), or NULL with grid_zfast given */
+int gcb_xdr_encode(const gcb_tgrid *tg, const float *grid_zfast, const float *grid_xfast,
+                   const char *header, uint8_t *out, size_t cap, size_t *written);
+int gcb_grid_write(const char *path, const gcb_tgrid *tg, const float *grid_zfast,
+                   const float *grid_xfast, const char *header);
+/* *grid_zfast is malloc'ed by the library (free with gcb_free); b is rebuilt as a + mx*delta */
+int gcb_grid_read(const char *path, gcb_tgrid *tg, char header[GCB_HEADER_MAX + 1], float **grid_zfast);
+int gcb_plt_write(const char *path, const gcb_tgrid *tg, const float *grid_zfast, float unit);
+int gcb_ascii_write(const char *path, const gcb_tgrid *tg, const float *grid_zfast, float unit);
+void gcb_free(void *p);
+
+/* ------------------------------------------------------------------------
+ * Analysis on the GPU.  Replaces readjust_tgrid (a_ri3Dc.c:133-201) and the
+ * reductions of a_ri3Dc's main (a_ri3Dc.c:488-762), with the reference's f32
+ * summation order per output element so results are bit-identical.
+ * ---------------------------------------------------------------------- */
+enum { GCB_UNIT_UNITY, GCB_UNIT_SPC, GCB_UNIT_MOLAR, GCB_UNIT_ANG, GCB_UNIT_VOXEL, GCB_UNIT_NR };  /* count.h:28 */
+
+typedef struct {
+  int unit;                /* GCB_UNIT_*  (-unit) */
+  float min_occ;           /* -minocc, in the chosen unit */
+  int rad_ba_nr, rad_ba_step;   /* hidden -radnr / -radstep (0, 1 by default) */
+  int setmask;             /* GCB_SET_R|Z1|Z2: crop as readjust_tgrid with the values below */
+  float radius, z1, z2;
+  int device;
+} gcb_analysis_opts;
+
+typedef struct {
+  gcb_tgrid tg;            /* the (possibly cropped) grid that was analysed */
+  gcb_cavity geometry;     /* tgrid2cavity of it */
+  float DeltaR; double dV; int iradNR; float unit_value;
+  double sumP, sumH;       /* a_ri3Dc.c:499-512 */
+  float volume, reff, average, height; int ivol;    /* a_ri3Dc.c:759-762 */
+  float *grid;             /* cropped grid, z fastest [mx][my][mz] */
+  float *xyp, *xzp, *yzp, *hxyp;        /* [mx][my] [mx][mz] [my][mz] [mx][my] */
+  float *zdf, *lzdf, *profile;          /* [mz][2] */
+  float *rweight;                       /* [iradNR] */
+  float *rdf, *hrdf;                    /* [iradNR][2] */
+  float *rzp, *hrzp;                    /* [iradNR][mz] */
+  int64_t kernel_launches;
+} gcb_analysis;
+
+float gcb_dens_unit(int unit, const gcb_tgrid *tg);      /* DensUnit[] (count.c:21-22, a_ri3Dc.c:516) */
+int gcb_analyse(const gcb_tgrid *tg, const float *grid_zfast, const gcb_analysis_opts *opts,
+                gcb_analysis *out);
+void gcb_analysis_free(gcb_analysis *a);
+
+/* a_gridcalc.c:132-189: time-weighted average of n grids of identical shape */
+int gcb_gridcalc(int ngrids, const float *const *grids_zfast, const float *tweights,
+                 const gcb_tgrid *tg, float *avg_zfast, float *tweight_out, int device);
+
+/* ------------------------------------------------------------------------
+ * Synthetic trajectories (benchmarks/tests): counter-based generator whose
+ * bits are reproducible on the CPU.  Writes device memory.
+ * ---------------------------------------------------------------------- */
+enum { GCB_GEN_UNIFORM = 0, GCB_GEN_QUANTISED = 1, GCB_GEN_PORE = 2, GCB_GEN_CLUSTER = 3 };
+typedef struct {
+  uint64_t seed; int mode; float L[3];
+  float slab_lo, slab_hi, pore_r; int nsites; float sigma; int box_period; float box_amp;
+} gcb_gen;
+int gcb_gen_device_frames(const gcb_gen *p, long frame0, long nframes, int natoms, float *x_dev, int device);
+
+/* device memory helpers so that non-CUDA hosts (C tools, ctypes) can hold frames on the GPU */
+int gcb_device_malloc(void **p, size_t bytes, int device);
+int gcb_device_free(void *p, int device);
+int gcb_host_alloc_pinned(void **p, size_t bytes);
+int gcb_host_free_pinned(void *p);
+int gcb_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, int device);
+int gcb_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, int device);
+int gcb_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -135,19 +135,23 @@ void gco_frame_weights(const float *t, long nframes, int dtweight, float *weight
 /* ------------------------------------------------------------------ */
 
 /* g_ri3Dc.c:144-147; returns the flat z-fastest cell, -1 if outside, -2 if
- * the quotient lands on or beyond mx (undefined behaviour in the reference,
- * dropped and counted here and in the CUDA path). */
+ * the atom passes all three bounds tests but a quotient lands on or beyond mx
+ * or is NaN (undefined behaviour in the reference, SURVEY 7.3 item 2: dropped
+ * and counted here and in the CUDA path).  The reference returns at the first
+ * failing bounds test, so an atom that is outside in any dimension is never
+ * dangerous: "outside" takes precedence over "overflow". */
 static inline long cell_of(const gco_geom *g, const float *x)
 {
-  int ijk[3], d;
+  int ijk[3], d, ovf = 0;
   for (d = 0; d < 3; d++) {
     float u = x[d] - g->a[d];
     float q;
     if (u < 0 || x[d] - g->b[d] >= 0) return -1;
     q = u / g->delta[d];
-    if (!(q < (float)g->mx[d])) return -2;
-    ijk[d] = (int)floor((double)q);
+    if (!(q < (float)g->mx[d])) { ovf = 1; ijk[d] = 0; }
+    else ijk[d] = (int)floor((double)q);
   }
+  if (ovf) return -2;
   return ((long)ijk[0] * g->mx[1] + ijk[1]) * g->mx[2] + ijk[2];  /* utilgmx.c:57-69 */
 }
 

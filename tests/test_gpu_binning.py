@@ -1,0 +1,330 @@
+"""GPU parity tests (run on the B200 box): the CUDA path through the C ABI against the CPU
+oracle on the same seeded inputs, and against the reference's golden files."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import gcutil as u
+import golden_cases as gc
+import gridcount_b200 as g
+from gridcount_b200 import _cabi as K
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [K.KERNEL_GATHER, K.KERNEL_STREAM]
+
+
+def to_ogeom(geom):
+    return u.Geom.from_buffer_copy(bytes(geom.tg))
+
+
+def oracle_counts(geom, x, gindex):
+    o = u.oracle()
+    og = to_ogeom(geom)
+    x = np.ascontiguousarray(x, np.float32)
+    gi = np.ascontiguousarray(gindex, np.int32)
+    counts = np.zeros(geom.shape, np.uint32)
+    hits = np.zeros(x.shape[0], np.uint64)
+    ovf = C.c_uint64(0)
+    o.gco_count_frames(C.byref(og), counts.ctypes.data_as(u.c_u32_p), u.fptr(x), x.shape[0], x.shape[1], u.iptr(gi),
+                       len(gi), hits.ctypes.data_as(u.c_u64_p), C.byref(ovf))
+    return counts, hits, ovf.value
+
+
+def oracle_occupancy(geom, x, gindex, w):
+    o = u.oracle()
+    og = to_ogeom(geom)
+    x = np.ascontiguousarray(x, np.float32)
+    gi = np.ascontiguousarray(gindex, np.int32)
+    w = np.ascontiguousarray(w, np.float32)
+    grid = np.zeros(geom.shape, np.float32)
+    sp = C.c_double(0)
+    o.gco_bin_frames(C.byref(og), u.fptr(grid), u.fptr(x), x.shape[0], x.shape[1], u.iptr(gi), len(gi), u.fptr(w),
+                     C.byref(sp), None, None)
+    return grid, sp.value
+
+
+# ----------------------------------------------------------------------------- generator
+@pytest.mark.parametrize("mode,kw", [(0, {}), (1, {}), (2, dict(slab=(2.2, 4.5), pore_r=0.8)),
+                                     (3, dict(nsites=7, sigma=0.1)), (0, dict(box_period=10, box_amp=0.002))])
+def test_generator_bits_match_oracle(mode, kw):
+    L = (4.0, 4.0, 6.7)
+    natoms, nframes = 777, 23
+    dev = g.DeviceFrames(nframes, natoms).generate(g.make_gen(42, L, mode, **kw), frame0=5)
+    got = dev.download()
+    want = u.gen_frames(u.make_gen(42, L, mode, **kw), 5, nframes, natoms)
+    u.assert_bits_equal(got, want, "generated frames")
+    dev.free()
+
+
+# ----------------------------------------------------------------------------- golden cases end to end
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", list(gc.CASES))
+def test_golden_density_file_byte_exact(name, kernel):
+    """frames -> GPU binning -> density -> XDR bytes == the file the reference wrote"""
+    c = gc.CASES[name]
+    ga = gc.parse_gargs(c["gargs"])
+    t, boxes, x, gindex = gc.case_inputs(name)
+    kw = {}
+    if ga["setmask"] & u.SET_CPOINT: kw["cpoint"] = ga["cpoint"]
+    if ga["setmask"] & u.SET_R: kw["radius"] = ga["R"]
+    if ga["setmask"] & u.SET_Z1: kw["z1"] = ga["z1"]
+    if ga["setmask"] & u.SET_Z2: kw["z2"] = ga["z2"]
+    geom = g.setup_geometry(boxes[0], c["delta"], **kw)
+    w, T = g.frame_weights(t, ga["dtweight"])
+    ctr = g.GridCounter(geom, gindex, c["natoms"], kernel=kernel, frames_per_batch=7)
+    ctr.add_frames(x, w)
+    st = ctr.stats()
+    assert st.frames == c["nframes"] and st.edge_overflow == 0
+    ocounts, ohits, _ = oracle_counts(geom, x, gindex)
+    np.testing.assert_array_equal(ctr.counts(), ocounts)
+    np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
+    occ, osumP = oracle_occupancy(geom, x, gindex, w)
+    u.assert_bits_equal(ctr.occupancy(), occ, "f32 occupancy")
+    assert st.sumP == osumP
+    tg, gz, gx = ctr.density(T, zfast=True, xfast=True)
+    grp = "OW" if c["stride"] != 1 else "System"
+    hdr = g.header_string(geom, T, st.sumP, grp, "traj.raw", ga["subtitle"], ga["dtweight"])
+    want = open(os.path.join(u.GOLDEN_DIR, name, "grid.dat"), "rb").read()
+    assert g.xdr_encode(tg, hdr, grid_xfast=gx) == want
+    assert g.xdr_encode(tg, hdr, grid_zfast=gz) == want
+    ctr.close()
+
+
+# ----------------------------------------------------------------------------- randomised shapes
+SHAPES = [
+    # natoms, gindex builder, nframes, box, delta
+    (2700, lambda n, r: np.arange(0, n, 3), 40, (3.0, 3.0, 3.0), 0.05),
+    (2049, lambda n, r: np.arange(n), 9, (2.98, 3.31, 4.07), (0.2, 0.2, 0.25)),          # natoms % 4 != 0
+    (61, lambda n, r: np.arange(0, n, 2), 300, (2.0, 2.0, 2.0), 0.1),                      # many frames per tile
+    (5000, lambda n, r: r.permutation(n)[:1234], 13, (4.0, 5.0, 6.0), (0.11, 0.13, 0.17)),  # unsorted group
+    (4099, lambda n, r: r.integers(0, n, 3000), 11, (4.0, 4.0, 4.0), 0.08),                # duplicates
+    (10000, lambda n, r: np.array([17, 4242, 9999]), 25, (5.0, 5.0, 5.0), 0.1),            # sparse (ions)
+    (3, lambda n, r: np.array([1]), 1, (1.0, 1.0, 1.0), 0.5),
+    (8192, lambda n, r: np.arange(n), 4, (6.0, 6.0, 6.0), 0.05),                            # exact tiles, no tail
+]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("shape", range(len(SHAPES)))
+def test_counts_bit_exact_random_shapes(shape, kernel):
+    natoms, mk, nframes, L, delta = SHAPES[shape]
+    rng = np.random.default_rng(100 + shape)
+    gindex = mk(natoms, rng).astype(np.int32)
+    # positions reach a little outside the box so that drops happen on every side
+    x = u.gen_frames(u.make_gen(500 + shape, tuple(1.1 * v for v in L)), 0, nframes, natoms)
+    x -= np.float32(0.05) * np.asarray(L, np.float32)
+    geom = g.setup_geometry(L, delta)
+    ocounts, ohits, oovf = oracle_counts(geom, x, gindex)
+    ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel)
+    ctr.add_frames(x)                                    # host path, pageable memory
+    np.testing.assert_array_equal(ctr.counts(), ocounts)
+    np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
+    st = ctr.stats()
+    assert st.hits == ohits.sum() == ocounts.sum(dtype=np.uint64)
+    assert st.edge_overflow == oovf
+    # device-resident path gives the same grid (and doubles it)
+    dev = g.DeviceFrames(nframes, natoms).upload(x)
+    ctr.add_device_frames(dev)
+    np.testing.assert_array_equal(ctr.counts(), 2 * ocounts)
+    np.testing.assert_array_equal(ctr.hits_per_frame(), np.concatenate([ohits, ohits]))
+    dev.free()
+    ctr.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_special_values_and_edge_overflow(kernel):
+    # a geometry where b - 1ulp bins to mx: the hit is dropped and counted
+    L, delta = (9.4928503, 9.4928503, 3.0), (0.100521415, 0.100521415, 0.1)
+    geom = g.setup_geometry(L, delta)
+    assert geom.edge_vulnerable
+    natoms, nframes = 64, 3
+    x = u.gen_frames(u.make_gen(9, L), 0, nframes, natoms)
+    b = np.array(geom.tg.b[:], np.float32)
+    a = np.array(geom.tg.a[:], np.float32)
+    x[0, 0] = (np.nextafter(b[0], np.float32(-1)), 1.0, 1.0)        # edge overflow in x
+    x[0, 1] = (np.nan, 1.0, 1.0)                                    # NaN passes both bounds tests
+    x[0, 2] = (np.inf, 1.0, 1.0)
+    x[0, 3] = (-np.inf, 1.0, 1.0)
+    x[0, 4] = (a[0], a[1], a[2])                                    # exactly on the lower corner: inside
+    x[0, 5] = (b[0], 1.0, 1.0)                                      # exactly on the upper edge: outside
+    x[0, 6] = (np.nan, -5.0, 1.0)                                   # outside wins over NaN
+    x[1, 7] = (1.0, 1.0, np.float32(-0.0))
+    gindex = np.arange(natoms, dtype=np.int32)
+    ocounts, ohits, oovf = oracle_counts(geom, x, gindex)
+    assert oovf == 2
+    ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel)
+    ctr.add_frames(x)
+    np.testing.assert_array_equal(ctr.counts(), ocounts)
+    np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
+    assert ctr.stats().edge_overflow == oovf
+    ctr.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_pbc_rect_wrap(kernel):
+    o = u.oracle()
+    L = (3.0, 3.5, 4.0)
+    natoms, nframes = 3000, 6
+    x = u.gen_frames(u.make_gen(77, tuple(1.6 * v for v in L)), 0, nframes, natoms)
+    x -= np.float32(0.3) * np.asarray(L, np.float32)                # spans about [-0.3 L, 1.3 L)
+    boxes = np.tile(u.box9(L), (nframes, 1)).astype(np.float32)
+    boxes[:, 0] *= np.linspace(1.0, 1.01, nframes, dtype=np.float32)     # breathing box: wrap uses each frame's box
+    geom = g.setup_geometry(L, 0.1)
+    gindex = np.arange(0, natoms, 3, dtype=np.int32)
+    xw = x.copy()
+    o.gco_wrap_frames(u.fptr(xw), nframes, natoms, u.fptr(boxes))
+    ocounts, ohits, _ = oracle_counts(geom, xw, gindex)
+    ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel, pbc=K.PBC_RECT)
+    ctr.add_frames(x, box=boxes)
+    np.testing.assert_array_equal(ctr.counts(), ocounts)
+    np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
+    # without the opt-in the reference behaviour (drop) is kept
+    ctr2 = g.GridCounter(geom, gindex, natoms, kernel=kernel)
+    ctr2.add_frames(x)
+    np.testing.assert_array_equal(ctr2.counts(), oracle_counts(geom, x, gindex)[0])
+    ctr.close(); ctr2.close()
+
+
+# ----------------------------------------------------------------------------- f32 accumulation semantics
+def _weights(kind, n, rng):
+    if kind == "const01":
+        return np.full(n, 0.1, np.float32)
+    if kind == "jitter":              # dt = t_f - t_{f-1} of f32 times f*0.1: varies in the last bits
+        t = (np.arange(n + 1, dtype=np.float32) * np.float32(0.1)).astype(np.float32)
+        return (t[1:] - t[:-1]).astype(np.float32)
+    if kind == "blocks":              # long runs of equal weight -> integer path + fold
+        return np.repeat(np.array([0.1, 0.3, 0.1, 2.0], np.float32), (n + 3) // 4)[:n]
+    if kind == "mixed":
+        w = np.repeat(np.array([1.0, 0.7], np.float32), n // 2)
+        w[n // 3] = 0.123
+        return np.resize(w, n).astype(np.float32)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kind", ["const01", "jitter", "blocks", "mixed"])
+def test_occupancy_reproduces_reference_f32_accumulation(kind, kernel):
+    """`grid[i][j][k] += weight` in f32, frame after frame (g_ri3Dc.c:149): bit-exact for any weights"""
+    rng = np.random.default_rng(5)
+    L = (1.5, 1.5, 1.5)
+    natoms, nframes = 6000, 96                   # ~400 hits per cell: deep into f32 rounding for w = 0.1
+    geom = g.setup_geometry(L, 0.25)
+    x = u.gen_frames(u.make_gen(31, L), 0, nframes, natoms)
+    gindex = np.arange(natoms, dtype=np.int32)
+    w = _weights(kind, nframes, rng)
+    occ, osumP = oracle_occupancy(geom, x, gindex, w)
+    ocounts, ohits, _ = oracle_counts(geom, x, gindex)
+    ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel, frames_per_batch=10)
+    ctr.add_frames(x[:50], w[:50])
+    ctr.add_frames(x[50:], w[50:])
+    u.assert_bits_equal(ctr.occupancy(), occ, "occupancy (%s)" % kind)
+    np.testing.assert_array_equal(ctr.counts(), ocounts)
+    st = ctr.stats()
+    assert st.sumP == osumP
+    assert bool(st.uniform_weight) == (kind == "const01")
+    # density = occupancy / ((double)(float)dV * T)
+    T = float(np.sum(w.astype(np.float64)))
+    og = to_ogeom(geom)
+    dens = occ.copy()
+    u.oracle().gco_normalise(C.byref(og), u.fptr(dens), T)
+    tg, gz, gx = ctr.density(T, zfast=True, xfast=True)
+    u.assert_bits_equal(gz, dens, "density")
+    u.assert_bits_equal(gx, np.ascontiguousarray(dens.transpose(2, 1, 0)), "density, file order")
+    assert tg.tweight == np.float32(T)
+    ctr.close()
+
+
+def test_reset_and_slot_interface():
+    L = (2.0, 2.0, 2.0)
+    natoms, nframes = 1000, 12
+    geom = g.setup_geometry(L, 0.1)
+    x = u.gen_frames(u.make_gen(3, L), 0, nframes, natoms)
+    gindex = np.arange(0, natoms, 3, dtype=np.int32)
+    ocounts, ohits, _ = oracle_counts(geom, x, gindex)
+    ctr = g.GridCounter(geom, gindex, natoms, frames_per_batch=5, nslots=2)
+    ctr.add_frames(x)
+    ctr.reset()
+    assert ctr.counts().sum() == 0 and ctr.stats().frames == 0
+    # zero-copy producer interface: fill the pinned slots directly
+    done = 0
+    slot = 0
+    while done < nframes:
+        p = K.c_float_p()
+        cap = C.c_long(0)
+        K.check(K.lib.gcb_counter_slot(ctr.h, slot, C.byref(p), C.byref(cap)), "slot")
+        n = min(cap.value, nframes - done)
+        C.memmove(p, x[done:done + n].ctypes.data, n * natoms * 12)
+        K.check(K.lib.gcb_counter_submit_slot(ctr.h, slot, n, None, None), "submit")
+        done += n
+        slot = (slot + 1) % 2
+    np.testing.assert_array_equal(ctr.counts(), ocounts)
+    np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
+    # pinned caller memory is DMA'd directly
+    pin = g.PinnedFrames(nframes, natoms)
+    pin.array[:] = x
+    ctr.add_frames(pin.array)
+    np.testing.assert_array_equal(ctr.counts(), 2 * ocounts)
+    pin.free()
+    ctr.close()
+
+
+# ----------------------------------------------------------------------------- full-size properties
+def test_full_size_c2_properties():
+    """BASELINE config 2 shape (60k atoms, 20k OW, 80x80x134) on 512 generated frames: size-independent
+    invariants + a replayable prefix against the oracle."""
+    L = (8.0, 8.0, 13.4)
+    natoms, nframes = 60000, 512
+    gen = g.make_gen(20261021, L, K.GEN_PORE, slab=(4.7, 8.7), pore_r=0.8)
+    dev = g.DeviceFrames(nframes, natoms).generate(gen)
+    geom = g.setup_geometry(L, 0.1)
+    assert geom.shape == (80, 80, 134) and not geom.edge_vulnerable
+    gindex = np.arange(0, natoms, 3, dtype=np.int32)
+    res = {}
+    for kernel in KERNELS:
+        ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel)
+        ctr.add_device_frames(dev)
+        res[kernel] = (ctr.counts(), ctr.hits_per_frame())
+        st = ctr.stats()
+        assert st.hits == res[kernel][0].sum(dtype=np.uint64) == res[kernel][1].sum()
+        assert st.hits == nframes * len(gindex)            # every generated atom is inside this grid
+        # linearity: binning the two halves separately adds up
+        a = g.GridCounter(geom, gindex, natoms, kernel=kernel)
+        a.add_device_frames(dev, 0, 200)
+        b = g.GridCounter(geom, gindex, natoms, kernel=kernel)
+        b.add_device_frames(dev, 200, nframes - 200)
+        np.testing.assert_array_equal(a.counts() + b.counts(), res[kernel][0])
+        a.close(); b.close(); ctr.close()
+    np.testing.assert_array_equal(res[K.KERNEL_GATHER][0], res[K.KERNEL_STREAM][0])
+    # replayable prefix on the CPU oracle
+    x = u.gen_frames(u.make_gen(20261021, L, 2, slab=(4.7, 8.7), pore_r=0.8), 0, 24, natoms)
+    ocounts, ohits, _ = oracle_counts(geom, x, gindex)
+    ctr = g.GridCounter(geom, gindex, natoms)
+    ctr.add_device_frames(dev, 0, 24)
+    np.testing.assert_array_equal(ctr.counts(), ocounts)
+    # the membrane slab is empty outside the pore
+    cz = ocounts.sum(axis=(0, 1))
+    assert cz[50:85].max() < cz[:40].min()
+    ctr.close(); dev.free()
+
+
+@pytest.mark.parametrize("cfg", [((20.0, 20.0, 20.0), 0.05, (400, 400, 400), 300000, 6),
+                                 ((10.0, 10.0, 10.0), 0.02, (500, 500, 500), 99999, 10)])
+def test_large_grids(cfg):
+    """BASELINE configs 3 and 4 geometry (grid larger than L2): counts against the oracle on a prefix"""
+    L, delta, shape, natoms, nframes = cfg
+    geom = g.setup_geometry(L, delta)
+    assert geom.shape == shape
+    gindex = np.arange(0, natoms, 3, dtype=np.int32)
+    dev = g.DeviceFrames(nframes, natoms).generate(g.make_gen(7, L))
+    x = dev.download()
+    ocounts, ohits, _ = oracle_counts(geom, x, gindex)
+    for kernel in KERNELS:
+        ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel)
+        ctr.add_device_frames(dev)
+        np.testing.assert_array_equal(ctr.counts(), ocounts)
+        np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
+        ctr.close()
+    dev.free()
