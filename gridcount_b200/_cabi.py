@@ -103,6 +103,9 @@ SIGNATURES = {
     "gcb_counter_occupancy": (C.c_int, [C.c_void_p, c_float_p]),
     "gcb_counter_density": (C.c_int, [C.c_void_p, C.c_double, c_float_p, c_float_p, C.POINTER(TGrid)]),
     "gcb_counter_device_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gcb_counter_device_density": (C.c_int, [C.c_void_p, C.c_double, C.POINTER(C.c_void_p)]),
+    "gcb_counter_event_record": (C.c_int, [C.c_void_p, C.c_int]),
+    "gcb_counter_event_elapsed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "gcb_counter_timer_start": (C.c_int, [C.c_void_p]),
     "gcb_counter_timer_stop": (C.c_int, [C.c_void_p, c_float_p]),
     "gcb_nccl_unique_id": (C.c_int, [C.c_char_p]),

@@ -220,6 +220,17 @@ class GridCounter:
     def reset(self):
         check(lib.gcb_counter_reset(self.h), "gcb_counter_reset")
 
+    reset_grid = reset
+
+    def density_device(self, T_tot):
+        """K2 only; the density stays in HBM (returns the device pointer)"""
+        p = C.c_void_p()
+        check(lib.gcb_counter_device_density(self.h, T_tot, C.byref(p)), "gcb_counter_device_density")
+        return p
+
+    def density_into(self, T_tot, out_zfast):
+        check(lib.gcb_counter_density(self.h, T_tot, _fptr(out_zfast), None, None), "gcb_counter_density")
+
     def add_frames(self, x, weights=None, box=None):
         """x: host array [F][natoms][3] (numpy or PinnedFrames.array)"""
         x = np.ascontiguousarray(x, np.float32)
@@ -274,6 +285,14 @@ class GridCounter:
         tg = K.TGrid()
         check(lib.gcb_counter_density(self.h, T_tot, _fptr(gz), _fptr(gx), C.byref(tg)), "gcb_counter_density")
         return tg, gz, gx
+
+    def event_record(self, i):
+        check(lib.gcb_counter_event_record(self.h, i), "gcb_counter_event_record")
+
+    def event_elapsed(self, i, j):
+        ms = C.c_float(0)
+        check(lib.gcb_counter_event_elapsed(self.h, i, j, C.byref(ms)), "gcb_counter_event_elapsed")
+        return ms.value
 
     def timer_start(self):
         check(lib.gcb_counter_timer_start(self.h), "gcb_counter_timer_start")

@@ -434,12 +434,14 @@ struct Slot {
   float *d_box3 = nullptr, *h_box3 = nullptr;
   long cap = 0;                       // frames
   long pending = 0;                   // frames whose hit counts have not been collected yet
+  size_t frame0 = 0;                  // global index of the first pending frame
 };
 
 struct DevHits {                      // hit counters of an add_device_frames call awaiting collection
   unsigned long long *d = nullptr;
   float *d_box3 = nullptr;
   long n = 0;
+  size_t frame0 = 0;
 };
 
 }  // namespace
@@ -479,7 +481,7 @@ struct gcb_counter {
   int64_t launches = 0;
   void *nccl = nullptr;               // ncclComm_t, see nccl_reduce.cpp
   int nranks = 1, rank = 0;
-  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  std::vector<cudaEvent_t> events;
   bool reduced = false;               // statistics below are global after gcb_counter_allreduce
   uint64_t global_frames = 0;
 };
@@ -626,7 +628,7 @@ int collect_slot(gcb_counter *c, Slot &s)
 {
   if (s.pending == 0) return GCB_OK;
   GCB_CUDA(cudaEventSynchronize(s.consumed));
-  for (long f = 0; f < s.pending; f++) c->hits_per_frame.push_back(s.h_hits[f]);
+  for (long f = 0; f < s.pending; f++) c->hits_per_frame[s.frame0 + f] = s.h_hits[f];
   s.pending = 0;
   return GCB_OK;
 }
@@ -680,6 +682,8 @@ int submit_slot(gcb_counter *c, Slot &s, const float *src, bool src_pinned, long
   // the next copy into this slot must wait for the kernels that read it
   GCB_CUDA(cudaStreamWaitEvent(s.copy, s.consumed, 0));
   s.pending = n;
+  s.frame0 = c->hits_per_frame.size();        // frames keep their submission order whatever slot they used
+  c->hits_per_frame.resize(s.frame0 + (size_t)n, 0);
   for (long f = 0; f < n; f++) c->weight_per_frame.push_back(w ? w[f] : 1.0f);
   return GCB_OK;
 }
@@ -699,7 +703,7 @@ void free_counter(gcb_counter *c)
   for (auto &d : c->devhits) { cudaFree(d.d); cudaFree(d.d_box3); }
   cudaFree(c->d_gindex); cudaFree(c->d_rank); cudaFree(c->d_runcnt); cudaFree(c->d_total); cudaFree(c->d_acc);
   cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2);
-  if (c->t0) { cudaEventDestroy(c->t0); cudaEventDestroy(c->t1); }
+  for (auto e : c->events) if (e) cudaEventDestroy(e);
   if (c->compute) cudaStreamDestroy(c->compute);
   delete c;
 }
@@ -860,8 +864,6 @@ int gcb_counter_add_device_frames(gcb_counter *c, const float *x_dev, long nfram
     return gcb::fail(GCB_ERR_ARG, "gcb_counter_add_device_frames: bad argument");
   if (nframes == 0) return GCB_OK;
   GCB_CUDA(cudaSetDevice(c->opts.device));
-  // keep submission order of the hit counters: drain staged slots first
-  for (auto &s : c->slots) { int rc = collect_slot(c, s); if (rc) return rc; }
   DevHits h;
   h.n = nframes;
   GCB_CUDA(cudaMalloc(&h.d, sizeof(unsigned long long) * (nframes + 2)));
@@ -873,6 +875,8 @@ int gcb_counter_add_device_frames(gcb_counter *c, const float *x_dev, long nfram
     GCB_CUDA(cudaMalloc(&h.d_box3, sizeof(float) * 3 * nframes));
     GCB_CUDA(cudaMemcpy(h.d_box3, b3.data(), sizeof(float) * 3 * nframes, cudaMemcpyHostToDevice));
   }
+  h.frame0 = c->hits_per_frame.size();
+  c->hits_per_frame.resize(h.frame0 + (size_t)nframes, 0);
   c->devhits.push_back(h);
   int rc = bin_device_batch(c, x_dev, nframes, weight, h.d_box3, h.d);
   if (rc) return rc;
@@ -889,7 +893,7 @@ int gcb_counter_sync(gcb_counter *c)
   for (auto &h : c->devhits) {
     std::vector<unsigned long long> tmp((size_t)h.n);
     GCB_CUDA(cudaMemcpy(tmp.data(), h.d, sizeof(unsigned long long) * h.n, cudaMemcpyDeviceToHost));
-    for (long f = 0; f < h.n; f++) c->hits_per_frame.push_back(tmp[f]);
+    for (long f = 0; f < h.n; f++) c->hits_per_frame[h.frame0 + f] = tmp[f];
     cudaFree(h.d); cudaFree(h.d_box3);
   }
   c->devhits.clear();
@@ -981,6 +985,17 @@ static int density_to_device(gcb_counter *c, double denom)
   return GCB_OK;
 }
 
+int gcb_counter_device_density(gcb_counter *c, double T_tot, float **grid_zfast_dev)
+{
+  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  const float dV = (float)gcb_delta_v(&c->tg);
+  int rc = density_to_device(c, (double)dV * T_tot);
+  if (rc) return rc;
+  if (grid_zfast_dev) *grid_zfast_dev = c->d_out;
+  return GCB_OK;
+}
+
 int gcb_counter_occupancy(gcb_counter *c, float *occ_zfast)
 {
   if (!c || !occ_zfast) return gcb::fail(GCB_ERR_ARG, "null argument");
@@ -1015,23 +1030,34 @@ int gcb_counter_density(gcb_counter *c, double T_tot, float *grid_zfast, float *
   return GCB_OK;
 }
 
-int gcb_counter_timer_start(gcb_counter *c)
+int gcb_counter_event_record(gcb_counter *c, int id)
 {
-  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
+  if (!c || id < 0 || id >= GCB_MAX_EVENTS) return gcb::fail(GCB_ERR_ARG, "gcb_counter_event_record: bad argument");
   GCB_CUDA(cudaSetDevice(c->opts.device));
-  if (!c->t0) { GCB_CUDA(cudaEventCreate(&c->t0)); GCB_CUDA(cudaEventCreate(&c->t1)); }
-  GCB_CUDA(cudaEventRecord(c->t0, c->compute));
+  if ((int)c->events.size() <= id) c->events.resize((size_t)id + 1, nullptr);
+  if (!c->events[id]) GCB_CUDA(cudaEventCreate(&c->events[id]));
+  GCB_CUDA(cudaEventRecord(c->events[id], c->compute));
   return GCB_OK;
 }
 
+int gcb_counter_event_elapsed(gcb_counter *c, int id0, int id1, float *ms)
+{
+  if (!c || !ms || id0 < 0 || id1 < 0 || id0 >= (int)c->events.size() || id1 >= (int)c->events.size() ||
+      !c->events[id0] || !c->events[id1])
+    return gcb::fail(GCB_ERR_STATE, "gcb_counter_event_elapsed: events %d/%d were not recorded", id0, id1);
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  GCB_CUDA(cudaEventSynchronize(c->events[id1]));
+  GCB_CUDA(cudaEventElapsedTime(ms, c->events[id0], c->events[id1]));
+  return GCB_OK;
+}
+
+int gcb_counter_timer_start(gcb_counter *c) { return gcb_counter_event_record(c, 0); }
+
 int gcb_counter_timer_stop(gcb_counter *c, float *ms)
 {
-  if (!c || !ms || !c->t0) return gcb::fail(GCB_ERR_STATE, "gcb_counter_timer_stop without start");
-  GCB_CUDA(cudaSetDevice(c->opts.device));
-  GCB_CUDA(cudaEventRecord(c->t1, c->compute));
-  GCB_CUDA(cudaEventSynchronize(c->t1));
-  GCB_CUDA(cudaEventElapsedTime(ms, c->t0, c->t1));
-  return GCB_OK;
+  int rc = gcb_counter_event_record(c, 1);
+  if (rc) return rc;
+  return gcb_counter_event_elapsed(c, 0, 1, ms);
 }
 
 int gcb_gen_device_frames(const gcb_gen *p, long frame0, long nframes, int natoms, float *x_dev, int device)

@@ -144,11 +144,18 @@ int gcb_counter_occupancy(gcb_counter *c, float *occ_zfast);
  * output may be NULL.  Sets tg_out->tweight = (float)T_tot when tg_out != NULL. */
 int gcb_counter_density(gcb_counter *c, double T_tot, float *grid_zfast, float *grid_xfast,
                         gcb_tgrid *tg_out);
-/* device pointers for callers that keep results on the GPU (valid until destroy) */
+/* device pointers for callers that keep results on the GPU (valid until the next
+ * call that produces the same kind of result, or destroy); the work is enqueued on
+ * the counter's stream, gcb_counter_sync waits for it */
 int gcb_counter_device_counts(gcb_counter *c, uint32_t **counts_dev);
-/* CUDA-event stopwatch on the stream the binning kernels are launched on:
- * start records an event, stop records a second one, waits for it and returns
- * the device time between them in milliseconds. */
+int gcb_counter_device_density(gcb_counter *c, double T_tot, float **grid_zfast_dev);
+/* CUDA events on the stream the binning kernels are launched on.  _event_record
+ * enqueues event number `id` (0..GCB_MAX_EVENTS-1) without blocking;
+ * _event_elapsed waits for event `id1` and returns the device time between the
+ * two in milliseconds.  timer_start/stop are the pair (0, 1) with the wait. */
+#define GCB_MAX_EVENTS 4096
+int gcb_counter_event_record(gcb_counter *c, int id);
+int gcb_counter_event_elapsed(gcb_counter *c, int id0, int id1, float *ms);
 int gcb_counter_timer_start(gcb_counter *c);
 int gcb_counter_timer_stop(gcb_counter *c, float *ms);
 

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) red_random(uint32_t *grid, uint32_t ncell
   }
 }
 
-__global__ void __launch_bounds__(256) smem_atomics(uint32_t *out, int iters, int ncells)
+__global__ void __launch_bounds__(1024) smem_atomics(uint32_t *out, int iters, int ncells)
 {
   extern __shared__ uint32_t h[];
   for (int i = threadIdx.x; i < ncells; i += blockDim.x) h[i] = 0;
@@ -103,6 +103,7 @@ int main()
     for (int rep = 0; rep < 5; rep++) {
       CK(cudaEventRecord(a));
       smem_atomics<<<blocks, 1024, ncells * 4>>>(out, iters, ncells);
+      CK(cudaGetLastError());
       CK(cudaEventRecord(b));
       CK(cudaEventSynchronize(b));
       float ms; CK(cudaEventElapsedTime(&ms, a, b));
