@@ -130,22 +130,26 @@ bin_gather_kernel(const float *__restrict__ x, int natoms, const int *__restrict
 }
 
 // ---------------------------------------------------------------------------
-// K1b  streaming kernel: persistent CTAs pull fixed-size tiles of the raw
-// frame array into shared memory with TMA bulk copies (cp.async.bulk +
-// mbarrier, a STAGES-deep ring), then each lane picks its selected atoms out
-// of the tile through the sorted index group.  HBM sees only full-line
-// streaming reads; the gather happens in shared memory (stride 3 or 9 words,
-// both conflict free).
+// K1b  streaming kernel.  Persistent, warp-specialised CTAs: one producer warp
+// pulls fixed-size tiles of the raw frame array into a shared-memory ring with
+// TMA bulk copies (cp.async.bulk + mbarrier, full/empty barrier pairs, no
+// __syncthreads in the loop); eight consumer warps pick their selected atoms
+// out of the tile through the sorted index group, convert to bins and fire
+// one RED per hit.  HBM sees only full-line streaming reads (evict-first);
+// the gather happens in shared memory (stride 3 or 9 words: conflict free).
 //
 // Tiles are TILE_ATOMS atoms of the FLAT array (frame boundaries fall inside
 // tiles); TILE_ATOMS*3 floats is a multiple of both 3 and 4, so atoms never
 // straddle tiles and every tile starts 16-byte aligned.
 // ---------------------------------------------------------------------------
-constexpr int STREAM_THREADS = 256;
-constexpr int TILE_ATOMS = 2048;
+constexpr int CONSUMER_WARPS = 8;
+constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
+constexpr int STREAM_THREADS = CONSUMER_THREADS + 32;     // + producer warp
+constexpr int TILE_ATOMS = 3072;                          // 1024 selected per tile for 3-site water
 constexpr int TILE_FLOATS = TILE_ATOMS * 3;
-constexpr int TILE_BYTES = TILE_FLOATS * 4;      // 24 KiB
+constexpr int TILE_BYTES = TILE_FLOATS * 4;               // 36 KiB
 constexpr int STAGES = 3;
+constexpr int UNROLL = 4;
 
 struct TileMeta {
   long long f0;          // frame of the tile's first atom
@@ -155,10 +159,9 @@ struct TileMeta {
 };
 
 struct StreamSmem {
-  alignas(128) float tile[STAGES][TILE_FLOATS];
-  alignas(8) unsigned long long full[STAGES];
+  float tile[STAGES][TILE_FLOATS];
+  unsigned long long full[STAGES], empty[STAGES];
   TileMeta meta[STAGES];
-  unsigned long long hits[STAGES][2];
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -170,6 +173,10 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
 {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
@@ -191,92 +198,154 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
       ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy) : "memory");
 }
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// Same result as cell_of(), ~3x fewer instructions and no MUFU/F2I: the
+// quotient u/delta is estimated as u * fl(1/delta); whenever the estimate is
+// farther than 2^-22 (relative) from an integer, the estimate, the exact
+// quotient and the IEEE-rounded quotient the reference computes all share the
+// same floor, which is read from the mantissa after adding 1.5*2^23.
+// Otherwise (about 1e-5 of the atoms) the IEEE division is done.
+struct FastDim { int i; bool bad; };
+__device__ __forceinline__ FastDim bin_dim(float u, float delta, float inv, float fmx)
+{
+  const float MAGIC = 12582912.0f;                 // 1.5 * 2^23
+  float p = __fmul_rn(u, inv);
+  float r = __fadd_rn(p, MAGIC);
+  float nf = __fsub_rn(r, MAGIC);                  // nearest integer to p
+  const float d = fabsf(__fsub_rn(p, nf));
+  if (!(d > __fmul_rn(p, 2.384185791015625e-07f)) || !(p < 4194304.0f)) {     // 2^-22
+    p = __fdiv_rn(u, delta);                       // the reference's own operation
+    r = __fadd_rn(p, MAGIC);
+    nf = __fsub_rn(r, MAGIC);
+    if (!(p < 4194304.0f)) return {0, true};       // NaN or absurdly far out
+  }
+  FastDim o;
+  o.i = (__float_as_int(r) - 0x4B400000) - (nf > p ? 1 : 0);
+  o.bad = !(p < fmx);
+  return o;
+}
+
+struct GridParamsFast {
+  float a[3], b[3], delta[3], inv[3], fmx[3];
+  int my, mz;
+};
+
+__device__ __forceinline__ int cell_of_fast(const GridParamsFast &P, float x, float y, float z)
+{
+  const float ux = __fsub_rn(x, P.a[0]), uy = __fsub_rn(y, P.a[1]), uz = __fsub_rn(z, P.a[2]);
+  const bool outside = (ux < 0.0f) | (__fsub_rn(x, P.b[0]) >= 0.0f) |
+                       (uy < 0.0f) | (__fsub_rn(y, P.b[1]) >= 0.0f) |
+                       (uz < 0.0f) | (__fsub_rn(z, P.b[2]) >= 0.0f);
+  if (outside) return -1;
+  const FastDim bx = bin_dim(ux, P.delta[0], P.inv[0], P.fmx[0]);
+  const FastDim by = bin_dim(uy, P.delta[1], P.inv[1], P.fmx[1]);
+  const FastDim bz = bin_dim(uz, P.delta[2], P.inv[2], P.fmx[2]);
+  if (bx.bad | by.bad | bz.bad) return -2;
+  return (bx.i * P.my + by.i) * P.mz + bz.i;
+}
 
 template <int MODE, bool PBC>
 __global__ void __launch_bounds__(STREAM_THREADS)
 bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict__ gindex, unsigned gnx,
-                  const unsigned *__restrict__ rank, long long ntiles, GridParams P,
+                  const unsigned *__restrict__ rank, long long ntiles, GridParamsFast P,
                   uint32_t *__restrict__ counts, float *__restrict__ acc, float w,
                   const float *__restrict__ box3, unsigned long long *__restrict__ hits,
                   unsigned long long *__restrict__ diag)
 {
-  extern __shared__ unsigned char smem_raw[];
-  StreamSmem &S = *reinterpret_cast<StreamSmem *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StreamSmem &S = *reinterpret_cast<StreamSmem *>(smem_raw);
   const int tid = threadIdx.x;
-  unsigned long long policy = 0;
-
-  auto issue = [&](long long t, int stage) {       // thread 0 only
-    const long long g0 = t * TILE_ATOMS;
-    const long long f0 = g0 / natoms;
-    const int r0 = (int)(g0 - f0 * natoms);
-    const long long g1 = g0 + TILE_ATOMS;
-    const long long f1 = g1 / natoms;
-    const int r1 = (int)(g1 - f1 * natoms);
-    const unsigned rel0 = __ldg(rank + r0);
-    TileMeta m;
-    m.f0 = f0; m.r0 = r0; m.rel0 = rel0;
-    m.nsel = (unsigned)((f1 - f0) * (long long)gnx + (long long)__ldg(rank + r1) - (long long)rel0);
-    S.meta[stage] = m;
-    S.hits[stage][0] = 0; S.hits[stage][1] = 0;
-    mbar_expect_tx(&S.full[stage], TILE_BYTES);
-    tma_load_1d(S.tile[stage], x + (size_t)t * TILE_FLOATS, TILE_BYTES, &S.full[stage], policy);
-  };
 
   if (tid == 0) {
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    for (int s = 0; s < STAGES; s++) mbar_init(&S.full[s], 1);
+    for (int s = 0; s < STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], CONSUMER_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; s++) {
-      const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
-      if (t < ntiles) issue(t, s);
-    }
-  }
-  __syncthreads();   // meta of the first tiles visible
 
+  if (tid < 32) {
+    // ---------------- producer warp (one lane) ----------------
+    if (tid == 0) {
+      unsigned long long policy;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      int it = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int stage = it % STAGES;
+        if (it >= STAGES) mbar_wait(&S.empty[stage], (unsigned)(it / STAGES - 1) & 1u);
+        const long long g0 = t * TILE_ATOMS, g1 = g0 + TILE_ATOMS;
+        const long long f0 = g0 / natoms, f1 = g1 / natoms;
+        const int r0 = (int)(g0 - f0 * natoms), r1 = (int)(g1 - f1 * natoms);
+        const unsigned rel0 = __ldg(rank + r0);
+        TileMeta m;
+        m.f0 = f0; m.r0 = r0; m.rel0 = rel0;
+        m.nsel = (unsigned)((f1 - f0) * (long long)gnx + (long long)__ldg(rank + r1) - (long long)rel0);
+        S.meta[stage] = m;                         // published by the mbarrier's release/acquire
+        mbar_expect_tx(&S.full[stage], TILE_BYTES);
+        tma_load_1d(S.tile[stage], x + (size_t)t * TILE_FLOATS, TILE_BYTES, &S.full[stage], policy);
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps ----------------
+  const unsigned ctid = (unsigned)tid - 32u;
+  const int lane = tid & 31;
   int it = 0;
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
     const int stage = it % STAGES;
-    const unsigned parity = (unsigned)(it / STAGES) & 1u;
-    mbar_wait(&S.full[stage], parity);
+    mbar_wait(&S.full[stage], (unsigned)(it / STAGES) & 1u);
     const TileMeta m = S.meta[stage];
-    const float *tile = S.tile[stage];
+    const uint32_t tile = smem_addr(S.tile[stage]);
     unsigned c0 = 0, c1 = 0;            // hits in frame f0 / f0+1 (later frames go straight to global)
-    for (unsigned s = tid; s < m.nsel; s += STREAM_THREADS) {
-      unsigned rel = m.rel0 + s;
-      unsigned df = 0;
-      if (rel >= gnx) { df = rel / gnx; rel -= df * gnx; }
-      const int idx = __ldg(gindex + rel);
-      const int local = (int)((long long)df * natoms + idx - m.r0);
-      float px = tile[3 * local], py = tile[3 * local + 1], pz = tile[3 * local + 2];
-      if (PBC) {
-        const float *L = box3 + 3 * (m.f0 + df);
-        px = wrap1(px, __ldg(L)); py = wrap1(py, __ldg(L + 1)); pz = wrap1(pz, __ldg(L + 2));
+    for (unsigned base = 0; base < m.nsel; base += CONSUMER_THREADS * UNROLL) {
+      int local[UNROLL];
+      unsigned df[UNROLL];
+      bool valid[UNROLL];
+#pragma unroll
+      for (int k = 0; k < UNROLL; k++) {
+        const unsigned s = base + k * CONSUMER_THREADS + ctid;
+        valid[k] = s < m.nsel;
+        unsigned rel = m.rel0 + s;
+        df[k] = 0;
+        if (rel >= gnx) { df[k] = rel / gnx; rel -= df[k] * gnx; }
+        const int idx = valid[k] ? __ldg(gindex + rel) : m.r0;
+        local[k] = (int)((long long)df[k] * natoms + idx - m.r0);
       }
-      const int cell = cell_of(P, px, py, pz);
-      if (cell >= 0) {
-        deposit<MODE>(counts, acc, cell, w);
-        if (df == 0) c0++;
-        else if (df == 1) c1++;
-        else atomicAdd(hits + m.f0 + df, 1ull);
-      } else if (cell == -2) {
-        atomicAdd(diag, 1ull);
+      float px[UNROLL], py[UNROLL], pz[UNROLL];
+#pragma unroll
+      for (int k = 0; k < UNROLL; k++) {
+        const uint32_t p = tile + 12u * (uint32_t)(valid[k] ? local[k] : 0);
+        px[k] = lds_f32(p); py[k] = lds_f32(p + 4); pz[k] = lds_f32(p + 8);
+      }
+#pragma unroll
+      for (int k = 0; k < UNROLL; k++) {
+        if (!valid[k]) continue;
+        if (PBC) {
+          const float *L = box3 + 3 * (m.f0 + df[k]);
+          px[k] = wrap1(px[k], __ldg(L)); py[k] = wrap1(py[k], __ldg(L + 1)); pz[k] = wrap1(pz[k], __ldg(L + 2));
+        }
+        const int cell = cell_of_fast(P, px[k], py[k], pz[k]);
+        if (cell >= 0) {
+          deposit<MODE>(counts, acc, cell, w);
+          if (df[k] == 0) c0++;
+          else if (df[k] == 1) c1++;
+          else atomicAdd(hits + m.f0 + df[k], 1ull);
+        } else if (cell == -2) {
+          atomicAdd(diag, 1ull);
+        }
       }
     }
     c0 = __reduce_add_sync(0xffffffffu, c0);
     c1 = __reduce_add_sync(0xffffffffu, c1);
-    if ((tid & 31) == 0) {
-      if (c0) atomicAdd(&S.hits[stage][0], (unsigned long long)c0);
-      if (c1) atomicAdd(&S.hits[stage][1], (unsigned long long)c1);
-    }
-    __syncthreads();                    // everyone is done with this stage's tile and hit counters
-    if (tid == 0) {
-      if (S.hits[stage][0]) atomicAdd(hits + m.f0, S.hits[stage][0]);
-      if (S.hits[stage][1]) atomicAdd(hits + m.f0 + 1, S.hits[stage][1]);
-      const long long tn = t + (long long)STAGES * gridDim.x;
-      if (tn < ntiles) issue(tn, stage);   // its smem writes are published by the mbarrier (release/acquire)
+    if (lane == 0) {
+      if (c0) atomicAdd(hits + m.f0, (unsigned long long)c0);
+      if (c1) atomicAdd(hits + m.f0 + 1, (unsigned long long)c1);
+      mbar_arrive(&S.empty[stage]);     // this warp is done with the stage (its LDS results are in registers)
     }
   }
 }
@@ -449,6 +518,7 @@ struct DevHits {                      // hit counters of an add_device_frames ca
 struct gcb_counter {
   gcb_tgrid tg{};
   GridParams P{};
+  GridParamsFast PF{};
   gcb_counter_opts opts{};
   int natoms = 0, gnx = 0;
   size_t ncells = 0;
@@ -524,7 +594,7 @@ int fold_pending(gcb_counter *c)
   return GCB_OK;
 }
 
-size_t stream_smem_bytes() { return sizeof(StreamSmem) + 128; }
+size_t stream_smem_bytes() { return sizeof(StreamSmem); }
 
 template <int MODE, bool PBC>
 int launch_bin(gcb_counter *c, const float *d_x, long nframes, float w, const float *d_box3,
@@ -551,7 +621,7 @@ int launch_bin(gcb_counter *c, const float *d_x, long nframes, float w, const fl
       const int per_sm = std::max(1, (int)((227 * 1024) / (stream_smem_bytes() + 1024)));
       const long long grid = std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
       bin_stream_kernel<MODE, PBC><<<(unsigned)grid, STREAM_THREADS, stream_smem_bytes(), c->compute>>>(
-          d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, c->P, cnt, c->d_acc, w, d_box3,
+          d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, c->PF, cnt, c->d_acc, w, d_box3,
           d_hits, c->d_diag);
       c->launches++;
       GCB_CUDA(cudaGetLastError());
@@ -742,6 +812,11 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
     c->P.a[d] = tg->a[d]; c->P.b[d] = tg->b[d]; c->P.delta[d] = tg->delta[d]; c->P.fmx[d] = (float)tg->mx[d];
   }
   c->P.my = tg->mx[1]; c->P.mz = tg->mx[2];
+  for (int d = 0; d < 3; d++) {
+    c->PF.a[d] = tg->a[d]; c->PF.b[d] = tg->b[d]; c->PF.delta[d] = tg->delta[d]; c->PF.fmx[d] = (float)tg->mx[d];
+    c->PF.inv[d] = 1.0f / tg->delta[d];
+  }
+  c->PF.my = tg->mx[1]; c->PF.mz = tg->mx[2];
 
 #define GCB_CREATE_CUDA(call)                                                                        \
   do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gcb::set_error("%s failed: %s", #call, cudaGetErrorString(e_)); \

@@ -164,6 +164,42 @@ def test_special_values_and_edge_overflow(kernel):
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("geo", [((3.0, 3.0, 3.0), 0.05), ((8.0, 8.0, 13.4), 0.1), ((2.98, 3.31, 4.07), (0.2, 0.21, 0.25)),
+                                 ((20.137, 20.137, 20.137), 0.05)])
+def test_cell_boundaries_bit_exact(geo, kernel):
+    """atoms placed on (and one ulp either side of) every cell boundary: the estimate-and-verify bin
+    conversion must agree with the reference's IEEE division exactly where it matters"""
+    L, delta = geo
+    geom = g.setup_geometry(L, delta)
+    a = np.array(geom.tg.a[:], np.float32)
+    dl = np.array(geom.tg.delta[:], np.float32)
+    mx = np.array(geom.tg.mx[:])
+    rng = np.random.default_rng(11)
+    pts = []
+    for d in range(3):
+        k = np.arange(0, mx[d] + 1, dtype=np.float32)
+        edge = (a[d] + k * dl[d]).astype(np.float32)                 # f32 product and sum, like a boundary estimate
+        for cand in (edge, np.nextafter(edge, np.float32(-1e9)), np.nextafter(edge, np.float32(1e9)),
+                     np.nextafter(np.nextafter(edge, np.float32(1e9)), np.float32(1e9))):
+            p = (a + rng.random((len(cand), 3), dtype=np.float32) * (mx * dl)).astype(np.float32)
+            p[:, d] = cand
+            pts.append(p)
+    x = np.concatenate(pts).astype(np.float32)
+    natoms = len(x)
+    x = x[None, :, :].repeat(2, axis=0)
+    x[1] = x[1, ::-1]
+    gindex = np.arange(natoms, dtype=np.int32)
+    ocounts, ohits, oovf = oracle_counts(geom, x, gindex)
+    ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel)
+    dev = g.DeviceFrames(2, natoms).upload(x)
+    ctr.add_device_frames(dev)
+    np.testing.assert_array_equal(ctr.counts(), ocounts)
+    np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
+    assert ctr.stats().edge_overflow == oovf
+    dev.free(); ctr.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
 def test_pbc_rect_wrap(kernel):
     o = u.oracle()
     L = (3.0, 3.5, 4.0)
