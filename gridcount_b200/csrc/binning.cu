@@ -156,7 +156,14 @@ struct TileMeta {
   int r0;                // atom index (within frame f0) of the tile's first atom
   unsigned rel0;         // rank[r0]: index-group position of the first selected atom, relative to frame f0
   unsigned nsel;         // selected atom-frames inside the tile
+  // arithmetic-progression groups: selected slot j sits at tile atom  (j < nA ? baseA : baseB) + j*step
+  unsigned nA;           // selected atoms of frame f0 inside the tile (the rest belong to frame f0+1)
+  int baseA, baseB;
 };
+
+// Index group of the form g0 + i*step, i < gnx (every water oxygen, all atoms, ...): the selected
+// atoms of a tile follow from arithmetic, no index or rank loads in the inner loop.
+struct ApGroup { int g0, step, tile_atoms; };
 
 struct StreamSmem {
   float tile[STAGES][TILE_FLOATS];
@@ -205,55 +212,69 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
   return v;
 }
 
-// Same result as cell_of(), ~3x fewer instructions and no MUFU/F2I: the
-// quotient u/delta is estimated as u * fl(1/delta); whenever the estimate is
-// farther than 2^-22 (relative) from an integer, the estimate, the exact
-// quotient and the IEEE-rounded quotient the reference computes all share the
-// same floor, which is read from the mantissa after adding 1.5*2^23.
-// Otherwise (about 1e-5 of the atoms) the IEEE division is done.
-struct FastDim { int i; bool bad; };
-__device__ __forceinline__ FastDim bin_dim(float u, float delta, float inv, float fmx)
-{
-  const float MAGIC = 12582912.0f;                 // 1.5 * 2^23
-  float p = __fmul_rn(u, inv);
-  float r = __fadd_rn(p, MAGIC);
-  float nf = __fsub_rn(r, MAGIC);                  // nearest integer to p
-  const float d = fabsf(__fsub_rn(p, nf));
-  if (!(d > __fmul_rn(p, 2.384185791015625e-07f)) || !(p < 4194304.0f)) {     // 2^-22
-    p = __fdiv_rn(u, delta);                       // the reference's own operation
-    r = __fadd_rn(p, MAGIC);
-    nf = __fsub_rn(r, MAGIC);
-    if (!(p < 4194304.0f)) return {0, true};       // NaN or absurdly far out
-  }
-  FastDim o;
-  o.i = (__float_as_int(r) - 0x4B400000) - (nf > p ? 1 : 0);
-  o.bad = !(p < fmx);
-  return o;
-}
-
+// Fast float -> bin for the streaming kernel.  Same result as cell_of() for every input, with
+// no division in the common case: the quotient u/delta is estimated as p = u * fl(1/delta)
+// (relative error < 2^-23 against the real quotient; the reference's IEEE quotient is within
+// 2^-24 of it).  floor(p) is read from the mantissa of (p - 0.5) + 1.5*2^23.  When p is farther
+// than p*2^-22 from both neighbouring integers, estimate, real quotient and IEEE quotient lie
+// between the same two integers and share that floor (`sure`).  Otherwise -- an atom within a few
+// ulp of a cell boundary, about 1e-4 of them -- the caller redoes the atom with cell_of_exact().
+// The host sets inv = NaN (nothing is ever `sure`) for geometries where an in-bounds atom could bin
+// to mx (gcb_edge_vulnerable) or with more than 2^21 cells along a dimension, so the fast path
+// needs no range check on the bin indices.
 struct GridParamsFast {
   float a[3], b[3], delta[3], inv[3], fmx[3];
   int my, mz;
+  int bias;                                          // 0x4B400000 * (my*mz + mz + 1), mod 2^32
 };
 
-__device__ __forceinline__ int cell_of_fast(const GridParamsFast &P, float x, float y, float z)
+struct FastCell { int cell; bool inside, sure; };
+
+__device__ __forceinline__ FastCell cell_of_fast(const GridParamsFast &P, float x, float y, float z)
 {
-  const float ux = __fsub_rn(x, P.a[0]), uy = __fsub_rn(y, P.a[1]), uz = __fsub_rn(z, P.a[2]);
-  const bool outside = (ux < 0.0f) | (__fsub_rn(x, P.b[0]) >= 0.0f) |
-                       (uy < 0.0f) | (__fsub_rn(y, P.b[1]) >= 0.0f) |
-                       (uz < 0.0f) | (__fsub_rn(z, P.b[2]) >= 0.0f);
-  if (outside) return -1;
-  const FastDim bx = bin_dim(ux, P.delta[0], P.inv[0], P.fmx[0]);
-  const FastDim by = bin_dim(uy, P.delta[1], P.inv[1], P.fmx[1]);
-  const FastDim bz = bin_dim(uz, P.delta[2], P.inv[2], P.fmx[2]);
-  if (bx.bad | by.bad | bz.bad) return -2;
-  return (bx.i * P.my + by.i) * P.mz + bz.i;
+  FastCell o;
+  // x - a < 0 <=> x < a and x - b >= 0 <=> x >= b: a difference of two finite floats is zero
+  // only when they are equal (subnormals are kept, -ftz=false), and its sign is the comparison's
+  o.inside = !((x < P.a[0]) | (x >= P.b[0]) | (y < P.a[1]) | (y >= P.b[1]) | (z < P.a[2]) | (z >= P.b[2]));
+  const float MAGIC = 12582912.0f;                   // 1.5 * 2^23
+  const float EPS = 2.384185791015625e-07f;          // 2^-22
+  const float px = __fmul_rn(__fsub_rn(x, P.a[0]), P.inv[0]);
+  const float py = __fmul_rn(__fsub_rn(y, P.a[1]), P.inv[1]);
+  const float pz = __fmul_rn(__fsub_rn(z, P.a[2]), P.inv[2]);
+  const float rx = __fadd_rn(__fsub_rn(px, 0.5f), MAGIC);
+  const float ry = __fadd_rn(__fsub_rn(py, 0.5f), MAGIC);
+  const float rz = __fadd_rn(__fsub_rn(pz, 0.5f), MAGIC);
+  // g = (p - floor) - 0.5 in [-0.5, 0.5]; sure <=> |g| < 0.5 - p * 2^-22
+  const float gx = __fsub_rn(__fsub_rn(px, __fsub_rn(rx, MAGIC)), 0.5f);
+  const float gy = __fsub_rn(__fsub_rn(py, __fsub_rn(ry, MAGIC)), 0.5f);
+  const float gz = __fsub_rn(__fsub_rn(pz, __fsub_rn(rz, MAGIC)), 0.5f);
+  o.sure = (fabsf(gx) < __fmaf_rn(px, -EPS, 0.5f)) & (fabsf(gy) < __fmaf_rn(py, -EPS, 0.5f)) &
+           (fabsf(gz) < __fmaf_rn(pz, -EPS, 0.5f));
+  o.cell = (__float_as_int(rx) * P.my + __float_as_int(ry)) * P.mz + __float_as_int(rz) - P.bias;
+  return o;
 }
 
-template <int MODE, bool PBC>
+// the reference's own operations (g_ri3Dc.c:145-147) for an atom already known to be inside [a, b).
+// Out of line and fed scalars, so the rare path costs the hot loop neither registers nor a stack copy.
+__device__ __noinline__ int cell_exact_scalar(float x, float y, float z, float a0, float a1, float a2, float d0,
+                                              float d1, float d2, float f0, float f1, float f2, int my, int mz)
+{
+  const float qx = __fdiv_rn(__fsub_rn(x, a0), d0);
+  const float qy = __fdiv_rn(__fsub_rn(y, a1), d1);
+  const float qz = __fdiv_rn(__fsub_rn(z, a2), d2);
+  if (!(qx < f0) | !(qy < f1) | !(qz < f2)) return -2;      // >= mx, or NaN
+  return (__float2int_rd(qx) * my + __float2int_rd(qy)) * mz + __float2int_rd(qz);
+}
+__device__ __forceinline__ int cell_of_exact(const GridParamsFast &P, float x, float y, float z)
+{
+  return cell_exact_scalar(x, y, z, P.a[0], P.a[1], P.a[2], P.delta[0], P.delta[1], P.delta[2], P.fmx[0], P.fmx[1],
+                           P.fmx[2], P.my, P.mz);
+}
+
+template <int MODE, bool PBC, bool AP>
 __global__ void __launch_bounds__(STREAM_THREADS)
 bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict__ gindex, unsigned gnx,
-                  const unsigned *__restrict__ rank, long long ntiles, GridParamsFast P,
+                  const unsigned *__restrict__ rank, long long ntiles, ApGroup G, GridParamsFast P,
                   uint32_t *__restrict__ counts, float *__restrict__ acc, float w,
                   const float *__restrict__ box3, unsigned long long *__restrict__ hits,
                   unsigned long long *__restrict__ diag)
@@ -277,16 +298,33 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int stage = it % STAGES;
         if (it >= STAGES) mbar_wait(&S.empty[stage], (unsigned)(it / STAGES - 1) & 1u);
-        const long long g0 = t * TILE_ATOMS, g1 = g0 + TILE_ATOMS;
+        const int tile_atoms = AP ? G.tile_atoms : TILE_ATOMS;
+        const long long g0 = t * tile_atoms, g1 = g0 + tile_atoms;
         const long long f0 = g0 / natoms, f1 = g1 / natoms;
         const int r0 = (int)(g0 - f0 * natoms), r1 = (int)(g1 - f1 * natoms);
-        const unsigned rel0 = __ldg(rank + r0);
         TileMeta m;
-        m.f0 = f0; m.r0 = r0; m.rel0 = rel0;
-        m.nsel = (unsigned)((f1 - f0) * (long long)gnx + (long long)__ldg(rank + r1) - (long long)rel0);
+        m.f0 = f0; m.r0 = r0;
+        if (AP) {
+          // frame f0 contributes atoms [r0, endA), frame f0+1 atoms [0, endB)   (tile_atoms <= natoms)
+          const int endA = min(natoms, r0 + tile_atoms), endB = r0 + tile_atoms - natoms;
+          const int iA0 = r0 <= G.g0 ? 0 : min((int)gnx, (r0 - G.g0 + G.step - 1) / G.step);
+          const int iA1 = endA <= G.g0 ? 0 : min((int)gnx, (endA - G.g0 + G.step - 1) / G.step);
+          const int nB = endB <= G.g0 ? 0 : min((int)gnx, (endB - G.g0 + G.step - 1) / G.step);
+          m.nA = (unsigned)(iA1 - iA0);
+          m.nsel = m.nA + (unsigned)nB;
+          m.baseA = G.g0 + iA0 * G.step - r0;
+          m.baseB = G.g0 + (natoms - r0) - (int)m.nA * G.step;
+          m.rel0 = 0;
+        } else {
+          const unsigned rel0 = __ldg(rank + r0);
+          m.rel0 = rel0;
+          m.nsel = (unsigned)((f1 - f0) * (long long)gnx + (long long)__ldg(rank + r1) - (long long)rel0);
+          m.nA = 0; m.baseA = 0; m.baseB = 0;
+        }
         S.meta[stage] = m;                         // published by the mbarrier's release/acquire
-        mbar_expect_tx(&S.full[stage], TILE_BYTES);
-        tma_load_1d(S.tile[stage], x + (size_t)t * TILE_FLOATS, TILE_BYTES, &S.full[stage], policy);
+        const unsigned bytes = (unsigned)tile_atoms * 12u;
+        mbar_expect_tx(&S.full[stage], bytes);
+        tma_load_1d(S.tile[stage], x + (size_t)t * ((size_t)tile_atoms * 3), bytes, &S.full[stage], policy);
       }
     }
     return;
@@ -302,6 +340,49 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
     const TileMeta m = S.meta[stage];
     const uint32_t tile = smem_addr(S.tile[stage]);
     unsigned c0 = 0, c1 = 0;            // hits in frame f0 / f0+1 (later frames go straight to global)
+    if (AP) {
+      const uint32_t addrA = tile + 12u * (uint32_t)m.baseA, addrB = tile + 12u * (uint32_t)m.baseB;
+      const uint32_t step12 = 12u * (uint32_t)G.step;
+      for (unsigned base = ctid; base < m.nsel; base += CONSUMER_THREADS * UNROLL) {
+        float px[UNROLL], py[UNROLL], pz[UNROLL];
+        bool valid[UNROLL], inB[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+          const unsigned j = base + k * CONSUMER_THREADS;
+          valid[k] = j < m.nsel;
+          inB[k] = j >= m.nA;
+          const uint32_t p = valid[k] ? (inB[k] ? addrB : addrA) + j * step12 : tile;
+          px[k] = lds_f32(p); py[k] = lds_f32(p + 4); pz[k] = lds_f32(p + 8);
+        }
+        unsigned rare = 0;
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+          if (PBC) {
+            const float *L = box3 + 3 * (m.f0 + (inB[k] ? 1 : 0));
+            px[k] = wrap1(px[k], __ldg(L)); py[k] = wrap1(py[k], __ldg(L + 1)); pz[k] = wrap1(pz[k], __ldg(L + 2));
+          }
+          const FastCell fc = cell_of_fast(P, px[k], py[k], pz[k]);
+          const bool go = valid[k] & fc.inside & fc.sure;
+          if (go) deposit<MODE>(counts, acc, fc.cell, w);
+          c0 += (go & !inB[k]) ? 1u : 0u;
+          c1 += (go & inB[k]) ? 1u : 0u;
+          rare |= (valid[k] & fc.inside & !fc.sure) ? (1u << k) : 0u;
+        }
+        if (rare) {                                  // atoms within a few ulp of a cell boundary
+#pragma unroll
+          for (int k = 0; k < UNROLL; k++) {
+            if (!((rare >> k) & 1u)) continue;
+            const int cell = cell_of_exact(P, px[k], py[k], pz[k]);
+            if (cell >= 0) {
+              deposit<MODE>(counts, acc, cell, w);
+              if (inB[k]) c1++; else c0++;
+            } else {
+              atomicAdd(diag, 1ull);
+            }
+          }
+        }
+      }
+    } else
     for (unsigned base = 0; base < m.nsel; base += CONSUMER_THREADS * UNROLL) {
       int local[UNROLL];
       unsigned df[UNROLL];
@@ -329,7 +410,8 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
           const float *L = box3 + 3 * (m.f0 + df[k]);
           px[k] = wrap1(px[k], __ldg(L)); py[k] = wrap1(py[k], __ldg(L + 1)); pz[k] = wrap1(pz[k], __ldg(L + 2));
         }
-        const int cell = cell_of_fast(P, px[k], py[k], pz[k]);
+        const FastCell fc = cell_of_fast(P, px[k], py[k], pz[k]);
+        const int cell = !fc.inside ? -1 : fc.sure ? fc.cell : cell_of_exact(P, px[k], py[k], pz[k]);
         if (cell >= 0) {
           deposit<MODE>(counts, acc, cell, w);
           if (df[k] == 0) c0++;
@@ -524,6 +606,8 @@ struct gcb_counter {
   size_t ncells = 0;
   int sm_count = 148;
   bool stream_ok = false;             // index group dense enough for the streaming kernel
+  bool ap_ok = false;                 // index group is g0 + i*step: arithmetic selection inside the tile
+  ApGroup ap{0, 1, TILE_ATOMS};
 
   std::vector<int> h_gindex;          // sorted copy of the index group
   int *d_gindex = nullptr;
@@ -596,6 +680,26 @@ int fold_pending(gcb_counter *c)
 
 size_t stream_smem_bytes() { return sizeof(StreamSmem); }
 
+template <int MODE, bool PBC, bool AP>
+int launch_stream(gcb_counter *c, const float *d_x, long long ntiles, uint32_t *cnt, float w, const float *d_box3,
+                  unsigned long long *d_hits)
+{
+  static bool attr_done = false;                 // one flag per instantiation
+  if (!attr_done) {
+    GCB_CUDA(cudaFuncSetAttribute(bin_stream_kernel<MODE, PBC, AP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)stream_smem_bytes()));
+    attr_done = true;
+  }
+  const int per_sm = std::max(1, (int)((227 * 1024) / (stream_smem_bytes() + 1024)));
+  const long long grid = std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
+  bin_stream_kernel<MODE, PBC, AP><<<(unsigned)grid, STREAM_THREADS, stream_smem_bytes(), c->compute>>>(
+      d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, c->ap, c->PF, cnt, c->d_acc, w, d_box3,
+      d_hits, c->d_diag);
+  c->launches++;
+  GCB_CUDA(cudaGetLastError());
+  return GCB_OK;
+}
+
 template <int MODE, bool PBC>
 int launch_bin(gcb_counter *c, const float *d_x, long nframes, float w, const float *d_box3,
                unsigned long long *d_hits)
@@ -606,26 +710,18 @@ int launch_bin(gcb_counter *c, const float *d_x, long nframes, float w, const fl
   long long e_begin = 0;
   const bool aligned = ((uintptr_t)d_x & 15u) == 0;
   const bool use_stream = aligned && c->opts.kernel != GCB_KERNEL_GATHER &&
-                          (c->stream_ok || c->opts.kernel == GCB_KERNEL_STREAM);
+                          (c->stream_ok || c->opts.kernel == GCB_KERNEL_STREAM ||
+                           c->opts.kernel == GCB_KERNEL_STREAM_INDEXED);
   if (use_stream) {
+    const bool ap = c->ap_ok && c->opts.kernel != GCB_KERNEL_STREAM_INDEXED;
+    const int tile_atoms = ap ? c->ap.tile_atoms : TILE_ATOMS;
     const long long total_atoms = (long long)nframes * c->natoms;
-    const long long ntiles = total_atoms / TILE_ATOMS;     // full tiles; the remainder goes to the gather kernel
+    const long long ntiles = total_atoms / tile_atoms;      // full tiles; the remainder goes to the gather kernel
     if (ntiles > 0) {
-      static bool attr_done[4] = {false, false, false, false};
-      const int which = MODE * 2 + (PBC ? 1 : 0);
-      if (!attr_done[which]) {
-        GCB_CUDA(cudaFuncSetAttribute(bin_stream_kernel<MODE, PBC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)stream_smem_bytes()));
-        attr_done[which] = true;
-      }
-      const int per_sm = std::max(1, (int)((227 * 1024) / (stream_smem_bytes() + 1024)));
-      const long long grid = std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
-      bin_stream_kernel<MODE, PBC><<<(unsigned)grid, STREAM_THREADS, stream_smem_bytes(), c->compute>>>(
-          d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, c->PF, cnt, c->d_acc, w, d_box3,
-          d_hits, c->d_diag);
-      c->launches++;
-      GCB_CUDA(cudaGetLastError());
-      const long long g1 = ntiles * TILE_ATOMS, f1 = g1 / c->natoms;
+      int rc = ap ? launch_stream<MODE, PBC, true>(c, d_x, ntiles, cnt, w, d_box3, d_hits)
+                  : launch_stream<MODE, PBC, false>(c, d_x, ntiles, cnt, w, d_box3, d_hits);
+      if (rc) return rc;
+      const long long g1 = ntiles * tile_atoms, f1 = g1 / c->natoms;
       e_begin = f1 * c->gnx + rank_host(c, (int)(g1 - f1 * c->natoms));
     }
   }
@@ -812,11 +908,15 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
     c->P.a[d] = tg->a[d]; c->P.b[d] = tg->b[d]; c->P.delta[d] = tg->delta[d]; c->P.fmx[d] = (float)tg->mx[d];
   }
   c->P.my = tg->mx[1]; c->P.mz = tg->mx[2];
-  for (int d = 0; d < 3; d++) {
-    c->PF.a[d] = tg->a[d]; c->PF.b[d] = tg->b[d]; c->PF.delta[d] = tg->delta[d]; c->PF.fmx[d] = (float)tg->mx[d];
-    c->PF.inv[d] = 1.0f / tg->delta[d];
+  {
+    const bool fast = !gcb_edge_vulnerable(tg) && tg->mx[0] < (1 << 21) && tg->mx[1] < (1 << 21) && tg->mx[2] < (1 << 21);
+    for (int d = 0; d < 3; d++) {
+      c->PF.a[d] = tg->a[d]; c->PF.b[d] = tg->b[d]; c->PF.delta[d] = tg->delta[d]; c->PF.fmx[d] = (float)tg->mx[d];
+      c->PF.inv[d] = fast ? 1.0f / tg->delta[d] : NAN;
+    }
+    c->PF.my = tg->mx[1]; c->PF.mz = tg->mx[2];
+    c->PF.bias = (int)(0x4B400000u * ((uint32_t)tg->mx[1] * (uint32_t)tg->mx[2] + (uint32_t)tg->mx[2] + 1u));
   }
-  c->PF.my = tg->mx[1]; c->PF.mz = tg->mx[2];
 
 #define GCB_CREATE_CUDA(call)                                                                        \
   do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { gcb::set_error("%s failed: %s", #call, cudaGetErrorString(e_)); \
@@ -841,6 +941,18 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
   }
   // streaming reads every byte of every frame: worth it while >= 1/8 of the 32-byte sectors are wanted anyway
   c->stream_ok = (double)gnx * 8.0 >= (double)natoms && (long long)natoms * 3 >= 1;
+  {
+    // arithmetic progression?  (duplicates or irregular groups take the indexed path)
+    const int step = gnx >= 2 ? c->h_gindex[1] - c->h_gindex[0] : 1;
+    bool ap = gnx >= 1 && step >= 1 && natoms >= 256;
+    for (int i = 2; ap && i < gnx; i++) ap = c->h_gindex[i] - c->h_gindex[i - 1] == step;
+    c->ap_ok = ap;
+    if (ap) {
+      c->ap.g0 = c->h_gindex[0];
+      c->ap.step = step;
+      c->ap.tile_atoms = std::min(TILE_ATOMS, natoms & ~3);     // <= natoms: a tile spans at most two frames
+    }
+  }
 
   GCB_CREATE_CUDA(cudaMalloc(&c->d_gindex, sizeof(int) * std::max(gnx, 1)));
   GCB_CREATE_CUDA(cudaMalloc(&c->d_rank, sizeof(unsigned) * rank.size()));
@@ -848,8 +960,11 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
   GCB_CREATE_CUDA(cudaMalloc(&c->d_diag, sizeof(unsigned long long) * 2));
   if (gnx) GCB_CREATE_CUDA(cudaMemcpy(c->d_gindex, c->h_gindex.data(), sizeof(int) * gnx, cudaMemcpyHostToDevice));
   GCB_CREATE_CUDA(cudaMemcpy(c->d_rank, rank.data(), sizeof(unsigned) * rank.size(), cudaMemcpyHostToDevice));
-  GCB_CREATE_CUDA(cudaMemset(c->d_runcnt, 0, sizeof(uint32_t) * c->ncells));
-  GCB_CREATE_CUDA(cudaMemset(c->d_diag, 0, sizeof(unsigned long long) * 2));
+  // on the compute stream: it is non-blocking, a legacy-stream cudaMemset could still be
+  // running when the first binning kernel starts and would wipe its deposits
+  GCB_CREATE_CUDA(cudaMemsetAsync(c->d_runcnt, 0, sizeof(uint32_t) * c->ncells, c->compute));
+  GCB_CREATE_CUDA(cudaMemsetAsync(c->d_diag, 0, sizeof(unsigned long long) * 2, c->compute));
+  GCB_CREATE_CUDA(cudaStreamSynchronize(c->compute));
 #undef GCB_CREATE_CUDA
   *out = c;
   return GCB_OK;

@@ -90,8 +90,9 @@ enum {
   GCB_PBC_NONE = 0,        /* reference behaviour: atoms outside [a,b) are dropped (g_ri3Dc.c:145) */
   GCB_PBC_RECT = 1         /* opt-in single-image rectangular wrap as count.c:88-92 before binning */
 };
-enum {                     /* kernel selection (GCB_KERNEL_AUTO picks by index-group density) */
-  GCB_KERNEL_AUTO = 0, GCB_KERNEL_GATHER = 1, GCB_KERNEL_STREAM = 2
+enum {                     /* kernel selection (GCB_KERNEL_AUTO picks by index-group density and regularity) */
+  GCB_KERNEL_AUTO = 0, GCB_KERNEL_GATHER = 1, GCB_KERNEL_STREAM = 2,
+  GCB_KERNEL_STREAM_INDEXED = 3   /* streaming kernel without the arithmetic-progression shortcut */
 };
 
 typedef struct {
