@@ -359,3 +359,15 @@ def analyse(tg, grid_zfast, unit="unity", min_occ=0.0, radius=None, z1=None, z2=
         return out
     finally:
         lib.gcb_analysis_free(C.byref(a))
+
+
+def gridcalc(tg, grids_zfast, tweights, device=0):
+    """a_gridcalc's time-weighted average (a_gridcalc.c:176-189) -> (avg [mx,my,mz] f32, total weight)"""
+    grids = [np.ascontiguousarray(a, np.float32) for a in grids_zfast]
+    ptrs = (K.c_float_p * len(grids))(*[_fptr(a) for a in grids])
+    tw = np.ascontiguousarray(tweights, np.float32)
+    avg = np.zeros(tg.shape, np.float32)
+    two = C.c_float(0)
+    check(lib.gcb_gridcalc(len(grids), ptrs, _fptr(tw), C.byref(tg), _fptr(avg), C.byref(two), device),
+          "gcb_gridcalc")
+    return avg, two.value

@@ -1,9 +1,575 @@
-// K3 placeholder: filled in by the analysis milestone.
+// K3: a_ri3Dc's reductions over a finished density grid (a_ri3Dc.c:133-201 crop, :488-762
+// analysis) and a_gridcalc's weighted average (a_gridcalc.c:176-189), on the GPU.
+//
+// The reference sums in f32 in one fixed order (k outer, j, i inner; a_ri3Dc.c:567-703), so a
+// tree or double-precision reduction would differ from it by the REFERENCE's rounding error
+// (~1e-6..1e-5 relative on these sizes).  Every output element here is therefore one sequential
+// chain in the reference's order; the parallelism is ACROSS outputs:
+//
+//   xyp/hxyp [mx][my]   chain over k            one thread per (i,j), reads the x-fastest copy
+//   xzp      [mx][mz]   chain over j            one thread per (i,k), k fastest
+//   yzp      [my][mz]   chain over i            one thread per (j,k), k fastest
+//   zdf/lzdf/profile[k] chain over (j,i)        one thread per k
+//   rzp/hrzp [r][mz]    chain over bin r's cells in (j,i) order, one thread per (r,k)
+//   rdf/hrdf/rweight[r] chain over k, then bin r's cells: one thread per r
+//   sumP (f64), average (f32): whole-grid chains: one consumer thread each, fed through shared
+//                       memory by the rest of its block from the x-fastest copy (linear order)
+//
+// Compiled with -fmad=false: ci*ci + cj*cj and the divide-then-add steps are separate f32
+// operations as in the reference binary.
 #include "gcb_internal.h"
-extern "C" {
-int gcb_analyse(const gcb_tgrid *, const float *, const gcb_analysis_opts *, gcb_analysis *)
-{ return gcb::fail(GCB_ERR_STATE, "gcb_analyse: not built yet"); }
-void gcb_analysis_free(gcb_analysis *) {}
-int gcb_gridcalc(int, const float *const *, const float *, const gcb_tgrid *, float *, float *, int)
-{ return gcb::fail(GCB_ERR_STATE, "gcb_gridcalc: not built yet"); }
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+namespace {
+
+const double kPi = 3.14159265358979323846;        // M_PI (utilgmx.h:23-28)
+
+struct Dims { int mx, my, mz; };
+
+// z-fastest [mx][my][mz] -> x-fastest [mz][my][mx]
+__global__ void an_transpose_kernel(const float *__restrict__ in, float *__restrict__ out, Dims d)
+{
+  __shared__ float tile[32][33];
+  const int j = blockIdx.z, i0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r, k = k0 + threadIdx.x;
+    if (i < d.mx && k < d.mz) tile[r][threadIdx.x] = in[((size_t)i * d.my + j) * d.mz + k];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r, i = i0 + threadIdx.x;
+    if (i < d.mx && k < d.mz) out[((size_t)k * d.my + j) * d.mx + i] = tile[threadIdx.x][r];
+  }
 }
+
+// readjust_tgrid's copy loop (a_ri3Dc.c:194-197)
+__global__ void an_crop_kernel(const float *__restrict__ in, Dims o, float *__restrict__ out, Dims n, int bx, int by, int bz)
+{
+  const size_t total = (size_t)n.mx * n.my * n.mz;
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(c % n.mz);
+    const size_t r = c / n.mz;
+    const int j = (int)(r % n.my), i = (int)(r / n.my);
+    out[c] = in[((size_t)(i + bx) * o.my + (j + by)) * o.mz + (k + bz)];
+  }
+}
+
+// xyp[i][j] += g/((real)mz*U) over k; hxyp[i][j] += 1.0/((real)mz*1) when g <= min_occ  (a_ri3Dc.c:573-580)
+__global__ void an_xy_kernel(const float *__restrict__ gx, Dims d, float d_xy, float min_occ, double h_inc,
+                             float *__restrict__ xyp, float *__restrict__ hxyp)
+{
+  const int n = d.mx * d.my;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;        // t = j*mx + i
+  if (t >= n) return;
+  const int j = t / d.mx, i = t - j * d.mx;
+  float s = 0.0f, h = 0.0f;
+  for (int k = 0; k < d.mz; k++) {
+    const float v = gx[(size_t)k * n + t];
+    s = __fadd_rn(s, __fdiv_rn(v, d_xy));
+    if (v <= min_occ) h = (float)((double)h + h_inc);
+  }
+  xyp[(size_t)i * d.my + j] = s;
+  hxyp[(size_t)i * d.my + j] = h;
+}
+
+// xzp[i][k] += g/((real)my*U) over j   (a_ri3Dc.c:575-576)
+__global__ void an_xz_kernel(const float *__restrict__ g, Dims d, float d_xz, float *__restrict__ xzp)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;        // t = i*mz + k
+  if (t >= d.mx * d.mz) return;
+  const int i = t / d.mz, k = t - i * d.mz;
+  float s = 0.0f;
+  for (int j = 0; j < d.my; j++) s = __fadd_rn(s, __fdiv_rn(g[((size_t)i * d.my + j) * d.mz + k], d_xz));
+  xzp[t] = s;
+}
+
+// yzp[j][k] += g/((real)mx*U) over i   (a_ri3Dc.c:577-578)
+__global__ void an_yz_kernel(const float *__restrict__ g, Dims d, float d_yz, float *__restrict__ yzp)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;        // t = j*mz + k
+  if (t >= d.my * d.mz) return;
+  const int j = t / d.mz, k = t - j * d.mz;
+  float s = 0.0f;
+  for (int i = 0; i < d.mx; i++) s = __fadd_rn(s, __fdiv_rn(g[((size_t)i * d.my + j) * d.mz + k], d_yz));
+  yzp[t] = s;
+}
+
+struct SliceParams {
+  float min_occ, d_zdf, DeltaR, U, a_z, delta_z;
+  double dV;
+};
+
+// per-slice chains (a_ri3Dc.c:589-613, 661-695): zdf, lzdf, Rgyr2 -> profile; nocc[k] = occupied
+// in-circle cells of the slice.  Tables are [j][i]: c2 = ci*ci+cj*cj, flags bit0 = bInCircle(i,j).
+__global__ void an_slice_kernel(const float *__restrict__ g, Dims d, const float *__restrict__ c2tab,
+                                const unsigned char *__restrict__ flags, SliceParams p, float *__restrict__ zdf,
+                                float *__restrict__ lzdf, float *__restrict__ profile, unsigned *__restrict__ nocc)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= d.mz) return;
+  float zs = 0.0f, lz = 0.0f, rg = 0.0f;
+  unsigned n = 0;
+  for (int j = 0; j < d.my; j++) {
+    const float *row = c2tab + (size_t)j * d.mx;
+    const unsigned char *frow = flags + (size_t)j * d.mx;
+#pragma unroll 4
+    for (int i = 0; i < d.mx; i++) {
+      const float v = g[((size_t)i * d.my + j) * d.mz + k];
+      if (v > p.min_occ && (frow[i] & 1)) {
+        n++;
+        lz = __fadd_rn(lz, v);
+        rg = __fadd_rn(rg, __fmul_rn(v, row[i]));
+      }
+      zs = __fadd_rn(zs, v);
+    }
+  }
+  const float z = (float)((double)p.a_z + ((double)k + 0.5) * (double)p.delta_z);        // a_ri3Dc.c:665
+  zdf[2 * k] = z; lzdf[2 * k] = z; profile[2 * k] = z;
+  zdf[2 * k + 1] = __fdiv_rn(zs, p.d_zdf);                                               // :666
+  rg = (float)((double)rg / (0.5 * (double)lz));                                         // :672
+  profile[2 * k + 1] = (float)(sqrt((double)rg) * (double)p.DeltaR);                     // :675
+  const float Agyr = (float)(kPi * (double)rg);                                          // :677
+  const float den = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(p.delta_z, Agyr), p.DeltaR), p.DeltaR), p.U);
+  lzdf[2 * k + 1] = (float)((double)lz * p.dV / (double)den);                            // :695
+  nocc[k] = n;
+}
+
+// rzp[r][k] / hrzp[r][k] raw sums (a_ri3Dc.c:640-649): thread per (r,k), chain over bin r's cells
+__global__ void an_rz_kernel(const float *__restrict__ g, Dims d, const int *__restrict__ bin_start,
+                             const int *__restrict__ bin_cells, int nr, float min_occ, float *__restrict__ rzp,
+                             float *__restrict__ hrzp)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;        // t = r*mz + k
+  if (t >= nr * d.mz) return;
+  const int r = t / d.mz, k = t - r * d.mz;
+  float s = 0.0f, h = 0.0f;
+  for (int c = bin_start[r]; c < bin_start[r + 1]; c++) {
+    const float v = g[(size_t)bin_cells[c] * d.mz + k];
+    if (v > min_occ) s = __fadd_rn(s, v); else h = __fadd_rn(h, 1.0f);
+  }
+  rzp[t] = s; hrzp[t] = h;
+}
+
+// rdf[r][1], hrdf[r][1], rweight[r] raw sums (a_ri3Dc.c:627-645): thread per r, chain over k then cells
+__global__ void an_rdf_kernel(const float *__restrict__ g, Dims d, const int *__restrict__ bin_start,
+                              const int *__restrict__ bin_cells, int nr, float min_occ, double rw_inc,
+                              float *__restrict__ rdf, float *__restrict__ hrdf, float *__restrict__ rweight)
+{
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nr) return;
+  float s = 0.0f, h = 0.0f, rw = 0.0f;
+  const int c0 = bin_start[r], c1 = bin_start[r + 1];
+  for (int k = 0; k < d.mz; k++) {
+#pragma unroll 4
+    for (int c = c0; c < c1; c++) {
+      const float v = g[(size_t)bin_cells[c] * d.mz + k];
+      rw = (float)((double)rw + rw_inc);
+      if (v > min_occ) s = __fadd_rn(s, v); else h = __fadd_rn(h, 1.0f);
+    }
+  }
+  rdf[2 * r + 1] = s; hrdf[2 * r + 1] = h; rweight[r] = rw;
+}
+
+// Whole-grid chains in (k,j,i) order over the x-fastest copy, which is linear memory order.
+// block 0: sumP += (double)g (a_ri3Dc.c:499-508) and the count behind sumH
+// block 1: average += g for cells with irad < iradNR (a_ri3Dc.c:633); masked cells add +0.0f,
+//          which leaves any partial sum that started at +0 unchanged bit for bit
+constexpr int CHAIN_THREADS = 256;
+constexpr int CHAIN_CHUNK = 2048;
+__global__ void __launch_bounds__(CHAIN_THREADS)
+an_chain_kernel(const float *__restrict__ gx, size_t ncells, int nxy, const unsigned char *__restrict__ flags,
+                float min_occ_raw, double *__restrict__ sumP_out, unsigned long long *__restrict__ nholes_out,
+                float *__restrict__ average_out)
+{
+  __shared__ __align__(16) float buf[2][CHAIN_CHUNK];
+  __shared__ unsigned long long holes_sh;
+  const bool is_avg = blockIdx.x == 1;
+  const int tid = threadIdx.x;
+  constexpr int PER = CHAIN_CHUNK / CHAIN_THREADS;
+  if (tid == 0) holes_sh = 0;
+  unsigned long long holes = 0;
+  double sd = 0.0;
+  float sf = 0.0f;
+  const size_t nchunks = (ncells + CHAIN_CHUNK - 1) / CHAIN_CHUNK;
+  float regs[PER];
+  auto load = [&](size_t c) {
+#pragma unroll
+    for (int r = 0; r < PER; r++) {
+      const size_t idx = c * CHAIN_CHUNK + (size_t)r * CHAIN_THREADS + tid;
+      float v = 0.0f;
+      if (idx < ncells) {
+        v = gx[idx];
+        if (is_avg) { if (!(flags[idx % (size_t)nxy] & 2)) v = 0.0f; }
+        else if (v <= min_occ_raw) holes++;
+      }
+      regs[r] = v;
+    }
+  };
+  auto stash = [&](int b) {
+#pragma unroll
+    for (int r = 0; r < PER; r++) buf[b][r * CHAIN_THREADS + tid] = regs[r];
+  };
+  load(0);
+  stash(0);
+  __syncthreads();
+  for (size_t c = 0; c < nchunks; c++) {
+    const int b = (int)(c & 1);
+    if (c + 1 < nchunks) load(c + 1);
+    if (tid == 0) {
+      const size_t left = ncells - c * CHAIN_CHUNK;
+      const int n = left < (size_t)CHAIN_CHUNK ? (int)left : CHAIN_CHUNK;
+      const float4 *q = reinterpret_cast<const float4 *>(buf[b]);
+      int e = 0;
+      if (is_avg) {
+        for (; e + 4 <= n; e += 4) {
+          const float4 v = q[e >> 2];
+          sf = __fadd_rn(sf, v.x); sf = __fadd_rn(sf, v.y); sf = __fadd_rn(sf, v.z); sf = __fadd_rn(sf, v.w);
+        }
+        for (; e < n; e++) sf = __fadd_rn(sf, buf[b][e]);
+      } else {
+        for (; e + 4 <= n; e += 4) {
+          const float4 v = q[e >> 2];
+          sd = __dadd_rn(sd, (double)v.x); sd = __dadd_rn(sd, (double)v.y);
+          sd = __dadd_rn(sd, (double)v.z); sd = __dadd_rn(sd, (double)v.w);
+        }
+        for (; e < n; e++) sd = __dadd_rn(sd, (double)buf[b][e]);
+      }
+    }
+    if (c + 1 < nchunks) stash(b ^ 1);
+    __syncthreads();
+  }
+  if (!is_avg) {
+    atomicAdd(&holes_sh, holes);
+    __syncthreads();
+    if (tid == 0) { *sumP_out = sd; *nholes_out = holes_sh; }
+  } else if (tid == 0) {
+    *average_out = sf;
+  }
+}
+
+// a_gridcalc.c:180-189: a += g * w with w double, f32 store
+__global__ void gridcalc_axpy_kernel(float *__restrict__ avg, const float *__restrict__ g, double w, size_t n)
+{
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x)
+    avg[c] = (float)__dadd_rn((double)avg[c], __dmul_rn((double)g[c], w));
+}
+
+// a_ri3Dc.c:128-130
+float discrete_adjust(float x_old, float x_new, float delta)
+{
+  const float q = (x_old - x_new) / delta;
+  const int n = -(int)((double)q + (x_old > x_new ? 0.5 : -0.5));
+  return (float)n * delta;
+}
+
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+#define AN_CUDA(call)                                                                            \
+  do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                                          \
+      gcb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return GCB_ERR_CUDA; } } while (0)
+
+template <class T> float *host_copy(const DevBuf &b, size_t n, int *rc)
+{
+  T *h = (T *)malloc(std::max<size_t>(n, 1) * sizeof(T));
+  if (!h) { *rc = gcb::fail(GCB_ERR_NOMEM, "out of memory"); return nullptr; }
+  if (n && cudaMemcpy(h, b.p, n * sizeof(T), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    free(h);
+    *rc = gcb::fail(GCB_ERR_CUDA, "copying an analysis result back failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return (float *)h;
+}
+
+int blocks_for(size_t n, int threads) { return (int)std::max<size_t>(1, (n + threads - 1) / threads); }
+
+}  // namespace
+
+extern "C" {
+
+int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analysis_opts *opts, gcb_analysis *out)
+{
+  if (!tg_in || !grid_zfast || !opts || !out) return gcb::fail(GCB_ERR_ARG, "gcb_analyse: null argument");
+  if (opts->unit < 0 || opts->unit >= GCB_UNIT_NR) return gcb::fail(GCB_ERR_ARG, "gcb_analyse: unknown unit %d", opts->unit);
+  if (tg_in->mx[0] <= 0 || tg_in->mx[1] <= 0 || tg_in->mx[2] <= 0) return gcb::fail(GCB_ERR_ARG, "gcb_analyse: empty grid");
+  if (gcb_device_count() <= 0) return gcb::fail(GCB_ERR_CUDA, "no CUDA device: libgridcount_b200 has no CPU fallback");
+  memset(out, 0, sizeof(*out));
+  AN_CUDA(cudaSetDevice(opts->device));
+
+  // ---- geometry: update_tgrid + readjust_tgrid (a_ri3Dc.c:473-486) on the host ----------------
+  gcb_tgrid old = *tg_in;
+  gcb_update_tgrid(&old);                                     // b = a + mx*Delta (a_ri3Dc.c:474)
+  gcb_tgrid tg = old;
+  gcb_cavity user{};
+  user.radius = opts->radius; user.z1 = opts->z1; user.z2 = opts->z2;
+  bool cropped = false;
+  int base[3] = {0, 0, 0};
+  {
+    const float dsum = tg.delta[0] + tg.delta[1];
+    const float DeltaR = (float)(0.5 * (double)dsum);
+    const float R_new = user.radius;
+    if (opts->setmask & GCB_SET_Z1) { tg.a[2] += discrete_adjust(tg.a[2], user.z1, tg.delta[2]); cropped = true; }
+    if (opts->setmask & GCB_SET_Z2) { tg.b[2] += discrete_adjust(tg.b[2], user.z2, tg.delta[2]); cropped = true; }
+    if (tg.a[2] >= tg.b[2])
+      return gcb::fail(GCB_ERR_RANGE, "FAILURE: Apparently z2 =< z1, or either of them was too large for the given grid.");
+    gcb_tgrid2cavity(&tg, &user);
+    if (opts->setmask & GCB_SET_R) { user.radius += discrete_adjust(user.radius, R_new, DeltaR); cropped = true; }
+    if (cropped) {
+      int rc = gcb_setup_tgrid(&tg, &user, old.delta);
+      if (rc) return gcb::fail(GCB_ERR_RANGE, "FAILURE while readjusting the grid.");
+      tg.tweight = old.tweight;
+      for (int d = 0; d < 3; d++) {
+        base[d] = (int)((tg.a[d] - old.a[d]) / tg.delta[d]);
+        if (base[d] < 0 || base[d] + tg.mx[d] > old.mx[d])
+          return gcb::fail(GCB_ERR_RANGE, "readjusted grid does not lie inside the stored one (dimension %d)", d);
+      }
+    }
+  }
+  const Dims od{old.mx[0], old.mx[1], old.mx[2]}, d{tg.mx[0], tg.mx[1], tg.mx[2]};
+  const size_t ocells = (size_t)od.mx * od.my * od.mz, ncells = (size_t)d.mx * d.my * d.mz;
+  const int nxy = d.mx * d.my;
+  const float fmx = (float)d.mx, fmy = (float)d.my, fmz = (float)d.mz;
+
+  gcb_cavity geometry{};
+  gcb_tgrid2cavity(&tg, &geometry);                           // a_ri3Dc.c:486
+  const float DeltaR = (float)(0.5 * (double)(tg.delta[0] + tg.delta[1]));      // :488
+  const double dV = gcb_delta_v(&tg);                         // :495
+  const float U = gcb_dens_unit(opts->unit, &tg);             // DensUnit[nunit], :516
+  const float Uunity = gcb_dens_unit(GCB_UNIT_UNITY, nullptr);
+  const float min_occ_raw = opts->min_occ;                    // sumH uses the unscaled value (:504)
+  const float min_occ = min_occ_raw * U;                      // :517
+  int iradNR = (int)floor((double)(geometry.radius / DeltaR));                  // :544
+  if (iradNR < 0) iradNR = 0;
+
+  // ---- per-(i,j) tables (a_ri3Dc.c:586-592, 625), [j][i] order = the traversal order -----------
+  std::vector<float> c2tab((size_t)nxy);
+  std::vector<unsigned char> flags((size_t)nxy);
+  std::vector<int> irad((size_t)nxy);
+  {
+    const float rcirc = geometry.radius / DeltaR;
+    const float cx = (float)((double)fmx / 2.0), cy = (float)((double)fmy / 2.0);
+    for (int j = 0; j < d.my; j++) {
+      const float cj = (float)(((double)(float)j + 0.5) - (double)fmy / 2.0);
+      for (int i = 0; i < d.mx; i++) {
+        const float ci = (float)(((double)(float)i + 0.5) - (double)fmx / 2.0);
+        const float c2 = ci * ci + cj * cj;
+        const float ex = (float)i - cx, ey = (float)j - cy;
+        const int ir = (int)floor(sqrt((double)c2));
+        const size_t t = (size_t)j * d.mx + i;
+        c2tab[t] = c2;
+        irad[t] = ir;
+        flags[t] = (unsigned char)((ex * ex + ey * ey <= rcirc * rcirc ? 1 : 0) | (ir < iradNR ? 2 : 0));
+      }
+    }
+  }
+  // cells of each radial bin in (j,i) order, as z-fastest row numbers i*my + j
+  std::vector<int> bin_start((size_t)iradNR + 1, 0), bin_cells;
+  {
+    for (size_t t = 0; t < (size_t)nxy; t++) if (irad[t] < iradNR) bin_start[(size_t)irad[t] + 1]++;
+    for (int r = 0; r < iradNR; r++) bin_start[(size_t)r + 1] += bin_start[r];
+    bin_cells.resize((size_t)bin_start[iradNR]);
+    std::vector<int> fill(bin_start.begin(), bin_start.end() - 1);
+    for (int j = 0; j < d.my; j++)
+      for (int i = 0; i < d.mx; i++) {
+        const int r = irad[(size_t)j * d.mx + i];
+        if (r < iradNR) bin_cells[(size_t)fill[r]++] = i * d.my + j;
+      }
+  }
+  const long long ncyl = iradNR > 0 ? bin_start[iradNR] : 0;
+
+  // ---- device buffers --------------------------------------------------------------------------
+  DevBuf d_in, d_g, d_gx, d_c2, d_flags, d_bs, d_bc, d_xyp, d_hxyp, d_xzp, d_yzp, d_zdf, d_lzdf, d_prof, d_nocc,
+      d_rzp, d_hrzp, d_rdf, d_hrdf, d_rw, d_scal;
+  const size_t nrz = (size_t)iradNR * d.mz;
+  AN_CUDA(cudaMalloc(&d_in.p, ocells * 4));
+  AN_CUDA(cudaMemcpy(d_in.p, grid_zfast, ocells * 4, cudaMemcpyHostToDevice));
+  int64_t launches = 0;
+  const float *g = d_in.as<float>();
+  if (cropped) {
+    AN_CUDA(cudaMalloc(&d_g.p, ncells * 4));
+    an_crop_kernel<<<std::min(blocks_for(ncells, 256), 148 * 16), 256>>>(d_in.as<float>(), od, d_g.as<float>(), d, base[0], base[1], base[2]);
+    launches++;
+    g = d_g.as<float>();
+  }
+  AN_CUDA(cudaMalloc(&d_gx.p, ncells * 4));
+  AN_CUDA(cudaMalloc(&d_c2.p, (size_t)nxy * 4));
+  AN_CUDA(cudaMalloc(&d_flags.p, (size_t)nxy));
+  AN_CUDA(cudaMalloc(&d_bs.p, bin_start.size() * 4));
+  AN_CUDA(cudaMalloc(&d_bc.p, std::max<size_t>(bin_cells.size(), 1) * 4));
+  AN_CUDA(cudaMalloc(&d_xyp.p, (size_t)nxy * 4));
+  AN_CUDA(cudaMalloc(&d_hxyp.p, (size_t)nxy * 4));
+  AN_CUDA(cudaMalloc(&d_xzp.p, (size_t)d.mx * d.mz * 4));
+  AN_CUDA(cudaMalloc(&d_yzp.p, (size_t)d.my * d.mz * 4));
+  AN_CUDA(cudaMalloc(&d_zdf.p, (size_t)d.mz * 8));
+  AN_CUDA(cudaMalloc(&d_lzdf.p, (size_t)d.mz * 8));
+  AN_CUDA(cudaMalloc(&d_prof.p, (size_t)d.mz * 8));
+  AN_CUDA(cudaMalloc(&d_nocc.p, (size_t)d.mz * 4));
+  AN_CUDA(cudaMalloc(&d_rzp.p, std::max<size_t>(nrz, 1) * 4));
+  AN_CUDA(cudaMalloc(&d_hrzp.p, std::max<size_t>(nrz, 1) * 4));
+  AN_CUDA(cudaMalloc(&d_rdf.p, ((size_t)iradNR + 1) * 8));
+  AN_CUDA(cudaMalloc(&d_hrdf.p, ((size_t)iradNR + 1) * 8));
+  AN_CUDA(cudaMalloc(&d_rw.p, ((size_t)iradNR + 1) * 4));
+  AN_CUDA(cudaMalloc(&d_scal.p, 32));
+  AN_CUDA(cudaMemcpy(d_c2.p, c2tab.data(), (size_t)nxy * 4, cudaMemcpyHostToDevice));
+  AN_CUDA(cudaMemcpy(d_flags.p, flags.data(), (size_t)nxy, cudaMemcpyHostToDevice));
+  AN_CUDA(cudaMemcpy(d_bs.p, bin_start.data(), bin_start.size() * 4, cudaMemcpyHostToDevice));
+  if (!bin_cells.empty()) AN_CUDA(cudaMemcpy(d_bc.p, bin_cells.data(), bin_cells.size() * 4, cudaMemcpyHostToDevice));
+  AN_CUDA(cudaMemset(d_rdf.p, 0, ((size_t)iradNR + 1) * 8));
+  AN_CUDA(cudaMemset(d_hrdf.p, 0, ((size_t)iradNR + 1) * 8));
+  AN_CUDA(cudaMemset(d_scal.p, 0, 32));
+
+  // ---- kernels: independent chains on independent streams --------------------------------------
+  cudaStream_t st[4];
+  for (auto &s : st) AN_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  AN_CUDA(cudaDeviceSynchronize());                           // uploads / crop (legacy stream) done
+  {
+    dim3 block(32, 8), grid((d.mz + 31) / 32, (d.mx + 31) / 32, d.my);
+    an_transpose_kernel<<<grid, block, 0, st[0]>>>(g, d_gx.as<float>(), d);
+    launches++;
+  }
+  const float d_xy = fmz * U, d_xz = fmy * U, d_yz = fmx * U;               // a_ri3Dc.c:573-578 divisors
+  const double h_inc = 1.0 / (double)(fmz * Uunity);                       // :580
+  const double rw_inc = 1.0 / (double)fmz;                                 // :637
+  an_xy_kernel<<<blocks_for(nxy, 128), 128, 0, st[0]>>>(d_gx.as<float>(), d, d_xy, min_occ, h_inc, d_xyp.as<float>(), d_hxyp.as<float>());
+  double *d_sumP = d_scal.as<double>();
+  unsigned long long *d_holes = reinterpret_cast<unsigned long long *>(d_scal.as<char>() + 8);
+  float *d_avg = reinterpret_cast<float *>(d_scal.as<char>() + 16);
+  an_chain_kernel<<<2, CHAIN_THREADS, 0, st[0]>>>(d_gx.as<float>(), ncells, nxy, d_flags.as<unsigned char>(), min_occ_raw, d_sumP, d_holes, d_avg);
+  an_xz_kernel<<<blocks_for((size_t)d.mx * d.mz, 128), 128, 0, st[1]>>>(g, d, d_xz, d_xzp.as<float>());
+  an_yz_kernel<<<blocks_for((size_t)d.my * d.mz, 128), 128, 0, st[1]>>>(g, d, d_yz, d_yzp.as<float>());
+  SliceParams sp;
+  sp.min_occ = min_occ; sp.d_zdf = fmx * fmy * U; sp.DeltaR = DeltaR; sp.U = U; sp.a_z = tg.a[2]; sp.delta_z = tg.delta[2];
+  sp.dV = dV;
+  an_slice_kernel<<<blocks_for(d.mz, 32), 32, 0, st[2]>>>(g, d, d_c2.as<float>(), d_flags.as<unsigned char>(), sp, d_zdf.as<float>(),
+                                                           d_lzdf.as<float>(), d_prof.as<float>(), d_nocc.as<unsigned>());
+  launches += 5;
+  if (iradNR > 0) {
+    an_rz_kernel<<<blocks_for(nrz, 128), 128, 0, st[3]>>>(g, d, d_bs.as<int>(), d_bc.as<int>(), iradNR, min_occ, d_rzp.as<float>(), d_hrzp.as<float>());
+    an_rdf_kernel<<<blocks_for(iradNR, 32), 32, 0, st[3]>>>(g, d, d_bs.as<int>(), d_bc.as<int>(), iradNR, min_occ, rw_inc, d_rdf.as<float>(),
+                                                             d_hrdf.as<float>(), d_rw.as<float>());
+    launches += 2;
+  }
+  cudaError_t kerr = cudaGetLastError();
+  for (auto &s : st) { cudaError_t e = cudaStreamSynchronize(s); if (kerr == cudaSuccess) kerr = e; cudaStreamDestroy(s); }
+  if (kerr != cudaSuccess) return gcb::fail(GCB_ERR_CUDA, "analysis kernels failed: %s", cudaGetErrorString(kerr));
+
+  // ---- results back; the O(iradNR*mz) normalisations (a_ri3Dc.c:717-762) on the host ----------
+  int rc = GCB_OK;
+  out->grid = host_copy<float>(cropped ? d_g : d_in, ncells, &rc);
+  out->xyp = host_copy<float>(d_xyp, nxy, &rc); out->hxyp = host_copy<float>(d_hxyp, nxy, &rc);
+  out->xzp = host_copy<float>(d_xzp, (size_t)d.mx * d.mz, &rc); out->yzp = host_copy<float>(d_yzp, (size_t)d.my * d.mz, &rc);
+  out->zdf = host_copy<float>(d_zdf, (size_t)d.mz * 2, &rc); out->lzdf = host_copy<float>(d_lzdf, (size_t)d.mz * 2, &rc);
+  out->profile = host_copy<float>(d_prof, (size_t)d.mz * 2, &rc);
+  out->rweight = host_copy<float>(d_rw, iradNR, &rc);
+  out->rdf = host_copy<float>(d_rdf, (size_t)iradNR * 2, &rc); out->hrdf = host_copy<float>(d_hrdf, (size_t)iradNR * 2, &rc);
+  out->rzp = host_copy<float>(d_rzp, nrz, &rc); out->hrzp = host_copy<float>(d_hrzp, nrz, &rc);
+  std::vector<unsigned> nocc((size_t)d.mz);
+  char scal[32];
+  if (!rc && cudaMemcpy(nocc.data(), d_nocc.p, (size_t)d.mz * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = gcb::fail(GCB_ERR_CUDA, "D2H failed");
+  if (!rc && cudaMemcpy(scal, d_scal.p, 32, cudaMemcpyDeviceToHost) != cudaSuccess) rc = gcb::fail(GCB_ERR_CUDA, "D2H failed");
+  if (rc) { gcb_analysis_free(out); return rc; }
+
+  const size_t mz = (size_t)d.mz;
+  for (int r = 0; r < iradNR; r++) {                          // a_ri3Dc.c:717-726
+    const float rw = out->rweight[r];
+    out->rdf[2 * r] = out->hrdf[2 * r] = (float)r * DeltaR;
+    out->rdf[2 * r + 1] /= rw * fmz * U;
+    out->hrdf[2 * r + 1] /= rw * fmz * Uunity;
+    for (size_t k = 0; k < mz; k++) {
+      out->rzp[(size_t)r * mz + k] /= rw * U;
+      out->hrzp[(size_t)r * mz + k] /= rw * Uunity;
+    }
+  }
+  if (opts->rad_ba_step > 0) {                                // a_ri3Dc.c:731-757, with its `irad+1` indexing
+    if (opts->rad_ba_nr > 0 && opts->rad_ba_nr + opts->rad_ba_step > iradNR + 1) {
+      gcb_analysis_free(out);
+      return gcb::fail(GCB_ERR_RANGE, "-radnr %d / -radstep %d reach beyond the %d radial bins", opts->rad_ba_nr, opts->rad_ba_step, iradNR);
+    }
+    const float stp = (float)opts->rad_ba_step;
+    for (int r = 0; r < opts->rad_ba_nr; r += opts->rad_ba_step) {
+      for (int i = 1; i < opts->rad_ba_step; i++) {
+        out->rdf[2 * r + 1] += out->rdf[2 * (r + i) + 1];
+        out->hrdf[2 * r + 1] += out->hrdf[2 * (r + i) + 1];
+        for (size_t k = 0; k < mz; k++) {
+          out->rzp[(size_t)r * mz + k] += out->rzp[(size_t)(r + 1) * mz + k];
+          out->hrzp[(size_t)r * mz + k] += out->hrzp[(size_t)(r + 1) * mz + k];
+        }
+      }
+      out->rdf[2 * r + 1] /= stp; out->hrdf[2 * r + 1] /= stp;
+      for (size_t k = 0; k < mz; k++) { out->rzp[(size_t)r * mz + k] /= stp; out->hrzp[(size_t)r * mz + k] /= stp; }
+      for (int i = 1; i < opts->rad_ba_step; i++) {
+        out->rdf[2 * (r + 1) + 1] = out->rdf[2 * r + 1];
+        out->hrdf[2 * (r + 1) + 1] = out->hrdf[2 * r + 1];
+        for (size_t k = 0; k < mz; k++) {
+          out->rzp[(size_t)(r + 1) * mz + k] = out->rzp[(size_t)r * mz + k];
+          out->hrzp[(size_t)(r + 1) * mz + k] = out->hrzp[(size_t)r * mz + k];
+        }
+      }
+    }
+  }
+
+  double sumP; unsigned long long nholes; float average;
+  memcpy(&sumP, scal, 8); memcpy(&nholes, scal + 8, 8); memcpy(&average, scal + 16, 4);
+  unsigned long long nocc_total = 0;
+  for (unsigned v : nocc) nocc_total += v;
+  // `volume++` on a float (a_ri3Dc.c:594) stops counting at 2^24
+  float volume = nocc_total > (1ull << 24) ? 16777216.0f : (float)nocc_total;
+  volume = (float)((double)volume * dV);                      // :759
+  const int ivol = (int)(ncyl * d.mz);                        // `ivol++` per cell with irad < iradNR (:634)
+  out->tg = tg;
+  out->geometry = geometry;
+  out->DeltaR = DeltaR; out->dV = dV; out->iradNR = iradNR; out->unit_value = U;
+  out->sumP = sumP * dV;                                      // :510-511
+  out->sumH = (double)nholes * dV;
+  out->height = tg.b[2] - tg.a[2];                            // :760
+  out->volume = volume;
+  out->reff = (float)sqrt((double)volume / (kPi * (double)out->height));   // :761
+  out->average = average / ((float)ivol * U);                 // :762
+  out->ivol = ivol;
+  out->kernel_launches = launches;
+  return GCB_OK;
+}
+
+void gcb_analysis_free(gcb_analysis *a)
+{
+  if (!a) return;
+  free(a->grid); free(a->xyp); free(a->xzp); free(a->yzp); free(a->hxyp); free(a->zdf); free(a->lzdf);
+  free(a->profile); free(a->rweight); free(a->rdf); free(a->hrdf); free(a->rzp); free(a->hrzp);
+  a->grid = a->xyp = a->xzp = a->yzp = a->hxyp = a->zdf = a->lzdf = a->profile = a->rweight = nullptr;
+  a->rdf = a->hrdf = a->rzp = a->hrzp = nullptr;
+}
+
+int gcb_gridcalc(int ngrids, const float *const *grids_zfast, const float *tweights, const gcb_tgrid *tg,
+                 float *avg_zfast, float *tweight_out, int device)
+{
+  if (ngrids <= 0 || !grids_zfast || !tweights || !tg || !avg_zfast)
+    return gcb::fail(GCB_ERR_ARG, "gcb_gridcalc: bad argument");
+  if (gcb_device_count() <= 0) return gcb::fail(GCB_ERR_CUDA, "no CUDA device: libgridcount_b200 has no CPU fallback");
+  AN_CUDA(cudaSetDevice(device));
+  const size_t n = gcb::cells(*tg);
+  double sumT = 0;
+  for (int f = 0; f < ngrids; f++) sumT += (double)tweights[f];               // a_gridcalc.c:143
+  DevBuf d_avg, d_g;
+  AN_CUDA(cudaMalloc(&d_avg.p, n * 4));
+  AN_CUDA(cudaMalloc(&d_g.p, n * 4));
+  AN_CUDA(cudaMemset(d_avg.p, 0, n * 4));
+  for (int f = 0; f < ngrids; f++) {
+    const double w = (double)tweights[f] / sumT;                               // :182
+    AN_CUDA(cudaMemcpy(d_g.p, grids_zfast[f], n * 4, cudaMemcpyHostToDevice));
+    gridcalc_axpy_kernel<<<std::min(blocks_for(n, 256), 148 * 16), 256>>>(d_avg.as<float>(), d_g.as<float>(), w, n);
+    AN_CUDA(cudaGetLastError());
+  }
+  AN_CUDA(cudaMemcpy(avg_zfast, d_avg.p, n * 4, cudaMemcpyDeviceToHost));
+  if (tweight_out) *tweight_out = (float)sumT;                                 // :170
+  return GCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+"""GPU parity tests for K3: gcb_analyse / gcb_gridcalc through the C ABI against the golden output
+of the UNMODIFIED reference's a_ri3Dc / a_gridcalc, and against the CPU oracle on larger grids."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import gcutil as u
+import golden_cases as gc
+import gridcount_b200 as g
+from test_oracle_golden import ANALYSES, check_analysis_against_golden, decode_golden, _read
+
+pytestmark = pytest.mark.gpu
+
+ARRAYS = ["xyp", "xzp", "yzp", "hxyp", "zdf", "lzdf", "profile", "rweight", "rdf", "hrdf", "rzp", "hrzp"]
+
+
+def gpu_analysis(tg, grid, aa):
+    kw = {}
+    if aa["setmask"] & u.SET_R: kw["radius"] = aa["R"]
+    if aa["setmask"] & u.SET_Z1: kw["z1"] = aa["z1"]
+    if aa["setmask"] & u.SET_Z2: kw["z2"] = aa["z2"]
+    r = g.analyse(tg, grid, unit=aa["unit"], min_occ=aa["minocc"], rad_ba_nr=aa["radnr"], rad_ba_step=aa["radstep"],
+                  **kw)
+    scal = dict(volume=r["volume"], reff=r["reff"], sumP=r["sumP"], sumH=r["sumH"], dV=r["dV"], average=r["average"],
+                ivol=r["ivol"], iradNR=r["iradNR"], radius=r["geometry"].radius, unit_value=r["unit_value"])
+    return r, scal
+
+
+@pytest.mark.parametrize("name,run", ANALYSES)
+def test_analysis_matches_reference_output(name, run):
+    """grid file -> gcb_grid_read -> gcb_analyse == what the reference's a_ri3Dc printed, bit for bit"""
+    aa = gc.parse_aargs(gc.CASES[name]["analyses"][run])
+    tg, hdr, grid = g.grid_read(os.path.join(u.GOLDEN_DIR, name, "grid.dat"))
+    r, scal = gpu_analysis(tg, grid, aa)
+    og = u.Geom.from_buffer_copy(bytes(r["tg"]))
+    check_analysis_against_golden(og, r["grid"], aa, {k: r[k] for k in ARRAYS}, scal,
+                                  os.path.join(u.GOLDEN_DIR, name, run))
+    assert r["kernel_launches"] >= 6
+
+
+@pytest.mark.parametrize("name,run", [(n, r) for n, r in ANALYSES if "-plt" in gc.CASES[n]["analyses"][r]])
+def test_plt_of_cropped_grid_byte_exact(name, run, tmp_path):
+    aa = gc.parse_aargs(gc.CASES[name]["analyses"][run])
+    tg, hdr, grid = g.grid_read(os.path.join(u.GOLDEN_DIR, name, "grid.dat"))
+    r, scal = gpu_analysis(tg, grid, aa)
+    path = tmp_path / "out.plt"
+    g._cabi.check(g._cabi.lib.gcb_plt_write(str(path).encode(), C.byref(r["tg"]), u.fptr(r["grid"]), r["unit_value"]),
+                  "gcb_plt_write")
+    assert _read(path) == _read(os.path.join(u.GOLDEN_DIR, name, run, "plt.dat"))
+
+
+def oracle_analysis(og, grid, unit, min_occ):
+    o = u.oracle()
+    an = u.Analysis()
+    an.unit = u.UNITS[unit]
+    an.min_occ = min_occ
+    an.rad_ba_nr, an.rad_ba_step = 0, 1
+    grid = np.ascontiguousarray(grid, np.float32)
+    assert o.gco_analyse(C.byref(og), u.fptr(grid), C.byref(an)) == 0
+    arrs = u.analysis_arrays(an, og)
+    scal = dict(volume=an.volume, reff=an.reff, sumP=an.sumP, sumH=an.sumH, dV=an.dV, average=an.average,
+                ivol=an.ivol, iradNR=an.iradNR)
+    o.gco_analysis_free(C.byref(an))
+    return arrs, scal
+
+
+@pytest.mark.parametrize("cfg", [((8.0, 8.0, 13.4), 0.1, (80, 80, 134), "SPC", 0.0),
+                                 ((8.0, 8.0, 13.4), 0.1, (80, 80, 134), "molar", 0.7),
+                                 ((3.0, 3.0, 3.0), 0.05, (60, 60, 60), "Voxel", 0.001),
+                                 ((5.03, 4.41, 6.2), (0.1, 0.09, 0.2), None, "unity", 0.0)])
+def test_analysis_bit_exact_vs_oracle_on_binned_density(cfg):
+    """BASELINE config-2 / config-1 sized grids: bin a synthetic pore trajectory on the GPU, analyse the
+    density on the GPU, compare every output with the oracle's sequential f32 sums bit for bit"""
+    L, delta, shape, unit, minocc = cfg
+    geom = g.setup_geometry(L, delta)
+    if shape:
+        assert geom.shape == shape
+    natoms, nframes = 6000, 40
+    gindex = np.arange(0, natoms, 3, dtype=np.int32)
+    gen = g.make_gen(99, L, g._cabi.GEN_PORE, slab=(0.35 * L[2], 0.65 * L[2]), pore_r=0.8)
+    dev = g.DeviceFrames(nframes, natoms).generate(gen)
+    ctr = g.GridCounter(geom, gindex, natoms)
+    ctr.add_device_frames(dev, weights=np.full(nframes, 2.0, np.float32))
+    tg, dens, _ = ctr.density(2.0 * nframes)
+    ctr.close(); dev.free()
+    r = g.analyse(tg, dens, unit=unit, min_occ=minocc)
+    og = u.Geom.from_buffer_copy(bytes(tg))
+    u.oracle().gco_update_b(C.byref(og))
+    arrs, scal = oracle_analysis(og, dens, unit, minocc)
+    for k in ARRAYS:
+        u.assert_bits_equal(r[k], arrs[k], k)
+    for k in ("volume", "reff", "average"):
+        u.assert_bits_equal(np.float32(r[k]), np.float32(scal[k]), k)
+    for k in ("sumP", "sumH", "dV"):
+        u.assert_bits_equal(np.float64(r[k]), np.float64(scal[k]), k)
+    assert r["ivol"] == scal["ivol"] and r["iradNR"] == scal["iradNR"]
+
+
+def test_analysis_crop_errors():
+    tg, hdr, grid = g.grid_read(os.path.join(u.GOLDEN_DIR, "pore", "grid.dat"))
+    with pytest.raises(g._cabi.GcbError):
+        g.analyse(tg, grid, z1=5.0, z2=2.0)            # z2 <= z1 (a_ri3Dc.c:163-165)
+
+
+def test_gridcalc_matches_reference_output():
+    grids, tws, tg = [], [], None
+    for n in gc.GRIDCALC["inputs"]:
+        tg, hdr, grid = g.grid_read(os.path.join(u.GOLDEN_DIR, n, "grid.dat"))
+        grids.append(grid)
+        tws.append(tg.tweight)
+    avg, tw = g.gridcalc(tg, grids, tws)
+    want_g, want_hdr, want_grid = decode_golden(os.path.join(u.GOLDEN_DIR, "gridcalc", "avg.dat"))
+    assert want_g.tweight == tw
+    u.assert_bits_equal(avg, want_grid, "a_gridcalc average")
