@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -165,10 +166,11 @@ struct TileMeta {
 // atoms of a tile follow from arithmetic, no index or rank loads in the inner loop.
 struct ApGroup { int g0, step, tile_atoms; };
 
+template <int NST>
 struct StreamSmem {
-  float tile[STAGES][TILE_FLOATS];
-  unsigned long long full[STAGES], empty[STAGES];
-  TileMeta meta[STAGES];
+  float tile[NST][TILE_FLOATS];
+  unsigned long long full[NST], empty[NST];
+  TileMeta meta[NST];
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -271,20 +273,144 @@ __device__ __forceinline__ int cell_of_exact(const GridParamsFast &P, float x, f
                            P.fmx[2], P.my, P.mz);
 }
 
-template <int MODE, bool PBC, bool AP>
+// ---------------------------------------------------------------------------
+// Where a hit goes.
+//
+// DirectSink: one RED per hit into the global grid (L2-resident when the grid is small).  On B200
+// that is bounded by the L2 tag/atomic rate, not by HBM: every hit is its own 32-byte-sector
+// request, and half of them cross to the other die's L2 partition (profiles/k1_r01c_summary.json).
+//
+// RouteSink: the shared-memory privatisation.  The grid is cut into `nb` buckets, each small
+// enough to be counted in one CTA's shared memory (or, for grids beyond L2, into 32 MB slabs that
+// stay L2-resident).  The streaming kernel does not touch the grid: it converts a hit into a
+// (bucket, local cell) key, stages keys per bucket in shared memory and writes them out in whole
+// 128-byte lines into this CTA's private segment of the bucket's key buffer (no global atomics,
+// no cursors).  A second kernel (route_count_*) then owns one bucket per CTA, counts its keys with
+// shared-memory atomics and adds the tile to the grid with plain coalesced stores.  L2 sees 4 bytes
+// of coalesced traffic per hit each way instead of a scattered sector request.
+// ---------------------------------------------------------------------------
+template <int MODE>
+struct DirectSink {
+  static constexpr int NSTAGES = STAGES;
+  static constexpr size_t EXTRA_SMEM = 0;
+  uint32_t *counts; float *acc; float w;
+  // `smem` is the sink's share of the dynamic shared memory (unused here)
+  __device__ __forceinline__ void init(void *, unsigned) const {}
+  __device__ __forceinline__ void hit(void *, int cell) const { deposit<MODE>(counts, acc, cell, w); }
+  __device__ __forceinline__ void tile_end(void *, unsigned) const {}
+  __device__ __forceinline__ void finish(void *, unsigned) const {}
+};
+
+constexpr int ROUTE_NB_MAX = 128;          // buckets
+constexpr int ROUTE_STAGE_KEYS = 8192;     // staged keys per CTA, split evenly over the buckets in use
+
+struct RouteMap {                          // cell <-> (bucket, local cell)
+  int sh_b; unsigned mask_b; int sh_hi, sh_lo; unsigned mask_lo;
+  __host__ __device__ __forceinline__ unsigned bucket(unsigned cell) const { return (cell >> sh_b) & mask_b; }
+  __host__ __device__ __forceinline__ unsigned local(unsigned cell) const { return ((cell >> sh_hi) << sh_lo) | (cell & mask_lo); }
+  __host__ __device__ __forceinline__ unsigned cell(unsigned b, unsigned l) const
+  {
+    return ((l >> sh_lo) << sh_hi) | (b << sh_b) | (l & mask_lo);
+  }
+};
+
+struct RouteStage {
+  uint32_t keys[ROUTE_STAGE_KEYS];
+  uint32_t fill[ROUTE_NB_MAX];             // keys staged (may run past `cap`: the excess went straight to the grid)
+  uint32_t pos[ROUTE_NB_MAX];              // keys already written to this CTA's segment
+};
+
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_THREADS) : "memory"); }
+
+struct RouteSink {
+  static constexpr int NSTAGES = 2;        // 2 x 36 KiB ring + 33 KiB staging: two CTAs per SM
+  static constexpr size_t EXTRA_SMEM = sizeof(RouteStage);
+  uint32_t *keys_g;                        // [nb][gridDim][seg_cap]
+  uint32_t *seg_len;                       // [nb][gridDim]
+  uint32_t *counts;                        // the grid, for the overflow fallback only
+  unsigned seg_cap;                        // multiple of 32
+  int nb, cap;                             // buckets in use, staged keys per bucket
+  RouteMap map;
+
+  __device__ __forceinline__ void init(void *smem, unsigned ctid) const
+  {
+    RouteStage *st = static_cast<RouteStage *>(smem);
+    for (unsigned i = ctid; i < ROUTE_NB_MAX; i += CONSUMER_THREADS) { st->fill[i] = 0; st->pos[i] = 0; }
+    consumer_barrier();
+  }
+  __device__ __forceinline__ void hit(void *smem, int cell) const
+  {
+    RouteStage *st = static_cast<RouteStage *>(smem);
+    const unsigned b = map.bucket((unsigned)cell);
+    const unsigned slot = atomicAdd(&st->fill[b], 1u);
+    if (slot < (unsigned)cap) st->keys[b * cap + slot] = map.local((unsigned)cell);
+    else atomicAdd(counts + cell, 1u);     // staging overflow (pathologically clustered input): still exact
+  }
+  // write the full 128-byte lines (everything when `all`) of every bucket to this CTA's segments.
+  // Warp w owns buckets w, w+8, ...: its lanes look at 32 of them at once and only the buckets
+  // that have a line to write are visited.
+  __device__ __forceinline__ void flush(void *smem, unsigned ctid, bool all) const
+  {
+    RouteStage *st = static_cast<RouteStage *>(smem);
+    const unsigned warp = ctid >> 5, lane = ctid & 31;
+    for (unsigned base = warp; base < (unsigned)nb; base += CONSUMER_WARPS * 32) {
+      const unsigned mine = base + CONSUMER_WARPS * lane;
+      const unsigned n_mine = mine < (unsigned)nb ? min(st->fill[mine], (unsigned)cap) : 0u;
+      unsigned todo = __ballot_sync(0xffffffffu, all ? n_mine > 0u : n_mine >= 32u);
+      while (todo) {
+        const int src_lane = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const unsigned b = base + CONSUMER_WARPS * (unsigned)src_lane;
+        const unsigned n = __shfl_sync(0xffffffffu, n_mine, src_lane);
+        const unsigned nout = all ? n : (n & ~31u);
+        const unsigned pos = st->pos[b];
+        const uint32_t *src = st->keys + b * cap;
+        const bool fits = pos + nout <= seg_cap;
+        if (fits) {
+          uint32_t *dst = keys_g + ((size_t)b * gridDim.x + blockIdx.x) * seg_cap + pos;
+          for (unsigned k = lane; k < nout; k += 32) dst[k] = src[k];
+        } else {                           // segment full: count these keys directly
+          for (unsigned k = lane; k < nout; k += 32) atomicAdd(counts + map.cell(b, src[k]), 1u);
+        }
+        const unsigned rem = n - nout;     // < 32 keys stay staged
+        const uint32_t v = lane < rem ? src[nout + lane] : 0u;
+        __syncwarp();
+        if (lane < rem) st->keys[b * cap + lane] = v;
+        if (lane == 0) { st->fill[b] = rem; if (fits) st->pos[b] = pos + nout; }
+      }
+    }
+  }
+  __device__ __forceinline__ void tile_end(void *smem, unsigned ctid) const
+  {
+    consumer_barrier();                    // every hit of the tile is staged
+    flush(smem, ctid, false);
+    consumer_barrier();                    // staging compacted before the next tile appends
+  }
+  __device__ __forceinline__ void finish(void *smem, unsigned ctid) const
+  {
+    RouteStage *st = static_cast<RouteStage *>(smem);
+    consumer_barrier();
+    flush(smem, ctid, true);
+    consumer_barrier();
+    for (unsigned b = ctid; b < (unsigned)nb; b += CONSUMER_THREADS)
+      seg_len[(size_t)b * gridDim.x + blockIdx.x] = st->pos[b];
+  }
+};
+
+template <class SINK, bool PBC, bool AP>
 __global__ void __launch_bounds__(STREAM_THREADS)
 bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict__ gindex, unsigned gnx,
-                  const unsigned *__restrict__ rank, long long ntiles, ApGroup G, GridParamsFast P,
-                  uint32_t *__restrict__ counts, float *__restrict__ acc, float w,
+                  const unsigned *__restrict__ rank, long long ntiles, ApGroup G, GridParamsFast P, SINK sink,
                   const float *__restrict__ box3, unsigned long long *__restrict__ hits,
                   unsigned long long *__restrict__ diag)
 {
+  constexpr int NST = SINK::NSTAGES;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  StreamSmem &S = *reinterpret_cast<StreamSmem *>(smem_raw);
+  StreamSmem<NST> &S = *reinterpret_cast<StreamSmem<NST> *>(smem_raw);
   const int tid = threadIdx.x;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], CONSUMER_WARPS); }
+    for (int s = 0; s < NST; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], CONSUMER_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -296,8 +422,8 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
       int it = 0;
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int stage = it % STAGES;
-        if (it >= STAGES) mbar_wait(&S.empty[stage], (unsigned)(it / STAGES - 1) & 1u);
+        const int stage = it % NST;
+        if (it >= NST) mbar_wait(&S.empty[stage], (unsigned)(it / NST - 1) & 1u);
         const int tile_atoms = AP ? G.tile_atoms : TILE_ATOMS;
         const long long g0 = t * tile_atoms, g1 = g0 + tile_atoms;
         const long long f0 = g0 / natoms, f1 = g1 / natoms;
@@ -333,10 +459,12 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
   // ---------------- consumer warps ----------------
   const unsigned ctid = (unsigned)tid - 32u;
   const int lane = tid & 31;
+  void *const sink_smem = smem_raw + ((sizeof(StreamSmem<NST>) + 15) & ~(size_t)15);
+  sink.init(sink_smem, ctid);
   int it = 0;
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-    const int stage = it % STAGES;
-    mbar_wait(&S.full[stage], (unsigned)(it / STAGES) & 1u);
+    const int stage = it % NST;
+    mbar_wait(&S.full[stage], (unsigned)(it / NST) & 1u);
     const TileMeta m = S.meta[stage];
     const uint32_t tile = smem_addr(S.tile[stage]);
     unsigned c0 = 0, c1 = 0;            // hits in frame f0 / f0+1 (later frames go straight to global)
@@ -363,7 +491,7 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
           }
           const FastCell fc = cell_of_fast(P, px[k], py[k], pz[k]);
           const bool go = valid[k] & fc.inside & fc.sure;
-          if (go) deposit<MODE>(counts, acc, fc.cell, w);
+          if (go) sink.hit(sink_smem, fc.cell);
           c0 += (go & !inB[k]) ? 1u : 0u;
           c1 += (go & inB[k]) ? 1u : 0u;
           rare |= (valid[k] & fc.inside & !fc.sure) ? (1u << k) : 0u;
@@ -374,7 +502,7 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
             if (!((rare >> k) & 1u)) continue;
             const int cell = cell_of_exact(P, px[k], py[k], pz[k]);
             if (cell >= 0) {
-              deposit<MODE>(counts, acc, cell, w);
+              sink.hit(sink_smem, cell);
               if (inB[k]) c1++; else c0++;
             } else {
               atomicAdd(diag, 1ull);
@@ -413,7 +541,7 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
         const FastCell fc = cell_of_fast(P, px[k], py[k], pz[k]);
         const int cell = !fc.inside ? -1 : fc.sure ? fc.cell : cell_of_exact(P, px[k], py[k], pz[k]);
         if (cell >= 0) {
-          deposit<MODE>(counts, acc, cell, w);
+          sink.hit(sink_smem, cell);
           if (df[k] == 0) c0++;
           else if (df[k] == 1) c1++;
           else atomicAdd(hits + m.f0 + df[k], 1ull);
@@ -428,6 +556,66 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
       if (c0) atomicAdd(hits + m.f0, (unsigned long long)c0);
       if (c1) atomicAdd(hits + m.f0 + 1, (unsigned long long)c1);
       mbar_arrive(&S.empty[stage]);     // this warp is done with the stage (its LDS results are in registers)
+    }
+    sink.tile_end(sink_smem, ctid);
+  }
+  sink.finish(sink_smem, ctid);
+}
+
+// ---------------------------------------------------------------------------
+// Second phase of the routed path.
+// route_count_smem_kernel: CTA b owns bucket b.  Its slice of the grid (cells whose 32-cell run
+// number is b mod nb) lives in shared memory for the duration of the kernel; the keys of all the
+// streaming CTAs' segments are read once, coalesced, and counted with shared-memory atomics; the
+// tile is then added to the grid with plain stores (no other CTA touches these cells).
+// route_count_slab_kernel: buckets are contiguous 32 MB slabs of a grid that does not fit L2;
+// all CTAs work through the buckets in the same order so the REDs of one slab stay L2-resident.
+// ---------------------------------------------------------------------------
+constexpr int COUNT_THREADS = 1024;
+
+__global__ void __launch_bounds__(COUNT_THREADS)
+route_count_smem_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ seg_len, int nseg,
+                        unsigned seg_cap, unsigned tile_cells, RouteMap map, uint32_t *__restrict__ counts,
+                        unsigned ncells)
+{
+  extern __shared__ uint32_t tile_sh[];
+  const unsigned b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (unsigned l = tid; l < tile_cells; l += COUNT_THREADS) tile_sh[l] = 0;
+  __syncthreads();
+  for (int seg = (int)warp; seg < nseg; seg += COUNT_THREADS / 32) {
+    const unsigned len = __ldg(seg_len + (size_t)b * nseg + seg);
+    const uint32_t *p = keys + ((size_t)b * nseg + seg) * seg_cap;
+    unsigned k = lane;
+    for (; k + 96 < len; k += 128) {
+      const uint32_t k0 = __ldcs(p + k), k1 = __ldcs(p + k + 32), k2 = __ldcs(p + k + 64), k3 = __ldcs(p + k + 96);
+      atomicAdd(&tile_sh[k0], 1u); atomicAdd(&tile_sh[k1], 1u); atomicAdd(&tile_sh[k2], 1u); atomicAdd(&tile_sh[k3], 1u);
+    }
+    for (; k < len; k += 32) atomicAdd(&tile_sh[__ldcs(p + k)], 1u);
+  }
+  __syncthreads();
+  for (unsigned l = tid; l < tile_cells; l += COUNT_THREADS) {
+    const uint32_t n = tile_sh[l];
+    if (n) {
+      const unsigned cell = map.cell(b, l);
+      if (cell < ncells) counts[cell] += n;
+    }
+  }
+}
+
+constexpr unsigned SLAB_CHUNK = 2048;
+__global__ void __launch_bounds__(256)
+route_count_slab_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ seg_len, int nseg,
+                        unsigned seg_cap, int nb, RouteMap map, uint32_t *__restrict__ counts)
+{
+  const unsigned nchunk = (seg_cap + SLAB_CHUNK - 1) / SLAB_CHUNK;
+  const unsigned nitems = (unsigned)nseg * nchunk;
+  for (int b = 0; b < nb; b++) {
+    for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const unsigned seg = item / nchunk, k0 = (item - seg * nchunk) * SLAB_CHUNK;
+      const unsigned len = __ldg(seg_len + (size_t)b * nseg + seg);
+      const unsigned k1 = min(len, k0 + SLAB_CHUNK);
+      const uint32_t *p = keys + ((size_t)b * nseg + seg) * seg_cap;
+      for (unsigned k = k0 + threadIdx.x; k < k1; k += 256) atomicAdd(counts + map.cell((unsigned)b, __ldcs(p + k)), 1u);
     }
   }
 }
@@ -608,6 +796,15 @@ struct gcb_counter {
   bool stream_ok = false;             // index group dense enough for the streaming kernel
   bool ap_ok = false;                 // index group is g0 + i*step: arithmetic selection inside the tile
   ApGroup ap{0, 1, TILE_ATOMS};
+  // routed (shared-memory privatised) path
+  int route_mode = 0;                 // 0 none, 1 interleaved buckets counted in shared memory, 2 L2-sized slabs
+  RouteMap route_map{};
+  int route_nb = 0;
+  unsigned route_tile_cells = 0;
+  long long route_units = 0;          // atom-frames per routing round
+  uint32_t *d_keys = nullptr, *d_seglen = nullptr;
+  unsigned route_seg_cap = 0;
+  int route_grid = 0;                 // streaming CTAs the key buffer is laid out for
 
   std::vector<int> h_gindex;          // sorted copy of the index group
   int *d_gindex = nullptr;
@@ -678,25 +875,107 @@ int fold_pending(gcb_counter *c)
   return GCB_OK;
 }
 
-size_t stream_smem_bytes() { return sizeof(StreamSmem); }
+template <class SINK>
+size_t stream_smem_bytes() { return ((sizeof(StreamSmem<SINK::NSTAGES>) + 15) & ~(size_t)15) + SINK::EXTRA_SMEM; }
 
-template <int MODE, bool PBC, bool AP>
-int launch_stream(gcb_counter *c, const float *d_x, long long ntiles, uint32_t *cnt, float w, const float *d_box3,
-                  unsigned long long *d_hits)
+template <class SINK, bool PBC, bool AP>
+int launch_stream(gcb_counter *c, const float *d_x, long long ntiles, const SINK &sink, int grid_cap,
+                  const float *d_box3, unsigned long long *d_hits, int *grid_out)
 {
   static bool attr_done = false;                 // one flag per instantiation
+  const size_t smem = stream_smem_bytes<SINK>();
   if (!attr_done) {
-    GCB_CUDA(cudaFuncSetAttribute(bin_stream_kernel<MODE, PBC, AP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)stream_smem_bytes()));
+    GCB_CUDA(cudaFuncSetAttribute(bin_stream_kernel<SINK, PBC, AP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  const int per_sm = std::max(1, (int)((227 * 1024) / (stream_smem_bytes() + 1024)));
-  const long long grid = std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
-  bin_stream_kernel<MODE, PBC, AP><<<(unsigned)grid, STREAM_THREADS, stream_smem_bytes(), c->compute>>>(
-      d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, c->ap, c->PF, cnt, c->d_acc, w, d_box3,
-      d_hits, c->d_diag);
+  const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+  long long grid = std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
+  if (grid_cap > 0) grid = std::min<long long>(grid, grid_cap);
+  bin_stream_kernel<SINK, PBC, AP><<<(unsigned)grid, STREAM_THREADS, smem, c->compute>>>(
+      d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, c->ap, c->PF, sink, d_box3, d_hits, c->d_diag);
   c->launches++;
   GCB_CUDA(cudaGetLastError());
+  if (grid_out) *grid_out = (int)grid;
+  return GCB_OK;
+}
+
+// the part of a batch the streaming kernel leaves: fewer than one tile of atoms at the end
+template <int MODE, bool PBC>
+int launch_gather(gcb_counter *c, const float *d_x, long long e_begin, long long e_end, uint32_t *cnt, float w,
+                  const float *d_box3, unsigned long long *d_hits)
+{
+  if (e_begin >= e_end) return GCB_OK;
+  const long long chunk = (long long)GATHER_THREADS * GATHER_ITEMS;
+  const long long nchunks = (e_end - e_begin + chunk - 1) / chunk;
+  const long long grid = std::min<long long>(nchunks, (long long)c->sm_count * 8);
+  bin_gather_kernel<MODE, PBC><<<(unsigned)grid, GATHER_THREADS, 0, c->compute>>>(
+      d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, e_begin, e_end, c->P, cnt, c->d_acc, w, d_box3, d_hits, c->d_diag);
+  c->launches++;
+  GCB_CUDA(cudaGetLastError());
+  return GCB_OK;
+}
+
+// Routed path: frames are processed in rounds of ~route_units atom-frames; per round one streaming
+// kernel that only writes keys, the gather kernel for the sub-tile tail, one counting kernel.
+template <bool PBC>
+int launch_routed(gcb_counter *c, const float *d_x, long nframes, const float *d_box3, unsigned long long *d_hits)
+{
+  const bool ap = c->ap_ok && c->opts.kernel != GCB_KERNEL_STREAM_INDEXED;
+  const int tile_atoms = ap ? c->ap.tile_atoms : TILE_ATOMS;
+  const size_t smem = stream_smem_bytes<RouteSink>();
+  const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+  const int G = c->sm_count * per_sm;
+  long fpr = (long)std::max<long long>(4, (c->route_units / std::max(c->gnx, 1)) & ~3LL);   // frames per round, multiple of 4:
+  fpr = std::min<long>(fpr, (nframes + 3) & ~3L);                                             // every round starts 16-byte aligned
+  // key buffer: [nb][G][seg_cap]; twice the even share per segment, anything beyond goes straight to the grid
+  const long long round_units = (long long)fpr * c->gnx;
+  const unsigned seg_cap = (unsigned)(((2 * round_units / ((long long)G * c->route_nb) + 96) + 31) & ~31LL);
+  if (!c->d_keys || seg_cap > c->route_seg_cap || G != c->route_grid) {
+    GCB_CUDA(cudaStreamSynchronize(c->compute));
+    cudaFree(c->d_keys); cudaFree(c->d_seglen);
+    c->d_keys = nullptr; c->d_seglen = nullptr;
+    GCB_CUDA(cudaMalloc(&c->d_keys, sizeof(uint32_t) * (size_t)c->route_nb * G * seg_cap));
+    GCB_CUDA(cudaMalloc(&c->d_seglen, sizeof(uint32_t) * (size_t)c->route_nb * G));
+    c->route_seg_cap = seg_cap;
+    c->route_grid = G;
+  }
+  if (c->route_mode == 1) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      GCB_CUDA(cudaFuncSetAttribute(route_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done = true;
+    }
+  }
+  for (long f0 = 0; f0 < nframes; f0 += fpr) {
+    const long n = std::min(fpr, nframes - f0);
+    const float *xs = d_x + (size_t)f0 * c->natoms * 3;
+    const float *bs = d_box3 ? d_box3 + 3 * f0 : nullptr;
+    const long long total_e = (long long)n * c->gnx, total_atoms = (long long)n * c->natoms;
+    const long long ntiles = total_atoms / tile_atoms;
+    long long e_begin = 0;
+    if (ntiles > 0) {
+      RouteSink sink;
+      sink.keys_g = c->d_keys; sink.seg_len = c->d_seglen; sink.counts = c->d_runcnt; sink.seg_cap = c->route_seg_cap;
+      sink.nb = c->route_nb; sink.cap = ROUTE_STAGE_KEYS / c->route_nb; sink.map = c->route_map;
+      int grid = 0;
+      int rc = ap ? launch_stream<RouteSink, PBC, true>(c, xs, ntiles, sink, G, bs, d_hits + f0, &grid)
+                  : launch_stream<RouteSink, PBC, false>(c, xs, ntiles, sink, G, bs, d_hits + f0, &grid);
+      if (rc) return rc;
+      if (c->route_mode == 1) {
+        route_count_smem_kernel<<<c->route_nb, COUNT_THREADS, c->route_tile_cells * sizeof(uint32_t), c->compute>>>(
+            c->d_keys, c->d_seglen, grid, c->route_seg_cap, c->route_tile_cells, c->route_map, c->d_runcnt, (unsigned)c->ncells);
+      } else {
+        route_count_slab_kernel<<<c->sm_count * 8, 256, 0, c->compute>>>(c->d_keys, c->d_seglen, grid, c->route_seg_cap,
+                                                                         c->route_nb, c->route_map, c->d_runcnt);
+      }
+      c->launches++;
+      GCB_CUDA(cudaGetLastError());
+      const long long g1 = ntiles * tile_atoms, f1 = g1 / c->natoms;
+      e_begin = f1 * c->gnx + rank_host(c, (int)(g1 - f1 * c->natoms));
+    }
+    int rc = launch_gather<MODE_COUNT, PBC>(c, xs, e_begin, total_e, c->d_runcnt, 1.0f, bs, d_hits + f0);
+    if (rc) return rc;
+  }
   return GCB_OK;
 }
 
@@ -709,33 +988,30 @@ int launch_bin(gcb_counter *c, const float *d_x, long nframes, float w, const fl
   uint32_t *cnt = MODE == MODE_COUNT ? c->d_runcnt : c->d_total;
   long long e_begin = 0;
   const bool aligned = ((uintptr_t)d_x & 15u) == 0;
-  const bool use_stream = aligned && c->opts.kernel != GCB_KERNEL_GATHER &&
-                          (c->stream_ok || c->opts.kernel == GCB_KERNEL_STREAM ||
-                           c->opts.kernel == GCB_KERNEL_STREAM_INDEXED);
+  const int k = c->opts.kernel;
+  const bool use_stream = aligned && k != GCB_KERNEL_GATHER &&
+                          (c->stream_ok || k == GCB_KERNEL_STREAM || k == GCB_KERNEL_STREAM_INDEXED || k == GCB_KERNEL_ROUTED);
+  // AUTO takes the routed path for grids beyond L2 (slabs: 1.2-1.3x the direct kernel, profiles/perf_r01.md); for
+  // shared-memory sized buckets the two-kernel round still loses to direct L2 REDs and is only used on request
+  if (use_stream && MODE == MODE_COUNT && c->route_mode != 0 && k != GCB_KERNEL_STREAM && k != GCB_KERNEL_STREAM_INDEXED &&
+      (k == GCB_KERNEL_ROUTED || (c->route_mode == 2 && total_e >= (1LL << 20))))
+    return launch_routed<PBC>(c, d_x, nframes, d_box3, d_hits);
   if (use_stream) {
-    const bool ap = c->ap_ok && c->opts.kernel != GCB_KERNEL_STREAM_INDEXED;
+    const bool ap = c->ap_ok && k != GCB_KERNEL_STREAM_INDEXED;
     const int tile_atoms = ap ? c->ap.tile_atoms : TILE_ATOMS;
     const long long total_atoms = (long long)nframes * c->natoms;
     const long long ntiles = total_atoms / tile_atoms;      // full tiles; the remainder goes to the gather kernel
     if (ntiles > 0) {
-      int rc = ap ? launch_stream<MODE, PBC, true>(c, d_x, ntiles, cnt, w, d_box3, d_hits)
-                  : launch_stream<MODE, PBC, false>(c, d_x, ntiles, cnt, w, d_box3, d_hits);
+      DirectSink<MODE> sink;
+      sink.counts = cnt; sink.acc = c->d_acc; sink.w = w;
+      int rc = ap ? launch_stream<DirectSink<MODE>, PBC, true>(c, d_x, ntiles, sink, 0, d_box3, d_hits, nullptr)
+                  : launch_stream<DirectSink<MODE>, PBC, false>(c, d_x, ntiles, sink, 0, d_box3, d_hits, nullptr);
       if (rc) return rc;
       const long long g1 = ntiles * tile_atoms, f1 = g1 / c->natoms;
       e_begin = f1 * c->gnx + rank_host(c, (int)(g1 - f1 * c->natoms));
     }
   }
-  if (e_begin < total_e) {
-    const long long chunk = (long long)GATHER_THREADS * GATHER_ITEMS;
-    const long long nchunks = (total_e - e_begin + chunk - 1) / chunk;
-    const long long grid = std::min<long long>(nchunks, (long long)c->sm_count * 8);
-    bin_gather_kernel<MODE, PBC><<<(unsigned)grid, GATHER_THREADS, 0, c->compute>>>(
-        d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, e_begin, total_e, c->P, cnt, c->d_acc, w, d_box3, d_hits,
-        c->d_diag);
-    c->launches++;
-    GCB_CUDA(cudaGetLastError());
-  }
-  return GCB_OK;
+  return launch_gather<MODE, PBC>(c, d_x, e_begin, total_e, cnt, w, d_box3, d_hits);
 }
 
 template <int MODE>
@@ -868,7 +1144,7 @@ void free_counter(gcb_counter *c)
   }
   for (auto &d : c->devhits) { cudaFree(d.d); cudaFree(d.d_box3); }
   cudaFree(c->d_gindex); cudaFree(c->d_rank); cudaFree(c->d_runcnt); cudaFree(c->d_total); cudaFree(c->d_acc);
-  cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2);
+  cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2); cudaFree(c->d_keys); cudaFree(c->d_seglen);
   for (auto e : c->events) if (e) cudaEventDestroy(e);
   if (c->compute) cudaStreamDestroy(c->compute);
   delete c;
@@ -954,6 +1230,26 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
     }
   }
 
+  {
+    // routed path geometry.  Interleaved: bucket = (cell / 32) mod 128, the bucket's cells fit one CTA's
+    // shared memory.  Slabs (grid well beyond what stays L2-resident next to the coordinate stream):
+    // bucket = cell / 2^23 (32 MB of counters each).
+    const char *env = getenv("GCB_ROUTE_UNITS");
+    c->route_units = env ? atoll(env) : (16LL << 20);
+    if (c->route_units < 4096) c->route_units = 4096;
+    const size_t tile_cells = ((c->ncells + 32 * ROUTE_NB_MAX - 1) / (32 * ROUTE_NB_MAX)) * 32;
+    if (tile_cells * sizeof(uint32_t) <= 192 * 1024) {
+      c->route_mode = 1;
+      c->route_nb = ROUTE_NB_MAX;
+      c->route_tile_cells = (unsigned)tile_cells;
+      c->route_map = RouteMap{5, ROUTE_NB_MAX - 1, 12, 5, 31u};
+    } else if (c->ncells * sizeof(uint32_t) > ((size_t)48 << 20)) {
+      c->route_mode = 2;
+      c->route_nb = (int)((c->ncells + (1u << 23) - 1) >> 23);
+      c->route_map = RouteMap{23, 0xFFu, 31, 23, (1u << 23) - 1};
+    }
+    if (getenv("GCB_NO_ROUTE")) c->route_mode = 0;
+  }
   GCB_CREATE_CUDA(cudaMalloc(&c->d_gindex, sizeof(int) * std::max(gnx, 1)));
   GCB_CREATE_CUDA(cudaMalloc(&c->d_rank, sizeof(unsigned) * rank.size()));
   GCB_CREATE_CUDA(cudaMalloc(&c->d_runcnt, sizeof(uint32_t) * c->ncells));

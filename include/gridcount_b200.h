@@ -92,7 +92,8 @@ enum {
 };
 enum {                     /* kernel selection (GCB_KERNEL_AUTO picks by index-group density and regularity) */
   GCB_KERNEL_AUTO = 0, GCB_KERNEL_GATHER = 1, GCB_KERNEL_STREAM = 2,
-  GCB_KERNEL_STREAM_INDEXED = 3   /* streaming kernel without the arithmetic-progression shortcut */
+  GCB_KERNEL_STREAM_INDEXED = 3,  /* streaming kernel without the arithmetic-progression shortcut */
+  GCB_KERNEL_ROUTED = 4           /* streaming kernel + shared-memory privatised counting (two kernels per round) */
 };
 
 typedef struct {

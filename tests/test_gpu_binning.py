@@ -13,7 +13,7 @@ from gridcount_b200 import _cabi as K
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [K.KERNEL_GATHER, K.KERNEL_STREAM, K.KERNEL_STREAM_INDEXED]
+KERNELS = [K.KERNEL_GATHER, K.KERNEL_STREAM, K.KERNEL_STREAM_INDEXED, K.KERNEL_ROUTED]
 
 
 def to_ogeom(geom):

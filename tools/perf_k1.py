@@ -27,7 +27,7 @@ def main():
     geom = g.setup_geometry(L, delta)
     gindex = np.arange(0, natoms, stride, dtype=np.int32)
     dev = g.DeviceFrames(nframes, natoms).generate(g.make_gen(1, L))
-    for kname, kernel in (("gather", K.KERNEL_GATHER), ("stream", K.KERNEL_STREAM)):
+    for kname, kernel in (("gather", K.KERNEL_GATHER), ("stream", K.KERNEL_STREAM), ("routed", K.KERNEL_ROUTED)):
         ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel)
         for _ in range(3):
             ctr.add_device_frames(dev)
