@@ -314,8 +314,8 @@ def run_gpu_arm(args, rank, local_rank, world):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e = {"value": units_per_step * e2e_steps / e2e_s * 1e-9, "unit": UNIT,
-           "h2d_bytes_per_step": int(F) * natoms * 12 + F * 0,
-           "d2h_bytes_per_step": int(geom.cells * 4 + F * 8), "steps": e2e_steps,
+           "h2d_bytes_per_step": int(F) * natoms * 12 * world,
+           "d2h_bytes_per_step": int(geom.cells * 4 + F * 8) * world, "steps": e2e_steps,
            "ms_per_step": e2e_s / e2e_steps * 1e3,
            "path": "gcb_counter_add_frames(pinned host x[F][natoms][3]) -> gcb_counter_density(host grid)"}
     pin.free()

@@ -1663,23 +1663,44 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c,
     if (rc) return rc;
     c->uniform = false;
   }
-  // scalars: frames, hits, overflow as u64; sumP as f64 (rank order of the sum is NCCL's)
-  unsigned long long sc[3] = {(unsigned long long)c->hits_per_frame.size(), c->hits_total, c->edge_overflow};
-  double sp = c->sumP;
-  unsigned long long *d_sc = nullptr;
-  double *d_sp = nullptr;
-  GCB_CUDA(cudaMalloc(&d_sc, sizeof(sc)));
-  GCB_CUDA(cudaMalloc(&d_sp, sizeof(double)));
-  GCB_CUDA(cudaMemcpyAsync(d_sc, sc, sizeof(sc), cudaMemcpyHostToDevice, c->compute));
-  GCB_CUDA(cudaMemcpyAsync(d_sp, &sp, sizeof(double), cudaMemcpyHostToDevice, c->compute));
-  rc = allreduce(d_sc, d_sc, 3, U64, c->nccl, c->compute);
-  if (!rc) rc = allreduce(d_sp, d_sp, 1, F64, c->nccl, c->compute);
-  if (rc) { cudaFree(d_sc); cudaFree(d_sp); return rc; }
-  GCB_CUDA(cudaMemcpyAsync(sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, c->compute));
-  GCB_CUDA(cudaMemcpyAsync(&sp, d_sp, sizeof(double), cudaMemcpyDeviceToHost, c->compute));
+  // Statistics.  Ranks hold contiguous frame shards in rank order, so gathering the per-frame hit counts and
+  // weights (an all-gather written as a sum of disjoint slots) lets every rank redo the reference's frame-ordered
+  // `sumP += (double)weight` chain (g_ri3Dc.c:151,426) over ALL frames: bit-identical to a single-GPU run.
+  std::vector<unsigned long long> nfr((size_t)c->nranks, 0ull);
+  nfr[(size_t)c->rank] = c->hits_per_frame.size();
+  unsigned long long *d_tmp = nullptr;
+  GCB_CUDA(cudaMalloc(&d_tmp, sizeof(unsigned long long) * nfr.size()));
+  GCB_CUDA(cudaMemcpyAsync(d_tmp, nfr.data(), sizeof(unsigned long long) * nfr.size(), cudaMemcpyHostToDevice, c->compute));
+  rc = allreduce(d_tmp, d_tmp, nfr.size(), U64, c->nccl, c->compute);
+  if (rc) { cudaFree(d_tmp); return rc; }
+  GCB_CUDA(cudaMemcpyAsync(nfr.data(), d_tmp, sizeof(unsigned long long) * nfr.size(), cudaMemcpyDeviceToHost, c->compute));
   GCB_CUDA(cudaStreamSynchronize(c->compute));
-  cudaFree(d_sc); cudaFree(d_sp);
-  c->global_frames = sc[0]; c->hits_total = sc[1]; c->edge_overflow = sc[2]; c->sumP = sp;
+  cudaFree(d_tmp);
+  size_t total_frames = 0, my_off = 0;
+  for (int r = 0; r < c->nranks; r++) { if (r == c->rank) my_off = total_frames; total_frames += (size_t)nfr[(size_t)r]; }
+  std::vector<unsigned long long> fr(2 * total_frames + 1, 0ull);          // [hits | weight bits | edge overflow]
+  for (size_t f = 0; f < c->hits_per_frame.size(); f++) {
+    fr[my_off + f] = c->hits_per_frame[f];
+    uint32_t wbits; memcpy(&wbits, &c->weight_per_frame[f], 4);
+    fr[total_frames + my_off + f] = wbits;
+  }
+  fr[2 * total_frames] = c->edge_overflow;
+  GCB_CUDA(cudaMalloc(&d_tmp, sizeof(unsigned long long) * fr.size()));
+  GCB_CUDA(cudaMemcpyAsync(d_tmp, fr.data(), sizeof(unsigned long long) * fr.size(), cudaMemcpyHostToDevice, c->compute));
+  rc = allreduce(d_tmp, d_tmp, fr.size(), U64, c->nccl, c->compute);
+  if (rc) { cudaFree(d_tmp); return rc; }
+  GCB_CUDA(cudaMemcpyAsync(fr.data(), d_tmp, sizeof(unsigned long long) * fr.size(), cudaMemcpyDeviceToHost, c->compute));
+  GCB_CUDA(cudaStreamSynchronize(c->compute));
+  cudaFree(d_tmp);
+  double sp = 0;
+  unsigned long long hits = 0;
+  for (size_t f = 0; f < total_frames; f++) {
+    const uint32_t wbits = (uint32_t)fr[total_frames + f];
+    float wf; memcpy(&wf, &wbits, 4);
+    sp = gcb::seq_add_f64(sp, (double)wf, fr[f]);
+    hits += fr[f];
+  }
+  c->global_frames = total_frames; c->hits_total = hits; c->edge_overflow = fr[2 * total_frames]; c->sumP = sp;
   c->reduced = true;
   return GCB_OK;
 }
