@@ -143,14 +143,26 @@ bin_gather_kernel(const float *__restrict__ x, int natoms, const int *__restrict
 // tiles); TILE_ATOMS*3 floats is a multiple of both 3 and 4, so atoms never
 // straddle tiles and every tile starts 16-byte aligned.
 // ---------------------------------------------------------------------------
-constexpr int CONSUMER_WARPS = 8;
+#ifndef GCB_CONSUMER_WARPS
+#define GCB_CONSUMER_WARPS 8
+#endif
+#ifndef GCB_STAGES
+#define GCB_STAGES 3
+#endif
+#ifndef GCB_UNROLL
+#define GCB_UNROLL 4
+#endif
+#ifndef GCB_EXPERIMENT
+#define GCB_EXPERIMENT 0
+#endif
+constexpr int CONSUMER_WARPS = GCB_CONSUMER_WARPS;
 constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
 constexpr int STREAM_THREADS = CONSUMER_THREADS + 32;     // + producer warp
 constexpr int TILE_ATOMS = 3072;                          // 1024 selected per tile for 3-site water
 constexpr int TILE_FLOATS = TILE_ATOMS * 3;
 constexpr int TILE_BYTES = TILE_FLOATS * 4;               // 36 KiB
-constexpr int STAGES = 3;
-constexpr int UNROLL = 4;
+constexpr int STAGES = GCB_STAGES;
+constexpr int UNROLL = GCB_UNROLL;
 
 struct TileMeta {
   long long f0;          // frame of the tile's first atom
@@ -214,18 +226,18 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
   return v;
 }
 
-// Fast float -> bin for the streaming kernel.  Same result as cell_of() for every input, with
-// no division in the common case: the quotient u/delta is estimated as p = u * fl(1/delta)
-// (relative error < 2^-23 against the real quotient; the reference's IEEE quotient is within
-// 2^-24 of it).  floor(p) is read from the mantissa of (p - 0.5) + 1.5*2^23.  When p is farther
-// than p*2^-22 from both neighbouring integers, estimate, real quotient and IEEE quotient lie
-// between the same two integers and share that floor (`sure`).  Otherwise -- an atom within a few
-// ulp of a cell boundary, about 1e-4 of them -- the caller redoes the atom with cell_of_exact().
-// The host sets inv = NaN (nothing is ever `sure`) for geometries where an in-bounds atom could bin
-// to mx (gcb_edge_vulnerable) or with more than 2^21 cells along a dimension, so the fast path
-// needs no range check on the bin indices.
+// Fast float -> bin for the streaming kernel.  Same result as cell_of() for every input, with no
+// division in the common case.  The real quotient R = u/delta is bracketed by two products,
+//   p_lo = u * fl((1/delta)(1 - 2^-21))  <  R (1 - 2^-24)   and   p_hi = u * fl((1/delta)(1 + 2^-21))  >  R (1 + 2^-24)
+// (three f32 roundings of 2^-24 each cannot eat the 2^-21 margin), and the reference's IEEE quotient
+// fl(R) lies within 2^-24 of R, hence strictly between them.  floor() of each product is read from
+// the mantissa after a round-DOWN addition of 1.5*2^23.  When both floors agree (`sure`), that is
+// floor(fl(R)).  Otherwise -- an atom within a few ulp of a cell boundary, ~1e-4 of them -- the
+// caller redoes the atom with cell_of_exact().  The host sets the reciprocals to NaN (nothing is
+// ever `sure`) for geometries where an in-bounds atom could bin to mx (gcb_edge_vulnerable) or with
+// more than 2^21 cells along a dimension, so the fast path needs no range check on the indices.
 struct GridParamsFast {
-  float a[3], b[3], delta[3], inv[3], fmx[3];
+  float a[3], b[3], delta[3], inv_lo[3], inv_hi[3], fmx[3];
   int my, mz;
   int bias;                                          // 0x4B400000 * (my*mz + mz + 1), mod 2^32
 };
@@ -239,20 +251,12 @@ __device__ __forceinline__ FastCell cell_of_fast(const GridParamsFast &P, float 
   // only when they are equal (subnormals are kept, -ftz=false), and its sign is the comparison's
   o.inside = !((x < P.a[0]) | (x >= P.b[0]) | (y < P.a[1]) | (y >= P.b[1]) | (z < P.a[2]) | (z >= P.b[2]));
   const float MAGIC = 12582912.0f;                   // 1.5 * 2^23
-  const float EPS = 2.384185791015625e-07f;          // 2^-22
-  const float px = __fmul_rn(__fsub_rn(x, P.a[0]), P.inv[0]);
-  const float py = __fmul_rn(__fsub_rn(y, P.a[1]), P.inv[1]);
-  const float pz = __fmul_rn(__fsub_rn(z, P.a[2]), P.inv[2]);
-  const float rx = __fadd_rn(__fsub_rn(px, 0.5f), MAGIC);
-  const float ry = __fadd_rn(__fsub_rn(py, 0.5f), MAGIC);
-  const float rz = __fadd_rn(__fsub_rn(pz, 0.5f), MAGIC);
-  // g = (p - floor) - 0.5 in [-0.5, 0.5]; sure <=> |g| < 0.5 - p * 2^-22
-  const float gx = __fsub_rn(__fsub_rn(px, __fsub_rn(rx, MAGIC)), 0.5f);
-  const float gy = __fsub_rn(__fsub_rn(py, __fsub_rn(ry, MAGIC)), 0.5f);
-  const float gz = __fsub_rn(__fsub_rn(pz, __fsub_rn(rz, MAGIC)), 0.5f);
-  o.sure = (fabsf(gx) < __fmaf_rn(px, -EPS, 0.5f)) & (fabsf(gy) < __fmaf_rn(py, -EPS, 0.5f)) &
-           (fabsf(gz) < __fmaf_rn(pz, -EPS, 0.5f));
-  o.cell = (__float_as_int(rx) * P.my + __float_as_int(ry)) * P.mz + __float_as_int(rz) - P.bias;
+  const float ux = __fsub_rn(x, P.a[0]), uy = __fsub_rn(y, P.a[1]), uz = __fsub_rn(z, P.a[2]);
+  const float lx = __fadd_rd(__fmul_rn(ux, P.inv_lo[0]), MAGIC), hx = __fadd_rd(__fmul_rn(ux, P.inv_hi[0]), MAGIC);
+  const float ly = __fadd_rd(__fmul_rn(uy, P.inv_lo[1]), MAGIC), hy = __fadd_rd(__fmul_rn(uy, P.inv_hi[1]), MAGIC);
+  const float lz = __fadd_rd(__fmul_rn(uz, P.inv_lo[2]), MAGIC), hz = __fadd_rd(__fmul_rn(uz, P.inv_hi[2]), MAGIC);
+  o.sure = (lx == hx) & (ly == hy) & (lz == hz);
+  o.cell = (__float_as_int(lx) * P.my + __float_as_int(ly)) * P.mz + __float_as_int(lz) - P.bias;
   return o;
 }
 
@@ -315,76 +319,113 @@ struct RouteMap {                          // cell <-> (bucket, local cell)
 };
 
 struct RouteStage {
-  uint32_t keys[ROUTE_STAGE_KEYS];
-  uint32_t fill[ROUTE_NB_MAX];             // keys staged (may run past `cap`: the excess went straight to the grid)
-  uint32_t pos[ROUTE_NB_MAX];              // keys already written to this CTA's segment
+  uint32_t keys[ROUTE_STAGE_KEYS];         // one ring of `cap` keys per bucket
+  uint32_t tail[ROUTE_NB_MAX];             // keys appended so far (slots handed out)
+  uint32_t head[ROUTE_NB_MAX];             // keys that have left the ring; always a multiple of 32 until the end
+  uint32_t pos[ROUTE_NB_MAX];              // keys written to this CTA's segment (== head unless the segment filled up)
 };
 
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_THREADS) : "memory"); }
 
 struct RouteSink {
-  static constexpr int NSTAGES = 2;        // 2 x 36 KiB ring + 33 KiB staging: two CTAs per SM
+  static constexpr int NSTAGES = 2;        // 2 x 36 KiB tile ring + 34 KiB staging: two CTAs per SM
   static constexpr size_t EXTRA_SMEM = sizeof(RouteStage);
   uint32_t *keys_g;                        // [nb][gridDim][seg_cap]
   uint32_t *seg_len;                       // [nb][gridDim]
   uint32_t *counts;                        // the grid, for the overflow fallback only
   unsigned seg_cap;                        // multiple of 32
-  int nb, cap;                             // buckets in use, staged keys per bucket
+  int nb, cap;                             // buckets in use; ring size per bucket (power of two, >= 64)
   RouteMap map;
 
   __device__ __forceinline__ void init(void *smem, unsigned ctid) const
   {
     RouteStage *st = static_cast<RouteStage *>(smem);
-    for (unsigned i = ctid; i < ROUTE_NB_MAX; i += CONSUMER_THREADS) { st->fill[i] = 0; st->pos[i] = 0; }
+    for (unsigned i = ctid; i < ROUTE_NB_MAX; i += CONSUMER_THREADS) { st->tail[i] = 0; st->head[i] = 0; st->pos[i] = 0; }
     consumer_barrier();
   }
   __device__ __forceinline__ void hit(void *smem, int cell) const
   {
+#if GCB_EXPERIMENT == 3
+    if (cell == 0x7fffffff) atomicAdd(counts, 1u);
+    return;
+#endif
     RouteStage *st = static_cast<RouteStage *>(smem);
     const unsigned b = map.bucket((unsigned)cell);
-    const unsigned slot = atomicAdd(&st->fill[b], 1u);
-    if (slot < (unsigned)cap) st->keys[b * cap + slot] = map.local((unsigned)cell);
-    else atomicAdd(counts + cell, 1u);     // staging overflow (pathologically clustered input): still exact
+    const unsigned h = st->head[b];        // only flush() changes it, and never while hits are appended
+    const unsigned slot = atomicAdd(&st->tail[b], 1u);
+    if (slot - h < (unsigned)cap) st->keys[b * cap + (slot & (cap - 1))] = map.local((unsigned)cell);
+    else atomicAdd(counts + cell, 1u);     // ring full (pathologically clustered input): counted directly, still exact
   }
-  // write the full 128-byte lines (everything when `all`) of every bucket to this CTA's segments.
-  // Warp w owns buckets w, w+8, ...: its lanes look at 32 of them at once and only the buckets
-  // that have a line to write are visited.
+  // Move the complete 128-byte lines (everything when `all`) of every bucket from the rings to this CTA's
+  // segments.  Runs between two consumer barriers: no hit is appended meanwhile.  Warp w owns buckets
+  // w, w+W, ...: each lane inspects one of them and updates its ring state; the copies are then done by
+  // groups of 8 lanes, one bucket per group, 16 bytes per lane (a line never wraps: heads are multiples of 32),
+  // so a warp moves four lines per step instead of walking its buckets one after the other.
   __device__ __forceinline__ void flush(void *smem, unsigned ctid, bool all) const
   {
     RouteStage *st = static_cast<RouteStage *>(smem);
-    const unsigned warp = ctid >> 5, lane = ctid & 31;
+    const unsigned warp = ctid >> 5, lane = ctid & 31, grp = lane >> 3, sub = lane & 7;
     for (unsigned base = warp; base < (unsigned)nb; base += CONSUMER_WARPS * 32) {
       const unsigned mine = base + CONSUMER_WARPS * lane;
-      const unsigned n_mine = mine < (unsigned)nb ? min(st->fill[mine], (unsigned)cap) : 0u;
-      unsigned todo = __ballot_sync(0xffffffffu, all ? n_mine > 0u : n_mine >= 32u);
-      while (todo) {
-        const int src_lane = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const unsigned b = base + CONSUMER_WARPS * (unsigned)src_lane;
-        const unsigned n = __shfl_sync(0xffffffffu, n_mine, src_lane);
-        const unsigned nout = all ? n : (n & ~31u);
-        const unsigned pos = st->pos[b];
-        const uint32_t *src = st->keys + b * cap;
-        const bool fits = pos + nout <= seg_cap;
-        if (fits) {
-          uint32_t *dst = keys_g + ((size_t)b * gridDim.x + blockIdx.x) * seg_cap + pos;
-          for (unsigned k = lane; k < nout; k += 32) dst[k] = src[k];
-        } else {                           // segment full: count these keys directly
-          for (unsigned k = lane; k < nout; k += 32) atomicAdd(counts + map.cell(b, src[k]), 1u);
+      unsigned nout_mine = 0, h_mine = 0, pos_mine = 0;
+      bool fits_mine = true;
+      if (mine < (unsigned)nb) {
+        h_mine = st->head[mine];
+        pos_mine = st->pos[mine];
+        const unsigned t = st->tail[mine];
+        const unsigned n = min(t - h_mine, (unsigned)cap);          // valid keys in the ring
+        if (t - h_mine > (unsigned)cap) st->tail[mine] = h_mine + cap;     // the excess was counted directly
+        nout_mine = all ? n : (n & ~31u);
+        fits_mine = pos_mine + nout_mine <= seg_cap;
+        if (nout_mine) {
+          st->head[mine] = h_mine + nout_mine;
+          if (fits_mine) st->pos[mine] = pos_mine + nout_mine;
         }
-        const unsigned rem = n - nout;     // < 32 keys stay staged
-        const uint32_t v = lane < rem ? src[nout + lane] : 0u;
-        __syncwarp();
-        if (lane < rem) st->keys[b * cap + lane] = v;
-        if (lane == 0) { st->fill[b] = rem; if (fits) st->pos[b] = pos + nout; }
+      }
+      unsigned todo = __ballot_sync(0xffffffffu, nout_mine > 0u);
+      while (todo) {
+        const unsigned src = __fns(todo, 0, (int)grp + 1);            // the grp-th bucket still to do (or none)
+        const bool have = src < 32u;
+        const unsigned sl = have ? src : 0u;
+        const unsigned b = base + CONSUMER_WARPS * sl;
+        const unsigned nout = __shfl_sync(0xffffffffu, nout_mine, sl);
+        const unsigned h = __shfl_sync(0xffffffffu, h_mine, sl);
+        const unsigned pos = __shfl_sync(0xffffffffu, pos_mine, sl);
+        const bool fits = __shfl_sync(0xffffffffu, (int)fits_mine, sl) != 0;
+        if (have) {
+          const uint32_t *ring = st->keys + b * cap;
+          if (fits) {
+            uint32_t *dst = keys_g + ((size_t)b * gridDim.x + blockIdx.x) * seg_cap + pos;
+            const unsigned n4 = nout & ~3u;
+            for (unsigned k = sub * 4; k < n4; k += 32)
+              *reinterpret_cast<uint4 *>(dst + k) = *reinterpret_cast<const uint4 *>(ring + ((h + k) & (cap - 1)));
+            for (unsigned k = n4 + sub; k < nout; k += 8) dst[k] = ring[(h + k) & (cap - 1)];     // final flush only
+          } else {                         // segment full: count these keys directly
+            for (unsigned k = sub; k < nout; k += 8) atomicAdd(counts + map.cell(b, ring[(h + k) & (cap - 1)]), 1u);
+          }
+        }
+        // drop the (up to) four buckets just handled
+        todo &= todo - 1; todo &= todo - 1; todo &= todo - 1; todo &= todo - 1;
       }
     }
   }
   __device__ __forceinline__ void tile_end(void *smem, unsigned ctid) const
   {
+#if GCB_EXPERIMENT == 3
+    return;
+#endif
+#if GCB_EXPERIMENT != 2
     consumer_barrier();                    // every hit of the tile is staged
+#endif
+#if GCB_EXPERIMENT != 4
     flush(smem, ctid, false);
-    consumer_barrier();                    // staging compacted before the next tile appends
+#else
+    RouteStage *st = static_cast<RouteStage *>(smem);
+    for (unsigned i = ctid; i < ROUTE_NB_MAX; i += CONSUMER_THREADS) { st->tail[i] = 0; }
+#endif
+#if GCB_EXPERIMENT != 2
+    consumer_barrier();                    // heads advanced before the next tile appends
+#endif
   }
   __device__ __forceinline__ void finish(void *smem, unsigned ctid) const
   {
@@ -956,7 +997,9 @@ int launch_routed(gcb_counter *c, const float *d_x, long nframes, const float *d
     if (ntiles > 0) {
       RouteSink sink;
       sink.keys_g = c->d_keys; sink.seg_len = c->d_seglen; sink.counts = c->d_runcnt; sink.seg_cap = c->route_seg_cap;
-      sink.nb = c->route_nb; sink.cap = ROUTE_STAGE_KEYS / c->route_nb; sink.map = c->route_map;
+      sink.nb = c->route_nb; sink.map = c->route_map;
+      sink.cap = 64;
+      while (sink.cap * 2 * c->route_nb <= ROUTE_STAGE_KEYS) sink.cap *= 2;
       int grid = 0;
       int rc = ap ? launch_stream<RouteSink, PBC, true>(c, xs, ntiles, sink, G, bs, d_hits + f0, &grid)
                   : launch_stream<RouteSink, PBC, false>(c, xs, ntiles, sink, G, bs, d_hits + f0, &grid);
@@ -1188,7 +1231,9 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
     const bool fast = !gcb_edge_vulnerable(tg) && tg->mx[0] < (1 << 21) && tg->mx[1] < (1 << 21) && tg->mx[2] < (1 << 21);
     for (int d = 0; d < 3; d++) {
       c->PF.a[d] = tg->a[d]; c->PF.b[d] = tg->b[d]; c->PF.delta[d] = tg->delta[d]; c->PF.fmx[d] = (float)tg->mx[d];
-      c->PF.inv[d] = fast ? 1.0f / tg->delta[d] : NAN;
+      const double inv = (double)(1.0f / tg->delta[d]);
+      c->PF.inv_lo[d] = fast ? (float)(inv * (1.0 - 4.76837158203125e-07)) : NAN;       // 2^-21
+      c->PF.inv_hi[d] = fast ? (float)(inv * (1.0 + 4.76837158203125e-07)) : NAN;
     }
     c->PF.my = tg->mx[1]; c->PF.mz = tg->mx[2];
     c->PF.bias = (int)(0x4B400000u * ((uint32_t)tg->mx[1] * (uint32_t)tg->mx[2] + (uint32_t)tg->mx[2] + 1u));
@@ -1245,6 +1290,8 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
       c->route_map = RouteMap{5, ROUTE_NB_MAX - 1, 12, 5, 31u};
     } else if (c->ncells * sizeof(uint32_t) > ((size_t)48 << 20)) {
       c->route_mode = 2;
+      // every round turns the whole grid over in L2 once (read + write-back of each slab): long rounds amortise it
+      if (!env) c->route_units = 192LL << 20;
       c->route_nb = (int)((c->ncells + (1u << 23) - 1) >> 23);
       c->route_map = RouteMap{23, 0xFFu, 31, 23, (1u << 23) - 1};
     }
