@@ -71,6 +71,12 @@ class Analysis(C.Structure):
                 ("kernel_launches", C.c_int64)]
 
 
+class XtcFrame(C.Structure):
+    _fields_ = [("payload_offset", C.c_uint64), ("payload_bytes", C.c_uint32), ("natoms", C.c_int), ("step", C.c_int),
+                ("time", C.c_float), ("box", C.c_float * 9), ("precision", C.c_float),
+                ("minint", C.c_int * 3), ("maxint", C.c_int * 3), ("smallidx", C.c_int)]
+
+
 class Gen(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("mode", C.c_int), ("L", C.c_float * 3),
                 ("slab_lo", C.c_float), ("slab_hi", C.c_float), ("pore_r", C.c_float),
@@ -111,6 +117,9 @@ SIGNATURES = {
     "gcb_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "gcb_counter_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "gcb_counter_allreduce": (C.c_int, [C.c_void_p]),
+    "gcb_xtc_scan": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(XtcFrame), C.c_long, c_long_p, C.POINTER(C.c_size_t)]),
+    "gcb_xtc_decode_device": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(XtcFrame), C.c_long, C.c_int, C.c_void_p, C.c_int]),
+    "gcb_counter_add_xtc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(XtcFrame), C.c_long, c_float_p]),
     "gcb_header": (C.c_int, [C.c_char_p, C.c_char_p, C.c_double, C.c_char_p, C.POINTER(Cavity), C.POINTER(TGrid),
                              C.c_double, C.c_char_p, C.c_int]),
     "gcb_xdr_size": (C.c_size_t, [C.POINTER(TGrid), C.c_char_p]),

@@ -191,6 +191,54 @@ class PinnedFrames:
             pass
 
 
+class XtcBuffer:
+    """The bytes of an .xtc file (or any run of whole frames) plus the table of its frame headers."""
+
+    def __init__(self, data, pinned=False):
+        data = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else data
+        self.nbytes = int(data.nbytes)
+        self._pin = None
+        if pinned:
+            p = C.c_void_p()
+            check(lib.gcb_host_alloc_pinned(C.byref(p), max(self.nbytes, 16)), "gcb_host_alloc_pinned")
+            C.memmove(p.value, data.ctypes.data, self.nbytes)
+            self._pin = p
+            self.ptr = p
+            self._keep = None
+        else:
+            self._keep = np.ascontiguousarray(data)
+            self.ptr = C.c_void_p(self._keep.ctypes.data)
+        n = C.c_long(0)
+        used = C.c_size_t(0)
+        check(lib.gcb_xtc_scan(self.ptr, self.nbytes, None, 0, C.byref(n), C.byref(used)), "gcb_xtc_scan")
+        self.nframes = n.value
+        self.frames = (K.XtcFrame * max(self.nframes, 1))()
+        check(lib.gcb_xtc_scan(self.ptr, self.nbytes, self.frames, self.nframes, C.byref(n), C.byref(used)), "gcb_xtc_scan")
+        self.consumed = used.value
+        self.natoms = self.frames[0].natoms if self.nframes else 0
+
+    @property
+    def times(self):
+        return np.array([self.frames[i].time for i in range(self.nframes)], np.float32)
+
+    def decode_to_device(self, device=0):
+        dev = DeviceFrames(self.nframes, self.natoms, device)
+        check(lib.gcb_xtc_decode_device(self.ptr, self.nbytes, self.frames, self.nframes, self.natoms, dev.ptr, device),
+              "gcb_xtc_decode_device")
+        return dev
+
+    def free(self):
+        if self._pin:
+            lib.gcb_host_free_pinned(self._pin)
+            self._pin = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class GridCounter:
     """The g_ri3Dc binning loop (g_ri3Dc.c:410-429) on one GPU."""
 
@@ -250,6 +298,12 @@ class GridCounter:
         b = None if box is None else np.ascontiguousarray(box, np.float32)
         check(lib.gcb_counter_add_device_frames(self.h, dev.frame_ptr(first), count, _fptr(w), _fptr(b)),
               "gcb_counter_add_device_frames")
+
+    def add_xtc(self, xtc, weights=None):
+        """xtc: XtcBuffer (compressed frames in host memory); decoded and binned on the GPU"""
+        w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+        check(lib.gcb_counter_add_xtc(self.h, xtc.ptr, xtc.nbytes, xtc.frames, xtc.nframes, _fptr(w)),
+              "gcb_counter_add_xtc")
 
     def sync(self):
         check(lib.gcb_counter_sync(self.h), "gcb_counter_sync")

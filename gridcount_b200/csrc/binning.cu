@@ -152,15 +152,11 @@ bin_gather_kernel(const float *__restrict__ x, int natoms, const int *__restrict
 #ifndef GCB_UNROLL
 #define GCB_UNROLL 4
 #endif
-#ifndef GCB_EXPERIMENT
-#define GCB_EXPERIMENT 0
-#endif
 constexpr int CONSUMER_WARPS = GCB_CONSUMER_WARPS;
 constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
 constexpr int STREAM_THREADS = CONSUMER_THREADS + 32;     // + producer warp
 constexpr int TILE_ATOMS = 3072;                          // 1024 selected per tile for 3-site water
-constexpr int TILE_FLOATS = TILE_ATOMS * 3;
-constexpr int TILE_BYTES = TILE_FLOATS * 4;               // 36 KiB
+constexpr int TILE_FLOATS = TILE_ATOMS * 3;                  // 36 KiB per tile
 constexpr int STAGES = GCB_STAGES;
 constexpr int UNROLL = GCB_UNROLL;
 
@@ -345,10 +341,6 @@ struct RouteSink {
   }
   __device__ __forceinline__ void hit(void *smem, int cell) const
   {
-#if GCB_EXPERIMENT == 3
-    if (cell == 0x7fffffff) atomicAdd(counts, 1u);
-    return;
-#endif
     RouteStage *st = static_cast<RouteStage *>(smem);
     const unsigned b = map.bucket((unsigned)cell);
     const unsigned h = st->head[b];        // only flush() changes it, and never while hits are appended
@@ -411,21 +403,9 @@ struct RouteSink {
   }
   __device__ __forceinline__ void tile_end(void *smem, unsigned ctid) const
   {
-#if GCB_EXPERIMENT == 3
-    return;
-#endif
-#if GCB_EXPERIMENT != 2
     consumer_barrier();                    // every hit of the tile is staged
-#endif
-#if GCB_EXPERIMENT != 4
     flush(smem, ctid, false);
-#else
-    RouteStage *st = static_cast<RouteStage *>(smem);
-    for (unsigned i = ctid; i < ROUTE_NB_MAX; i += CONSUMER_THREADS) { st->tail[i] = 0; }
-#endif
-#if GCB_EXPERIMENT != 2
     consumer_barrier();                    // heads advanced before the next tile appends
-#endif
   }
   __device__ __forceinline__ void finish(void *smem, unsigned ctid) const
   {
@@ -846,6 +826,15 @@ struct gcb_counter {
   uint32_t *d_keys = nullptr, *d_seglen = nullptr;
   unsigned route_seg_cap = 0;
   int route_grid = 0;                 // streaming CTAs the key buffer is laid out for
+  // xtc path: two sets of {compressed bytes, frame table, status, decoded frames}, copy stream + events
+  struct XtcSet {
+    uint8_t *d_buf = nullptr; size_t buf_cap = 0;
+    void *d_meta = nullptr, *h_meta = nullptr; int *d_status = nullptr, *h_status = nullptr; long frames_cap = 0;
+    float *d_x = nullptr; size_t x_cap = 0;
+    cudaEvent_t copied = nullptr, consumed = nullptr;
+    long nframes = 0; long first = 0;
+  } xtc[2];
+  cudaStream_t xtc_copy = nullptr;
 
   std::vector<int> h_gindex;          // sorted copy of the index group
   int *d_gindex = nullptr;
@@ -1188,6 +1177,12 @@ void free_counter(gcb_counter *c)
   for (auto &d : c->devhits) { cudaFree(d.d); cudaFree(d.d_box3); }
   cudaFree(c->d_gindex); cudaFree(c->d_rank); cudaFree(c->d_runcnt); cudaFree(c->d_total); cudaFree(c->d_acc);
   cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2); cudaFree(c->d_keys); cudaFree(c->d_seglen);
+  for (auto &x : c->xtc) {
+    cudaFree(x.d_buf); cudaFree(x.d_meta); cudaFree(x.d_status); cudaFree(x.d_x); cudaFreeHost(x.h_meta); cudaFreeHost(x.h_status);
+    if (x.copied) cudaEventDestroy(x.copied);
+    if (x.consumed) cudaEventDestroy(x.consumed);
+  }
+  if (c->xtc_copy) cudaStreamDestroy(c->xtc_copy);
   for (auto e : c->events) if (e) cudaEventDestroy(e);
   if (c->compute) cudaStreamDestroy(c->compute);
   delete c;
@@ -1414,6 +1409,88 @@ int gcb_counter_add_device_frames(gcb_counter *c, const float *x_dev, long nfram
   int rc = bin_device_batch(c, x_dev, nframes, weight, h.d_box3, h.d);
   if (rc) return rc;
   for (long f = 0; f < nframes; f++) c->weight_per_frame.push_back(weight ? weight[f] : 1.0f);
+  return GCB_OK;
+}
+
+extern "C" int gcb_xtc_decode_on_stream_(const uint8_t *buf_dev, const gcb_xtc_frame *frames, long nframes, int natoms,
+                                         float *x_dev, void *meta_dev, int *status_dev, void *stream, void *meta_host_pinned);
+extern "C" size_t gcb_xtc_meta_bytes_(long nframes);
+
+int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gcb_xtc_frame *frames, long nframes,
+                        const float *weight)
+{
+  if (!c || !buf || !frames || nframes < 0) return gcb::fail(GCB_ERR_ARG, "gcb_counter_add_xtc: bad argument");
+  if (nframes == 0) return GCB_OK;
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  if (!c->xtc_copy) {
+    GCB_CUDA(cudaStreamCreateWithFlags(&c->xtc_copy, cudaStreamNonBlocking));
+    for (auto &x : c->xtc) {
+      GCB_CUDA(cudaEventCreateWithFlags(&x.copied, cudaEventDisableTiming));
+      GCB_CUDA(cudaEventCreateWithFlags(&x.consumed, cudaEventDisableTiming));
+    }
+  }
+  const size_t frame_bytes = (size_t)c->natoms * 12;
+  // frames per batch: thousands, so that one-thread-per-frame decoding fills the GPU; decoded frames <= 4 GiB per set
+  const char *env = getenv("GCB_XTC_BATCH");
+  long per = env ? atol(env) : (long)std::min<size_t>(16384, std::max<size_t>(64, ((size_t)4 << 30) / frame_bytes));
+  per = std::max<long>(4, per & ~3L);                         // batches start 16-byte aligned in the decoded array
+  std::vector<float> box3;
+  int set = 0;
+  auto check_set = [&](gcb_counter::XtcSet &x) -> int {       // wait for a set's batch, look at the decoder's verdicts
+    if (x.nframes == 0) return GCB_OK;
+    GCB_CUDA(cudaEventSynchronize(x.consumed));
+    for (long f = 0; f < x.nframes; f++)
+      if (x.h_status[f]) { x.nframes = 0; return gcb::fail(GCB_ERR_FORMAT, "xtc frame %ld: damaged compressed stream", x.first + f); }
+    x.nframes = 0;
+    return GCB_OK;
+  };
+  for (long f0 = 0; f0 < nframes; f0 += per, set ^= 1) {
+    const long n = std::min(per, nframes - f0);
+    gcb_counter::XtcSet &x = c->xtc[set];
+    int rc = check_set(x);
+    if (rc) return rc;
+    size_t lo = frames[f0].payload_offset, hi = 0;
+    for (long f = f0; f < f0 + n; f++) {
+      if (frames[f].natoms != c->natoms) return gcb::fail(GCB_ERR_FORMAT, "xtc frame %ld has %d atoms, the counter %d", f, frames[f].natoms, c->natoms);
+      const size_t b = frames[f].payload_offset;
+      const size_t nb = frames[f].natoms <= 9 ? (size_t)frames[f].natoms * 12 : ((size_t)frames[f].payload_bytes + 3) & ~(size_t)3;
+      if (b + nb > len) return gcb::fail(GCB_ERR_ARG, "xtc frame %ld lies outside the buffer", f);
+      lo = std::min(lo, b); hi = std::max(hi, b + nb);
+    }
+    lo &= ~(size_t)3;
+    if (hi - lo + 16 > x.buf_cap) { cudaFree(x.d_buf); x.d_buf = nullptr; x.buf_cap = (hi - lo) + (hi - lo) / 8 + 16; GCB_CUDA(cudaMalloc(&x.d_buf, x.buf_cap)); }
+    if (n > x.frames_cap) {
+      cudaFree(x.d_meta); cudaFree(x.d_status); cudaFreeHost(x.h_meta); cudaFreeHost(x.h_status);
+      x.d_meta = x.h_meta = nullptr; x.d_status = x.h_status = nullptr;
+      x.frames_cap = n;
+      GCB_CUDA(cudaMalloc(&x.d_meta, gcb_xtc_meta_bytes_(n)));
+      GCB_CUDA(cudaMalloc(&x.d_status, sizeof(int) * (size_t)n));
+      GCB_CUDA(cudaHostAlloc(&x.h_meta, gcb_xtc_meta_bytes_(n), cudaHostAllocDefault));
+      GCB_CUDA(cudaHostAlloc((void **)&x.h_status, sizeof(int) * (size_t)n, cudaHostAllocDefault));
+    }
+    if ((size_t)n * frame_bytes + 16 > x.x_cap) { cudaFree(x.d_x); x.d_x = nullptr; x.x_cap = (size_t)n * frame_bytes + 16; GCB_CUDA(cudaMalloc(&x.d_x, x.x_cap)); }
+    // compressed bytes on the copy stream, everything else on the compute stream
+    GCB_CUDA(cudaMemcpyAsync(x.d_buf, buf + lo, hi - lo, cudaMemcpyHostToDevice, c->xtc_copy));
+    GCB_CUDA(cudaEventRecord(x.copied, c->xtc_copy));
+    GCB_CUDA(cudaStreamWaitEvent(c->compute, x.copied, 0));
+    std::vector<gcb_xtc_frame> rel(frames + f0, frames + f0 + n);
+    for (auto &r : rel) r.payload_offset -= lo;
+    rc = gcb_xtc_decode_on_stream_(x.d_buf, rel.data(), n, c->natoms, x.d_x, x.d_meta, x.d_status, c->compute, x.h_meta);
+    if (rc) return rc;
+    GCB_CUDA(cudaMemcpyAsync(x.h_status, x.d_status, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->compute));
+    const float *boxarg = nullptr;
+    if (c->opts.pbc == GCB_PBC_RECT) {
+      box3.resize((size_t)n * 9);
+      for (long f = 0; f < n; f++) memcpy(&box3[(size_t)f * 9], frames[f0 + f].box, sizeof(float) * 9);
+      boxarg = box3.data();
+    }
+    rc = gcb_counter_add_device_frames(c, x.d_x, n, weight ? weight + f0 : nullptr, boxarg);
+    if (rc) return rc;
+    GCB_CUDA(cudaEventRecord(x.consumed, c->compute));
+    GCB_CUDA(cudaStreamWaitEvent(c->xtc_copy, x.consumed, 0));      // the next copy into this set waits for its kernels
+    x.nframes = n; x.first = f0;
+  }
+  for (auto &x : c->xtc) { int rc = check_set(x); if (rc) return rc; }
   return GCB_OK;
 }
 

@@ -169,6 +169,32 @@ int gcb_counter_comm_init(gcb_counter *c, const char id[128], int rank, int nran
 int gcb_counter_allreduce(gcb_counter *c);
 
 /* ------------------------------------------------------------------------
+ * XTC trajectories decoded on the GPU.  Replaces, for .xtc input, the frames that
+ * read_first_x / read_next_x deliver to the frame loop (g_ri3Dc.c:392,428; the decoder
+ * itself is Gromacs' xdr3dfcoord, not part of the reference tree).  The host parses the
+ * frame headers only; compressed payloads cross PCIe as they are (about a third of the
+ * float coordinates) and one GPU thread decodes one frame.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  uint64_t payload_offset;  /* byte offset of the compressed coordinates in the scanned buffer */
+  uint32_t payload_bytes;   /* 0 for frames of <= 9 atoms, which are stored as plain floats */
+  int natoms, step;
+  float time, box[9], precision;
+  int minint[3], maxint[3], smallidx;
+} gcb_xtc_frame;
+/* frames == NULL counts; stops quietly at an incomplete trailing frame; *consumed = bytes of whole frames */
+int gcb_xtc_scan(const uint8_t *buf, size_t len, gcb_xtc_frame *frames, long cap, long *nframes_out,
+                 size_t *consumed);
+/* host bytes -> x_dev[nframes][natoms][3] on the device (synchronous) */
+int gcb_xtc_decode_device(const uint8_t *buf, size_t len, const gcb_xtc_frame *frames, long nframes,
+                          int natoms, float *x_dev, int device);
+/* decode + bin: the xtc counterpart of gcb_counter_add_frames.  `buf` is host memory (pinned memory is
+ * copied asynchronously); weight[f] as in gcb_counter_add_frames; with GCB_PBC_RECT the boxes of the
+ * frame headers are used. */
+int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gcb_xtc_frame *frames,
+                        long nframes, const float *weight);
+
+/* ------------------------------------------------------------------------
  * Grid files and header.  Replaces the header string (g_ri3Dc.c:462-473),
  * grid_write / grid_read (grid3D.c:22-106), xdr_grid_v2 and the
  * (un)serialisers (xdr_grid.c:89-158), density_write_plt / _ascii
