@@ -186,6 +186,58 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def xtc_section(g, ctr, dev, wl, geom, gindex):
+    """256 frames of the workload written as XTC (precision 1000) by the host codec (host/libgcbhost.so):
+    single-thread host decode rate, GPU decode rate, and the binning job driven from pinned XTC bytes."""
+    import gcutil as u
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host"), "libgcbhost.so"])
+    H = C.CDLL(os.path.join(ROOT, "host", "libgcbhost.so"))
+    H.gh_xtc_encode_frame.argtypes = [C.c_int, C.c_int, C.c_float, u.c_float_p, u.c_float_p, C.c_float, u.c_u8_p, C.c_size_t]
+    H.gh_xtc_encode_frame.restype = C.c_size_t
+    H.gh_xtc_decode_frame.argtypes = [u.c_u8_p, C.c_size_t, C.c_void_p, u.c_float_p, C.c_int]
+    H.gh_xtc_decode_frame.restype = C.c_size_t
+    natoms, NF = wl["natoms"], 256
+    x = dev.download(0, NF)
+    b9 = u.box9(wl["L"])
+    buf = np.zeros(natoms * 16 + 256, np.uint8)
+    parts = []
+    for f in range(NF):
+        n = H.gh_xtc_encode_frame(natoms, f, float(f), u.fptr(b9), u.fptr(x[f]), 1000.0, buf.ctypes.data_as(u.c_u8_p), len(buf))
+        assert n > 0
+        parts.append(buf[:n].tobytes())
+    data = b"".join(parts)
+    raw = np.frombuffer(data, np.uint8).copy()
+    info = (C.c_char * 64)()
+    out = np.zeros((natoms, 3), np.float32)
+    t0 = time.perf_counter()
+    off = 0
+    for f in range(NF):
+        view = raw[off:]
+        off += H.gh_xtc_decode_frame(view.ctypes.data_as(u.c_u8_p), len(view), C.cast(info, C.c_void_p), u.fptr(out), natoms)
+    host_s = time.perf_counter() - t0
+    REP = 16                                     # 4096 frames per call: enough frames for one-thread-per-frame decoding
+    xb = g.XtcBuffer(data * REP, pinned=True)
+    w = np.ones(xb.nframes, np.float32)
+    d = xb.decode_to_device(); d.free()          # warm-up
+    t0 = time.perf_counter()
+    d = xb.decode_to_device()
+    gpu_decode_s = time.perf_counter() - t0
+    d.free()
+    ctr.reset_grid(); ctr.add_xtc(xb, w); ctr.sync()
+    t0 = time.perf_counter()
+    ctr.reset_grid(); ctr.add_xtc(xb, w); ctr.sync()
+    e2e_s = time.perf_counter() - t0
+    res = {"frames": xb.nframes, "compressed_bytes_per_atom": len(data) / (NF * natoms),
+           "host_decode_atoms_per_s": NF * natoms / host_s, "host_decode_threads": 1,
+           "gpu_decode_atoms_per_s": xb.nframes * natoms / gpu_decode_s,
+           "gpu_decode_note": "includes H2D of the compressed bytes and the device allocation",
+           "e2e_from_xtc_bytes_G_atom_frames_per_s": xb.nframes * len(gindex) / e2e_s * 1e-9,
+           "data": "synthetic uniform positions compress to ~5 B/atom; real water compresses further"}
+    xb.free()
+    ctr.reset_grid()
+    return res
+
+
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
@@ -320,6 +372,14 @@ def run_gpu_arm(args, rank, local_rank, world):
            "path": "gcb_counter_add_frames(pinned host x[F][natoms][3]) -> gcb_counter_density(host grid)"}
     pin.free()
 
+    # ---- XTC decode, timed separately (north star): host decoder vs GPU decoder on the same frames ----
+    xtc = None
+    if rank == 0 and world == 1:
+        try:
+            xtc = xtc_section(g, ctr, dev, wl, geom, gindex)
+        except Exception as e:          # the section is informative; never let it take the headline down
+            xtc = {"error": str(e)[:200]}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------
     cpu = None
     if rank == 0 and world == 1:
@@ -348,7 +408,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                            "parallelism": "frame-sharded x%d, one NCCL u32 all-reduce per job" % world,
                            "step": "reset + K1 bin 10000 frames + (all-reduce) + K2 density"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "xtc": xtc}
         print(json.dumps(line), flush=True)
     ctr.close()
     dev.free()

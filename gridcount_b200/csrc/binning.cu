@@ -829,7 +829,7 @@ struct gcb_counter {
   // xtc path: two sets of {compressed bytes, frame table, status, decoded frames}, copy stream + events
   struct XtcSet {
     uint8_t *d_buf = nullptr; size_t buf_cap = 0;
-    void *d_meta = nullptr, *h_meta = nullptr; int *d_status = nullptr, *h_status = nullptr; long frames_cap = 0;
+    void *d_meta = nullptr, *h_meta = nullptr, *d_work = nullptr; int *d_status = nullptr, *h_status = nullptr; long frames_cap = 0;
     float *d_x = nullptr; size_t x_cap = 0;
     cudaEvent_t copied = nullptr, consumed = nullptr;
     long nframes = 0; long first = 0;
@@ -1178,7 +1178,7 @@ void free_counter(gcb_counter *c)
   cudaFree(c->d_gindex); cudaFree(c->d_rank); cudaFree(c->d_runcnt); cudaFree(c->d_total); cudaFree(c->d_acc);
   cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2); cudaFree(c->d_keys); cudaFree(c->d_seglen);
   for (auto &x : c->xtc) {
-    cudaFree(x.d_buf); cudaFree(x.d_meta); cudaFree(x.d_status); cudaFree(x.d_x); cudaFreeHost(x.h_meta); cudaFreeHost(x.h_status);
+    cudaFree(x.d_buf); cudaFree(x.d_meta); cudaFree(x.d_status); cudaFree(x.d_x); cudaFree(x.d_work); cudaFreeHost(x.h_meta); cudaFreeHost(x.h_status);
     if (x.copied) cudaEventDestroy(x.copied);
     if (x.consumed) cudaEventDestroy(x.consumed);
   }
@@ -1413,7 +1413,8 @@ int gcb_counter_add_device_frames(gcb_counter *c, const float *x_dev, long nfram
 }
 
 extern "C" int gcb_xtc_decode_on_stream_(const uint8_t *buf_dev, const gcb_xtc_frame *frames, long nframes, int natoms,
-                                         float *x_dev, void *meta_dev, int *status_dev, void *stream, void *meta_host_pinned);
+                                         float *x_dev, void *meta_dev, int *status_dev, void *stream, void *meta_host_pinned, void *work_dev);
+extern "C" size_t gcb_xtc_work_bytes_(long nframes, int natoms);
 extern "C" size_t gcb_xtc_meta_bytes_(long nframes);
 
 int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gcb_xtc_frame *frames, long nframes,
@@ -1430,9 +1431,10 @@ int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gc
     }
   }
   const size_t frame_bytes = (size_t)c->natoms * 12;
-  // frames per batch: thousands, so that one-thread-per-frame decoding fills the GPU; decoded frames <= 4 GiB per set
+  // frames per batch: hundreds to thousands (one warp per frame walks the stream); decoded frames <= 4 GiB per set
   const char *env = getenv("GCB_XTC_BATCH");
   long per = env ? atol(env) : (long)std::min<size_t>(16384, std::max<size_t>(64, ((size_t)4 << 30) / frame_bytes));
+  if (!env) per = std::min(per, std::max<long>(512, (nframes + 3) / 4));   // a few batches, so that copies overlap decoding
   per = std::max<long>(4, per & ~3L);                         // batches start 16-byte aligned in the decoded array
   std::vector<float> box3;
   int set = 0;
@@ -1460,11 +1462,12 @@ int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gc
     lo &= ~(size_t)3;
     if (hi - lo + 16 > x.buf_cap) { cudaFree(x.d_buf); x.d_buf = nullptr; x.buf_cap = (hi - lo) + (hi - lo) / 8 + 16; GCB_CUDA(cudaMalloc(&x.d_buf, x.buf_cap)); }
     if (n > x.frames_cap) {
-      cudaFree(x.d_meta); cudaFree(x.d_status); cudaFreeHost(x.h_meta); cudaFreeHost(x.h_status);
-      x.d_meta = x.h_meta = nullptr; x.d_status = x.h_status = nullptr;
+      cudaFree(x.d_meta); cudaFree(x.d_status); cudaFree(x.d_work); cudaFreeHost(x.h_meta); cudaFreeHost(x.h_status);
+      x.d_meta = x.h_meta = x.d_work = nullptr; x.d_status = x.h_status = nullptr;
       x.frames_cap = n;
       GCB_CUDA(cudaMalloc(&x.d_meta, gcb_xtc_meta_bytes_(n)));
       GCB_CUDA(cudaMalloc(&x.d_status, sizeof(int) * (size_t)n));
+      GCB_CUDA(cudaMalloc(&x.d_work, gcb_xtc_work_bytes_(n, c->natoms)));
       GCB_CUDA(cudaHostAlloc(&x.h_meta, gcb_xtc_meta_bytes_(n), cudaHostAllocDefault));
       GCB_CUDA(cudaHostAlloc((void **)&x.h_status, sizeof(int) * (size_t)n, cudaHostAllocDefault));
     }
@@ -1475,7 +1478,7 @@ int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gc
     GCB_CUDA(cudaStreamWaitEvent(c->compute, x.copied, 0));
     std::vector<gcb_xtc_frame> rel(frames + f0, frames + f0 + n);
     for (auto &r : rel) r.payload_offset -= lo;
-    rc = gcb_xtc_decode_on_stream_(x.d_buf, rel.data(), n, c->natoms, x.d_x, x.d_meta, x.d_status, c->compute, x.h_meta);
+    rc = gcb_xtc_decode_on_stream_(x.d_buf, rel.data(), n, c->natoms, x.d_x, x.d_meta, x.d_status, c->compute, x.h_meta, x.d_work);
     if (rc) return rc;
     GCB_CUDA(cudaMemcpyAsync(x.h_status, x.d_status, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->compute));
     const float *boxarg = nullptr;

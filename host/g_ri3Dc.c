@@ -11,6 +11,7 @@
  * .xtc, multi-frame .gro or the raw GCTRJ1 test format.  Extra options: -gpu, -pbc.
  */
 #include "gcb_host.h"
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -26,7 +27,7 @@ static const char *synopsis =
 
 int main(int argc, char **argv)
 {
-  int bdtWeight = 1, bMolecular = 0, ngroups = 1, device = 0, bPbc = 0;
+  int bdtWeight = 1, bMolecular = 0, ngroups = 1, device = 0, bPbc = 0, bHostDecode = 0;
   gcb_cavity cavity;
   float Delta[3] = {0.05f, 0.05f, 0.05f};
   const char *subtitle = "";
@@ -45,6 +46,7 @@ int main(int argc, char **argv)
       {"-ng", GH_INT, &ngroups, NULL, 0},
       {"-gpu", GH_INT, &device, "CUDA device to use", 0},
       {"-pbc", GH_BOOL, &bPbc, "wrap atoms once into the rectangular box before counting (the reference does not)", 0},
+      {"-hostdecode", GH_BOOL, &bHostDecode, "decode .xtc frames on the host instead of on the GPU", 0},
   };
   gh_file fnm[] = {
       {"-f", "traj", ".xtc", GH_F_READ, "Trajectory: xtc gro raw", 0, NULL, NULL, 0},
@@ -115,13 +117,53 @@ int main(int argc, char **argv)
   gcb_counter *ctr;
   CHECK(gcb_counter_create(&ctr, &tg, grp->atoms, grp->n, natoms, &copt));
 
+  long nframes = 0;
+  double T_tot = 0;
+  float tlast = fr.time - dt0;                 /* g_ri3Dc.c:394 */
+  const size_t tl = strlen(trxname);
+  if (!bHostDecode && tl > 4 && !strcmp(trxname + tl - 4, ".xtc")) {
+    /* ---- .xtc: the file goes to the GPU as it is; only the frame headers are read here ---- */
+    gh_traj_close(trj);
+    FILE *f = fopen(trxname, "rb");
+    if (!f) gh_fatal("Cannot read trajectory %s", trxname);
+    fseek(f, 0, SEEK_END);
+    const size_t len = (size_t)ftell(f);
+    rewind(f);
+    void *pin = NULL;
+    CHECK(gcb_host_alloc_pinned(&pin, len + 16));
+    if (fread(pin, 1, len, f) != len) gh_fatal("Cannot read trajectory %s", trxname);
+    fclose(f);
+    long nall = 0, i;
+    CHECK(gcb_xtc_scan((const uint8_t *)pin, len, NULL, 0, &nall, NULL));
+    gcb_xtc_frame *frames = (gcb_xtc_frame *)malloc(sizeof(gcb_xtc_frame) * (size_t)(nall > 0 ? nall : 1));
+    CHECK(gcb_xtc_scan((const uint8_t *)pin, len, frames, nall, &nall, NULL));
+    /* -b / -e / -dt as read_next_x applies them */
+    double t0sel = 0;
+    int have0 = 0;
+    for (i = 0; i < nall; i++) {
+      const double t = frames[i].time;
+      if (ts.have_b && t < ts.b) continue;
+      if (ts.have_e && t > ts.e) break;
+      if (ts.have_dt && ts.dt > 0) {
+        if (!have0) { have0 = 1; t0sel = t; }
+        const double r = fmod(t - t0sel, ts.dt);
+        if (fabs(r) > 1e-4 * ts.dt && fabs(r - ts.dt) > 1e-4 * ts.dt) continue;
+      }
+      frames[nframes++] = frames[i];
+    }
+    float *tt = (float *)malloc(sizeof(float) * (size_t)(nframes > 0 ? nframes : 1));
+    float *w = (float *)malloc(sizeof(float) * (size_t)(nframes > 0 ? nframes : 1));
+    for (i = 0; i < nframes; i++) tt[i] = frames[i].time;
+    CHECK(gcb_frame_weights(tt, nframes, bdtWeight, &tlast, w, &T_tot));        /* g_ri3Dc.c:413-416 */
+    CHECK(gcb_counter_add_xtc(ctr, (const uint8_t *)pin, len, frames, nframes, w));
+    free(tt); free(w); free(frames);
+    gcb_host_free_pinned(pin);
+  } else {
   /* ---- main loop over frames: batches through the pinned slots ---- */
   const int NSLOTS = 3;
   int slot = 0;
-  long cap = 0, n = 0, nframes = 0;
+  long cap = 0, n = 0;
   float *xs = NULL, *w, *boxes, *tbuf;
-  float tlast = fr.time - dt0;                 /* g_ri3Dc.c:394 */
-  double T_tot = 0;
   CHECK(gcb_counter_slot(ctr, slot, &xs, &cap));
   w = (float *)malloc(sizeof(float) * (size_t)cap);
   tbuf = (float *)malloc(sizeof(float) * (size_t)cap);
@@ -143,6 +185,8 @@ int main(int argc, char **argv)
     }
   }
   gh_traj_close(trj);
+  free(w); free(tbuf); free(boxes);
+  }
 
   gcb_stats st;
   CHECK(gcb_counter_stats(ctr, &st));
@@ -160,7 +204,7 @@ int main(int argc, char **argv)
   if (gcb_grid_write(gh_fn(fnm, NFILE, "-grid"), &tgout, NULL, xfast, header) != GCB_OK)
     gh_msg("Writing the 3D grid failed.\n%s\n", gcb_last_error());
   gcb_counter_destroy(ctr);
-  free(xfast); free(w); free(tbuf); free(boxes); free(x);
+  free(xfast); free(x);
   if (groups) gh_ndx_free(groups, ng);
   gh_msg("\n");
   return 0;

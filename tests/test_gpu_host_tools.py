@@ -101,6 +101,14 @@ def test_g_ri3Dc_from_xtc_counts_decoded_coordinates(tmp_path):
                          "-z2", "5.5", "-cpoint", "2.05", "1.95", "3.0"], tmp, stdin=b"1\n")
     tg, hdr, dens = g.grid_read(os.path.join(tmp, "grid.dat"))
     assert b"{grp}OW" in hdr and b"{XTC}traj.xtc" in hdr
+    # frames decoded on the host instead of on the GPU: the same file
+    run_tool("g_ri3Dc", ["-f", "traj.xtc", "-n", "grp.ndx", "-grid", "grid_host.dat", "-delta", "0.2", "-R", "1.5", "-z1", "1.0",
+                         "-z2", "5.5", "-cpoint", "2.05", "1.95", "3.0", "-hostdecode"], tmp, stdin=b"OW\n")
+    assert open(os.path.join(tmp, "grid.dat"), "rb").read() == open(os.path.join(tmp, "grid_host.dat"), "rb").read()
+    # -b/-e select the same frames on both paths
+    for extra, out in ((["-b", "10", "-e", "30"], "sel_gpu.dat"), (["-b", "10", "-e", "30", "-hostdecode"], "sel_host.dat")):
+        run_tool("g_ri3Dc", ["-f", "traj.xtc", "-n", "grp.ndx", "-grid", out, "-delta", "0.2"] + extra, tmp, stdin=b"1\n")
+    assert open(os.path.join(tmp, "sel_gpu.dat"), "rb").read() == open(os.path.join(tmp, "sel_host.dat"), "rb").read()
     # decoded coordinates through the same reader
     from test_host_tools_cpu import FrameInfo
     L = C.CDLL(os.path.join(HOST, "libgcbhost.so"))
