@@ -364,3 +364,44 @@ def test_large_grids(cfg):
         np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
         ctr.close()
     dev.free()
+
+
+def test_full_size_c2_properties():
+    """BASELINE config 2 at FULL size (60 000 atoms, 20 000 OW, 10 000 frames, 80x80x134): too large for the oracle,
+    so size-independent properties: every generated atom lies in the grid (total = frames*gnx, per-frame hits = gnx);
+    direct, routed and gather kernels agree cell for cell; counting is additive over frame ranges; and the first
+    64 frames match the oracle."""
+    L, natoms, F = (8.0, 8.0, 13.4), 60000, 10000
+    geom = g.setup_geometry(L, 0.1)
+    assert geom.shape == (80, 80, 134)
+    gindex = np.arange(0, natoms, 3, dtype=np.int32)
+    gen = g.make_gen(20261021, L, K.GEN_PORE, slab=(4.7, 8.7), pore_r=0.8)
+    dev = g.DeviceFrames(F, natoms).generate(gen)
+    ref = None
+    for kernel in (K.KERNEL_STREAM, K.KERNEL_ROUTED, K.KERNEL_GATHER):
+        ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel)
+        ctr.add_device_frames(dev)
+        c = ctr.counts()
+        st = ctr.stats()
+        assert st.hits == F * len(gindex) == int(c.sum(dtype=np.uint64)) and st.edge_overflow == 0
+        assert np.all(ctr.hits_per_frame() == len(gindex))
+        if ref is None:
+            ref = c
+        else:
+            assert np.array_equal(c, ref), "kernel %d differs from the streaming kernel" % kernel
+        ctr.close()
+    # additivity over frame ranges (odd split so that tiles straddle the cut)
+    cut = 3333
+    a = g.GridCounter(geom, gindex, natoms)
+    a.add_device_frames(dev, first=0, count=cut)
+    b = g.GridCounter(geom, gindex, natoms, kernel=K.KERNEL_GATHER)     # the second range starts unaligned for TMA
+    b.add_device_frames(dev, first=cut, count=F - cut)
+    assert np.array_equal(a.counts() + b.counts(), ref)
+    a.close(); b.close()
+    # oracle on a prefix
+    x = dev.download(0, 64)
+    oc, oh, _ = oracle_counts(geom, x, gindex)
+    p = g.GridCounter(geom, gindex, natoms)
+    p.add_device_frames(dev, first=0, count=64)
+    assert np.array_equal(p.counts(), oc)
+    p.close(); dev.free()
