@@ -626,11 +626,13 @@ route_count_smem_kernel(const uint32_t *__restrict__ keys, const uint32_t *__res
 constexpr unsigned SLAB_CHUNK = 2048;
 __global__ void __launch_bounds__(256)
 route_count_slab_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ seg_len, int nseg,
-                        unsigned seg_cap, int nb, RouteMap map, uint32_t *__restrict__ counts)
+                        unsigned seg_cap, int b, RouteMap map, uint32_t *__restrict__ counts)
 {
+  // one launch per slab: the launches are ordered on the stream, so exactly one 32 MB slab is being
+  // updated at any time and its REDs stay in L2 (CTAs of one long kernel drift apart and thrash it)
   const unsigned nchunk = (seg_cap + SLAB_CHUNK - 1) / SLAB_CHUNK;
   const unsigned nitems = (unsigned)nseg * nchunk;
-  for (int b = 0; b < nb; b++) {
+  {
     for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
       const unsigned seg = item / nchunk, k0 = (item - seg * nchunk) * SLAB_CHUNK;
       const unsigned len = __ldg(seg_len + (size_t)b * nseg + seg);
@@ -997,8 +999,12 @@ int launch_routed(gcb_counter *c, const float *d_x, long nframes, const float *d
         route_count_smem_kernel<<<c->route_nb, COUNT_THREADS, c->route_tile_cells * sizeof(uint32_t), c->compute>>>(
             c->d_keys, c->d_seglen, grid, c->route_seg_cap, c->route_tile_cells, c->route_map, c->d_runcnt, (unsigned)c->ncells);
       } else {
-        route_count_slab_kernel<<<c->sm_count * 8, 256, 0, c->compute>>>(c->d_keys, c->d_seglen, grid, c->route_seg_cap,
-                                                                         c->route_nb, c->route_map, c->d_runcnt);
+        for (int b = 0; b < c->route_nb; b++) {
+          route_count_slab_kernel<<<c->sm_count * 8, 256, 0, c->compute>>>(c->d_keys, c->d_seglen, grid, c->route_seg_cap, b,
+                                                                           c->route_map, c->d_runcnt);
+          c->launches++;
+        }
+        c->launches--;
       }
       c->launches++;
       GCB_CUDA(cudaGetLastError());
