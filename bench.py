@@ -294,16 +294,17 @@ def run_gpu_arm(args, rank, local_rank, world):
         step_device()
     ctr.sync()
     launches0 = ctr.stats().kernel_launches
-    sampler = ClockSampler(device)
+    sampler = ClockSampler(device) if rank == 0 else None     # one poller per job: nvidia-smi polling perturbs launches
     barrier()
-    sampler.start()
+    if sampler:
+        sampler.start()
     ctr.event_record(2)
     for s in range(args.steps):
         step_device(ev=4 + 2 * s)
     ctr.event_record(3)
     ctr.sync()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     ms_total = ctr.event_elapsed(2, 3)
     k1_ms = [ctr.event_elapsed(4 + 2 * s, 5 + 2 * s) for s in range(args.steps)]
     launches = ctr.stats().kernel_launches - launches0

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <ctime>
 #include <new>
 #include <vector>
 
@@ -801,6 +802,7 @@ struct Slot {
 
 struct DevHits {                      // hit counters of an add_device_frames call awaiting collection
   unsigned long long *d = nullptr;
+  size_t cap = 0;
   float *d_box3 = nullptr;
   long n = 0;
   size_t frame0 = 0;
@@ -837,6 +839,9 @@ struct gcb_counter {
     long nframes = 0; long first = 0;
   } xtc[2];
   cudaStream_t xtc_copy = nullptr;
+  // multi-GPU statistics scratch
+  unsigned long long *d_scr = nullptr, *h_scr = nullptr;
+  size_t scr_words = 0;
 
   std::vector<int> h_gindex;          // sorted copy of the index group
   int *d_gindex = nullptr;
@@ -855,6 +860,7 @@ struct gcb_counter {
   std::vector<Slot> slots;
   int next_slot = 0;
   std::vector<DevHits> devhits;
+  std::vector<std::pair<size_t, unsigned long long *>> hit_pool;
 
   std::vector<uint64_t> hits_per_frame;
   std::vector<float> weight_per_frame;
@@ -1181,6 +1187,7 @@ void free_counter(gcb_counter *c)
     cudaFree(s.d_box3); cudaFreeHost(s.h_box3);
   }
   for (auto &d : c->devhits) { cudaFree(d.d); cudaFree(d.d_box3); }
+  for (auto &p : c->hit_pool) cudaFree(p.second);
   cudaFree(c->d_gindex); cudaFree(c->d_rank); cudaFree(c->d_runcnt); cudaFree(c->d_total); cudaFree(c->d_acc);
   cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2); cudaFree(c->d_keys); cudaFree(c->d_seglen);
   for (auto &x : c->xtc) {
@@ -1189,6 +1196,7 @@ void free_counter(gcb_counter *c)
     if (x.consumed) cudaEventDestroy(x.consumed);
   }
   if (c->xtc_copy) cudaStreamDestroy(c->xtc_copy);
+  cudaFree(c->d_scr); cudaFreeHost(c->h_scr);
   for (auto e : c->events) if (e) cudaEventDestroy(e);
   if (c->compute) cudaStreamDestroy(c->compute);
   delete c;
@@ -1400,10 +1408,17 @@ int gcb_counter_add_device_frames(gcb_counter *c, const float *x_dev, long nfram
   GCB_CUDA(cudaSetDevice(c->opts.device));
   DevHits h;
   h.n = nframes;
-  GCB_CUDA(cudaMalloc(&h.d, sizeof(unsigned long long) * (nframes + 2)));
+  // per-frame hit counters: taken from the pool of buffers earlier calls have returned (no allocation in steady state)
+  for (size_t k = 0; k < c->hit_pool.size(); k++)
+    if (c->hit_pool[k].first >= (size_t)nframes + 2) {
+      h.d = c->hit_pool[k].second; h.cap = c->hit_pool[k].first;
+      c->hit_pool.erase(c->hit_pool.begin() + (long)k);
+      break;
+    }
+  if (!h.d) { h.cap = (size_t)nframes + 2; GCB_CUDA(cudaMalloc(&h.d, sizeof(unsigned long long) * h.cap)); }
   GCB_CUDA(cudaMemsetAsync(h.d, 0, sizeof(unsigned long long) * (nframes + 2), c->compute));
   if (c->opts.pbc == GCB_PBC_RECT) {
-    if (!box) { cudaFree(h.d); return gcb::fail(GCB_ERR_ARG, "GCB_PBC_RECT needs the per-frame box"); }
+    if (!box) { c->hit_pool.emplace_back(h.cap, h.d); return gcb::fail(GCB_ERR_ARG, "GCB_PBC_RECT needs the per-frame box"); }
     std::vector<float> b3((size_t)nframes * 3);
     for (long f = 0; f < nframes; f++) { b3[3 * f] = box[9 * f]; b3[3 * f + 1] = box[9 * f + 4]; b3[3 * f + 2] = box[9 * f + 8]; }
     GCB_CUDA(cudaMalloc(&h.d_box3, sizeof(float) * 3 * nframes));
@@ -1513,7 +1528,8 @@ int gcb_counter_sync(gcb_counter *c)
     std::vector<unsigned long long> tmp((size_t)h.n);
     GCB_CUDA(cudaMemcpy(tmp.data(), h.d, sizeof(unsigned long long) * h.n, cudaMemcpyDeviceToHost));
     for (long f = 0; f < h.n; f++) c->hits_per_frame[h.frame0 + f] = tmp[f];
-    cudaFree(h.d); cudaFree(h.d_box3);
+    c->hit_pool.emplace_back(h.cap, h.d);
+    cudaFree(h.d_box3);
   }
   c->devhits.clear();
   unsigned long long diag[2];
@@ -1753,33 +1769,55 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c,
   enum { U32 = 3, U64 = 5, F32 = 7, F64 = 8 };
   if (c->nranks <= 1 || !c->nccl) return gcb_counter_sync(c);
   GCB_CUDA(cudaSetDevice(c->opts.device));
+  static const bool trace = getenv("GCB_TRACE") != nullptr;
+  auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+  const double t_begin = now();
   int rc = gcb_counter_sync(c);
   if (rc) return rc;
-  // agree on whether a single weight run covers all ranks
-  // (an all-gather expressed as a sum of one-hot slots: one collective type for everything)
+  const double t_sync = now();
+  // Persistent scratch (device + pinned mirror): no allocation, and only two host synchronisations, per call.
+  auto scratch = [&](size_t words) -> int {
+    if (words <= c->scr_words) return GCB_OK;
+    cudaFree(c->d_scr); cudaFreeHost(c->h_scr);
+    c->d_scr = nullptr; c->h_scr = nullptr; c->scr_words = 0;
+    const size_t cap = words + words / 2 + 64;
+    GCB_CUDA(cudaMalloc(&c->d_scr, sizeof(unsigned long long) * cap));
+    GCB_CUDA(cudaHostAlloc((void **)&c->h_scr, sizeof(unsigned long long) * cap, cudaHostAllocDefault));
+    c->scr_words = cap;
+    return GCB_OK;
+  };
+  // 1. all-gather (written as a sum of disjoint slots: one collective type for everything) of each rank's
+  //    {has frames, weight bits, uniform, has f32 accumulator, frame count}
+  const size_t R = (size_t)c->nranks;
+  rc = scratch(R * 5);
+  if (rc) return rc;
   uint32_t wb; memcpy(&wb, &c->w_first, 4);
-  std::vector<unsigned long long> slots((size_t)c->nranks * 4, 0ull), out((size_t)c->nranks * 4, 0ull);
-  slots[(size_t)c->rank * 4 + 0] = c->any ? 1ull : 0ull;
-  slots[(size_t)c->rank * 4 + 1] = wb;
-  slots[(size_t)c->rank * 4 + 2] = c->uniform ? 1ull : 0ull;
-  slots[(size_t)c->rank * 4 + 3] = (c->d_acc != nullptr) ? 1ull : 0ull;
-  unsigned long long *d_slots = nullptr;
-  GCB_CUDA(cudaMalloc(&d_slots, sizeof(unsigned long long) * slots.size()));
-  GCB_CUDA(cudaMemcpyAsync(d_slots, slots.data(), sizeof(unsigned long long) * slots.size(), cudaMemcpyHostToDevice, c->compute));
-  rc = allreduce(d_slots, d_slots, slots.size(), U64, c->nccl, c->compute);
-  if (rc) { cudaFree(d_slots); return rc; }
-  GCB_CUDA(cudaMemcpyAsync(out.data(), d_slots, sizeof(unsigned long long) * out.size(), cudaMemcpyDeviceToHost, c->compute));
+  memset(c->h_scr, 0, sizeof(unsigned long long) * R * 5);
+  c->h_scr[(size_t)c->rank * 5 + 0] = c->any ? 1ull : 0ull;
+  c->h_scr[(size_t)c->rank * 5 + 1] = wb;
+  c->h_scr[(size_t)c->rank * 5 + 2] = c->uniform ? 1ull : 0ull;
+  c->h_scr[(size_t)c->rank * 5 + 3] = (c->d_acc != nullptr) ? 1ull : 0ull;
+  c->h_scr[(size_t)c->rank * 5 + 4] = c->hits_per_frame.size();
+  GCB_CUDA(cudaMemcpyAsync(c->d_scr, c->h_scr, sizeof(unsigned long long) * R * 5, cudaMemcpyHostToDevice, c->compute));
+  rc = allreduce(c->d_scr, c->d_scr, R * 5, U64, c->nccl, c->compute);
+  if (rc) return rc;
+  GCB_CUDA(cudaMemcpyAsync(c->h_scr, c->d_scr, sizeof(unsigned long long) * R * 5, cudaMemcpyDeviceToHost, c->compute));
   GCB_CUDA(cudaStreamSynchronize(c->compute));
-  cudaFree(d_slots);
   bool global_uniform = true, any_acc = false, have_w = false;
   uint32_t w0 = 0;
+  size_t total_frames = 0, my_off = 0;
   for (int r = 0; r < c->nranks; r++) {
-    if (!out[(size_t)r * 4 + 0]) continue;
-    if (!out[(size_t)r * 4 + 2]) global_uniform = false;
-    if (out[(size_t)r * 4 + 3]) any_acc = true;
-    if (!have_w) { w0 = (uint32_t)out[(size_t)r * 4 + 1]; have_w = true; }
-    else if (w0 != (uint32_t)out[(size_t)r * 4 + 1]) global_uniform = false;
+    const unsigned long long *o = c->h_scr + (size_t)r * 5;
+    if (r == c->rank) my_off = total_frames;
+    total_frames += (size_t)o[4];
+    if (!o[0]) continue;
+    if (!o[2]) global_uniform = false;
+    if (o[3]) any_acc = true;
+    if (!have_w) { w0 = (uint32_t)o[1]; have_w = true; }
+    else if (w0 != (uint32_t)o[1]) global_uniform = false;
   }
+  const double t_gather = now();
+  // 2. the grids
   if (global_uniform && !any_acc) {
     // the common case: one integer grid per rank, one weight: sum the counts
     rc = allreduce(c->d_runcnt, c->d_runcnt, c->ncells, U32, c->nccl, c->compute);
@@ -1796,44 +1834,48 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c,
     if (rc) return rc;
     c->uniform = false;
   }
-  // Statistics.  Ranks hold contiguous frame shards in rank order, so gathering the per-frame hit counts and
-  // weights (an all-gather written as a sum of disjoint slots) lets every rank redo the reference's frame-ordered
-  // `sumP += (double)weight` chain (g_ri3Dc.c:151,426) over ALL frames: bit-identical to a single-GPU run.
-  std::vector<unsigned long long> nfr((size_t)c->nranks, 0ull);
-  nfr[(size_t)c->rank] = c->hits_per_frame.size();
-  unsigned long long *d_tmp = nullptr;
-  GCB_CUDA(cudaMalloc(&d_tmp, sizeof(unsigned long long) * nfr.size()));
-  GCB_CUDA(cudaMemcpyAsync(d_tmp, nfr.data(), sizeof(unsigned long long) * nfr.size(), cudaMemcpyHostToDevice, c->compute));
-  rc = allreduce(d_tmp, d_tmp, nfr.size(), U64, c->nccl, c->compute);
-  if (rc) { cudaFree(d_tmp); return rc; }
-  GCB_CUDA(cudaMemcpyAsync(nfr.data(), d_tmp, sizeof(unsigned long long) * nfr.size(), cudaMemcpyDeviceToHost, c->compute));
-  GCB_CUDA(cudaStreamSynchronize(c->compute));
-  cudaFree(d_tmp);
-  size_t total_frames = 0, my_off = 0;
-  for (int r = 0; r < c->nranks; r++) { if (r == c->rank) my_off = total_frames; total_frames += (size_t)nfr[(size_t)r]; }
-  std::vector<unsigned long long> fr(2 * total_frames + 1, 0ull);          // [hits | weight bits | edge overflow]
+  double t_grid = 0;
+  if (trace) { cudaStreamSynchronize(c->compute); t_grid = now(); }
+  // 3. Statistics.  Ranks hold contiguous frame shards in rank order, so gathering the per-frame hit counts and
+  //    weights lets every rank redo the reference's frame-ordered `sumP += (double)weight` chain
+  //    (g_ri3Dc.c:151,426) over ALL frames: bit-identical to a single-GPU run.
+  const size_t nfr_words = 2 * total_frames + 1;                       // [hits | weight bits | edge overflow]
+  rc = scratch(nfr_words);
+  if (rc) return rc;
+  unsigned long long *fr = c->h_scr;
+  memset(fr, 0, sizeof(unsigned long long) * nfr_words);
   for (size_t f = 0; f < c->hits_per_frame.size(); f++) {
     fr[my_off + f] = c->hits_per_frame[f];
     uint32_t wbits; memcpy(&wbits, &c->weight_per_frame[f], 4);
     fr[total_frames + my_off + f] = wbits;
   }
   fr[2 * total_frames] = c->edge_overflow;
-  GCB_CUDA(cudaMalloc(&d_tmp, sizeof(unsigned long long) * fr.size()));
-  GCB_CUDA(cudaMemcpyAsync(d_tmp, fr.data(), sizeof(unsigned long long) * fr.size(), cudaMemcpyHostToDevice, c->compute));
-  rc = allreduce(d_tmp, d_tmp, fr.size(), U64, c->nccl, c->compute);
-  if (rc) { cudaFree(d_tmp); return rc; }
-  GCB_CUDA(cudaMemcpyAsync(fr.data(), d_tmp, sizeof(unsigned long long) * fr.size(), cudaMemcpyDeviceToHost, c->compute));
+  GCB_CUDA(cudaMemcpyAsync(c->d_scr, fr, sizeof(unsigned long long) * nfr_words, cudaMemcpyHostToDevice, c->compute));
+  rc = allreduce(c->d_scr, c->d_scr, nfr_words, U64, c->nccl, c->compute);
+  if (rc) return rc;
+  GCB_CUDA(cudaMemcpyAsync(fr, c->d_scr, sizeof(unsigned long long) * nfr_words, cudaMemcpyDeviceToHost, c->compute));
   GCB_CUDA(cudaStreamSynchronize(c->compute));
-  cudaFree(d_tmp);
+  const double t_frames = now();
+  // consecutive frames of equal weight are one run of identical additions: one closed-form call per run
   double sp = 0;
-  unsigned long long hits = 0;
+  unsigned long long hits = 0, run_hits = 0;
+  uint32_t run_w = 0;
   for (size_t f = 0; f < total_frames; f++) {
     const uint32_t wbits = (uint32_t)fr[total_frames + f];
-    float wf; memcpy(&wf, &wbits, 4);
-    sp = gcb::seq_add_f64(sp, (double)wf, fr[f]);
+    if (wbits != run_w && run_hits) {
+      float wf; memcpy(&wf, &run_w, 4);
+      sp = gcb::seq_add_f64(sp, (double)wf, run_hits);
+      run_hits = 0;
+    }
+    run_w = wbits;
+    run_hits += fr[f];
     hits += fr[f];
   }
+  if (run_hits) { float wf; memcpy(&wf, &run_w, 4); sp = gcb::seq_add_f64(sp, (double)wf, run_hits); }
   c->global_frames = total_frames; c->hits_total = hits; c->edge_overflow = fr[2 * total_frames]; c->sumP = sp;
   c->reduced = true;
+  if (trace && c->rank == 0)
+    fprintf(stderr, "[gcb allreduce] wait for binning %.3f ms, rank table %.3f ms, grid %.3f ms, frame gather %.3f ms, sumP chain %.3f ms\n",
+            t_sync - t_begin, t_gather - t_sync, t_grid - t_gather, t_frames - t_grid, now() - t_frames);
   return GCB_OK;
 }
