@@ -1328,15 +1328,22 @@ int gcb_counter_reset(gcb_counter *c)
 {
   if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
   GCB_CUDA(cudaSetDevice(c->opts.device));
-  int rc = gcb_counter_sync(c);
-  if (rc) return rc;
+  // No host synchronisation: everything below is ordered on the compute stream behind the work already
+  // queued, and results that were never collected are simply dropped (their counter buffers go back to the
+  // pool; later launches that reuse them are ordered on the same stream).
+  for (auto &s : c->slots) s.pending = 0;
+  for (auto &h : c->devhits) {
+    c->hit_pool.emplace_back(h.cap, h.d);
+    if (h.d_box3) { GCB_CUDA(cudaStreamSynchronize(c->compute)); cudaFree(h.d_box3); }
+  }
+  c->devhits.clear();
   GCB_CUDA(cudaMemsetAsync(c->d_runcnt, 0, sizeof(uint32_t) * c->ncells, c->compute));
   if (c->d_acc) {
     GCB_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(float) * c->ncells, c->compute));
     GCB_CUDA(cudaMemsetAsync(c->d_total, 0, sizeof(uint32_t) * c->ncells, c->compute));
   }
   GCB_CUDA(cudaMemsetAsync(c->d_diag, 0, sizeof(unsigned long long) * 2, c->compute));
-  GCB_CUDA(cudaStreamSynchronize(c->compute));
+  c->reduced = false; c->global_frames = 0;
   c->have_run = false; c->any = false; c->uniform = true; c->w_cur = 0; c->w_first = 0;
   c->hits_per_frame.clear(); c->weight_per_frame.clear();
   c->sumP = 0; c->sumP_frames = 0; c->hits_total = 0; c->edge_overflow = 0;

@@ -25,7 +25,9 @@ def main():
     L, delta, natoms, F = (4.0, 4.0, 6.7), 0.1, 3000, 64          # frames per rank
     geom = g.setup_geometry(L, delta)
     gindex = np.arange(0, natoms, 3, dtype=np.int32)
-    gen = g.make_gen(5, L, g._cabi.GEN_PORE, slab=(2.2, 4.5), pore_r=0.8)
+    # breathing box (BASELINE config 5: pressure coupling): the grid is fixed by the first frame's box, atoms that
+    # end up outside are dropped by the reference and by every rank alike
+    gen = g.make_gen(5, L, g._cabi.GEN_PORE, slab=(2.2, 4.5), pore_r=0.8, box_period=16, box_amp=0.01)
     dev = g.DeviceFrames(F, natoms, local).generate(gen, frame0=rank * F)
     w = np.full(F, 0.1, np.float32)
     ctr = g.GridCounter(geom, gindex, natoms, device=local)
@@ -40,7 +42,7 @@ def main():
     ok = True
     if rank == 0:
         og = u.Geom.from_buffer_copy(bytes(geom.tg))
-        x = u.gen_frames(u.make_gen(5, L, 2, slab=(2.2, 4.5), pore_r=0.8), 0, F * world, natoms)
+        x = u.gen_frames(u.make_gen(5, L, 2, slab=(2.2, 4.5), pore_r=0.8, box_period=16, box_amp=0.01), 0, F * world, natoms)
         want = np.zeros(geom.shape, np.uint32)
         hits = np.zeros(F * world, np.uint64)
         u.oracle().gco_count_frames(C.byref(og), want.ctypes.data_as(u.c_u32_p), u.fptr(x), F * world, natoms,
@@ -51,6 +53,7 @@ def main():
         u.oracle().gco_bin_frames(C.byref(og), u.fptr(occ), u.fptr(x), F * world, natoms, u.iptr(gindex), len(gindex),
                                   u.fptr(wall), C.byref(sp), None, None)
         u.oracle().gco_normalise(C.byref(og), u.fptr(occ), 0.1 * F * world)
+        assert 0 < int(hits.sum()) < F * world * len(gindex), "the breathing box should push some atoms out of the grid"
         ok = (np.array_equal(counts, want) and st.frames == F * world and st.hits == int(hits.sum())
               and np.array_equal(dens.view(np.uint32), occ.view(np.uint32)) and st.sumP == sp.value)
         print("MULTI_GPU_PARITY", "OK" if ok else "FAIL", "world", world, "hits", st.hits, flush=True)
