@@ -920,11 +920,12 @@ template <class SINK, bool PBC, bool AP>
 int launch_stream(gcb_counter *c, const float *d_x, long long ntiles, const SINK &sink, int grid_cap,
                   const float *d_box3, unsigned long long *d_hits, int *grid_out)
 {
-  static bool attr_done = false;                 // one flag per instantiation
+  static bool attr_done[64] = {false};           // per instantiation and per device (the attribute is per context)
   const size_t smem = stream_smem_bytes<SINK>();
-  if (!attr_done) {
+  const int dv = c->opts.device & 63;
+  if (!attr_done[dv]) {
     GCB_CUDA(cudaFuncSetAttribute(bin_stream_kernel<SINK, PBC, AP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done[dv] = true;
   }
   const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
   long long grid = std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
@@ -978,10 +979,10 @@ int launch_routed(gcb_counter *c, const float *d_x, long nframes, const float *d
     c->route_grid = G;
   }
   if (c->route_mode == 1) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {false};
+    if (!attr_done[c->opts.device & 63]) {
       GCB_CUDA(cudaFuncSetAttribute(route_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_done = true;
+      attr_done[c->opts.device & 63] = true;
     }
   }
   for (long f0 = 0; f0 < nframes; f0 += fpr) {

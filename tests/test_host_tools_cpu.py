@@ -173,3 +173,31 @@ def test_tools_link_and_follow_the_option_conventions(tool, tmp_path):
         assert p.returncode == 1 and b"needs a value" in p.stderr
         p = subprocess.run([exe, "-m"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, cwd=str(tmp_path))
         assert p.returncode == 1 and b"-m option not working" in p.stderr          # g_ri3Dc.c:357-358
+
+
+def test_xtc_scan_reads_the_frame_table(host):
+    """gcb_xtc_scan (product library, host code): offsets, sizes and header fields of every frame; an
+    incomplete trailing frame is left for the next read; a wrong magic number is an error"""
+    import gridcount_b200 as g
+    from gridcount_b200 import _cabi as K
+    rng = np.random.default_rng(9)
+    parts, sizes = [], []
+    for f, n in enumerate((300, 300, 300)):
+        buf = encode(host, water_like(n // 3, 3.0, rng), step=f, time=0.25 * f, box=(3, 4, 5))
+        parts.append(buf.tobytes()); sizes.append(len(buf))
+    tiny = encode(host, (rng.random((4, 3)) * 3).astype(np.float32), step=9, time=9.0)
+    data = b"".join(parts)
+    xb = g.XtcBuffer(data + data[:100])            # a truncated fourth frame
+    assert xb.nframes == 3 and xb.consumed == len(data) and xb.natoms == 300
+    off = 0
+    for f in range(3):
+        fr = xb.frames[f]
+        assert fr.payload_offset == off + 92 and fr.step == f and fr.time == np.float32(0.25 * f) and fr.precision == 1000.0
+        assert (fr.payload_bytes + 3) // 4 * 4 == sizes[f] - 92 and list(fr.box)[::4] == [3.0, 4.0, 5.0]
+        assert all(fr.minint[d] <= fr.maxint[d] for d in range(3)) and 9 <= fr.smallidx <= 72
+        off += sizes[f]
+    small = g.XtcBuffer(tiny.tobytes())
+    assert small.nframes == 1 and small.frames[0].payload_bytes == 0 and small.frames[0].natoms == 4
+    bad = bytearray(data); bad[1] = 7
+    with pytest.raises(K.GcbError):
+        g.XtcBuffer(bytes(bad))
