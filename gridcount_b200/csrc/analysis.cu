@@ -3,24 +3,32 @@
 //
 // The reference sums in f32 in one fixed order (k outer, j, i inner; a_ri3Dc.c:567-703), so a
 // tree or double-precision reduction would differ from it by the REFERENCE's rounding error
-// (~1e-6..1e-5 relative on these sizes).  Every output element here is therefore one sequential
-// chain in the reference's order; the parallelism is ACROSS outputs:
+// (~1e-6..1e-5 relative on these sizes; its f32 `average` even saturates on large grids).  Every
+// output element is therefore evaluated as the reference's sequential chain, bit for bit:
 //
-//   xyp/hxyp [mx][my]   chain over k            one thread per (i,j), reads the x-fastest copy
-//   xzp      [mx][mz]   chain over j            one thread per (i,k), k fastest
-//   yzp      [my][mz]   chain over i            one thread per (j,k), k fastest
-//   zdf/lzdf/profile[k] chain over (j,i)        one thread per k
-//   rzp/hrzp [r][mz]    chain over bin r's cells in (j,i) order, one thread per (r,k)
-//   rdf/hrdf/rweight[r] chain over k, then bin r's cells: one thread per r
-//   sumP (f64), average (f32): whole-grid chains: one consumer thread each, fed through shared
-//                       memory by the rest of its block from the x-fastest copy (linear order)
+//   short chains: one thread per output, parallel ACROSS outputs
+//     xyp/hxyp [mx][my]   chain over k            thread per (i,j), reads the x-fastest copy
+//     xzp      [mx][mz]   chain over j            thread per (i,k), k fastest
+//     yzp      [my][mz]   chain over i            thread per (j,k), k fastest
+//     rzp/hrzp [r][mz]    chain over bin r's cells in (j,i) order, thread per (r,k)
+//   long chains: parallel INSIDE the chain, by the exact scan of the rounding recurrence (seqsum.cuh)
+//     zdf/lzdf/profile[k] chain over the slice's (j,i) cells      one block per (k, chain)
+//     rdf/hrdf[r]         chain over k, then bin r's cells        one block per r
+//     sumP (f64), average (f32): whole-grid chains                one cooperative grid, all SMs
+//     rweight[r]          constant increments: closed form per exponent, on the host
+//   The scans need finite cells >= 0 (any density); otherwise a flag is raised and the serial
+//   one-thread-per-chain kernels (an_chain_kernel, an_slice_kernel, an_rdf_kernel) take over.
 //
 // Compiled with -fmad=false: ci*ci + cj*cj and the divide-then-add steps are separate f32
 // operations as in the reference binary.
 #include "gcb_internal.h"
+#include "seqsum.cuh"
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -174,10 +182,200 @@ __global__ void an_rdf_kernel(const float *__restrict__ g, Dims d, const int *__
   rdf[2 * r + 1] = s; hrdf[2 * r + 1] = h; rweight[r] = rw;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Scan forms of the long chains (seqsum.cuh): same bits as the serial kernels above for grids whose
+// cells are finite and >= 0; otherwise `bad_out` is raised and the host runs the serial kernels.
+// They read the x-fastest copy gx[k][j][i], where a slice's (j,i) traversal is linear memory.
+// ---------------------------------------------------------------------------------------------------
+// One block per (slice k, chain): chain 0 = zdf, 1 = lzdf (and the count nocc), 2 = Rgyr2; raw sums go to
+// raw[chain][k], an_slice_finish_kernel turns them into the three profiles.
+constexpr int SLICE_THREADS = 256;
+__global__ void __launch_bounds__(SLICE_THREADS)
+an_slice_scan_kernel(const float *__restrict__ gx, Dims d, const float *__restrict__ c2tab,
+                     const unsigned char *__restrict__ flags, float min_occ, float *__restrict__ raw,
+                     unsigned *__restrict__ nocc, int *__restrict__ bad_out)
+{
+  __shared__ seqsum::BlockScratch scratch;
+  __shared__ unsigned nocc_sh;
+  const int k = blockIdx.x, chain = blockIdx.y;
+  const size_t nxy = (size_t)d.mx * d.my;
+  const float *sl = gx + (size_t)k * nxy;
+  bool bad = false;
+  float s;
+  if (chain == 0) {
+    s = seqsum::block_chain<float, 8, SLICE_THREADS>(nxy, [&](size_t t) { return t < nxy ? __ldg(sl + t) : 0.0f; }, scratch, &bad);
+  } else if (chain == 1) {
+    if (threadIdx.x == 0) nocc_sh = 0;
+    s = seqsum::block_chain<float, 8, SLICE_THREADS>(nxy, [&](size_t t) {
+      if (t >= nxy) return 0.0f;
+      const float v = __ldg(sl + t);
+      return (v > min_occ && (__ldg(flags + t) & 1)) ? v : 0.0f; }, scratch, &bad);
+    unsigned n = 0;
+    for (size_t t = threadIdx.x; t < nxy; t += SLICE_THREADS) n += (__ldg(sl + t) > min_occ && (__ldg(flags + t) & 1)) ? 1u : 0u;
+    n = __reduce_add_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&nocc_sh, n);
+    __syncthreads();
+    if (threadIdx.x == 0) nocc[k] = nocc_sh;
+  } else {
+    s = seqsum::block_chain<float, 8, SLICE_THREADS>(nxy, [&](size_t t) {
+      if (t >= nxy) return 0.0f;
+      const float v = __ldg(sl + t);
+      return (v > min_occ && (__ldg(flags + t) & 1)) ? __fmul_rn(v, __ldg(c2tab + t)) : 0.0f; }, scratch, &bad);
+  }
+  if (threadIdx.x == 0) { raw[(size_t)chain * d.mz + k] = s; if (bad) atomicExch(bad_out, 1); }
+}
+
+__global__ void an_slice_finish_kernel(const float *__restrict__ raw, int mz, SliceParams p, float *__restrict__ zdf,
+                                       float *__restrict__ lzdf, float *__restrict__ profile)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= mz) return;
+  const float zs = raw[k], lz = raw[mz + k];
+  float rg = raw[2 * mz + k];
+  const float z = (float)((double)p.a_z + ((double)k + 0.5) * (double)p.delta_z);        // a_ri3Dc.c:665
+  zdf[2 * k] = z; lzdf[2 * k] = z; profile[2 * k] = z;
+  zdf[2 * k + 1] = __fdiv_rn(zs, p.d_zdf);                                               // :666
+  rg = (float)((double)rg / (0.5 * (double)lz));                                         // :672
+  profile[2 * k + 1] = (float)(sqrt((double)rg) * (double)p.DeltaR);                     // :675
+  const float Agyr = (float)(kPi * (double)rg);                                          // :677
+  const float den = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(p.delta_z, Agyr), p.DeltaR), p.DeltaR), p.U);
+  lzdf[2 * k + 1] = (float)((double)lz * p.dV / (double)den);                            // :695
+}
+
+// One block per radial bin r: rdf[r][1] chains the occupied cells over k, then bin r's cells in (j,i)
+// order (a_ri3Dc.c:627-645); hrdf[r][1] is a chain of +1.0f over the other cells, i.e. min(count, 2^24).
+// bin_xy[] lists each bin's cells as j*mx + i.
+constexpr int RDF_THREADS = 256;
+__global__ void __launch_bounds__(RDF_THREADS)
+an_rdf_scan_kernel(const float *__restrict__ gx, Dims d, const int *__restrict__ bin_start,
+                   const int *__restrict__ bin_xy, float min_occ, float *__restrict__ rdf, float *__restrict__ hrdf,
+                   int *__restrict__ bad_out)
+{
+  __shared__ seqsum::BlockScratch scratch;
+  __shared__ unsigned long long holes_sh;
+  const int r = blockIdx.x;
+  const int c0 = bin_start[r];
+  const unsigned nc = (unsigned)(bin_start[r + 1] - c0);
+  const size_t nxy = (size_t)d.mx * d.my, n = (size_t)nc * d.mz;
+  if (threadIdx.x == 0) holes_sh = 0;
+  bool bad = false;
+  const bool small = n <= 0xffffffffull;
+  auto cell = [&](size_t t) {
+    size_t k, c;
+    if (small) { const uint32_t kk = (uint32_t)t / nc; k = kk; c = (uint32_t)t - kk * nc; }
+    else { k = t / nc; c = t - k * nc; }
+    return __ldg(gx + k * nxy + (size_t)__ldg(bin_xy + c0 + c));
+  };
+  const float s = seqsum::block_chain<float, 8, RDF_THREADS>(
+      n, [&](size_t t) { if (t >= n) return 0.0f; const float v = cell(t); return v > min_occ ? v : 0.0f; }, scratch, &bad);
+  unsigned long long holes = 0;
+  for (size_t t = threadIdx.x; t < n; t += RDF_THREADS) holes += cell(t) > min_occ ? 0u : 1u;
+  holes = __reduce_add_sync(0xffffffffu, (unsigned)holes);
+  if ((threadIdx.x & 31) == 0 && holes) atomicAdd(&holes_sh, holes);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (bad) atomicExch(bad_out, 1);
+    rdf[2 * r + 1] = s;
+    hrdf[2 * r + 1] = holes_sh > (1ull << 24) ? 16777216.0f : (float)holes_sh;
+  }
+}
+
 // Whole-grid chains in (k,j,i) order over the x-fastest copy, which is linear memory order.
 // block 0: sumP += (double)g (a_ri3Dc.c:499-508) and the count behind sumH
 // block 1: average += g for cells with irad < iradNR (a_ri3Dc.c:633); masked cells add +0.0f,
 //          which leaves any partial sum that started at +0 unchanged bit for bit
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_T = 8;
+__global__ void __launch_bounds__(SCAN_THREADS)
+an_chain_scan_kernel(const float *__restrict__ gx, size_t ncells, int nxy, const unsigned char *__restrict__ flags,
+                     float min_occ_raw, double *__restrict__ sumP_out, unsigned long long *__restrict__ nholes_out,
+                     float *__restrict__ average_out, int *__restrict__ bad_out)
+{
+  __shared__ seqsum::BlockScratch scratch;
+  bool bad = false;
+  if (blockIdx.x == 0) {
+    const double s = seqsum::block_chain<double, SCAN_T, SCAN_THREADS>(
+        ncells, [&](size_t i) { return i < ncells ? __ldg(gx + i) : 0.0f; }, scratch, &bad);
+    if (threadIdx.x == 0) {
+      if (bad) atomicExch(bad_out, 1);
+      *sumP_out = s;
+    }
+  } else if (blockIdx.x == 1) {
+    const bool small = ncells <= 0xffffffffull;
+    const float s = seqsum::block_chain<float, SCAN_T, SCAN_THREADS>(
+        ncells,
+        [&](size_t i) {
+          if (i >= ncells) return 0.0f;
+          const size_t t = small ? (size_t)((uint32_t)i % (uint32_t)nxy) : i % (size_t)nxy;
+          return (__ldg(flags + t) & 2) ? __ldg(gx + i) : 0.0f;
+        },
+        scratch, &bad);
+    if (threadIdx.x == 0) {
+      if (bad) atomicExch(bad_out, 1);
+      *average_out = s;
+    }
+  } else {                                  // the count behind sumH (a_ri3Dc.c:504): order-free
+    unsigned long long holes = 0;
+    for (size_t i = (size_t)(blockIdx.x - 2) * SCAN_THREADS + threadIdx.x; i < ncells; i += (size_t)(gridDim.x - 2) * SCAN_THREADS)
+      holes += __ldg(gx + i) <= min_occ_raw ? 1u : 0u;
+    holes = __reduce_add_sync(0xffffffffu, (unsigned)holes);          // per-lane counts stay far below 2^32/32
+    if ((threadIdx.x & 31) == 0 && holes) atomicAdd(nholes_out, holes);
+  }
+}
+
+// The same two chains spread over a cooperative grid (seqsum::GridChain): one block per SM, rounds
+// separated by grid-wide barriers.  fbuf holds 2 (round parity) x 2 (chains) x maxseg segment maps.
+__global__ void __launch_bounds__(SCAN_THREADS)
+an_chain_grid_kernel(const float *__restrict__ gx, size_t ncells, int nxy, const unsigned char *__restrict__ flags,
+                     float min_occ_raw, seqsum::Fn *__restrict__ fbuf, size_t maxseg, double *__restrict__ sumP_out,
+                     unsigned long long *__restrict__ nholes_out, float *__restrict__ average_out, int *__restrict__ bad_out)
+{
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ seqsum::BlockScratch sh;
+  if (threadIdx.x == 0) { sh.first_cross = SCAN_THREADS; sh.bad = 0; }
+  __syncthreads();
+  {                                         // the count behind sumH (a_ri3Dc.c:504): order-free
+    unsigned holes = 0;
+    for (size_t i = (size_t)blockIdx.x * SCAN_THREADS + threadIdx.x; i < ncells; i += (size_t)gridDim.x * SCAN_THREADS)
+      holes += __ldg(gx + i) <= min_occ_raw ? 1u : 0u;
+    holes = __reduce_add_sync(0xffffffffu, holes);
+    if ((threadIdx.x & 31) == 0 && holes) atomicAdd(nholes_out, (unsigned long long)holes);
+  }
+  auto load_all = [&](size_t i, float (&x)[SCAN_T]) {
+#pragma unroll
+    for (int j = 0; j < SCAN_T; j++) x[j] = i + j < ncells ? __ldg(gx + i + j) : 0.0f;
+  };
+  auto load_cyl = [&](size_t i, float (&x)[SCAN_T]) {              // cells with irad < iradNR (flag bit 1), else +0
+    unsigned t = i < ncells ? (unsigned)(i % (size_t)nxy) : 0u;
+#pragma unroll
+    for (int j = 0; j < SCAN_T; j++) {
+      x[j] = (i + j < ncells && (__ldg(flags + t) & 2)) ? __ldg(gx + i + j) : 0.0f;
+      if (++t == (unsigned)nxy) t = 0;
+    }
+  };
+  seqsum::GridChain<double, SCAN_T, SCAN_THREADS> A;
+  seqsum::GridChain<float, SCAN_T, SCAN_THREADS> B;
+  A.init(ncells); B.init(ncells);
+  bool bad = false;
+  for (int round = 0; !(A.done && B.done); round++) {
+    seqsum::Fn *fa = fbuf + (size_t)(round & 1) * 2 * maxseg, *fb = fa + maxseg;
+    A.phase1(ncells, load_all, fa, sh, bad_out);
+    B.phase1(ncells, load_cyl, fb, sh, bad_out);
+    grid.sync();
+    if (*(volatile int *)bad_out) return;                            // same value in every block: set before the barrier
+    A.phase2(ncells, load_all, fa, sh, &bad);
+    B.phase2(ncells, load_cyl, fb, sh, &bad);
+    if (bad) break;                                                  // every block computes the same `bad`
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (bad) atomicExch(bad_out + 1, 1);                             // a second word: bad_out[0] is read between barriers
+    *sumP_out = A.value(); *average_out = B.value();
+  }
+}
+
+// the serial form of the same two chains: one consumer thread each, fed through shared memory by the
+// rest of its block.  Used when the grid holds negative or non-finite cells (never for a density).
 constexpr int CHAIN_THREADS = 256;
 constexpr int CHAIN_CHUNK = 2048;
 __global__ void __launch_bounds__(CHAIN_THREADS)
@@ -371,22 +569,28 @@ int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analy
     }
   }
   // cells of each radial bin in (j,i) order, as z-fastest row numbers i*my + j
-  std::vector<int> bin_start((size_t)iradNR + 1, 0), bin_cells;
+  std::vector<int> bin_start((size_t)iradNR + 1, 0), bin_cells, bin_xy;
   {
     for (size_t t = 0; t < (size_t)nxy; t++) if (irad[t] < iradNR) bin_start[(size_t)irad[t] + 1]++;
     for (int r = 0; r < iradNR; r++) bin_start[(size_t)r + 1] += bin_start[r];
     bin_cells.resize((size_t)bin_start[iradNR]);
+    bin_xy.resize((size_t)bin_start[iradNR]);
     std::vector<int> fill(bin_start.begin(), bin_start.end() - 1);
     for (int j = 0; j < d.my; j++)
       for (int i = 0; i < d.mx; i++) {
         const int r = irad[(size_t)j * d.mx + i];
-        if (r < iradNR) bin_cells[(size_t)fill[r]++] = i * d.my + j;
+        if (r < iradNR) { bin_xy[(size_t)fill[r]] = j * d.mx + i; bin_cells[(size_t)fill[r]++] = i * d.my + j; }
       }
   }
   const long long ncyl = iradNR > 0 ? bin_start[iradNR] : 0;
 
+  static const bool trace = getenv("GCB_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t_start = now();
   // ---- device buffers --------------------------------------------------------------------------
-  DevBuf d_in, d_g, d_gx, d_c2, d_flags, d_bs, d_bc, d_xyp, d_hxyp, d_xzp, d_yzp, d_zdf, d_lzdf, d_prof, d_nocc,
+  DevBuf d_in, d_g, d_gx, d_c2, d_flags, d_bs, d_bc, d_bxy, d_fbuf, d_sraw, d_xyp, d_hxyp, d_xzp, d_yzp, d_zdf, d_lzdf, d_prof, d_nocc,
       d_rzp, d_hrzp, d_rdf, d_hrdf, d_rw, d_scal;
   const size_t nrz = (size_t)iradNR * d.mz;
   AN_CUDA(cudaMalloc(&d_in.p, ocells * 4));
@@ -404,6 +608,7 @@ int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analy
   AN_CUDA(cudaMalloc(&d_flags.p, (size_t)nxy));
   AN_CUDA(cudaMalloc(&d_bs.p, bin_start.size() * 4));
   AN_CUDA(cudaMalloc(&d_bc.p, std::max<size_t>(bin_cells.size(), 1) * 4));
+  AN_CUDA(cudaMalloc(&d_bxy.p, std::max<size_t>(bin_xy.size(), 1) * 4));
   AN_CUDA(cudaMalloc(&d_xyp.p, (size_t)nxy * 4));
   AN_CUDA(cudaMalloc(&d_hxyp.p, (size_t)nxy * 4));
   AN_CUDA(cudaMalloc(&d_xzp.p, (size_t)d.mx * d.mz * 4));
@@ -412,16 +617,21 @@ int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analy
   AN_CUDA(cudaMalloc(&d_lzdf.p, (size_t)d.mz * 8));
   AN_CUDA(cudaMalloc(&d_prof.p, (size_t)d.mz * 8));
   AN_CUDA(cudaMalloc(&d_nocc.p, (size_t)d.mz * 4));
+  AN_CUDA(cudaMalloc(&d_sraw.p, (size_t)d.mz * 12));
   AN_CUDA(cudaMalloc(&d_rzp.p, std::max<size_t>(nrz, 1) * 4));
   AN_CUDA(cudaMalloc(&d_hrzp.p, std::max<size_t>(nrz, 1) * 4));
   AN_CUDA(cudaMalloc(&d_rdf.p, ((size_t)iradNR + 1) * 8));
   AN_CUDA(cudaMalloc(&d_hrdf.p, ((size_t)iradNR + 1) * 8));
   AN_CUDA(cudaMalloc(&d_rw.p, ((size_t)iradNR + 1) * 4));
   AN_CUDA(cudaMalloc(&d_scal.p, 32));
+  const size_t maxseg = (ncells + (size_t)SCAN_THREADS * SCAN_T - 1) / ((size_t)SCAN_THREADS * SCAN_T) + 1;
+  AN_CUDA(cudaMalloc(&d_fbuf.p, 16 + 4 * maxseg * sizeof(seqsum::Fn)));
+  AN_CUDA(cudaMemset(d_fbuf.p, 0, 16));
   AN_CUDA(cudaMemcpy(d_c2.p, c2tab.data(), (size_t)nxy * 4, cudaMemcpyHostToDevice));
   AN_CUDA(cudaMemcpy(d_flags.p, flags.data(), (size_t)nxy, cudaMemcpyHostToDevice));
   AN_CUDA(cudaMemcpy(d_bs.p, bin_start.data(), bin_start.size() * 4, cudaMemcpyHostToDevice));
   if (!bin_cells.empty()) AN_CUDA(cudaMemcpy(d_bc.p, bin_cells.data(), bin_cells.size() * 4, cudaMemcpyHostToDevice));
+  if (!bin_xy.empty()) AN_CUDA(cudaMemcpy(d_bxy.p, bin_xy.data(), bin_xy.size() * 4, cudaMemcpyHostToDevice));
   AN_CUDA(cudaMemset(d_rdf.p, 0, ((size_t)iradNR + 1) * 8));
   AN_CUDA(cudaMemset(d_hrdf.p, 0, ((size_t)iradNR + 1) * 8));
   AN_CUDA(cudaMemset(d_scal.p, 0, 32));
@@ -430,11 +640,15 @@ int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analy
   cudaStream_t st[4];
   for (auto &s : st) AN_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   AN_CUDA(cudaDeviceSynchronize());                           // uploads / crop (legacy stream) done
+  const auto t_up = now();
   {
     dim3 block(32, 8), grid((d.mz + 31) / 32, (d.mx + 31) / 32, d.my);
     an_transpose_kernel<<<grid, block, 0, st[0]>>>(g, d_gx.as<float>(), d);
     launches++;
   }
+  cudaEvent_t gx_ready;                                       // the x-fastest copy exists: the other streams may read it
+  AN_CUDA(cudaEventCreateWithFlags(&gx_ready, cudaEventDisableTiming));
+  AN_CUDA(cudaEventRecord(gx_ready, st[0]));
   const float d_xy = fmz * U, d_xz = fmy * U, d_yz = fmx * U;               // a_ri3Dc.c:573-578 divisors
   const double h_inc = 1.0 / (double)(fmz * Uunity);                       // :580
   const double rw_inc = 1.0 / (double)fmz;                                 // :637
@@ -442,25 +656,88 @@ int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analy
   double *d_sumP = d_scal.as<double>();
   unsigned long long *d_holes = reinterpret_cast<unsigned long long *>(d_scal.as<char>() + 8);
   float *d_avg = reinterpret_cast<float *>(d_scal.as<char>() + 16);
-  an_chain_kernel<<<2, CHAIN_THREADS, 0, st[0]>>>(d_gx.as<float>(), ncells, nxy, d_flags.as<unsigned char>(), min_occ_raw, d_sumP, d_holes, d_avg);
+  int *d_bad = reinterpret_cast<int *>(d_scal.as<char>() + 24);
+  // whole-grid chains: a cooperative grid when the grid is large enough to feed one, else two blocks
+  int *d_bad_grid = reinterpret_cast<int *>(d_fbuf.as<char>());       // two flag words in front of the segment maps
+  bool coop = false;
+  if (ncells >= (size_t)SCAN_THREADS * SCAN_T * 16) {
+    int dev = 0, sms = 0, can = 0, per_sm = 0;
+    AN_CUDA(cudaGetDevice(&dev));
+    AN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    AN_CUDA(cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev));
+    AN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, an_chain_grid_kernel, SCAN_THREADS, 0));
+    if (can && per_sm > 0) {
+      const size_t segs = (ncells + (size_t)SCAN_THREADS * SCAN_T - 1) / ((size_t)SCAN_THREADS * SCAN_T);
+      const int nblk = (int)std::min<size_t>((size_t)sms * per_sm, std::max<size_t>(1, segs / 4));
+      const float *a_gx = d_gx.as<float>();
+      size_t a_n = ncells; int a_nxy = nxy;
+      const unsigned char *a_flags = d_flags.as<unsigned char>();
+      float a_min = min_occ_raw;
+      seqsum::Fn *a_fbuf = reinterpret_cast<seqsum::Fn *>(d_fbuf.as<char>() + 16);
+      size_t a_maxseg = maxseg;
+      void *args[] = {&a_gx, &a_n, &a_nxy, &a_flags, &a_min, &a_fbuf, &a_maxseg, &d_sumP, &d_holes, &d_avg, &d_bad_grid};
+      AN_CUDA(cudaLaunchCooperativeKernel((const void *)an_chain_grid_kernel, dim3(nblk), dim3(SCAN_THREADS), args, 0, st[0]));
+      coop = true;
+    }
+  }
+  if (!coop) {
+    const int hole_blocks = (int)std::min<size_t>(148, (ncells + SCAN_THREADS * 16 - 1) / (SCAN_THREADS * 16));
+    an_chain_scan_kernel<<<2 + hole_blocks, SCAN_THREADS, 0, st[0]>>>(d_gx.as<float>(), ncells, nxy, d_flags.as<unsigned char>(),
+                                                                       min_occ_raw, d_sumP, d_holes, d_avg, d_bad);
+  }
   an_xz_kernel<<<blocks_for((size_t)d.mx * d.mz, 128), 128, 0, st[1]>>>(g, d, d_xz, d_xzp.as<float>());
   an_yz_kernel<<<blocks_for((size_t)d.my * d.mz, 128), 128, 0, st[1]>>>(g, d, d_yz, d_yzp.as<float>());
   SliceParams sp;
   sp.min_occ = min_occ; sp.d_zdf = fmx * fmy * U; sp.DeltaR = DeltaR; sp.U = U; sp.a_z = tg.a[2]; sp.delta_z = tg.delta[2];
   sp.dV = dV;
-  an_slice_kernel<<<blocks_for(d.mz, 32), 32, 0, st[2]>>>(g, d, d_c2.as<float>(), d_flags.as<unsigned char>(), sp, d_zdf.as<float>(),
-                                                           d_lzdf.as<float>(), d_prof.as<float>(), d_nocc.as<unsigned>());
-  launches += 5;
+  AN_CUDA(cudaStreamWaitEvent(st[2], gx_ready, 0));
+  an_slice_scan_kernel<<<dim3(d.mz, 3), SLICE_THREADS, 0, st[2]>>>(d_gx.as<float>(), d, d_c2.as<float>(), d_flags.as<unsigned char>(), min_occ,
+                                                                   d_sraw.as<float>(), d_nocc.as<unsigned>(), d_bad);
+  an_slice_finish_kernel<<<blocks_for(d.mz, 128), 128, 0, st[2]>>>(d_sraw.as<float>(), d.mz, sp, d_zdf.as<float>(), d_lzdf.as<float>(),
+                                                                   d_prof.as<float>());
+  launches += 6;
   if (iradNR > 0) {
     an_rz_kernel<<<blocks_for(nrz, 128), 128, 0, st[3]>>>(g, d, d_bs.as<int>(), d_bc.as<int>(), iradNR, min_occ, d_rzp.as<float>(), d_hrzp.as<float>());
-    an_rdf_kernel<<<blocks_for(iradNR, 32), 32, 0, st[3]>>>(g, d, d_bs.as<int>(), d_bc.as<int>(), iradNR, min_occ, rw_inc, d_rdf.as<float>(),
-                                                             d_hrdf.as<float>(), d_rw.as<float>());
+    AN_CUDA(cudaStreamWaitEvent(st[3], gx_ready, 0));
+    an_rdf_scan_kernel<<<iradNR, RDF_THREADS, 0, st[3]>>>(d_gx.as<float>(), d, d_bs.as<int>(), d_bxy.as<int>(), min_occ, d_rdf.as<float>(),
+                                                          d_hrdf.as<float>(), d_bad);
     launches += 2;
   }
+  // rweight[r] is a chain of cells(r)*mz constant increments: data-independent, closed form per exponent
+  std::vector<float> rweight_host((size_t)iradNR);
+  for (int r = 0; r < iradNR; r++)
+    rweight_host[(size_t)r] = seqsum::inc_chain_f32(0.0f, rw_inc, (long long)(bin_start[(size_t)r + 1] - bin_start[r]) * d.mz);
   cudaError_t kerr = cudaGetLastError();
-  for (auto &s : st) { cudaError_t e = cudaStreamSynchronize(s); if (kerr == cudaSuccess) kerr = e; cudaStreamDestroy(s); }
-  if (kerr != cudaSuccess) return gcb::fail(GCB_ERR_CUDA, "analysis kernels failed: %s", cudaGetErrorString(kerr));
+  for (auto &s : st) { cudaError_t e = cudaStreamSynchronize(s); if (kerr == cudaSuccess) kerr = e; }
+  cudaEventDestroy(gx_ready);
+  if (kerr != cudaSuccess) { for (auto &s : st) cudaStreamDestroy(s); return gcb::fail(GCB_ERR_CUDA, "analysis kernels failed: %s", cudaGetErrorString(kerr)); }
+  bool serial = false;
+  {
+    int bad = 0, bad_grid[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(bad_grid, d_bad_grid, sizeof(bad_grid), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && (bad || bad_grid[0] || bad_grid[1])) {  // negative or non-finite cells: the scans' precondition fails, chain serially
+      serial = true;
+      e = cudaMemset(d_scal.p, 0, 32);
+      an_chain_kernel<<<2, CHAIN_THREADS, 0, st[0]>>>(d_gx.as<float>(), ncells, nxy, d_flags.as<unsigned char>(), min_occ_raw, d_sumP, d_holes, d_avg);
+      an_slice_kernel<<<blocks_for(d.mz, 32), 32, 0, st[2]>>>(g, d, d_c2.as<float>(), d_flags.as<unsigned char>(), sp, d_zdf.as<float>(),
+                                                               d_lzdf.as<float>(), d_prof.as<float>(), d_nocc.as<unsigned>());
+      launches += 2;
+      if (iradNR > 0) {
+        an_rdf_kernel<<<blocks_for(iradNR, 32), 32, 0, st[3]>>>(g, d, d_bs.as<int>(), d_bc.as<int>(), iradNR, min_occ, rw_inc, d_rdf.as<float>(),
+                                                                 d_hrdf.as<float>(), d_rw.as<float>());
+        launches++;
+      }
+      if (e == cudaSuccess) e = cudaGetLastError();
+      for (auto &s : st) { cudaError_t e2 = cudaStreamSynchronize(s); if (e == cudaSuccess) e = e2; }
+    }
+    for (auto &s : st) cudaStreamDestroy(s);
+    if (e != cudaSuccess) return gcb::fail(GCB_ERR_CUDA, "analysis kernels failed: %s", cudaGetErrorString(e));
+  }
+  if (!serial && iradNR > 0)
+    AN_CUDA(cudaMemcpy(d_rw.p, rweight_host.data(), (size_t)iradNR * 4, cudaMemcpyHostToDevice));
 
+  const auto t_kern = now();
   // ---- results back; the O(iradNR*mz) normalisations (a_ri3Dc.c:717-762) on the host ----------
   int rc = GCB_OK;
   out->grid = host_copy<float>(cropped ? d_g : d_in, ncells, &rc);
@@ -535,6 +812,9 @@ int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analy
   out->average = average / ((float)ivol * U);                 // :762
   out->ivol = ivol;
   out->kernel_launches = launches;
+  if (trace)
+    fprintf(stderr, "[gcb analyse] %dx%dx%d: tables+alloc+H2D %.3f ms, kernels %.3f ms%s, D2H+host finish %.3f ms\n", d.mx, d.my, d.mz,
+            ms(t_start, t_up), ms(t_up, t_kern), serial ? " (serial chains)" : "", ms(t_kern, now()));
   return GCB_OK;
 }
 

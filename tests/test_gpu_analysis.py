@@ -114,3 +114,43 @@ def test_gridcalc_matches_reference_output():
     want_g, want_hdr, want_grid = decode_golden(os.path.join(u.GOLDEN_DIR, "gridcalc", "avg.dat"))
     assert want_g.tweight == tw
     u.assert_bits_equal(avg, want_grid, "a_gridcalc average")
+
+
+def _synthetic(kind, shape, rng):
+    n = int(np.prod(shape))
+    if kind == "ones":                      # f32 `average` saturates at 2^24
+        return np.ones(shape, np.float32)
+    if kind == "halves":                    # every addition is a tie once the sum is large enough
+        return (rng.integers(0, 7, n) * 0.5).astype(np.float32).reshape(shape)
+    if kind == "wide":
+        return np.exp(rng.uniform(-40, 12, n)).astype(np.float32).reshape(shape)
+    if kind == "sparse":
+        return np.where(rng.random(n) < 0.9, 0, rng.random(n) * 55.5).astype(np.float32).reshape(shape)
+    if kind == "negative":                  # not a density: the serial chain takes over
+        x = rng.random(n).astype(np.float32).reshape(shape)
+        x[shape[0] // 2, shape[1] // 2, shape[2] // 3] = -2.5
+        return x
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind,L,delta", [("ones", (13.0, 13.0, 13.0), 0.05),       # 260^3 = 17.6 M cells > 2^24
+                                          ("halves", (6.0, 6.0, 9.0), 0.05),
+                                          ("wide", (6.0, 5.0, 4.0), 0.05),
+                                          ("sparse", (8.0, 8.0, 13.4), 0.1),
+                                          ("negative", (3.0, 3.0, 3.0), 0.05)])
+def test_whole_grid_chains_bit_exact_on_adversarial_grids(kind, L, delta):
+    """sumP (f64) and average (f32) are evaluated by a parallel scan of the rounding recurrence
+    (csrc/seqsum.cuh); they must equal the oracle's one-by-one sums whatever the cell values do"""
+    geom = g.setup_geometry(L, delta)
+    rng = np.random.default_rng(7)
+    grid = _synthetic(kind, geom.shape, rng)
+    tg = geom.tg
+    r = g.analyse(tg, grid, unit="unity", min_occ=0.25)
+    og = u.Geom.from_buffer_copy(bytes(tg))
+    u.oracle().gco_update_b(C.byref(og))
+    arrs, scal = oracle_analysis(og, grid, "unity", 0.25)
+    u.assert_bits_equal(np.float32(r["average"]), np.float32(scal["average"]), "average")
+    u.assert_bits_equal(np.float64(r["sumP"]), np.float64(scal["sumP"]), "sumP")
+    u.assert_bits_equal(np.float64(r["sumH"]), np.float64(scal["sumH"]), "sumH")
+    for k in ARRAYS:
+        u.assert_bits_equal(r[k], arrs[k], k)
