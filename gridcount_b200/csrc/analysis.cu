@@ -30,6 +30,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -466,8 +469,41 @@ float discrete_adjust(float x_old, float x_new, float delta)
 
 struct DevBuf {
   void *p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
+  bool owned = true;                   // false: a view into an Arena
+  ~DevBuf() { if (p && owned) cudaFree(p); }
   template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// all device buffers of one gcb_analyse call in a single allocation
+struct Arena {
+  char *base = nullptr;
+  size_t total = 0;
+  std::vector<std::pair<DevBuf *, size_t>> req;
+  void want(DevBuf &b, size_t bytes)
+  {
+    req.emplace_back(&b, total);
+    total += (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+  }
+  cudaError_t commit()
+  {
+    const cudaError_t e = cudaMalloc(&base, total);
+    if (e == cudaSuccess) for (auto &r : req) { r.first->p = base + r.second; r.first->owned = false; }
+    return e;
+  }
+  ~Arena() { if (base) cudaFree(base); }
+};
+
+// the caller's grid copied into out->grid by a helper thread while the GPU works (uncropped analyses)
+struct HostGridCopy {
+  std::thread th;
+  float *dst = nullptr;
+  void start(const float *src, size_t n)
+  {
+    dst = (float *)malloc(std::max<size_t>(n, 1) * sizeof(float));
+    if (dst) th = std::thread([d = dst, src, n] { memcpy(d, src, n * sizeof(float)); });
+  }
+  float *finish() { if (th.joinable()) th.join(); float *r = dst; dst = nullptr; return r; }
+  ~HostGridCopy() { if (th.joinable()) th.join(); free(dst); }
 };
 
 #define AN_CUDA(call)                                                                            \
@@ -592,40 +628,47 @@ int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analy
   // ---- device buffers --------------------------------------------------------------------------
   DevBuf d_in, d_g, d_gx, d_c2, d_flags, d_bs, d_bc, d_bxy, d_fbuf, d_sraw, d_xyp, d_hxyp, d_xzp, d_yzp, d_zdf, d_lzdf, d_prof, d_nocc,
       d_rzp, d_hrzp, d_rdf, d_hrdf, d_rw, d_scal;
+  Arena arena;
+  HostGridCopy host_grid;
+  if (!cropped) {
+    host_grid.start(grid_zfast, ncells);
+    if (!host_grid.dst) return gcb::fail(GCB_ERR_NOMEM, "out of memory");
+  }
   const size_t nrz = (size_t)iradNR * d.mz;
-  AN_CUDA(cudaMalloc(&d_in.p, ocells * 4));
+  const size_t maxseg = (ncells + (size_t)SCAN_THREADS * SCAN_T - 1) / ((size_t)SCAN_THREADS * SCAN_T) + 1;
+  arena.want(d_in, ocells * 4);
+  if (cropped) arena.want(d_g, ncells * 4);
+  arena.want(d_gx, ncells * 4);
+  arena.want(d_c2, (size_t)nxy * 4);
+  arena.want(d_flags, (size_t)nxy);
+  arena.want(d_bs, bin_start.size() * 4);
+  arena.want(d_bc, bin_cells.size() * 4);
+  arena.want(d_bxy, bin_xy.size() * 4);
+  arena.want(d_xyp, (size_t)nxy * 4);
+  arena.want(d_hxyp, (size_t)nxy * 4);
+  arena.want(d_xzp, (size_t)d.mx * d.mz * 4);
+  arena.want(d_yzp, (size_t)d.my * d.mz * 4);
+  arena.want(d_zdf, (size_t)d.mz * 8);
+  arena.want(d_lzdf, (size_t)d.mz * 8);
+  arena.want(d_prof, (size_t)d.mz * 8);
+  arena.want(d_nocc, (size_t)d.mz * 4);
+  arena.want(d_sraw, (size_t)d.mz * 12);
+  arena.want(d_rzp, nrz * 4);
+  arena.want(d_hrzp, nrz * 4);
+  arena.want(d_rdf, ((size_t)iradNR + 1) * 8);
+  arena.want(d_hrdf, ((size_t)iradNR + 1) * 8);
+  arena.want(d_rw, ((size_t)iradNR + 1) * 4);
+  arena.want(d_scal, 32);
+  arena.want(d_fbuf, 16 + 4 * maxseg * sizeof(seqsum::Fn));
+  AN_CUDA(arena.commit());
   AN_CUDA(cudaMemcpy(d_in.p, grid_zfast, ocells * 4, cudaMemcpyHostToDevice));
   int64_t launches = 0;
   const float *g = d_in.as<float>();
   if (cropped) {
-    AN_CUDA(cudaMalloc(&d_g.p, ncells * 4));
     an_crop_kernel<<<std::min(blocks_for(ncells, 256), 148 * 16), 256>>>(d_in.as<float>(), od, d_g.as<float>(), d, base[0], base[1], base[2]);
     launches++;
     g = d_g.as<float>();
   }
-  AN_CUDA(cudaMalloc(&d_gx.p, ncells * 4));
-  AN_CUDA(cudaMalloc(&d_c2.p, (size_t)nxy * 4));
-  AN_CUDA(cudaMalloc(&d_flags.p, (size_t)nxy));
-  AN_CUDA(cudaMalloc(&d_bs.p, bin_start.size() * 4));
-  AN_CUDA(cudaMalloc(&d_bc.p, std::max<size_t>(bin_cells.size(), 1) * 4));
-  AN_CUDA(cudaMalloc(&d_bxy.p, std::max<size_t>(bin_xy.size(), 1) * 4));
-  AN_CUDA(cudaMalloc(&d_xyp.p, (size_t)nxy * 4));
-  AN_CUDA(cudaMalloc(&d_hxyp.p, (size_t)nxy * 4));
-  AN_CUDA(cudaMalloc(&d_xzp.p, (size_t)d.mx * d.mz * 4));
-  AN_CUDA(cudaMalloc(&d_yzp.p, (size_t)d.my * d.mz * 4));
-  AN_CUDA(cudaMalloc(&d_zdf.p, (size_t)d.mz * 8));
-  AN_CUDA(cudaMalloc(&d_lzdf.p, (size_t)d.mz * 8));
-  AN_CUDA(cudaMalloc(&d_prof.p, (size_t)d.mz * 8));
-  AN_CUDA(cudaMalloc(&d_nocc.p, (size_t)d.mz * 4));
-  AN_CUDA(cudaMalloc(&d_sraw.p, (size_t)d.mz * 12));
-  AN_CUDA(cudaMalloc(&d_rzp.p, std::max<size_t>(nrz, 1) * 4));
-  AN_CUDA(cudaMalloc(&d_hrzp.p, std::max<size_t>(nrz, 1) * 4));
-  AN_CUDA(cudaMalloc(&d_rdf.p, ((size_t)iradNR + 1) * 8));
-  AN_CUDA(cudaMalloc(&d_hrdf.p, ((size_t)iradNR + 1) * 8));
-  AN_CUDA(cudaMalloc(&d_rw.p, ((size_t)iradNR + 1) * 4));
-  AN_CUDA(cudaMalloc(&d_scal.p, 32));
-  const size_t maxseg = (ncells + (size_t)SCAN_THREADS * SCAN_T - 1) / ((size_t)SCAN_THREADS * SCAN_T) + 1;
-  AN_CUDA(cudaMalloc(&d_fbuf.p, 16 + 4 * maxseg * sizeof(seqsum::Fn)));
   AN_CUDA(cudaMemset(d_fbuf.p, 0, 16));
   AN_CUDA(cudaMemcpy(d_c2.p, c2tab.data(), (size_t)nxy * 4, cudaMemcpyHostToDevice));
   AN_CUDA(cudaMemcpy(d_flags.p, flags.data(), (size_t)nxy, cudaMemcpyHostToDevice));
@@ -740,7 +783,7 @@ int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analy
   const auto t_kern = now();
   // ---- results back; the O(iradNR*mz) normalisations (a_ri3Dc.c:717-762) on the host ----------
   int rc = GCB_OK;
-  out->grid = host_copy<float>(cropped ? d_g : d_in, ncells, &rc);
+  out->grid = cropped ? host_copy<float>(d_g, ncells, &rc) : host_grid.finish();
   out->xyp = host_copy<float>(d_xyp, nxy, &rc); out->hxyp = host_copy<float>(d_hxyp, nxy, &rc);
   out->xzp = host_copy<float>(d_xzp, (size_t)d.mx * d.mz, &rc); out->yzp = host_copy<float>(d_yzp, (size_t)d.my * d.mz, &rc);
   out->zdf = host_copy<float>(d_zdf, (size_t)d.mz * 2, &rc); out->lzdf = host_copy<float>(d_lzdf, (size_t)d.mz * 2, &rc);

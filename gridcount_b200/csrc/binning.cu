@@ -842,6 +842,7 @@ struct gcb_counter {
   // multi-GPU statistics scratch
   unsigned long long *d_scr = nullptr, *h_scr = nullptr;
   size_t scr_words = 0;
+  cudaStream_t comm_stream = nullptr; // rank-table exchange, beside the compute stream
 
   std::vector<int> h_gindex;          // sorted copy of the index group
   int *d_gindex = nullptr;
@@ -1200,6 +1201,7 @@ void free_counter(gcb_counter *c)
   cudaFree(c->d_scr); cudaFreeHost(c->h_scr);
   for (auto e : c->events) if (e) cudaEventDestroy(e);
   if (c->compute) cudaStreamDestroy(c->compute);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   delete c;
 }
 
@@ -1540,9 +1542,11 @@ int gcb_counter_sync(gcb_counter *c)
     cudaFree(h.d_box3);
   }
   c->devhits.clear();
-  unsigned long long diag[2];
-  GCB_CUDA(cudaMemcpy(diag, c->d_diag, sizeof(diag), cudaMemcpyDeviceToHost));
-  c->edge_overflow = diag[0];
+  if (!c->reduced) {                  // after an all-reduce the statistics are the global ones
+    unsigned long long diag[2];
+    GCB_CUDA(cudaMemcpy(diag, c->d_diag, sizeof(diag), cudaMemcpyDeviceToHost));
+    c->edge_overflow = diag[0];
+  }
   // sumP: `sumP += (double)weight` once per hit, frame by frame (g_ri3Dc.c:151,426)
   for (; c->sumP_frames < c->hits_per_frame.size(); c->sumP_frames++) {
     const uint64_t h = c->hits_per_frame[c->sumP_frames];
@@ -1771,8 +1775,13 @@ extern "C" int gcb_counter_comm_attach_(gcb_counter *c, void *comm, int rank, in
 // Exact f32 occupancy needs one weight for the whole job (checked); with
 // differing weights per rank the f32 accumulators are summed instead, which is
 // no longer the reference's sequential order (documented in DESIGN.md).
-extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c,
-                                           int (*allreduce)(const void *, void *, size_t, int, void *, void *))
+//
+// Two host synchronisations per call, only the second one behind the binning kernels:
+//   1. the ranks' {weight, uniformity, frame count} table is exchanged on a separate stream, so it
+//      does not queue behind the binning work still running on the compute stream;
+//   2. the per-frame hit counters never visit the host on their way: they are copied device to device
+//      into the gather buffer, and the grid all-reduce and the gather go out as ONE NCCL group.
+extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops *ops)
 {
   enum { U32 = 3, U64 = 5, F32 = 7, F64 = 8 };
   if (c->nranks <= 1 || !c->nccl) return gcb_counter_sync(c);
@@ -1780,10 +1789,10 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c,
   static const bool trace = getenv("GCB_TRACE") != nullptr;
   auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
   const double t_begin = now();
-  int rc = gcb_counter_sync(c);
-  if (rc) return rc;
-  const double t_sync = now();
-  // Persistent scratch (device + pinned mirror): no allocation, and only two host synchronisations, per call.
+  int rc;
+  for (auto &s : c->slots) { rc = collect_slot(c, s); if (rc) return rc; }     // host-staged batches report through pinned memory
+  if (!c->comm_stream) GCB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  // Persistent scratch (device + pinned mirror): no allocation per call.
   auto scratch = [&](size_t words) -> int {
     if (words <= c->scr_words) return GCB_OK;
     cudaFree(c->d_scr); cudaFreeHost(c->h_scr);
@@ -1795,7 +1804,8 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c,
     return GCB_OK;
   };
   // 1. all-gather (written as a sum of disjoint slots: one collective type for everything) of each rank's
-  //    {has frames, weight bits, uniform, has f32 accumulator, frame count}
+  //    {has frames, weight bits, uniform, has f32 accumulator, frame count}: host-side knowledge, so it
+  //    travels while the binning kernels are still running
   const size_t R = (size_t)c->nranks;
   rc = scratch(R * 5);
   if (rc) return rc;
@@ -1806,11 +1816,11 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c,
   c->h_scr[(size_t)c->rank * 5 + 2] = c->uniform ? 1ull : 0ull;
   c->h_scr[(size_t)c->rank * 5 + 3] = (c->d_acc != nullptr) ? 1ull : 0ull;
   c->h_scr[(size_t)c->rank * 5 + 4] = c->hits_per_frame.size();
-  GCB_CUDA(cudaMemcpyAsync(c->d_scr, c->h_scr, sizeof(unsigned long long) * R * 5, cudaMemcpyHostToDevice, c->compute));
-  rc = allreduce(c->d_scr, c->d_scr, R * 5, U64, c->nccl, c->compute);
+  GCB_CUDA(cudaMemcpyAsync(c->d_scr, c->h_scr, sizeof(unsigned long long) * R * 5, cudaMemcpyHostToDevice, c->comm_stream));
+  rc = ops->allreduce(c->d_scr, c->d_scr, R * 5, U64, c->nccl, c->comm_stream);
   if (rc) return rc;
-  GCB_CUDA(cudaMemcpyAsync(c->h_scr, c->d_scr, sizeof(unsigned long long) * R * 5, cudaMemcpyDeviceToHost, c->compute));
-  GCB_CUDA(cudaStreamSynchronize(c->compute));
+  GCB_CUDA(cudaMemcpyAsync(c->h_scr, c->d_scr, sizeof(unsigned long long) * R * 5, cudaMemcpyDeviceToHost, c->comm_stream));
+  GCB_CUDA(cudaStreamSynchronize(c->comm_stream));
   bool global_uniform = true, any_acc = false, have_w = false;
   uint32_t w0 = 0;
   size_t total_frames = 0, my_off = 0;
@@ -1825,29 +1835,12 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c,
     else if (w0 != (uint32_t)o[1]) global_uniform = false;
   }
   const double t_gather = now();
-  // 2. the grids
-  if (global_uniform && !any_acc) {
-    // the common case: one integer grid per rank, one weight: sum the counts
-    rc = allreduce(c->d_runcnt, c->d_runcnt, c->ncells, U32, c->nccl, c->compute);
-    if (rc) return rc;
-    if (have_w) { memcpy(&c->w_cur, &w0, 4); c->w_first = c->w_cur; c->have_run = true; c->any = true; }
-  } else {
-    rc = fold_pending(c);
-    if (rc) return rc;
-    rc = ensure_acc(c);
-    if (rc) return rc;
-    rc = allreduce(c->d_acc, c->d_acc, c->ncells, F32, c->nccl, c->compute);
-    if (rc) return rc;
-    rc = allreduce(c->d_total, c->d_total, c->ncells, U32, c->nccl, c->compute);
-    if (rc) return rc;
-    c->uniform = false;
-  }
-  double t_grid = 0;
-  if (trace) { cudaStreamSynchronize(c->compute); t_grid = now(); }
-  // 3. Statistics.  Ranks hold contiguous frame shards in rank order, so gathering the per-frame hit counts and
-  //    weights lets every rank redo the reference's frame-ordered `sumP += (double)weight` chain
-  //    (g_ri3Dc.c:151,426) over ALL frames: bit-identical to a single-GPU run.
-  const size_t nfr_words = 2 * total_frames + 1;                       // [hits | weight bits | edge overflow]
+  // 2. Statistics buffer [hits | weight bits | edge overflow] over ALL frames.  Ranks hold contiguous frame
+  //    shards in rank order, so gathering the per-frame hit counts and weights lets every rank redo the
+  //    reference's frame-ordered `sumP += (double)weight` chain (g_ri3Dc.c:151,426): bit-identical to a
+  //    single-GPU run.  Host-known parts go up from the pinned mirror; counters of device-resident batches
+  //    and the overflow counter are copied in on the device, behind the kernels that produce them.
+  const size_t nfr_words = 2 * total_frames + 1;
   rc = scratch(nfr_words);
   if (rc) return rc;
   unsigned long long *fr = c->h_scr;
@@ -1857,12 +1850,47 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c,
     uint32_t wbits; memcpy(&wbits, &c->weight_per_frame[f], 4);
     fr[total_frames + my_off + f] = wbits;
   }
-  fr[2 * total_frames] = c->edge_overflow;
+  for (auto &h : c->devhits) for (long f = 0; f < h.n; f++) fr[my_off + h.frame0 + f] = 0;
   GCB_CUDA(cudaMemcpyAsync(c->d_scr, fr, sizeof(unsigned long long) * nfr_words, cudaMemcpyHostToDevice, c->compute));
-  rc = allreduce(c->d_scr, c->d_scr, nfr_words, U64, c->nccl, c->compute);
+  for (auto &h : c->devhits)
+    GCB_CUDA(cudaMemcpyAsync(c->d_scr + my_off + h.frame0, h.d, sizeof(unsigned long long) * h.n, cudaMemcpyDeviceToDevice, c->compute));
+  GCB_CUDA(cudaMemcpyAsync(c->d_scr + 2 * total_frames, c->d_diag, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->compute));
+  // 3. the grids and the statistics, one NCCL group
+  if (!(global_uniform && !any_acc)) {
+    rc = fold_pending(c);
+    if (rc) return rc;
+    rc = ensure_acc(c);
+    if (rc) return rc;
+  }
+  rc = ops->group_start();
   if (rc) return rc;
+  if (global_uniform && !any_acc) {
+    // the common case: one integer grid per rank, one weight: sum the counts
+    rc = ops->allreduce(c->d_runcnt, c->d_runcnt, c->ncells, U32, c->nccl, c->compute);
+  } else {
+    rc = ops->allreduce(c->d_acc, c->d_acc, c->ncells, F32, c->nccl, c->compute);
+    if (!rc) rc = ops->allreduce(c->d_total, c->d_total, c->ncells, U32, c->nccl, c->compute);
+  }
+  if (!rc) rc = ops->allreduce(c->d_scr, c->d_scr, nfr_words, U64, c->nccl, c->compute);
+  const int rc_end = ops->group_end();
+  if (rc) return rc;
+  if (rc_end) return rc_end;
+  if (global_uniform && !any_acc) {
+    if (have_w) { memcpy(&c->w_cur, &w0, 4); c->w_first = c->w_cur; c->have_run = true; c->any = true; }
+  } else {
+    c->uniform = false;
+  }
   GCB_CUDA(cudaMemcpyAsync(fr, c->d_scr, sizeof(unsigned long long) * nfr_words, cudaMemcpyDeviceToHost, c->compute));
   GCB_CUDA(cudaStreamSynchronize(c->compute));
+  const double t_grid = now();
+  // local bookkeeping that gcb_counter_sync would have done
+  for (auto &h : c->devhits) {
+    for (long f = 0; f < h.n; f++) c->hits_per_frame[h.frame0 + f] = fr[my_off + h.frame0 + f];
+    c->hit_pool.emplace_back(h.cap, h.d);
+    cudaFree(h.d_box3);
+  }
+  c->devhits.clear();
+  c->sumP_frames = c->hits_per_frame.size();
   const double t_frames = now();
   // consecutive frames of equal weight are one run of identical additions: one closed-form call per run
   double sp = 0;
@@ -1883,7 +1911,7 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c,
   c->global_frames = total_frames; c->hits_total = hits; c->edge_overflow = fr[2 * total_frames]; c->sumP = sp;
   c->reduced = true;
   if (trace && c->rank == 0)
-    fprintf(stderr, "[gcb allreduce] wait for binning %.3f ms, rank table %.3f ms, grid %.3f ms, frame gather %.3f ms, sumP chain %.3f ms\n",
-            t_sync - t_begin, t_gather - t_sync, t_grid - t_gather, t_frames - t_grid, now() - t_frames);
+    fprintf(stderr, "[gcb allreduce] rank table (beside the binning) %.3f ms, binning + grid/statistics group %.3f ms, sumP chain %.3f ms\n",
+            t_gather - t_begin, t_grid - t_gather, now() - t_frames);
   return GCB_OK;
 }

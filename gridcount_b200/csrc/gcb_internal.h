@@ -20,6 +20,13 @@ double seq_add_f64(double v, double w, uint64_t n);
 
 }  // namespace gcb
 
+// the collective operations gcb_counter_allreduce needs; bound to NCCL in nccl_reduce.cpp
+struct gcb_reduce_ops {
+  int (*allreduce)(const void *send, void *recv, size_t count, int nccl_dtype, void *comm, void *stream);
+  int (*group_start)(void);
+  int (*group_end)(void);
+};
+
 #define GCB_CUDA(call)                                                                          \
   do {                                                                                          \
     cudaError_t e_ = (call);                                                                    \

@@ -20,6 +20,8 @@ struct Nccl {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 Nccl g_nccl;
@@ -37,8 +39,10 @@ int load_nccl()
   g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(g_nccl.lib, "ncclGroupStart");
+  g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(g_nccl.lib, "ncclGroupEnd");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.GroupStart || !g_nccl.GroupEnd)
     return gcb::fail(GCB_ERR_NCCL, "libnccl.so.2 lacks the expected symbols");
   return GCB_OK;
 }
@@ -53,14 +57,16 @@ int load_nccl()
 
 // implemented in binning.cu (they need the counter's internals)
 extern "C" int gcb_counter_comm_attach_(gcb_counter *c, void *comm, int rank, int nranks);
-extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c,
-                                           int (*allreduce)(const void *, void *, size_t, int, void *, void *));
+extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops *ops);
 
 static int do_allreduce(const void *send, void *recv, size_t count, int dtype, void *comm, void *stream)
 {
   GCB_NCCL(g_nccl.AllReduce(send, recv, count, (ncclDataType_t)dtype, ncclSum, (ncclComm_t)comm, (cudaStream_t)stream));
   return GCB_OK;
 }
+
+static int do_group_start() { GCB_NCCL(g_nccl.GroupStart()); return GCB_OK; }
+static int do_group_end() { GCB_NCCL(g_nccl.GroupEnd()); return GCB_OK; }
 
 extern "C" {
 
@@ -91,7 +97,8 @@ int gcb_counter_comm_init(gcb_counter *c, const char id[128], int rank, int nran
 int gcb_counter_allreduce(gcb_counter *c)
 {
   if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
-  return gcb_counter_allreduce_impl_(c, do_allreduce);
+  static const gcb_reduce_ops ops = {do_allreduce, do_group_start, do_group_end};
+  return gcb_counter_allreduce_impl_(c, &ops);
 }
 
 }  // extern "C"

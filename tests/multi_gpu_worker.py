@@ -38,6 +38,7 @@ def main():
     ctr.allreduce()
     counts = ctr.counts()
     st = ctr.stats()
+    local_hits = ctr.hits_per_frame()           # this rank's shard; filled from the gathered counters
     tg, dens, _ = ctr.density(0.1 * F * world)
     ok = True
     if rank == 0:
@@ -55,7 +56,8 @@ def main():
         u.oracle().gco_normalise(C.byref(og), u.fptr(occ), 0.1 * F * world)
         assert 0 < int(hits.sum()) < F * world * len(gindex), "the breathing box should push some atoms out of the grid"
         ok = (np.array_equal(counts, want) and st.frames == F * world and st.hits == int(hits.sum())
-              and np.array_equal(dens.view(np.uint32), occ.view(np.uint32)) and st.sumP == sp.value)
+              and np.array_equal(dens.view(np.uint32), occ.view(np.uint32)) and st.sumP == sp.value
+              and np.array_equal(local_hits, hits[:F]))
         print("MULTI_GPU_PARITY", "OK" if ok else "FAIL", "world", world, "hits", st.hits, flush=True)
     ctr.close(); dev.free()
     dist.barrier()
