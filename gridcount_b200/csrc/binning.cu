@@ -843,6 +843,9 @@ struct gcb_counter {
   unsigned long long *d_scr = nullptr, *h_scr = nullptr;
   size_t scr_words = 0;
   cudaStream_t comm_stream = nullptr; // rank-table exchange, beside the compute stream
+  cudaEvent_t reduce_done = nullptr;  // behind the D2H of the gathered statistics
+  bool reduce_pending = false;        // host half of the last all-reduce still to do (finish_reduce)
+  size_t pend_total = 0, pend_off = 0, pend_ndev = 0, pend_nlocal = 0;
 
   std::vector<int> h_gindex;          // sorted copy of the index group
   int *d_gindex = nullptr;
@@ -1202,6 +1205,7 @@ void free_counter(gcb_counter *c)
   for (auto e : c->events) if (e) cudaEventDestroy(e);
   if (c->compute) cudaStreamDestroy(c->compute);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  if (c->reduce_done) cudaEventDestroy(c->reduce_done);
   delete c;
 }
 
@@ -1335,6 +1339,7 @@ int gcb_counter_reset(gcb_counter *c)
   // queued, and results that were never collected are simply dropped (their counter buffers go back to the
   // pool; later launches that reuse them are ordered on the same stream).
   for (auto &s : c->slots) s.pending = 0;
+  c->reduce_pending = false;          // statistics of a reduce nobody collected are dropped with the rest
   for (auto &h : c->devhits) {
     c->hit_pool.emplace_back(h.cap, h.d);
     if (h.d_box3) { GCB_CUDA(cudaStreamSynchronize(c->compute)); cudaFree(h.d_box3); }
@@ -1528,10 +1533,13 @@ int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gc
   return GCB_OK;
 }
 
+static int finish_reduce(gcb_counter *c);
+
 int gcb_counter_sync(gcb_counter *c)
 {
   if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
   GCB_CUDA(cudaSetDevice(c->opts.device));
+  { int rc = finish_reduce(c); if (rc) return rc; }
   for (auto &s : c->slots) { int rc = collect_slot(c, s); if (rc) return rc; }
   GCB_CUDA(cudaStreamSynchronize(c->compute));
   for (auto &h : c->devhits) {
@@ -1789,7 +1797,9 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops 
   static const bool trace = getenv("GCB_TRACE") != nullptr;
   auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
   const double t_begin = now();
-  int rc;
+  int rc = finish_reduce(c);                  // a previous reduce whose statistics nobody asked for
+  if (rc) return rc;
+  if (c->reduce_done) GCB_CUDA(cudaEventSynchronize(c->reduce_done));          // (or that a reset dropped): its D2H owns the pinned scratch
   for (auto &s : c->slots) { rc = collect_slot(c, s); if (rc) return rc; }     // host-staged batches report through pinned memory
   if (!c->comm_stream) GCB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
   // Persistent scratch (device + pinned mirror): no allocation per call.
@@ -1881,17 +1891,38 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops 
     c->uniform = false;
   }
   GCB_CUDA(cudaMemcpyAsync(fr, c->d_scr, sizeof(unsigned long long) * nfr_words, cudaMemcpyDeviceToHost, c->compute));
-  GCB_CUDA(cudaStreamSynchronize(c->compute));
-  const double t_grid = now();
-  // local bookkeeping that gcb_counter_sync would have done
-  for (auto &h : c->devhits) {
+  // The grids are reduced in stream order; the host half (per-frame counters -> sumP chain) is finished when
+  // somebody asks for it (finish_reduce), so the caller can queue the density and the next job meanwhile.
+  if (!c->reduce_done) GCB_CUDA(cudaEventCreateWithFlags(&c->reduce_done, cudaEventDisableTiming));
+  GCB_CUDA(cudaEventRecord(c->reduce_done, c->compute));
+  c->reduce_pending = true; c->pend_total = total_frames; c->pend_off = my_off; c->pend_ndev = c->devhits.size();
+  c->pend_nlocal = c->hits_per_frame.size();
+  c->global_frames = total_frames;
+  c->reduced = true;
+  if (trace && c->rank == 0)
+    fprintf(stderr, "[gcb allreduce] rank table (beside the binning) %.3f ms, queueing the grid/statistics group %.3f ms\n",
+            t_gather - t_begin, now() - t_gather);
+  return GCB_OK;
+}
+
+// host half of gcb_counter_allreduce: waits for the gathered statistics and redoes the frame-ordered chain
+static int finish_reduce(gcb_counter *c)
+{
+  if (!c->reduce_pending) return GCB_OK;
+  GCB_CUDA(cudaEventSynchronize(c->reduce_done));
+  c->reduce_pending = false;
+  const size_t total_frames = c->pend_total, my_off = c->pend_off;
+  const unsigned long long *fr = c->h_scr;
+  // local bookkeeping that gcb_counter_sync would have done, for the batches the reduce covered
+  const size_t ndev = std::min(c->pend_ndev, c->devhits.size());
+  for (size_t i = 0; i < ndev; i++) {
+    DevHits &h = c->devhits[i];
     for (long f = 0; f < h.n; f++) c->hits_per_frame[h.frame0 + f] = fr[my_off + h.frame0 + f];
     c->hit_pool.emplace_back(h.cap, h.d);
     cudaFree(h.d_box3);
   }
-  c->devhits.clear();
-  c->sumP_frames = c->hits_per_frame.size();
-  const double t_frames = now();
+  c->devhits.erase(c->devhits.begin(), c->devhits.begin() + (long)ndev);
+  c->sumP_frames = c->pend_nlocal;            // frames added after the reduce continue the chain from the global sum
   // consecutive frames of equal weight are one run of identical additions: one closed-form call per run
   double sp = 0;
   unsigned long long hits = 0, run_hits = 0;
@@ -1908,10 +1939,6 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops 
     hits += fr[f];
   }
   if (run_hits) { float wf; memcpy(&wf, &run_w, 4); sp = gcb::seq_add_f64(sp, (double)wf, run_hits); }
-  c->global_frames = total_frames; c->hits_total = hits; c->edge_overflow = fr[2 * total_frames]; c->sumP = sp;
-  c->reduced = true;
-  if (trace && c->rank == 0)
-    fprintf(stderr, "[gcb allreduce] rank table (beside the binning) %.3f ms, binning + grid/statistics group %.3f ms, sumP chain %.3f ms\n",
-            t_gather - t_begin, t_grid - t_gather, now() - t_frames);
+  c->hits_total = hits; c->edge_overflow = fr[2 * total_frames]; c->sumP = sp;
   return GCB_OK;
 }
