@@ -238,6 +238,35 @@ def xtc_section(g, ctr, dev, wl, geom, gindex):
     return res
 
 
+def k3_section(g, ctr, T_tot):
+    """a_ri3Dc's reductions (K3, gcb_analyse) over the job's density: wall time through the C ABI from a HOST grid
+    (H2D of the grid, all kernels, D2H of every output), with the oracle's single-thread time beside it.
+    Reported on its own line, not folded into the metric."""
+    import gcutil as u
+    tg, dens, _ = ctr.density(T_tot)
+    g.analyse(tg, dens, unit="SPC")                       # warm-up
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        r = g.analyse(tg, dens, unit="SPC")
+        ts.append(time.perf_counter() - t0)
+    og = u.Geom.from_buffer_copy(bytes(tg))
+    u.oracle().gco_update_b(C.byref(og))
+    an = u.Analysis()
+    an.unit = u.UNITS["SPC"]; an.rad_ba_step = 1
+    t0 = time.perf_counter()
+    u.oracle().gco_analyse(C.byref(og), u.fptr(dens), C.byref(an))
+    cpu_s = time.perf_counter() - t0
+    arrs = u.analysis_arrays(an, og)
+    same = all(np.array_equal(arrs[k].view(np.uint32), r[k].view(np.uint32)) for k in ("rzp", "zdf", "rdf", "xyp"))
+    same = same and np.float32(an.average).view(np.uint32) == np.float32(r["average"]).view(np.uint32) and an.sumP == r["sumP"]
+    u.oracle().gco_analysis_free(C.byref(an))
+    cells = int(np.prod(dens.shape))
+    return {"grid": list(dens.shape), "ms": float(np.median(ts)) * 1e3, "cells_per_s": cells / float(np.median(ts)),
+            "kernel_launches": int(r["kernel_launches"]), "oracle_ms_1_thread": cpu_s * 1e3, "bit_equal_to_oracle": bool(same),
+            "note": "host grid in, all profiles out; every sum is the reference's sequential f32/f64 chain, evaluated in parallel"}
+
+
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
@@ -373,6 +402,14 @@ def run_gpu_arm(args, rank, local_rank, world):
            "path": "gcb_counter_add_frames(pinned host x[F][natoms][3]) -> gcb_counter_density(host grid)"}
     pin.free()
 
+    # ---- a_ri3Dc's reductions over the job's density (K3), on its own line -----------------------
+    k3 = None
+    if rank == 0 and world == 1:
+        try:
+            k3 = k3_section(g, ctr, T_tot)
+        except Exception as e:
+            k3 = {"error": str(e)[:200]}
+
     # ---- XTC decode, timed separately (north star): host decoder vs GPU decoder on the same frames ----
     xtc = None
     if rank == 0 and world == 1:
@@ -409,7 +446,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                            "parallelism": "frame-sharded x%d, one NCCL u32 all-reduce per job" % world,
                            "step": "reset + K1 bin 10000 frames + (all-reduce) + K2 density"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu, "xtc": xtc}
+                "cpu_baseline": cpu, "a_ri3Dc": k3, "xtc": xtc}
         print(json.dumps(line), flush=True)
     ctr.close()
     dev.free()

@@ -126,6 +126,10 @@ SIGNATURES = {
     "gcb_xdr_encode": (C.c_int, [C.POINTER(TGrid), c_float_p, c_float_p, C.c_char_p, c_u8_p, C.c_size_t,
                                  C.POINTER(C.c_size_t)]),
     "gcb_grid_write": (C.c_int, [C.c_char_p, C.POINTER(TGrid), c_float_p, c_float_p, C.c_char_p]),
+    "gcb_counter_xdr": (C.c_int, [C.c_void_p, C.c_double, C.c_char_p, c_u8_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                  C.POINTER(TGrid)]),
+    "gcb_counter_grid_write": (C.c_int, [C.c_void_p, C.c_double, C.c_char_p, C.c_char_p, C.POINTER(TGrid)]),
+    "gcb_counter_plt": (C.c_int, [C.c_void_p, C.c_double, C.c_float, c_u8_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "gcb_grid_read": (C.c_int, [C.c_char_p, C.POINTER(TGrid), C.c_char_p, C.POINTER(c_float_p)]),
     "gcb_plt_write": (C.c_int, [C.c_char_p, C.POINTER(TGrid), c_float_p, C.c_float]),
     "gcb_ascii_write": (C.c_int, [C.c_char_p, C.POINTER(TGrid), c_float_p, C.c_float]),

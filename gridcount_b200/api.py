@@ -340,6 +340,28 @@ class GridCounter:
         check(lib.gcb_counter_density(self.h, T_tot, _fptr(gz), _fptr(gx), C.byref(tg)), "gcb_counter_density")
         return tg, gz, gx
 
+    def xdr(self, T_tot, header=b""):
+        """the finished density as the grid file image, reordered and byte-swapped on the device -> (tgrid, bytes)"""
+        tg = K.TGrid.from_buffer_copy(self.geom.tg)
+        n = lib.gcb_xdr_size(C.byref(tg), header)
+        buf = np.zeros(n, np.uint8)
+        wrote = C.c_size_t(0)
+        check(lib.gcb_counter_xdr(self.h, T_tot, header, buf.ctypes.data_as(K.c_u8_p), n, C.byref(wrote), C.byref(tg)),
+              "gcb_counter_xdr")
+        return tg, buf[:wrote.value].tobytes()
+
+    def grid_write(self, T_tot, path, header=b""):
+        tg = K.TGrid()
+        check(lib.gcb_counter_grid_write(self.h, T_tot, str(path).encode(), header, C.byref(tg)), "gcb_counter_grid_write")
+        return tg
+
+    def plt(self, T_tot, unit=1.0):
+        n = 44 + 4 * self.geom.cells
+        buf = np.zeros(n, np.uint8)
+        wrote = C.c_size_t(0)
+        check(lib.gcb_counter_plt(self.h, T_tot, unit, buf.ctypes.data_as(K.c_u8_p), n, C.byref(wrote)), "gcb_counter_plt")
+        return buf[:wrote.value].tobytes()
+
     def event_record(self, i):
         check(lib.gcb_counter_event_record(self.h, i), "gcb_counter_event_record")
 

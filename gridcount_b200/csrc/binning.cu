@@ -716,6 +716,29 @@ __global__ void zfast_to_xfast_kernel(const float *__restrict__ in, float *__res
   }
 }
 
+// The same reordering with the file's encoding fused in: EMIT 1 = XDR big-endian floats (grid3_serialise +
+// xdr_float, xdr_grid.c:113-126), EMIT 2 = gOpenMol plt cells `norm * grid` in host byte order (plt.c:69-75).
+template <int EMIT>
+__global__ void zfast_to_file_kernel(const float *__restrict__ in, uint32_t *__restrict__ out, int mx, int my, int mz, float scale)
+{
+  __shared__ float tile[32][33];
+  const int j = blockIdx.z;
+  const int i0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r, k = k0 + threadIdx.x;
+    if (i < mx && k < mz) tile[r][threadIdx.x] = in[((size_t)i * my + j) * mz + k];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r, i = i0 + threadIdx.x;
+    if (i < mx && k < mz) {
+      const float v = tile[threadIdx.x][r];
+      out[((size_t)k * my + j) * mx + i] = EMIT == 1 ? __byte_perm(__float_as_uint(v), 0u, 0x0123)
+                                                     : __float_as_uint(__fmul_rn(scale, v));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K4: counter-based synthetic frames; bit-identical to oracle/gc_oracle.c
 // ---------------------------------------------------------------------------
@@ -1682,6 +1705,86 @@ int gcb_counter_density(gcb_counter *c, double T_tot, float *grid_zfast, float *
   }
   GCB_CUDA(cudaStreamSynchronize(c->compute));
   if (tg_out) { *tg_out = c->tg; tg_out->tweight = (float)T_tot; }   // g_ri3Dc.c:460
+  return GCB_OK;
+}
+
+// The finished density as file images produced on the device.  The prologues are a few dozen bytes and
+// come from grid_io.cpp; the cell payload is reordered and encoded by zfast_to_file_kernel and copied
+// straight behind the prologue in the caller's buffer.
+extern "C" size_t gcb_xdr_prologue_(const gcb_tgrid *tg, const char *header, uint8_t *out);
+extern "C" size_t gcb_plt_prologue_(const gcb_tgrid *tg, uint8_t *out);
+
+static int emit_file_payload(gcb_counter *c, double T_tot, int emit, float scale, uint8_t *payload_out)
+{
+  const float dV = (float)gcb_delta_v(&c->tg);            // `real dV = DeltaV(&tgrid)` (g_ri3Dc.c:453)
+  int rc = density_to_device(c, (double)dV * T_tot);
+  if (rc) return rc;
+  if (!c->d_out2) GCB_CUDA(cudaMalloc(&c->d_out2, c->ncells * sizeof(float)));
+  dim3 block(32, 8), grid((c->tg.mx[2] + 31) / 32, (c->tg.mx[0] + 31) / 32, c->tg.mx[1]);
+  if (emit == 1)
+    zfast_to_file_kernel<1><<<grid, block, 0, c->compute>>>(c->d_out, (uint32_t *)c->d_out2, c->tg.mx[0], c->tg.mx[1], c->tg.mx[2], 1.0f);
+  else
+    zfast_to_file_kernel<2><<<grid, block, 0, c->compute>>>(c->d_out, (uint32_t *)c->d_out2, c->tg.mx[0], c->tg.mx[1], c->tg.mx[2], scale);
+  c->launches++;
+  GCB_CUDA(cudaGetLastError());
+  GCB_CUDA(cudaMemcpyAsync(payload_out, c->d_out2, c->ncells * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
+  GCB_CUDA(cudaStreamSynchronize(c->compute));
+  return GCB_OK;
+}
+
+int gcb_counter_xdr(gcb_counter *c, double T_tot, const char *header, uint8_t *out, size_t cap, size_t *written,
+                    gcb_tgrid *tg_out)
+{
+  if (!c || !out) return gcb::fail(GCB_ERR_ARG, "gcb_counter_xdr: null argument");
+  if (!header) header = "";
+  if (strlen(header) > GCB_HEADER_MAX) return gcb::fail(GCB_ERR_ARG, "header longer than %d bytes", GCB_HEADER_MAX);
+  if (c->ncells > GCB_NGRID_MAX) return gcb::fail(GCB_ERR_RANGE, "grid has %zu cells; the format allows %u", c->ncells, GCB_NGRID_MAX);
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  gcb_tgrid tg = c->tg;
+  tg.tweight = (float)T_tot;                               // g_ri3Dc.c:460
+  const size_t need = gcb_xdr_size(&tg, header);
+  if (cap < need) return gcb::fail(GCB_ERR_ARG, "gcb_counter_xdr: buffer of %zu bytes, need %zu", cap, need);
+  const size_t pro = gcb_xdr_prologue_(&tg, header, out);
+  int rc = emit_file_payload(c, T_tot, 1, 1.0f, out + pro);
+  if (rc) return rc;
+  if (written) *written = need;
+  if (tg_out) *tg_out = tg;
+  return GCB_OK;
+}
+
+int gcb_counter_grid_write(gcb_counter *c, double T_tot, const char *path, const char *header, gcb_tgrid *tg_out)
+{
+  if (!c || !path) return gcb::fail(GCB_ERR_ARG, "gcb_counter_grid_write: null argument");
+  gcb_tgrid tg = c->tg;
+  const size_t need = gcb_xdr_size(&tg, header ? header : "");
+  uint8_t *buf = nullptr;
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  GCB_CUDA(cudaHostAlloc((void **)&buf, need, cudaHostAllocDefault));     // pinned: the payload arrives by DMA
+  size_t n = 0;
+  int rc = gcb_counter_xdr(c, T_tot, header, buf, need, &n, tg_out);
+  if (!rc) {
+    FILE *fp = fopen(path, "wb");
+    if (!fp) rc = gcb::fail(GCB_ERR_IO, "cannot open %s for writing", path);
+    else {
+      const bool ok = fwrite(buf, 1, n, fp) == n;
+      if (fclose(fp) != 0 || !ok) rc = gcb::fail(GCB_ERR_IO, "short write to %s", path);
+    }
+  }
+  cudaFreeHost(buf);
+  return rc;
+}
+
+int gcb_counter_plt(gcb_counter *c, double T_tot, float unit, uint8_t *out, size_t cap, size_t *written)
+{
+  if (!c || !out) return gcb::fail(GCB_ERR_ARG, "gcb_counter_plt: null argument");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  const size_t need = 44 + 4 * c->ncells;
+  if (cap < need) return gcb::fail(GCB_ERR_ARG, "gcb_counter_plt: buffer of %zu bytes, need %zu", cap, need);
+  const size_t pro = gcb_plt_prologue_(&c->tg, out);
+  const float scale = (float)(1. / (double)unit);          // `real norm = 1./unit` (plt.c:48)
+  int rc = emit_file_payload(c, T_tot, 2, scale, out + pro);
+  if (rc) return rc;
+  if (written) *written = need;
   return GCB_OK;
 }
 

@@ -62,6 +62,36 @@ size_t gcb_xdr_size(const gcb_tgrid *tg, const char *header)
   return 4 + 4 + ((len + 3) & ~(size_t)3) + 4 + 4 + 4 + 3 * 4 + 3 * 4 + 3 * 4 + 4 + 4 * gcb::cells(*tg);
 }
 
+// everything of the xdr_grid_v2 record (xdr_grid.c:93-106) in front of the cells; returns its length
+size_t gcb_xdr_prologue_(const gcb_tgrid *tg, const char *header, uint8_t *out)
+{
+  Writer w{out};
+  w.u32(GCB_GRID_FF_VERSION);
+  w.str(header, strlen(header));
+  w.u32(0);                       // egtyREGULAR
+  w.f32(tg->tweight);
+  w.u32(3);                       // dim
+  for (int d = 0; d < 3; d++) w.u32((uint32_t)tg->mx[d]);
+  for (int d = 0; d < 3; d++) w.f32(tg->delta[d]);
+  for (int d = 0; d < 3; d++) w.f32(tg->a[d]);
+  w.u32((uint32_t)gcb::cells(*tg));
+  return (size_t)(w.p - out);
+}
+
+// the 44 bytes in front of a plt file's cells (plt.c:52-67), host byte order
+size_t gcb_plt_prologue_(const gcb_tgrid *tg, uint8_t *out)
+{
+  const int32_t head[5] = {3, 42, tg->mx[2], tg->mx[1], tg->mx[0]};   // rank, surface type, Z/Y/X dims
+  float corners[6];
+  for (int n = 0, d = 2; d >= 0; d--) {                              // Angstrom, Z then Y then X
+    corners[n++] = (float)(10. * (double)tg->a[d]);
+    corners[n++] = (float)(10. * (double)tg->b[d]);
+  }
+  memcpy(out, head, 20);
+  memcpy(out + 20, corners, 24);
+  return 44;
+}
+
 int gcb_xdr_encode(const gcb_tgrid *tg, const float *grid_zfast, const float *grid_xfast, const char *header,
                    uint8_t *out, size_t cap, size_t *written)
 {
@@ -72,17 +102,7 @@ int gcb_xdr_encode(const gcb_tgrid *tg, const float *grid_zfast, const float *gr
   if (n > GCB_NGRID_MAX) return gcb::fail(GCB_ERR_RANGE, "grid has %zu cells; the format allows %u", n, GCB_NGRID_MAX);
   const size_t need = gcb_xdr_size(tg, header);
   if (cap < need) return gcb::fail(GCB_ERR_ARG, "gcb_xdr_encode: buffer of %zu bytes, need %zu", cap, need);
-  Writer w{out};
-  // record of xdr_grid_v2 (xdr_grid.c:93-106)
-  w.u32(GCB_GRID_FF_VERSION);
-  w.str(header, len);
-  w.u32(0);                       // egtyREGULAR
-  w.f32(tg->tweight);
-  w.u32(3);                       // dim
-  for (int d = 0; d < 3; d++) w.u32((uint32_t)tg->mx[d]);
-  for (int d = 0; d < 3; d++) w.f32(tg->delta[d]);
-  for (int d = 0; d < 3; d++) w.f32(tg->a[d]);
-  w.u32((uint32_t)n);
+  Writer w{out + gcb_xdr_prologue_(tg, header, out)};
   if (grid_xfast) {
     for (size_t c = 0; c < n; c++) { uint32_t v = bswap(f2u(grid_xfast[c])); memcpy(w.p + 4 * c, &v, 4); }
   } else {
@@ -175,13 +195,9 @@ int gcb_plt_write(const char *path, const gcb_tgrid *tg, const float *grid, floa
   if (!fp) return gcb::fail(GCB_ERR_IO, "cannot open %s for writing", path);
   const int mx = tg->mx[0], my = tg->mx[1], mz = tg->mx[2];
   const float scale = (float)(1. / (double)unit);                 // `real norm = 1./unit` (plt.c:48)
-  int32_t head[5] = {3, 42, mz, my, mx};                          // rank, surface type, Z/Y/X dims (plt.c:52-60)
-  float corners[6];
-  for (int n = 0, d = 2; d >= 0; d--) {                           // Angstrom, Z then Y then X (plt.c:64-67)
-    corners[n++] = (float)(10. * (double)tg->a[d]);
-    corners[n++] = (float)(10. * (double)tg->b[d]);
-  }
-  bool ok = fwrite(head, 4, 5, fp) == 5 && fwrite(corners, 4, 6, fp) == 6;
+  uint8_t pro[44];
+  gcb_plt_prologue_(tg, pro);                                     // plt.c:52-67
+  bool ok = fwrite(pro, 1, sizeof(pro), fp) == sizeof(pro);
   std::vector<float> row((size_t)mx);
   for (int k = 0; k < mz && ok; k++)
     for (int j = 0; j < my && ok; j++) {

@@ -194,17 +194,16 @@ int main(int argc, char **argv)
   if (st.edge_overflow) gh_msg("WARNING: %lu atoms on the upper grid edge were dropped\n", (unsigned long)st.edge_overflow);
 
   /* ---- normalisation (g_ri3Dc.c:451-460), header (:462-473), file (:476-478) ---- */
-  const size_t cells = (size_t)tg.mx[0] * tg.mx[1] * tg.mx[2];
-  float *xfast = (float *)malloc(sizeof(float) * cells);
-  gcb_tgrid tgout;
-  CHECK(gcb_counter_density(ctr, T_tot, NULL, xfast, &tgout));
+  /* the file image is produced on the device (K2 + grid3_serialise's reordering + XDR byte order) */
+  gcb_tgrid tgout = tg;
+  tgout.tweight = (float)T_tot;
   char header[GCB_HEADER_MAX];
   CHECK(gcb_header(header, subtitle, T_tot, grp->name, &cavity, &tgout, st.sumP, trxname, bdtWeight));
   gh_msg("Writing 3D density grid with header\n%s\n", header);
-  if (gcb_grid_write(gh_fn(fnm, NFILE, "-grid"), &tgout, NULL, xfast, header) != GCB_OK)
+  if (gcb_counter_grid_write(ctr, T_tot, gh_fn(fnm, NFILE, "-grid"), header, &tgout) != GCB_OK)
     gh_msg("Writing the 3D grid failed.\n%s\n", gcb_last_error());
   gcb_counter_destroy(ctr);
-  free(xfast); free(x);
+  free(x);
   if (groups) gh_ndx_free(groups, ng);
   gh_msg("\n");
   return 0;

@@ -212,6 +212,16 @@ int gcb_grid_write(const char *path, const gcb_tgrid *tg, const float *grid_zfas
 /* *grid_zfast is malloc'ed by the library (free with gcb_free); b is rebuilt as a + mx*delta */
 int gcb_grid_read(const char *path, gcb_tgrid *tg, char header[GCB_HEADER_MAX + 1], float **grid_zfast);
 int gcb_plt_write(const char *path, const gcb_tgrid *tg, const float *grid_zfast, float unit);
+/* The same files for a counter's result, encoded ON THE DEVICE: K2, the z-fastest -> x-fastest reordering of
+ * grid3_serialise (xdr_grid.c:113-126) and the XDR big-endian byte order (or plt's `norm * grid`, plt.c:69-75)
+ * are one pass over the grid in HBM; the host writes only the prologue in front of the cells.  `out` receives
+ * the complete file image (gcb_xdr_size bytes; 44 + 4*cells for plt); pinned memory is filled by DMA.
+ * tweight is (float)T_tot as at g_ri3Dc.c:460. */
+int gcb_counter_xdr(gcb_counter *c, double T_tot, const char *header, uint8_t *out, size_t cap,
+                    size_t *written, gcb_tgrid *tg_out);
+int gcb_counter_grid_write(gcb_counter *c, double T_tot, const char *path, const char *header,
+                           gcb_tgrid *tg_out);
+int gcb_counter_plt(gcb_counter *c, double T_tot, float unit, uint8_t *out, size_t cap, size_t *written);
 int gcb_ascii_write(const char *path, const gcb_tgrid *tg, const float *grid_zfast, float unit);
 void gcb_free(void *p);
 

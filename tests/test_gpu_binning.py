@@ -90,6 +90,16 @@ def test_golden_density_file_byte_exact(name, kernel):
     want = open(os.path.join(u.GOLDEN_DIR, name, "grid.dat"), "rb").read()
     assert g.xdr_encode(tg, hdr, grid_xfast=gx) == want
     assert g.xdr_encode(tg, hdr, grid_zfast=gz) == want
+    # the same file image with the reordering and the XDR byte order done on the device
+    tg2, image = ctr.xdr(T, hdr)
+    assert image == want and bytes(tg2) == bytes(tg)
+    # gOpenMol plt of the density: device-encoded cells == the host writer's (plt.c:42-77)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        g._cabi.check(g._cabi.lib.gcb_plt_write(os.path.join(d, "a.plt").encode(), C.byref(tg), u.fptr(gz), 0.75), "gcb_plt_write")
+        assert ctr.plt(T, unit=0.75) == open(os.path.join(d, "a.plt"), "rb").read()
+        ctr.grid_write(T, os.path.join(d, "g.dat"), hdr)
+        assert open(os.path.join(d, "g.dat"), "rb").read() == want
     ctr.close()
 
 
