@@ -867,6 +867,7 @@ struct gcb_counter {
   size_t scr_words = 0;
   cudaStream_t comm_stream = nullptr; // rank-table exchange, beside the compute stream
   cudaEvent_t reduce_done = nullptr;  // behind the D2H of the gathered statistics
+  cudaEvent_t scr_up = nullptr, grp_done = nullptr;   // scratch uploaded / NCCL group finished
   bool reduce_pending = false;        // host half of the last all-reduce still to do (finish_reduce)
   size_t pend_total = 0, pend_off = 0, pend_ndev = 0, pend_nlocal = 0;
 
@@ -1207,6 +1208,7 @@ void free_counter(gcb_counter *c)
   if (!c) return;
   cudaSetDevice(c->opts.device);
   if (c->compute) cudaStreamSynchronize(c->compute);
+  if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   for (auto &s : c->slots) {
     if (s.copy) { cudaStreamSynchronize(s.copy); cudaStreamDestroy(s.copy); }
     if (s.copied) cudaEventDestroy(s.copied);
@@ -1229,6 +1231,8 @@ void free_counter(gcb_counter *c)
   if (c->compute) cudaStreamDestroy(c->compute);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->reduce_done) cudaEventDestroy(c->reduce_done);
+  if (c->scr_up) cudaEventDestroy(c->scr_up);
+  if (c->grp_done) cudaEventDestroy(c->grp_done);
   delete c;
 }
 
@@ -1964,7 +1968,12 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops 
     fr[total_frames + my_off + f] = wbits;
   }
   for (auto &h : c->devhits) for (long f = 0; f < h.n; f++) fr[my_off + h.frame0 + f] = 0;
-  GCB_CUDA(cudaMemcpyAsync(c->d_scr, fr, sizeof(unsigned long long) * nfr_words, cudaMemcpyHostToDevice, c->compute));
+  // the host-known part goes up on the side stream while the binning kernels are still running
+  if (!c->scr_up) GCB_CUDA(cudaEventCreateWithFlags(&c->scr_up, cudaEventDisableTiming));
+  if (!c->grp_done) GCB_CUDA(cudaEventCreateWithFlags(&c->grp_done, cudaEventDisableTiming));
+  GCB_CUDA(cudaMemcpyAsync(c->d_scr, fr, sizeof(unsigned long long) * nfr_words, cudaMemcpyHostToDevice, c->comm_stream));
+  GCB_CUDA(cudaEventRecord(c->scr_up, c->comm_stream));
+  GCB_CUDA(cudaStreamWaitEvent(c->compute, c->scr_up, 0));
   for (auto &h : c->devhits)
     GCB_CUDA(cudaMemcpyAsync(c->d_scr + my_off + h.frame0, h.d, sizeof(unsigned long long) * h.n, cudaMemcpyDeviceToDevice, c->compute));
   GCB_CUDA(cudaMemcpyAsync(c->d_scr + 2 * total_frames, c->d_diag, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->compute));
@@ -1993,11 +2002,14 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops 
   } else {
     c->uniform = false;
   }
-  GCB_CUDA(cudaMemcpyAsync(fr, c->d_scr, sizeof(unsigned long long) * nfr_words, cudaMemcpyDeviceToHost, c->compute));
+  // the gathered statistics come back on the side stream: the next job's kernels do not queue behind the copy
+  GCB_CUDA(cudaEventRecord(c->grp_done, c->compute));
+  GCB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->grp_done, 0));
+  GCB_CUDA(cudaMemcpyAsync(fr, c->d_scr, sizeof(unsigned long long) * nfr_words, cudaMemcpyDeviceToHost, c->comm_stream));
   // The grids are reduced in stream order; the host half (per-frame counters -> sumP chain) is finished when
   // somebody asks for it (finish_reduce), so the caller can queue the density and the next job meanwhile.
   if (!c->reduce_done) GCB_CUDA(cudaEventCreateWithFlags(&c->reduce_done, cudaEventDisableTiming));
-  GCB_CUDA(cudaEventRecord(c->reduce_done, c->compute));
+  GCB_CUDA(cudaEventRecord(c->reduce_done, c->comm_stream));
   c->reduce_pending = true; c->pend_total = total_frames; c->pend_off = my_off; c->pend_ndev = c->devhits.size();
   c->pend_nlocal = c->hits_per_frame.size();
   c->global_frames = total_frames;
