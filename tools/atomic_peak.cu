@@ -33,6 +33,28 @@ __global__ void __launch_bounds__(256) red_random(uint32_t *grid, uint32_t ncell
   }
 }
 
+// returning atomics on packed 8-bit counters: the narrow-counter path of K1 adds 1 << 8*(cell & 3) to the word
+// and looks at the old byte (spill at 127, carry alarm at 255)
+template <int ILP>
+__global__ void __launch_bounds__(256) atom_u8_random(uint32_t *grid, uint32_t ncells, int iters, uint32_t *sink)
+{
+  uint32_t s = mix(blockIdx.x * blockDim.x + threadIdx.x + 1);
+  uint32_t seen = 0;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < ILP; k++) {
+      s = s * 1664525u + 1013904223u;
+      const uint32_t cell = (uint32_t)(((uint64_t)mix(s) * ncells) >> 32);
+      const uint32_t sh = 8u * (cell & 3u);
+      const uint32_t old = atomicAdd(grid + (cell >> 2), 1u << sh);
+      const uint32_t ob = (old >> sh) & 255u;
+      if (ob == 127u) atomicSub(grid + (cell >> 2), 128u << sh);
+      seen |= ob == 255u ? 1u : 0u;
+    }
+  }
+  if (seen) *sink = 1;
+}
+
 __global__ void __launch_bounds__(1024) smem_atomics(uint32_t *out, int iters, int ncells)
 {
   extern __shared__ uint32_t h[];
@@ -92,6 +114,30 @@ int main()
     printf("%s{\"window_mb\": %zu, \"gops\": %.2f}", first ? "" : ", ", mb, ops / best * 1e-6);
     first = false;
     CK(cudaFree(g));
+  }
+  printf("],\n \"atom_u8_random\": [");
+  first = true;
+  for (size_t cells_m : {16, 64, 96, 125}) {                 // M cells of one byte each
+    const size_t bytes = cells_m << 20;
+    uint32_t *g, *sink;
+    CK(cudaMalloc(&g, bytes)); CK(cudaMalloc(&sink, 4));
+    CK(cudaMemset(g, 0, bytes)); CK(cudaMemset(sink, 0, 4));
+    const uint32_t ncells = (uint32_t)bytes;
+    const int blocks = sms * 8, iters = 256;
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+      CK(cudaMemset(g, 0, bytes));
+      CK(cudaEventRecord(a));
+      atom_u8_random<8><<<blocks, 256>>>(g, ncells, iters, sink);
+      CK(cudaEventRecord(b));
+      CK(cudaEventSynchronize(b));
+      float ms; CK(cudaEventElapsedTime(&ms, a, b));
+      if (rep > 0 && ms < best) best = ms;
+    }
+    const double ops = (double)blocks * 256 * iters * 8;
+    printf("%s{\"cells_m\": %zu, \"gops\": %.2f}", first ? "" : ", ", cells_m, ops / best * 1e-6);
+    first = false;
+    CK(cudaFree(g)); CK(cudaFree(sink));
   }
   printf("],\n");
   {
