@@ -294,10 +294,55 @@ template <int MODE>
 struct DirectSink {
   static constexpr int NSTAGES = STAGES;
   static constexpr size_t EXTRA_SMEM = 0;
+  static constexpr bool SETTLES = false;
   uint32_t *counts; float *acc; float w;
   // `smem` is the sink's share of the dynamic shared memory (unused here)
   __device__ __forceinline__ void init(void *, unsigned) const {}
-  __device__ __forceinline__ void hit(void *, int cell) const { deposit<MODE>(counts, acc, cell, w); }
+  __device__ __forceinline__ uint32_t hit(void *, int cell) const { deposit<MODE>(counts, acc, cell, w); return 0u; }
+  __device__ __forceinline__ void settle(int, uint32_t) const {}
+  __device__ __forceinline__ void tile_end(void *, unsigned) const {}
+  __device__ __forceinline__ void finish(void *, unsigned) const {}
+};
+
+// NarrowSink: L2-resident atomics for grids whose uint32 counters do not fit the L2 but whose BYTES do
+// (BASELINE config 3: 400^3 cells = 256 MB of uint32, 64 MB of bytes).  Four 8-bit counters share a word; a hit
+// is one returning atomic add of 1 << 8*(cell & 3).  The thread that takes a byte from 127 to 128 owes the
+// cell a spill: it subtracts the 128 again and logs the cell (128 hits, applied to the uint32 grid at the end
+// of the round), so a byte only ever exceeds 128 transiently.  A byte observed at 255 means a carry into the
+// neighbouring counter has happened or is about to: the round raises `alarm`, its packed counters and log are
+// thrown away and the round is redone by the direct uint32 kernel (narrow_resolve_kernel, `run_if`).  Exact
+// for every input; the alarm needs > 127 hits on one cell inside the few hundred nanoseconds between a
+// thread's add and its subtract.
+struct NarrowSink {
+  static constexpr int NSTAGES = STAGES;
+  static constexpr size_t EXTRA_SMEM = 0;
+  static constexpr bool SETTLES = true;
+  uint32_t *g8;                            // packed counters, (ncells + 3) / 4 words
+  uint32_t *log;                           // [gridDim][seg_cap] spilled cells
+  unsigned *log_n;                         // [gridDim]
+  unsigned seg_cap;
+  int *alarm;
+  __device__ __forceinline__ void init(void *, unsigned) const {}
+  // hit() only issues the atomic and hands its result back as a token; settle() looks at it.  The streaming
+  // kernel issues a whole unrolled group of hits before it settles any, so the L2 round trips overlap.
+  __device__ __forceinline__ uint32_t hit(void *, int cell) const
+  {
+    return atomicAdd(g8 + ((unsigned)cell >> 2), 1u << (8u * ((unsigned)cell & 3u)));
+  }
+  __device__ __forceinline__ void settle(int cell, uint32_t old) const
+  {
+    const unsigned sh = 8u * ((unsigned)cell & 3u);
+    uint32_t *w = g8 + ((unsigned)cell >> 2);
+    const uint32_t ob = (old >> sh) & 255u;
+    if (ob == 127u) {
+      atomicSub(w, 128u << sh);
+      const unsigned i = atomicAdd(log_n + blockIdx.x, 1u);
+      if (i < seg_cap) log[(size_t)blockIdx.x * seg_cap + i] = (uint32_t)cell;
+      else *alarm = 1;
+    } else if (ob == 255u) {
+      *alarm = 1;
+    }
+  }
   __device__ __forceinline__ void tile_end(void *, unsigned) const {}
   __device__ __forceinline__ void finish(void *, unsigned) const {}
 };
@@ -327,6 +372,7 @@ __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %
 struct RouteSink {
   static constexpr int NSTAGES = 2;        // 2 x 36 KiB tile ring + 34 KiB staging: two CTAs per SM
   static constexpr size_t EXTRA_SMEM = sizeof(RouteStage);
+  static constexpr bool SETTLES = false;
   uint32_t *keys_g;                        // [nb][gridDim][seg_cap]
   uint32_t *seg_len;                       // [nb][gridDim]
   uint32_t *counts;                        // the grid, for the overflow fallback only
@@ -340,7 +386,8 @@ struct RouteSink {
     for (unsigned i = ctid; i < ROUTE_NB_MAX; i += CONSUMER_THREADS) { st->tail[i] = 0; st->head[i] = 0; st->pos[i] = 0; }
     consumer_barrier();
   }
-  __device__ __forceinline__ void hit(void *smem, int cell) const
+  __device__ __forceinline__ void settle(int, uint32_t) const {}
+  __device__ __forceinline__ uint32_t hit(void *smem, int cell) const
   {
     RouteStage *st = static_cast<RouteStage *>(smem);
     const unsigned b = map.bucket((unsigned)cell);
@@ -348,6 +395,7 @@ struct RouteSink {
     const unsigned slot = atomicAdd(&st->tail[b], 1u);
     if (slot - h < (unsigned)cap) st->keys[b * cap + (slot & (cap - 1))] = map.local((unsigned)cell);
     else atomicAdd(counts + cell, 1u);     // ring full (pathologically clustered input): counted directly, still exact
+    return 0u;
   }
   // Move the complete 128-byte lines (everything when `all`) of every bucket from the rings to this CTA's
   // segments.  Runs between two consumer barriers: no hit is appended meanwhile.  Warp w owns buckets
@@ -419,14 +467,17 @@ struct RouteSink {
   }
 };
 
-template <class SINK, bool PBC, bool AP>
+template <class SINK, bool PBC, bool AP, bool GUARDED = false>
 __global__ void __launch_bounds__(STREAM_THREADS)
 bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict__ gindex, unsigned gnx,
                   const unsigned *__restrict__ rank, long long ntiles, ApGroup G, GridParamsFast P, SINK sink,
                   const float *__restrict__ box3, unsigned long long *__restrict__ hits,
-                  unsigned long long *__restrict__ diag)
+                  unsigned long long *__restrict__ diag, const int *__restrict__ run_if)
 {
   constexpr int NST = SINK::NSTAGES;
+  if constexpr (GUARDED) {                         // the redo of a narrow round: nothing to do unless it raised the alarm
+    if (*run_if == 0) return;                      // (a separate instantiation: the test costs the plain kernel a spill)
+  }
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StreamSmem<NST> &S = *reinterpret_cast<StreamSmem<NST> *>(smem_raw);
   const int tid = threadIdx.x;
@@ -483,6 +534,11 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
   const int lane = tid & 31;
   void *const sink_smem = smem_raw + ((sizeof(StreamSmem<NST>) + 15) & ~(size_t)15);
   sink.init(sink_smem, ctid);
+  unsigned pend_went = 0;               // SETTLES sinks: hits issued one step ago, results not looked at yet
+  int pend_cells[UNROLL];
+  uint32_t pend_tok[UNROLL];
+#pragma unroll
+  for (int k = 0; k < UNROLL; k++) { pend_cells[k] = 0; pend_tok[k] = 0u; }
   int it = 0;
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
     const int stage = it % NST;
@@ -505,6 +561,35 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
           px[k] = lds_f32(p); py[k] = lds_f32(p + 4); pz[k] = lds_f32(p + 8);
         }
         unsigned rare = 0;
+        if constexpr (SINK::SETTLES) {
+          // sinks whose atomics return a value: the group of this step is issued before the group of the
+          // previous step is settled, so two groups of L2 round trips are in flight per thread
+          unsigned went = 0;
+          int cells[UNROLL];
+          uint32_t tok[UNROLL];
+#pragma unroll
+          for (int k = 0; k < UNROLL; k++) {
+            if (PBC) {
+              const float *L = box3 + 3 * (m.f0 + (inB[k] ? 1 : 0));
+              px[k] = wrap1(px[k], __ldg(L)); py[k] = wrap1(py[k], __ldg(L + 1)); pz[k] = wrap1(pz[k], __ldg(L + 2));
+            }
+            const FastCell fc = cell_of_fast(P, px[k], py[k], pz[k]);
+            const bool go = valid[k] & fc.inside & fc.sure;
+            cells[k] = fc.cell;
+            tok[k] = 0u;
+            if (go) tok[k] = sink.hit(sink_smem, fc.cell);
+            went |= go ? (1u << k) : 0u;
+            c0 += (go & !inB[k]) ? 1u : 0u;
+            c1 += (go & inB[k]) ? 1u : 0u;
+            rare |= (valid[k] & fc.inside & !fc.sure) ? (1u << k) : 0u;
+          }
+#pragma unroll
+          for (int k = 0; k < UNROLL; k++) {
+            if ((pend_went >> k) & 1u) sink.settle(pend_cells[k], pend_tok[k]);
+            pend_cells[k] = cells[k]; pend_tok[k] = tok[k];
+          }
+          pend_went = went;
+        } else {
 #pragma unroll
         for (int k = 0; k < UNROLL; k++) {
           if (PBC) {
@@ -518,13 +603,14 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
           c1 += (go & inB[k]) ? 1u : 0u;
           rare |= (valid[k] & fc.inside & !fc.sure) ? (1u << k) : 0u;
         }
+        }
         if (rare) {                                  // atoms within a few ulp of a cell boundary
 #pragma unroll
           for (int k = 0; k < UNROLL; k++) {
             if (!((rare >> k) & 1u)) continue;
             const int cell = cell_of_exact(P, px[k], py[k], pz[k]);
             if (cell >= 0) {
-              sink.hit(sink_smem, cell);
+              sink.settle(cell, sink.hit(sink_smem, cell));
               if (inB[k]) c1++; else c0++;
             } else {
               atomicAdd(diag, 1ull);
@@ -563,7 +649,7 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
         const FastCell fc = cell_of_fast(P, px[k], py[k], pz[k]);
         const int cell = !fc.inside ? -1 : fc.sure ? fc.cell : cell_of_exact(P, px[k], py[k], pz[k]);
         if (cell >= 0) {
-          sink.hit(sink_smem, cell);
+          sink.settle(cell, sink.hit(sink_smem, cell));
           if (df[k] == 0) c0++;
           else if (df[k] == 1) c1++;
           else atomicAdd(hits + m.f0 + df[k], 1ull);
@@ -580,6 +666,11 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
       mbar_arrive(&S.empty[stage]);     // this warp is done with the stage (its LDS results are in registers)
     }
     sink.tile_end(sink_smem, ctid);
+  }
+  if constexpr (SINK::SETTLES) {
+#pragma unroll
+    for (int k = 0; k < UNROLL; k++)
+      if ((pend_went >> k) & 1u) sink.settle(pend_cells[k], pend_tok[k]);
   }
   sink.finish(sink_smem, ctid);
 }
@@ -671,6 +762,52 @@ __device__ float seq_add_dev(float v, float w, unsigned long long n)
 }
 
 // fold a finished weight run into the f32 accumulator: acc = acc (+)= w, runcnt times
+// End of a narrow round.  No alarm: the packed counters are added to the uint32 grid (every word is owned by
+// one thread, nothing else touches the grid meanwhile) and zeroed.  Alarm: they are zeroed only, and what the
+// round's streaming kernel added to the per-frame hit counters and the diagnostics is taken back, because the
+// guarded uint32 kernel behind this one redoes the round.  narrow_log_kernel then applies the spills.
+__global__ void __launch_bounds__(256)
+narrow_resolve_kernel(uint4 *__restrict__ g8, size_t nquads, uint32_t *__restrict__ counts, size_t ncells,
+                      const int *__restrict__ alarm, unsigned long long *__restrict__ hits, long nhits,
+                      unsigned long long *__restrict__ diag, const unsigned long long *__restrict__ diag_snap)
+{
+  const bool bad = *alarm != 0;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = g8[q];
+    if (!(v.x | v.y | v.z | v.w)) continue;
+    g8[q] = make_uint4(0u, 0u, 0u, 0u);
+    if (bad) continue;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (!w[k]) continue;
+      const size_t c0 = q * 16 + (size_t)k * 4;
+      if (c0 + 3 < ncells) {
+        uint4 *dst = reinterpret_cast<uint4 *>(counts + c0);
+        uint4 t = *dst;
+        t.x += w[k] & 255u; t.y += (w[k] >> 8) & 255u; t.z += (w[k] >> 16) & 255u; t.w += w[k] >> 24;
+        *dst = t;
+      } else {
+        for (int b = 0; b < 4; b++) if (c0 + b < ncells) counts[c0 + b] += (w[k] >> (8 * b)) & 255u;
+      }
+    }
+  }
+  if (bad) {
+    for (long f = (long)blockIdx.x * blockDim.x + threadIdx.x; f < nhits; f += (long)gridDim.x * blockDim.x) hits[f] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < 2) diag[threadIdx.x] = diag_snap[threadIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 2) diag[2] += 1ull;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+narrow_log_kernel(const uint32_t *__restrict__ log, const unsigned *__restrict__ log_n, unsigned seg_cap,
+                  uint32_t *__restrict__ counts, const int *__restrict__ alarm)
+{
+  if (*alarm != 0) return;
+  const unsigned n = min(log_n[blockIdx.x], seg_cap);
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(counts + log[(size_t)blockIdx.x * seg_cap + i], 128u);
+}
+
 __global__ void fold_run_kernel(uint32_t *__restrict__ runcnt, uint32_t *__restrict__ total,
                                 float *__restrict__ acc, float w, size_t n)
 {
@@ -853,6 +990,15 @@ struct gcb_counter {
   uint32_t *d_keys = nullptr, *d_seglen = nullptr;
   unsigned route_seg_cap = 0;
   int route_grid = 0;                 // streaming CTAs the key buffer is laid out for
+  // narrow (packed 8-bit, L2-resident) path
+  bool narrow_ok = false;             // AUTO takes it: uint32 grid beyond L2, one byte per cell inside it
+  long long narrow_units = 0;         // atom-frames per round
+  uint32_t *d_g8 = nullptr;           // packed counters, always all-zero between rounds
+  uint32_t *d_nlog = nullptr;         // [narrow_grid][narrow_seg_cap]
+  unsigned char *d_nctl = nullptr;    // int alarm | u64 diag_snap[2] (at 8) | unsigned log_n[narrow_grid] (at 32)
+  unsigned narrow_seg_cap = 0;
+  int narrow_grid = 0;
+  uint64_t narrow_rounds = 0, narrow_redone = 0;
   // xtc path: two sets of {compressed bytes, frame table, status, decoded frames}, copy stream + events
   struct XtcSet {
     uint8_t *d_buf = nullptr; size_t buf_cap = 0;
@@ -944,22 +1090,22 @@ int fold_pending(gcb_counter *c)
 template <class SINK>
 size_t stream_smem_bytes() { return ((sizeof(StreamSmem<SINK::NSTAGES>) + 15) & ~(size_t)15) + SINK::EXTRA_SMEM; }
 
-template <class SINK, bool PBC, bool AP>
+template <class SINK, bool PBC, bool AP, bool GUARDED = false>
 int launch_stream(gcb_counter *c, const float *d_x, long long ntiles, const SINK &sink, int grid_cap,
-                  const float *d_box3, unsigned long long *d_hits, int *grid_out)
+                  const float *d_box3, unsigned long long *d_hits, int *grid_out, const int *run_if = nullptr)
 {
   static bool attr_done[64] = {false};           // per instantiation and per device (the attribute is per context)
   const size_t smem = stream_smem_bytes<SINK>();
   const int dv = c->opts.device & 63;
   if (!attr_done[dv]) {
-    GCB_CUDA(cudaFuncSetAttribute(bin_stream_kernel<SINK, PBC, AP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GCB_CUDA(cudaFuncSetAttribute(bin_stream_kernel<SINK, PBC, AP, GUARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[dv] = true;
   }
   const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
   long long grid = std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
   if (grid_cap > 0) grid = std::min<long long>(grid, grid_cap);
-  bin_stream_kernel<SINK, PBC, AP><<<(unsigned)grid, STREAM_THREADS, smem, c->compute>>>(
-      d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, c->ap, c->PF, sink, d_box3, d_hits, c->d_diag);
+  bin_stream_kernel<SINK, PBC, AP, GUARDED><<<(unsigned)grid, STREAM_THREADS, smem, c->compute>>>(
+      d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, c->ap, c->PF, sink, d_box3, d_hits, c->d_diag, run_if);
   c->launches++;
   GCB_CUDA(cudaGetLastError());
   if (grid_out) *grid_out = (int)grid;
@@ -1052,6 +1198,74 @@ int launch_routed(gcb_counter *c, const float *d_x, long nframes, const float *d
   return GCB_OK;
 }
 
+// Narrow path: rounds of ~narrow_units atom-frames; per round the streaming kernel into the packed counters,
+// the resolve + log kernels, the guarded uint32 redo (returns at once unless the round raised the alarm), and
+// the gather kernel for the sub-tile tail (straight into the uint32 grid).
+template <bool PBC>
+int launch_narrow(gcb_counter *c, const float *d_x, long nframes, const float *d_box3, unsigned long long *d_hits)
+{
+  const bool ap = c->ap_ok && c->opts.kernel != GCB_KERNEL_STREAM_INDEXED;
+  const int tile_atoms = ap ? c->ap.tile_atoms : TILE_ATOMS;
+  const size_t smem = stream_smem_bytes<NarrowSink>();
+  const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+  const int G = c->sm_count * per_sm;
+  long fpr = (long)std::max<long long>(4, (c->narrow_units / std::max(c->gnx, 1)) & ~3LL);   // multiple of 4 frames:
+  fpr = std::min<long>(fpr, (nframes + 3) & ~3L);                                              // rounds start 16-byte aligned
+  const long long round_units = (long long)fpr * c->gnx;
+  const unsigned seg_cap = (unsigned)std::max<long long>(1024, 2 * (round_units / 128) / G + 64);
+  const size_t nquads = (c->ncells + 15) / 16;
+  if (!c->d_g8) {
+    GCB_CUDA(cudaMalloc(&c->d_g8, nquads * 16));
+    GCB_CUDA(cudaMemsetAsync(c->d_g8, 0, nquads * 16, c->compute));
+  }
+  if (!c->d_nlog || seg_cap > c->narrow_seg_cap || G != c->narrow_grid) {
+    GCB_CUDA(cudaStreamSynchronize(c->compute));
+    cudaFree(c->d_nlog); cudaFree(c->d_nctl);
+    c->d_nlog = nullptr; c->d_nctl = nullptr;
+    GCB_CUDA(cudaMalloc(&c->d_nlog, sizeof(uint32_t) * (size_t)G * seg_cap));
+    GCB_CUDA(cudaMalloc(&c->d_nctl, 32 + sizeof(unsigned) * (size_t)G));
+    c->narrow_seg_cap = seg_cap;
+    c->narrow_grid = G;
+  }
+  int *alarm = reinterpret_cast<int *>(c->d_nctl);
+  unsigned long long *diag_snap = reinterpret_cast<unsigned long long *>(c->d_nctl + 8);
+  unsigned *log_n = reinterpret_cast<unsigned *>(c->d_nctl + 32);
+  for (long f0 = 0; f0 < nframes; f0 += fpr) {
+    const long n = std::min(fpr, nframes - f0);
+    const float *xs = d_x + (size_t)f0 * c->natoms * 3;
+    const float *bs = d_box3 ? d_box3 + 3 * f0 : nullptr;
+    const long long total_e = (long long)n * c->gnx, total_atoms = (long long)n * c->natoms;
+    const long long ntiles = total_atoms / tile_atoms;
+    long long e_begin = 0;
+    if (ntiles > 0) {
+      GCB_CUDA(cudaMemsetAsync(c->d_nctl, 0, 32 + sizeof(unsigned) * (size_t)G, c->compute));
+      GCB_CUDA(cudaMemcpyAsync(diag_snap, c->d_diag, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->compute));
+      c->narrow_rounds++;
+      NarrowSink sink;
+      sink.g8 = c->d_g8; sink.log = c->d_nlog; sink.log_n = log_n; sink.seg_cap = c->narrow_seg_cap; sink.alarm = alarm;
+      int grid = 0;
+      int rc = ap ? launch_stream<NarrowSink, PBC, true>(c, xs, ntiles, sink, G, bs, d_hits + f0, &grid)
+                  : launch_stream<NarrowSink, PBC, false>(c, xs, ntiles, sink, G, bs, d_hits + f0, &grid);
+      if (rc) return rc;
+      narrow_resolve_kernel<<<c->sm_count * 8, 256, 0, c->compute>>>(reinterpret_cast<uint4 *>(c->d_g8), nquads, c->d_runcnt, c->ncells,
+                                                                     alarm, d_hits + f0, n, c->d_diag, diag_snap);
+      narrow_log_kernel<<<grid, 256, 0, c->compute>>>(c->d_nlog, log_n, c->narrow_seg_cap, c->d_runcnt, alarm);
+      c->launches += 2;
+      GCB_CUDA(cudaGetLastError());
+      DirectSink<MODE_COUNT> redo;
+      redo.counts = c->d_runcnt; redo.acc = c->d_acc; redo.w = 1.0f;
+      rc = ap ? launch_stream<DirectSink<MODE_COUNT>, PBC, true, true>(c, xs, ntiles, redo, 0, bs, d_hits + f0, nullptr, alarm)
+              : launch_stream<DirectSink<MODE_COUNT>, PBC, false, true>(c, xs, ntiles, redo, 0, bs, d_hits + f0, nullptr, alarm);
+      if (rc) return rc;
+      const long long g1 = ntiles * tile_atoms, f1 = g1 / c->natoms;
+      e_begin = f1 * c->gnx + rank_host(c, (int)(g1 - f1 * c->natoms));
+    }
+    int rc = launch_gather<MODE_COUNT, PBC>(c, xs, e_begin, total_e, c->d_runcnt, 1.0f, bs, d_hits + f0);
+    if (rc) return rc;
+  }
+  return GCB_OK;
+}
+
 template <int MODE, bool PBC>
 int launch_bin(gcb_counter *c, const float *d_x, long nframes, float w, const float *d_box3,
                unsigned long long *d_hits)
@@ -1063,9 +1277,12 @@ int launch_bin(gcb_counter *c, const float *d_x, long nframes, float w, const fl
   const bool aligned = ((uintptr_t)d_x & 15u) == 0;
   const int k = c->opts.kernel;
   const bool use_stream = aligned && k != GCB_KERNEL_GATHER &&
-                          (c->stream_ok || k == GCB_KERNEL_STREAM || k == GCB_KERNEL_STREAM_INDEXED || k == GCB_KERNEL_ROUTED);
+                          (c->stream_ok || k == GCB_KERNEL_STREAM || k == GCB_KERNEL_STREAM_INDEXED || k == GCB_KERNEL_ROUTED ||
+                           k == GCB_KERNEL_NARROW);
   // AUTO takes the routed path for grids beyond L2 (slabs: 1.2-1.3x the direct kernel, profiles/perf_r01.md); for
   // shared-memory sized buckets the two-kernel round still loses to direct L2 REDs and is only used on request
+  if (use_stream && MODE == MODE_COUNT && (k == GCB_KERNEL_NARROW || (k == GCB_KERNEL_AUTO && c->narrow_ok && total_e >= (1LL << 20))))
+    return launch_narrow<PBC>(c, d_x, nframes, d_box3, d_hits);
   if (use_stream && MODE == MODE_COUNT && c->route_mode != 0 && k != GCB_KERNEL_STREAM && k != GCB_KERNEL_STREAM_INDEXED &&
       (k == GCB_KERNEL_ROUTED || (c->route_mode == 2 && total_e >= (1LL << 20))))
     return launch_routed<PBC>(c, d_x, nframes, d_box3, d_hits);
@@ -1220,6 +1437,7 @@ void free_counter(gcb_counter *c)
   for (auto &p : c->hit_pool) cudaFree(p.second);
   cudaFree(c->d_gindex); cudaFree(c->d_rank); cudaFree(c->d_runcnt); cudaFree(c->d_total); cudaFree(c->d_acc);
   cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2); cudaFree(c->d_keys); cudaFree(c->d_seglen);
+  cudaFree(c->d_g8); cudaFree(c->d_nlog); cudaFree(c->d_nctl);
   for (auto &x : c->xtc) {
     cudaFree(x.d_buf); cudaFree(x.d_meta); cudaFree(x.d_status); cudaFree(x.d_x); cudaFree(x.d_work); cudaFreeHost(x.h_meta); cudaFreeHost(x.h_status);
     if (x.copied) cudaEventDestroy(x.copied);
@@ -1339,17 +1557,26 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
       c->route_map = RouteMap{23, 0xFFu, 31, 23, (1u << 23) - 1};
     }
     if (getenv("GCB_NO_ROUTE")) c->route_mode = 0;
+    // narrow path: the bytes must stay L2-resident next to the coordinate stream (random returning atomics
+    // hold 128 G/s up to a 96 MB window, profiles/atomic_peak_r01e.json)
+    const char *nenv = getenv("GCB_NARROW_UNITS");
+    c->narrow_units = nenv ? atoll(nenv) : (256LL << 20);
+    if (c->narrow_units < 4096) c->narrow_units = 4096;
+    // Measured (profiles/perf_r01e.txt): 36.9 G/s on C3 against 68.7 for the routed slabs, 66.9 on C2 against 111
+    // for plain REDs -- the returning atomics' replies share the L2->SM path with the coordinate stream.  AUTO
+    // therefore never takes this path; it stays selectable (GCB_KERNEL_NARROW, or GCB_NARROW=1 for AUTO).
+    c->narrow_ok = c->route_mode == 2 && c->ncells <= ((size_t)80 << 20) && getenv("GCB_NARROW") != nullptr;
   }
   GCB_CREATE_CUDA(cudaMalloc(&c->d_gindex, sizeof(int) * std::max(gnx, 1)));
   GCB_CREATE_CUDA(cudaMalloc(&c->d_rank, sizeof(unsigned) * rank.size()));
   GCB_CREATE_CUDA(cudaMalloc(&c->d_runcnt, sizeof(uint32_t) * c->ncells));
-  GCB_CREATE_CUDA(cudaMalloc(&c->d_diag, sizeof(unsigned long long) * 2));
+  GCB_CREATE_CUDA(cudaMalloc(&c->d_diag, sizeof(unsigned long long) * 4));   // [0] edge overflow, [2] narrow rounds redone
   if (gnx) GCB_CREATE_CUDA(cudaMemcpy(c->d_gindex, c->h_gindex.data(), sizeof(int) * gnx, cudaMemcpyHostToDevice));
   GCB_CREATE_CUDA(cudaMemcpy(c->d_rank, rank.data(), sizeof(unsigned) * rank.size(), cudaMemcpyHostToDevice));
   // on the compute stream: it is non-blocking, a legacy-stream cudaMemset could still be
   // running when the first binning kernel starts and would wipe its deposits
   GCB_CREATE_CUDA(cudaMemsetAsync(c->d_runcnt, 0, sizeof(uint32_t) * c->ncells, c->compute));
-  GCB_CREATE_CUDA(cudaMemsetAsync(c->d_diag, 0, sizeof(unsigned long long) * 2, c->compute));
+  GCB_CREATE_CUDA(cudaMemsetAsync(c->d_diag, 0, sizeof(unsigned long long) * 4, c->compute));
   GCB_CREATE_CUDA(cudaStreamSynchronize(c->compute));
 #undef GCB_CREATE_CUDA
   *out = c;
@@ -1377,7 +1604,8 @@ int gcb_counter_reset(gcb_counter *c)
     GCB_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(float) * c->ncells, c->compute));
     GCB_CUDA(cudaMemsetAsync(c->d_total, 0, sizeof(uint32_t) * c->ncells, c->compute));
   }
-  GCB_CUDA(cudaMemsetAsync(c->d_diag, 0, sizeof(unsigned long long) * 2, c->compute));
+  GCB_CUDA(cudaMemsetAsync(c->d_diag, 0, sizeof(unsigned long long) * 4, c->compute));
+  c->narrow_rounds = 0; c->narrow_redone = 0;
   c->reduced = false; c->global_frames = 0;
   c->have_run = false; c->any = false; c->uniform = true; c->w_cur = 0; c->w_first = 0;
   c->hits_per_frame.clear(); c->weight_per_frame.clear();
@@ -1578,9 +1806,10 @@ int gcb_counter_sync(gcb_counter *c)
   }
   c->devhits.clear();
   if (!c->reduced) {                  // after an all-reduce the statistics are the global ones
-    unsigned long long diag[2];
+    unsigned long long diag[4];
     GCB_CUDA(cudaMemcpy(diag, c->d_diag, sizeof(diag), cudaMemcpyDeviceToHost));
     c->edge_overflow = diag[0];
+    c->narrow_redone = diag[2];
   }
   // sumP: `sumP += (double)weight` once per hit, frame by frame (g_ri3Dc.c:151,426)
   for (; c->sumP_frames < c->hits_per_frame.size(); c->sumP_frames++) {
@@ -1604,6 +1833,8 @@ int gcb_counter_stats(gcb_counter *c, gcb_stats *out)
   out->uniform_weight = c->uniform ? 1 : 0;
   out->weight = c->w_first;
   out->kernel_launches = c->launches;
+  out->narrow_rounds = c->narrow_rounds;
+  out->narrow_redone = c->narrow_redone;
   return GCB_OK;
 }
 

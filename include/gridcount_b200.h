@@ -93,7 +93,9 @@ enum {
 enum {                     /* kernel selection (GCB_KERNEL_AUTO picks by index-group density and regularity) */
   GCB_KERNEL_AUTO = 0, GCB_KERNEL_GATHER = 1, GCB_KERNEL_STREAM = 2,
   GCB_KERNEL_STREAM_INDEXED = 3,  /* streaming kernel without the arithmetic-progression shortcut */
-  GCB_KERNEL_ROUTED = 4           /* streaming kernel + shared-memory privatised counting (two kernels per round) */
+  GCB_KERNEL_ROUTED = 4,          /* streaming kernel + shared-memory privatised counting (two kernels per round) */
+  GCB_KERNEL_NARROW = 5           /* streaming kernel into packed 8-bit L2-resident counters, folded per round;
+                                     exact, but slower than ROUTED on B200: never picked by AUTO */
 };
 
 typedef struct {
@@ -113,6 +115,8 @@ typedef struct {
   int uniform_weight;      /* 1 while every frame so far had the same weight */
   float weight;            /* that weight */
   int64_t kernel_launches; /* CUDA kernels launched by this counter so far */
+  uint64_t narrow_rounds;  /* rounds binned into packed 8-bit counters (GCB_KERNEL_NARROW) ... */
+  uint64_t narrow_redone;  /* ... of which a carry alarm had redone by the uint32 kernel (this rank) */
 } gcb_stats;
 
 int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex, int gnx,

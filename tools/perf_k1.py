@@ -27,7 +27,12 @@ def main():
     geom = g.setup_geometry(L, delta)
     gindex = np.arange(0, natoms, stride, dtype=np.int32)
     dev = g.DeviceFrames(nframes, natoms).generate(g.make_gen(1, L))
-    for kname, kernel in (("gather", K.KERNEL_GATHER), ("stream", K.KERNEL_STREAM), ("routed", K.KERNEL_ROUTED)):
+    kernels = (("gather", K.KERNEL_GATHER), ("stream", K.KERNEL_STREAM), ("routed", K.KERNEL_ROUTED),
+               ("narrow", K.KERNEL_NARROW), ("auto", K.KERNEL_AUTO))
+    only = os.environ.get("PERF_KERNELS")
+    for kname, kernel in kernels:
+        if only and kname not in only.split(","):
+            continue
         ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel)
         for _ in range(3):
             ctr.add_device_frames(dev)
@@ -42,6 +47,9 @@ def main():
         best, med = min(times), float(np.median(times))
         print("%s %s grid=%s atom-frames=%.3g  best %.3f ms (%.1f G/s, %.1f GB/s algorithmic)  median %.3f ms (%.1f G/s)"
               % (name, kname, geom.shape, af, best, af / best * 1e-6, af * 12 / best * 1e-6, med, af / med * 1e-6))
+        st = ctr.stats()
+        if st.narrow_rounds:
+            print("    narrow rounds %d, redone %d" % (st.narrow_rounds, st.narrow_redone))
         ctr.close()
     dev.free()
 
