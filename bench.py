@@ -365,6 +365,16 @@ def run_gpu_arm(args, rank, local_rank, world):
                 "frac_of_l2_atomic_peak": ((float(gnx) * F / (k1_avg_ms * 1e-3) * 1e-9) /
                                            traffic["l2_atomic_peak_gops"]) if traffic and
                 traffic.get("l2_atomic_peak_gops") else None}
+    if traffic:
+        # what the kernel really moves: every 32-byte sector of a frame holds part of a counted atom when one atom in
+        # three is counted, so DRAM traffic is 36 B per unit whatever the kernel does
+        roofline["dram_frac"] = traffic["dram_bytes_per_launch"] / (k1_avg_ms * 1e-3) * 1e-9 / peak
+        roofline["dram_bytes_per_unit"] = traffic["dram_bytes_per_launch"] / (float(gnx) * F)
+    # L2 work model fitted to three measurements: a RED costs 1.625 read sectors, the L2
+    # sustains 310 G sector-equivalents/s; this workload needs 36/32 read sectors + 1 RED per unit
+    l2_ceiling = 310.0 / (36.0 / 32.0 + 1.625)
+    roofline["l2_model_ceiling_g_units_s"] = l2_ceiling
+    roofline["frac_of_l2_model"] = (float(gnx) * F / (k1_avg_ms * 1e-3) * 1e-9) / l2_ceiling
 
     # ---- end to end: pinned host frames through the C ABI ----------------------------------
     HOSTF = 1000                                     # distinct frames kept in pinned memory (720 MB)
