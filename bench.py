@@ -258,7 +258,9 @@ def k3_section(g, ctr, T_tot):
     u.oracle().gco_analyse(C.byref(og), u.fptr(dens), C.byref(an))
     cpu_s = time.perf_counter() - t0
     arrs = u.analysis_arrays(an, og)
-    same = all(np.array_equal(arrs[k].view(np.uint32), r[k].view(np.uint32)) for k in ("rzp", "zdf", "rdf", "xyp"))
+    def _same(p, q):
+        return np.array_equal(np.isnan(p), np.isnan(q)) and bool(((p.view(np.uint32) == q.view(np.uint32)) | np.isnan(p)).all())
+    same = all(_same(arrs[k], r[k]) for k in ("rzp", "zdf", "rdf", "xyp"))
     same = same and np.float32(an.average).view(np.uint32) == np.float32(r["average"]).view(np.uint32) and an.sumP == r["sumP"]
     u.oracle().gco_analysis_free(C.byref(an))
     cells = int(np.prod(dens.shape))
