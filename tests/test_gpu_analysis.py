@@ -154,3 +154,22 @@ def test_whole_grid_chains_bit_exact_on_adversarial_grids(kind, L, delta):
     u.assert_bits_equal(np.float64(r["sumH"]), np.float64(scal["sumH"]), "sumH")
     for k in ARRAYS:
         u.assert_bits_equal(r[k], arrs[k], k)
+
+
+@pytest.mark.parametrize("shape_L,delta", [((3.0, 3.0, 3.0), 0.05), ((1.0, 1.0, 1.0), 0.5), ((0.9, 0.9, 5.0), (0.3, 0.3, 0.01))])
+def test_analysis_of_an_empty_grid_and_tiny_grids(shape_L, delta):
+    """all-zero density (0/0 = NaN in lzdf/profile, a_ri3Dc.c:672-695, must come out as NaN in the same places),
+    a 2x2x2 grid, a 3x3x500 needle: same bits as the oracle"""
+    geom = g.setup_geometry(shape_L, delta)
+    for fill in (0.0, 1.5):
+        grid = np.full(geom.shape, fill, np.float32)
+        r = g.analyse(geom.tg, grid, unit="unity", min_occ=0.0)
+        og = u.Geom.from_buffer_copy(bytes(geom.tg))
+        u.oracle().gco_update_b(C.byref(og))
+        arrs, scal = oracle_analysis(og, grid, "unity", 0.0)
+        for k in ARRAYS:
+            u.assert_bits_equal(r[k], arrs[k], "%s (fill %g)" % (k, fill))
+        for k in ("volume", "reff", "average"):
+            u.assert_bits_equal(np.float32(r[k]), np.float32(scal[k]), k)
+        for k in ("sumP", "sumH"):
+            u.assert_bits_equal(np.float64(r[k]), np.float64(scal[k]), k)

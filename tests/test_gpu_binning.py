@@ -453,3 +453,51 @@ def test_narrow_counters_spill_and_alarm_paths_stay_exact(kind):
     o2, _, _ = oracle_counts(geom, x[:8], gindex)
     np.testing.assert_array_equal(ctr.counts(), ocounts + o2)
     ctr.close()
+
+
+# ----------------------------------------------------------------------------- empty and degenerate inputs
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_empty_and_degenerate_inputs(kernel):
+    """empty index group, zero frames, every atom outside the grid, a one-cell grid: nothing is counted that the
+    reference would not count (g_ri3Dc.c:145 drops outside atoms silently), nothing crashes"""
+    L = (2.0, 2.0, 2.0)
+    geom = g.setup_geometry(L, 0.1)
+    natoms = 500
+    rng = np.random.default_rng(3)
+    x = (rng.random((6, natoms, 3)) * 2.0).astype(np.float32)
+    # (1) empty index group
+    ctr = g.GridCounter(geom, np.zeros(0, np.int32), natoms, kernel=kernel)
+    ctr.add_frames(x, np.ones(6, np.float32))
+    assert ctr.counts().sum() == 0 and ctr.stats().hits == 0 and ctr.stats().frames == 6
+    np.testing.assert_array_equal(ctr.hits_per_frame(), np.zeros(6, np.uint64))
+    ctr.close()
+    # (2) zero frames, then a real batch, then zero frames again
+    gindex = np.arange(natoms, dtype=np.int32)
+    ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel)
+    ctr.add_frames(x[:0], np.ones(0, np.float32))
+    assert ctr.stats().frames == 0 and ctr.counts().sum() == 0
+    ctr.add_frames(x, np.ones(6, np.float32))
+    ctr.add_frames(x[:0], np.ones(0, np.float32))
+    ocounts, ohits, _ = oracle_counts(geom, x, gindex)
+    np.testing.assert_array_equal(ctr.counts(), ocounts)
+    np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
+    ctr.close()
+    # (3) every atom outside [a, b): dropped, density identically zero
+    ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel)
+    far = x + np.float32(5.0)
+    far[0, :10] = -far[0, :10]
+    ctr.add_frames(far, np.ones(6, np.float32))
+    st = ctr.stats()
+    assert st.hits == 0 and st.edge_overflow == 0 and st.sumP == 0.0
+    tg, dens, _ = ctr.density(6.0)
+    assert not dens.any()
+    ctr.close()
+    # (4) one cell
+    one = g.setup_geometry(L, 2.0)
+    assert one.shape == (1, 1, 1)
+    ctr = g.GridCounter(one, gindex, natoms, kernel=kernel)
+    ctr.add_frames(x, np.ones(6, np.float32))
+    oc, oh, _ = oracle_counts(one, x, gindex)
+    np.testing.assert_array_equal(ctr.counts(), oc)
+    np.testing.assert_array_equal(ctr.hits_per_frame(), oh)
+    ctr.close()
