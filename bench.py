@@ -250,6 +250,15 @@ def k3_section(g, ctr, T_tot):
         t0 = time.perf_counter()
         r = g.analyse(tg, dens, unit="SPC")
         ts.append(time.perf_counter() - t0)
+    # the same with the density left in HBM (gcb_counter_device_density -> gcb_analyse_device): no grid over PCIe
+    dptr = ctr.density_device(T_tot)
+    ctr.sync()
+    g.analyse(tg, None, unit="SPC", grid_dev=dptr)
+    td = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        g.analyse(tg, None, unit="SPC", grid_dev=dptr)
+        td.append(time.perf_counter() - t0)
     og = u.Geom.from_buffer_copy(bytes(tg))
     u.oracle().gco_update_b(C.byref(og))
     an = u.Analysis()
@@ -265,6 +274,7 @@ def k3_section(g, ctr, T_tot):
     u.oracle().gco_analysis_free(C.byref(an))
     cells = int(np.prod(dens.shape))
     return {"grid": list(dens.shape), "ms": float(np.median(ts)) * 1e3, "cells_per_s": cells / float(np.median(ts)),
+            "ms_device_resident_grid": float(np.median(td)) * 1e3,
             "kernel_launches": int(r["kernel_launches"]), "oracle_ms_1_thread": cpu_s * 1e3, "bit_equal_to_oracle": bool(same),
             "note": "host grid in, all profiles out; every sum is the reference's sequential f32/f64 chain, evaluated in parallel"}
 

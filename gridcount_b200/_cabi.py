@@ -137,6 +137,7 @@ SIGNATURES = {
     "gcb_free": (None, [C.c_void_p]),
     "gcb_dens_unit": (C.c_float, [C.c_int, C.POINTER(TGrid)]),
     "gcb_analyse": (C.c_int, [C.POINTER(TGrid), c_float_p, C.POINTER(AnalysisOpts), C.POINTER(Analysis)]),
+    "gcb_analyse_device": (C.c_int, [C.POINTER(TGrid), C.c_void_p, C.POINTER(AnalysisOpts), C.POINTER(Analysis)]),
     "gcb_analysis_free": (None, [C.POINTER(Analysis)]),
     "gcb_gridcalc": (C.c_int, [C.c_int, C.POINTER(c_float_p), c_float_p, C.POINTER(TGrid), c_float_p, c_float_p,
                                C.c_int]),

@@ -397,9 +397,10 @@ ANALYSIS_2D = dict(xyp=("mx", "my"), xzp=("mx", "mz"), yzp=("my", "mz"), hxyp=("
 
 
 def analyse(tg, grid_zfast, unit="unity", min_occ=0.0, radius=None, z1=None, z2=None, rad_ba_nr=0, rad_ba_step=1,
-            device=0):
-    """a_ri3Dc's reductions (a_ri3Dc.c:488-762) on the GPU -> dict of arrays and scalars."""
-    grid = np.ascontiguousarray(grid_zfast, np.float32)
+            device=0, grid_dev=None):
+    """a_ri3Dc's reductions (a_ri3Dc.c:488-762) on the GPU -> dict of arrays and scalars.
+    grid_dev: device pointer of a z-fastest grid (GridCounter.density_device) instead of the host array."""
+    grid = None if grid_dev is not None else np.ascontiguousarray(grid_zfast, np.float32)
     o = K.AnalysisOpts()
     o.unit = K.UNITS[unit]
     o.min_occ = min_occ
@@ -415,7 +416,10 @@ def analyse(tg, grid_zfast, unit="unity", min_occ=0.0, radius=None, z1=None, z2=
         o.setmask |= K.SET_Z2
         o.z2 = z2
     a = K.Analysis()
-    check(lib.gcb_analyse(C.byref(tg), _fptr(grid), C.byref(o), C.byref(a)), "gcb_analyse")
+    if grid_dev is not None:
+        check(lib.gcb_analyse_device(C.byref(tg), grid_dev, C.byref(o), C.byref(a)), "gcb_analyse_device")
+    else:
+        check(lib.gcb_analyse(C.byref(tg), _fptr(grid), C.byref(o), C.byref(a)), "gcb_analyse")
     try:
         dims = dict(mx=a.tg.mx[0], my=a.tg.mx[1], mz=a.tg.mx[2], nr=a.iradNR)
         out = {}
@@ -426,7 +430,7 @@ def analyse(tg, grid_zfast, unit="unity", min_occ=0.0, radius=None, z1=None, z2=
             out[name] = (np.ctypeslib.as_array(p, shape=(n,)).reshape(shape).copy() if n
                          else np.zeros(shape, np.float32))
         n = a.tg.cells
-        out["grid"] = np.ctypeslib.as_array(a.grid, shape=(n,)).reshape(a.tg.shape).copy()
+        out["grid"] = np.ctypeslib.as_array(a.grid, shape=(n,)).reshape(a.tg.shape).copy() if a.grid else None
         tg2 = K.TGrid.from_buffer_copy(a.tg)
         cav = K.Cavity.from_buffer_copy(a.geometry)
         out.update(tg=tg2, geometry=cav, DeltaR=a.DeltaR, dV=a.dV, iradNR=a.iradNR, unit_value=a.unit_value,

@@ -527,9 +527,10 @@ int blocks_for(size_t n, int threads) { return (int)std::max<size_t>(1, (n + thr
 
 }  // namespace
 
-extern "C" {
-
-int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analysis_opts *opts, gcb_analysis *out)
+// `on_device`: grid_zfast is device memory on opts->device (a counter's density, gcb_counter_device_density) and
+// out->grid stays NULL unless the analysis crops; otherwise host memory in, out->grid always filled.
+static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on_device, const gcb_analysis_opts *opts,
+                        gcb_analysis *out)
 {
   if (!tg_in || !grid_zfast || !opts || !out) return gcb::fail(GCB_ERR_ARG, "gcb_analyse: null argument");
   if (opts->unit < 0 || opts->unit >= GCB_UNIT_NR) return gcb::fail(GCB_ERR_ARG, "gcb_analyse: unknown unit %d", opts->unit);
@@ -630,13 +631,13 @@ int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analy
       d_rzp, d_hrzp, d_rdf, d_hrdf, d_rw, d_scal;
   Arena arena;
   HostGridCopy host_grid;
-  if (!cropped) {
+  if (!cropped && !on_device) {
     host_grid.start(grid_zfast, ncells);
     if (!host_grid.dst) return gcb::fail(GCB_ERR_NOMEM, "out of memory");
   }
   const size_t nrz = (size_t)iradNR * d.mz;
   const size_t maxseg = (ncells + (size_t)SCAN_THREADS * SCAN_T - 1) / ((size_t)SCAN_THREADS * SCAN_T) + 1;
-  arena.want(d_in, ocells * 4);
+  if (!on_device) arena.want(d_in, ocells * 4);
   if (cropped) arena.want(d_g, ncells * 4);
   arena.want(d_gx, ncells * 4);
   arena.want(d_c2, (size_t)nxy * 4);
@@ -661,11 +662,13 @@ int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analy
   arena.want(d_scal, 32);
   arena.want(d_fbuf, 16 + 4 * maxseg * sizeof(seqsum::Fn));
   AN_CUDA(arena.commit());
-  AN_CUDA(cudaMemcpy(d_in.p, grid_zfast, ocells * 4, cudaMemcpyHostToDevice));
+  if (!on_device) AN_CUDA(cudaMemcpy(d_in.p, grid_zfast, ocells * 4, cudaMemcpyHostToDevice));
+  else AN_CUDA(cudaDeviceSynchronize());          // whatever stream is still producing the grid
   int64_t launches = 0;
-  const float *g = d_in.as<float>();
+  const float *g_in = on_device ? grid_zfast : d_in.as<float>();
+  const float *g = g_in;
   if (cropped) {
-    an_crop_kernel<<<std::min(blocks_for(ncells, 256), 148 * 16), 256>>>(d_in.as<float>(), od, d_g.as<float>(), d, base[0], base[1], base[2]);
+    an_crop_kernel<<<std::min(blocks_for(ncells, 256), 148 * 16), 256>>>(g_in, od, d_g.as<float>(), d, base[0], base[1], base[2]);
     launches++;
     g = d_g.as<float>();
   }
@@ -783,7 +786,7 @@ int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analy
   const auto t_kern = now();
   // ---- results back; the O(iradNR*mz) normalisations (a_ri3Dc.c:717-762) on the host ----------
   int rc = GCB_OK;
-  out->grid = cropped ? host_copy<float>(d_g, ncells, &rc) : host_grid.finish();
+  out->grid = cropped ? host_copy<float>(d_g, ncells, &rc) : (on_device ? nullptr : host_grid.finish());
   out->xyp = host_copy<float>(d_xyp, nxy, &rc); out->hxyp = host_copy<float>(d_hxyp, nxy, &rc);
   out->xzp = host_copy<float>(d_xzp, (size_t)d.mx * d.mz, &rc); out->yzp = host_copy<float>(d_yzp, (size_t)d.my * d.mz, &rc);
   out->zdf = host_copy<float>(d_zdf, (size_t)d.mz * 2, &rc); out->lzdf = host_copy<float>(d_lzdf, (size_t)d.mz * 2, &rc);
@@ -859,6 +862,18 @@ int gcb_analyse(const gcb_tgrid *tg_in, const float *grid_zfast, const gcb_analy
     fprintf(stderr, "[gcb analyse] %dx%dx%d: tables+alloc+H2D %.3f ms, kernels %.3f ms%s, D2H+host finish %.3f ms\n", d.mx, d.my, d.mz,
             ms(t_start, t_up), ms(t_up, t_kern), serial ? " (serial chains)" : "", ms(t_kern, now()));
   return GCB_OK;
+}
+
+extern "C" {
+
+int gcb_analyse(const gcb_tgrid *tg, const float *grid_zfast, const gcb_analysis_opts *opts, gcb_analysis *out)
+{
+  return analyse_impl(tg, grid_zfast, false, opts, out);
+}
+
+int gcb_analyse_device(const gcb_tgrid *tg, const float *grid_zfast_dev, const gcb_analysis_opts *opts, gcb_analysis *out)
+{
+  return analyse_impl(tg, grid_zfast_dev, true, opts, out);
 }
 
 void gcb_analysis_free(gcb_analysis *a)

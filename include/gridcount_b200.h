@@ -263,6 +263,10 @@ typedef struct {
 float gcb_dens_unit(int unit, const gcb_tgrid *tg);      /* DensUnit[] (count.c:21-22, a_ri3Dc.c:516) */
 int gcb_analyse(const gcb_tgrid *tg, const float *grid_zfast, const gcb_analysis_opts *opts,
                 gcb_analysis *out);
+/* the same over a grid that already sits in device memory on opts->device (gcb_counter_device_density):
+ * K1 -> K2 -> K3 without the grid crossing PCIe.  out->grid is NULL unless the analysis crops. */
+int gcb_analyse_device(const gcb_tgrid *tg, const float *grid_zfast_dev, const gcb_analysis_opts *opts,
+                       gcb_analysis *out);
 void gcb_analysis_free(gcb_analysis *a);
 
 /* a_gridcalc.c:132-189: time-weighted average of n grids of identical shape */

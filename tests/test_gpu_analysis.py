@@ -84,8 +84,17 @@ def test_analysis_bit_exact_vs_oracle_on_binned_density(cfg):
     ctr = g.GridCounter(geom, gindex, natoms)
     ctr.add_device_frames(dev, weights=np.full(nframes, 2.0, np.float32))
     tg, dens, _ = ctr.density(2.0 * nframes)
-    ctr.close(); dev.free()
+    dens_dev = ctr.density_device(2.0 * nframes)
+    ctr.sync()
     r = g.analyse(tg, dens, unit=unit, min_occ=minocc)
+    # the same with the density left in HBM: K1 -> K2 -> K3 without the grid crossing PCIe
+    rd = g.analyse(tg, None, unit=unit, min_occ=minocc, grid_dev=dens_dev)
+    assert rd["grid"] is None
+    for k in ARRAYS:
+        u.assert_bits_equal(rd[k], r[k], "device-resident " + k)
+    for k in ("volume", "reff", "average", "sumP", "sumH"):
+        assert np.float64(rd[k]).view(np.uint64) == np.float64(r[k]).view(np.uint64), k
+    ctr.close(); dev.free()
     og = u.Geom.from_buffer_copy(bytes(tg))
     u.oracle().gco_update_b(C.byref(og))
     arrs, scal = oracle_analysis(og, dens, unit, minocc)
