@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -361,6 +362,12 @@ an_chain_grid_kernel(const float *__restrict__ gx, size_t ncells, int nxy, const
   seqsum::GridChain<float, SCAN_T, SCAN_THREADS> B;
   A.init(ncells); B.init(ncells);
   bool bad = false;
+  A.prologue(ncells, load_all, sh, &bad, (size_t)4 * SCAN_THREADS * SCAN_T);
+  B.prologue(ncells, load_cyl, sh, &bad, (size_t)4 * SCAN_THREADS * SCAN_T);
+  if (bad) {                                                         // every block sees the same terms: uniform
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(bad_out + 1, 1);
+    return;
+  }
   for (int round = 0; !(A.done && B.done); round++) {
     seqsum::Fn *fa = fbuf + (size_t)(round & 1) * 2 * maxseg, *fb = fa + maxseg;
     A.phase1(ncells, load_all, fa, sh, bad_out);
@@ -475,22 +482,69 @@ struct DevBuf {
 };
 
 // all device buffers of one gcb_analyse call in a single allocation
+// Per device: one allocation of up to 64 MB and four streams are kept between calls (a C2-sized analysis is
+// 1 ms of kernels; cudaMalloc/cudaFree and stream creation cost as much again).  A second thread analysing on
+// the same device at the same time simply allocates its own.
+struct DeviceCache {
+  std::mutex m;
+  char *base = nullptr;
+  size_t cap = 0;
+  cudaStream_t st[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+DeviceCache g_cache[64];
+constexpr size_t CACHE_MAX = (size_t)64 << 20;
+
 struct Arena {
   char *base = nullptr;
   size_t total = 0;
+  DeviceCache *cache = nullptr;        // locked while this arena borrows its allocation
   std::vector<std::pair<DevBuf *, size_t>> req;
   void want(DevBuf &b, size_t bytes)
   {
     req.emplace_back(&b, total);
     total += (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
   }
-  cudaError_t commit()
+  cudaError_t commit(int device)
   {
-    const cudaError_t e = cudaMalloc(&base, total);
+    cudaError_t e = cudaSuccess;
+    DeviceCache &dc = g_cache[device & 63];
+    if (total <= CACHE_MAX && dc.m.try_lock()) {
+      cache = &dc;
+      if (dc.cap < total) {
+        if (dc.base) cudaFree(dc.base);
+        dc.base = nullptr; dc.cap = 0;
+        e = cudaMalloc(&dc.base, total);
+        if (e == cudaSuccess) dc.cap = total;
+      }
+      base = dc.base;
+    } else {
+      e = cudaMalloc(&base, total);
+    }
     if (e == cudaSuccess) for (auto &r : req) { r.first->p = base + r.second; r.first->owned = false; }
     return e;
   }
-  ~Arena() { if (base) cudaFree(base); }
+  ~Arena()
+  {
+    if (cache) cache->m.unlock();
+    else if (base) cudaFree(base);
+  }
+};
+
+// the four analysis streams of a device: cached when the cache is free, else created for the call
+struct Streams {
+  cudaStream_t st[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool owned = false;
+  cudaError_t get(DeviceCache *cache)
+  {
+    cudaStream_t *src = cache ? cache->st : st;
+    owned = cache == nullptr;
+    for (int i = 0; i < 4; i++) {
+      if (!src[i]) { const cudaError_t e = cudaStreamCreateWithFlags(&src[i], cudaStreamNonBlocking); if (e != cudaSuccess) return e; }
+      st[i] = src[i];
+    }
+    return cudaSuccess;
+  }
+  ~Streams() { if (owned) for (auto &s : st) if (s) cudaStreamDestroy(s); }
 };
 
 // the caller's grid copied into out->grid by a helper thread while the GPU works (uncropped analyses)
@@ -661,7 +715,7 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
   arena.want(d_rw, ((size_t)iradNR + 1) * 4);
   arena.want(d_scal, 32);
   arena.want(d_fbuf, 16 + 4 * maxseg * sizeof(seqsum::Fn));
-  AN_CUDA(arena.commit());
+  AN_CUDA(arena.commit(opts->device));
   if (!on_device) AN_CUDA(cudaMemcpy(d_in.p, grid_zfast, ocells * 4, cudaMemcpyHostToDevice));
   else AN_CUDA(cudaDeviceSynchronize());          // whatever stream is still producing the grid
   int64_t launches = 0;
@@ -683,8 +737,9 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
   AN_CUDA(cudaMemset(d_scal.p, 0, 32));
 
   // ---- kernels: independent chains on independent streams --------------------------------------
-  cudaStream_t st[4];
-  for (auto &s : st) AN_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  Streams streams;
+  AN_CUDA(streams.get(arena.cache));
+  cudaStream_t (&st)[4] = streams.st;
   AN_CUDA(cudaDeviceSynchronize());                           // uploads / crop (legacy stream) done
   const auto t_up = now();
   {
@@ -756,7 +811,7 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
   cudaError_t kerr = cudaGetLastError();
   for (auto &s : st) { cudaError_t e = cudaStreamSynchronize(s); if (kerr == cudaSuccess) kerr = e; }
   cudaEventDestroy(gx_ready);
-  if (kerr != cudaSuccess) { for (auto &s : st) cudaStreamDestroy(s); return gcb::fail(GCB_ERR_CUDA, "analysis kernels failed: %s", cudaGetErrorString(kerr)); }
+  if (kerr != cudaSuccess) return gcb::fail(GCB_ERR_CUDA, "analysis kernels failed: %s", cudaGetErrorString(kerr));
   bool serial = false;
   {
     int bad = 0, bad_grid[2] = {0, 0};
@@ -777,7 +832,6 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
       if (e == cudaSuccess) e = cudaGetLastError();
       for (auto &s : st) { cudaError_t e2 = cudaStreamSynchronize(s); if (e == cudaSuccess) e = e2; }
     }
-    for (auto &s : st) cudaStreamDestroy(s);
     if (e != cudaSuccess) return gcb::fail(GCB_ERR_CUDA, "analysis kernels failed: %s", cudaGetErrorString(e));
   }
   if (!serial && iradNR > 0)
@@ -787,17 +841,29 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
   // ---- results back; the O(iradNR*mz) normalisations (a_ri3Dc.c:717-762) on the host ----------
   int rc = GCB_OK;
   out->grid = cropped ? host_copy<float>(d_g, ncells, &rc) : (on_device ? nullptr : host_grid.finish());
-  out->xyp = host_copy<float>(d_xyp, nxy, &rc); out->hxyp = host_copy<float>(d_hxyp, nxy, &rc);
-  out->xzp = host_copy<float>(d_xzp, (size_t)d.mx * d.mz, &rc); out->yzp = host_copy<float>(d_yzp, (size_t)d.my * d.mz, &rc);
-  out->zdf = host_copy<float>(d_zdf, (size_t)d.mz * 2, &rc); out->lzdf = host_copy<float>(d_lzdf, (size_t)d.mz * 2, &rc);
-  out->profile = host_copy<float>(d_prof, (size_t)d.mz * 2, &rc);
-  out->rweight = host_copy<float>(d_rw, iradNR, &rc);
-  out->rdf = host_copy<float>(d_rdf, (size_t)iradNR * 2, &rc); out->hrdf = host_copy<float>(d_hrdf, (size_t)iradNR * 2, &rc);
-  out->rzp = host_copy<float>(d_rzp, nrz, &rc); out->hrzp = host_copy<float>(d_hrzp, nrz, &rc);
+  // everything else was laid out contiguously in the arena (d_xyp ... d_scal): one copy, then cut up on the host
+  const char *span0 = d_xyp.as<char>();
+  const size_t span = (size_t)(d_scal.as<char>() + 32 - span0);
+  std::vector<char> stage(span);
+  if (cudaMemcpy(stage.data(), span0, span, cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = gcb::fail(GCB_ERR_CUDA, "copying the analysis results back failed: %s", cudaGetErrorString(cudaGetLastError()));
+  auto cut = [&](const DevBuf &b, size_t n) -> float * {
+    float *h = (float *)malloc(std::max<size_t>(n, 1) * sizeof(float));
+    if (!h) { rc = gcb::fail(GCB_ERR_NOMEM, "out of memory"); return nullptr; }
+    if (n) memcpy(h, stage.data() + (b.as<char>() - span0), n * sizeof(float));
+    return h;
+  };
+  out->xyp = cut(d_xyp, nxy); out->hxyp = cut(d_hxyp, nxy);
+  out->xzp = cut(d_xzp, (size_t)d.mx * d.mz); out->yzp = cut(d_yzp, (size_t)d.my * d.mz);
+  out->zdf = cut(d_zdf, (size_t)d.mz * 2); out->lzdf = cut(d_lzdf, (size_t)d.mz * 2);
+  out->profile = cut(d_prof, (size_t)d.mz * 2);
+  out->rweight = cut(d_rw, iradNR);
+  out->rdf = cut(d_rdf, (size_t)iradNR * 2); out->hrdf = cut(d_hrdf, (size_t)iradNR * 2);
+  out->rzp = cut(d_rzp, nrz); out->hrzp = cut(d_hrzp, nrz);
   std::vector<unsigned> nocc((size_t)d.mz);
   char scal[32];
-  if (!rc && cudaMemcpy(nocc.data(), d_nocc.p, (size_t)d.mz * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = gcb::fail(GCB_ERR_CUDA, "D2H failed");
-  if (!rc && cudaMemcpy(scal, d_scal.p, 32, cudaMemcpyDeviceToHost) != cudaSuccess) rc = gcb::fail(GCB_ERR_CUDA, "D2H failed");
+  memcpy(nocc.data(), stage.data() + (d_nocc.as<char>() - span0), (size_t)d.mz * 4);
+  memcpy(scal, stage.data() + (d_scal.as<char>() - span0), 32);
   if (rc) { gcb_analysis_free(out); return rc; }
 
   const size_t mz = (size_t)d.mz;

@@ -381,6 +381,58 @@ struct GridChain {
     return left < W ? left : W;
   }
 
+  // Most exponent changes of a sum that starts at zero happen within its first few thousand terms (the k-th one
+  // near term 2^k / mean).  Every block therefore walks the first `limit` terms by itself, redundantly, one
+  // block-level scan per chunk or per exponent change, before the grid-wide rounds (one barrier each) begin.
+  template <class Load>
+  __device__ void prologue(size_t n, Load load, BlockScratch &sh, bool *bad, size_t limit)
+  {
+    const int tid = threadIdx.x;
+    const size_t end = n < limit ? n : limit;
+    while (pos < end && !done) {
+      float x[T];
+      load(pos + (size_t)tid * T, x);
+      bool ok = true;
+      Fn f; f.a0 = 0; f.a1 = 0;
+#pragma unroll
+      for (int j = 0; j < T; j++) {
+        if (pos + (size_t)tid * T + j >= end) x[j] = 0.0f;             // the rounds take over at `end`
+        const uint32_t xb = __float_as_uint(x[j]);
+        ok &= term_ok(xb);
+        f = then<R>(f, term<R>(xb, E));
+      }
+      if (!ok) sh.bad = 1;
+      Fn excl, incl, total;
+      block_scan<R, NT>(f, sh, excl, incl, total);
+      if (apply(incl, M) >= LIMIT) atomicMin(&sh.first_cross, tid);
+      __syncthreads();
+      if (sh.bad) { *bad = true; done = true; return; }
+      const int fc = sh.first_cross;
+      if (fc == NT) {
+        M = apply(total, M);
+        pos = end - pos > (size_t)CH ? pos + CH : end;
+        continue;
+      }
+      if (tid == fc) {
+        unsigned long long m = apply(excl, M);
+        const int j = walk<R, T>(x, E, m);
+        float xv = 0.0f;
+#pragma unroll
+        for (int q = 0; q < T; q++) if (q == j) xv = x[q];
+        sh.cross_M = m; sh.cross_j = j; sh.cross_x = xv;
+      }
+      __syncthreads();
+      const R snew = Tr<R>::add(Tr<R>::pack(E, sh.cross_M), sh.cross_x);
+      pos += (size_t)fc * T + sh.cross_j + 1;
+      __syncthreads();
+      if (tid == 0) sh.first_cross = NT;
+      __syncthreads();
+      if (!Tr<R>::finite(snew)) { *bad = true; done = true; return; }
+      Tr<R>::unpack(snew, E, M);
+    }
+    done = pos >= n;
+  }
+
   template <class Load>
   __device__ void phase1(size_t n, Load load, Fn *fbuf, BlockScratch &sh, int *bad_flag) const
   {
