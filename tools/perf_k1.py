@@ -16,6 +16,7 @@ SHAPES = {
     "c2all": ((8.0, 8.0, 13.4), 0.1, 60000, 1, 2000),
     "c3": ((20.0, 20.0, 20.0), 0.05, 1000000, 3, 256),
     "c4": ((10.0, 10.0, 10.0), 0.02, 100000, 3, 2048),
+    "c4k": ((10.0, 10.0, 10.0), 0.02, 100000, 3, 2048),     # clustered: Gaussians (sigma 0.1 nm) around 256 sites (SURVEY 8d "K")
 }
 
 
@@ -26,7 +27,8 @@ def main():
         nframes = int(sys.argv[2])
     geom = g.setup_geometry(L, delta)
     gindex = np.arange(0, natoms, stride, dtype=np.int32)
-    dev = g.DeviceFrames(nframes, natoms).generate(g.make_gen(1, L))
+    gen = g.make_gen(1, L, K.GEN_CLUSTER, nsites=256, sigma=0.1) if name.endswith("k") else g.make_gen(1, L)
+    dev = g.DeviceFrames(nframes, natoms).generate(gen)
     kernels = (("gather", K.KERNEL_GATHER), ("stream", K.KERNEL_STREAM), ("routed", K.KERNEL_ROUTED),
                ("narrow", K.KERNEL_NARROW), ("auto", K.KERNEL_AUTO))
     only = os.environ.get("PERF_KERNELS")
