@@ -279,6 +279,35 @@ def k3_section(g, ctr, T_tot):
             "note": "host grid in, all profiles out; every sum is the reference's sequential f32/f64 chain, evaluated in parallel"}
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this rank's threads (and with them its pinned staging memory, which is placed where the allocating
+    thread runs) to the NUMA node the GPU hangs off, so that H2D DMA reads do not cross the socket interconnect.
+    Best effort: returns a short description, or None when the topology cannot be read."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device).pci_bus_id if hasattr(torch.cuda.get_device_properties(device), "pci_bus_id") else None
+        if bus is None:
+            out = subprocess.check_output(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device)], text=True)
+            bus = out.strip()
+        bus = bus.lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:      # 00000000:1B:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
@@ -297,6 +326,7 @@ def run_gpu_arm(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank
     torch.cuda.set_device(device)
+    numa = bind_to_gpu_numa_node(device) if world > 1 else None
 
     def barrier():
         if dist is not None:
@@ -470,6 +500,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                 "config": {"workload": wl["name"], "grid": list(geom.shape), "distribution": "pore (generator mode 2)",
                            "frames_resident_gb": F * natoms * 12 / 1e9, "l2_policy": "inputs (7.2 GB) larger than L2",
                            "parallelism": "frame-sharded x%d, one NCCL u32 all-reduce per job" % world,
+                           "host_binding": numa,
                            "step": "reset + K1 bin 10000 frames + (all-reduce) + K2 density"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "a_ri3Dc": k3, "xtc": xtc}
