@@ -167,7 +167,12 @@ int gcb_counter_timer_stop(gcb_counter *c, float *ms);
 
 /* Frame-sharded multi-GPU: one counter per rank; integer sum of the private
  * grids and of the statistics over NCCL (the reference's manual equivalent is
- * a_gridcalc.c:180-189).  After the call every rank holds the global result. */
+ * a_gridcalc.c:180-189).  After the call every rank holds the global result.
+ * gcb_counter_allreduce returns once the collectives are queued behind the binning
+ * kernels (device-side consumers such as gcb_counter_density are ordered on the
+ * stream); the gathered per-frame statistics are waited for by the first getter that
+ * needs them (gcb_counter_stats, _hits_per_frame, _sync).  The uint32 cells are summed
+ * without an overflow check: 2^32 hits on one cell across all ranks wrap. */
 int gcb_nccl_unique_id(char id_out[128]);
 int gcb_counter_comm_init(gcb_counter *c, const char id[128], int rank, int nranks);
 int gcb_counter_allreduce(gcb_counter *c);
@@ -231,8 +236,11 @@ void gcb_free(void *p);
 
 /* ------------------------------------------------------------------------
  * Analysis on the GPU.  Replaces readjust_tgrid (a_ri3Dc.c:133-201) and the
- * reductions of a_ri3Dc's main (a_ri3Dc.c:488-762), with the reference's f32
- * summation order per output element so results are bit-identical.
+ * reductions of a_ri3Dc's main (a_ri3Dc.c:488-762).  Every output is the
+ * reference's sequential f32 (sumP: f64) chain in its k,j,i order, bit for bit;
+ * long chains are evaluated in parallel by an exact scan of the rounding
+ * recurrence (csrc/seqsum.cuh), which needs finite cells >= 0 -- grids with
+ * negative or non-finite cells take one-thread-per-chain kernels instead.
  * ---------------------------------------------------------------------- */
 enum { GCB_UNIT_UNITY, GCB_UNIT_SPC, GCB_UNIT_MOLAR, GCB_UNIT_ANG, GCB_UNIT_VOXEL, GCB_UNIT_NR };  /* count.h:28 */
 
