@@ -52,7 +52,7 @@ class Stats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("atom_frames", C.c_uint64), ("hits", C.c_uint64),
                 ("edge_overflow", C.c_uint64), ("sumP", C.c_double), ("uniform_weight", C.c_int),
                 ("weight", C.c_float), ("kernel_launches", C.c_int64), ("narrow_rounds", C.c_uint64),
-                ("narrow_redone", C.c_uint64)]
+                ("narrow_redone", C.c_uint64), ("saturated", C.c_int)]
 
 
 class AnalysisOpts(C.Structure):

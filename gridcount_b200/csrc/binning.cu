@@ -808,6 +808,18 @@ narrow_log_kernel(const uint32_t *__restrict__ log, const unsigned *__restrict__
   for (unsigned i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(counts + log[(size_t)blockIdx.x * seg_cap + i], 128u);
 }
 
+// Saturation guard of the uint32 cells.  The reference accumulates in f32, which stops moving after at most
+// ~2^26 additions of one weight, so a cell count clamped at 2^27 (or above) gives the same occupancy and density
+// bit for bit; a WRAPPED count would not.  The host keeps an upper bound on what any cell can hold (what was
+// binned since the last clamp) and runs this pass before the bound could reach 2^32: once per ~4.2e9 atom-frames.
+__global__ void clamp_counts_kernel(uint32_t *__restrict__ cnt, size_t n, uint32_t limit, unsigned long long *__restrict__ flag)
+{
+  bool any = false;
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x)
+    if (cnt[c] > limit) { cnt[c] = limit; any = true; }
+  if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(flag, 1ull);
+}
+
 __global__ void fold_run_kernel(uint32_t *__restrict__ runcnt, uint32_t *__restrict__ total,
                                 float *__restrict__ acc, float w, size_t n)
 {
@@ -999,6 +1011,7 @@ struct gcb_counter {
   unsigned narrow_seg_cap = 0;
   int narrow_grid = 0;
   uint64_t narrow_rounds = 0, narrow_redone = 0;
+  bool saturated = false;             // some cell was clamped (diag[3])
   // xtc path: two sets of {compressed bytes, frame table, status, decoded frames}, copy stream + events
   struct XtcSet {
     uint8_t *d_buf = nullptr; size_t buf_cap = 0;
@@ -1025,6 +1038,9 @@ struct gcb_counter {
   unsigned long long *d_diag = nullptr;
   float *d_out = nullptr, *d_out2 = nullptr;   // density / transpose outputs
 
+  // saturation guard (clamp_counts_kernel): upper bounds on any cell of d_runcnt / d_total
+  unsigned long long bound_run = 0, bound_total = 0;
+  unsigned long long clamp_at = 1ull << 27, clamp_ceiling = 0xffffffffull;
   bool have_run = false;              // d_runcnt holds hits of weight w_cur not yet folded into d_acc
   float w_cur = 0;
   bool uniform = true, any = false;
@@ -1074,11 +1090,30 @@ int elementwise_grid(const gcb_counter *c, size_t n)
   return (int)std::max<size_t>(1, std::min(b, cap));
 }
 
+// make sure `units` more hits fit into every cell of `cnt` (bound = what the fullest cell may hold now)
+int ensure_headroom(gcb_counter *c, uint32_t *cnt, unsigned long long &bound, unsigned long long units)
+{
+  if (bound + units <= c->clamp_ceiling) return GCB_OK;
+  if (bound > c->clamp_at) {
+    clamp_counts_kernel<<<elementwise_grid(c, c->ncells), 256, 0, c->compute>>>(cnt, c->ncells, (uint32_t)c->clamp_at, c->d_diag + 3);
+    c->launches++;
+    GCB_CUDA(cudaGetLastError());
+    bound = c->clamp_at;
+  }
+  if (bound + units > c->clamp_ceiling)
+    return gcb::fail(GCB_ERR_RANGE, "a single launch of %llu atom-frames cannot be guarded against uint32 overflow", units);
+  return GCB_OK;
+}
+
 int fold_pending(gcb_counter *c)
 {
   if (!c->have_run) return GCB_OK;
   int rc = ensure_acc(c);
   if (rc) return rc;
+  rc = ensure_headroom(c, c->d_total, c->bound_total, c->bound_run);
+  if (rc) return rc;
+  c->bound_total += c->bound_run;
+  c->bound_run = 0;
   fold_run_kernel<<<elementwise_grid(c, c->ncells), 256, 0, c->compute>>>(c->d_runcnt, c->d_total, c->d_acc,
                                                                            c->w_cur, c->ncells);
   c->launches++;
@@ -1326,8 +1361,11 @@ int bin_device_batch(gcb_counter *c, const float *d_x, long nframes, const float
   while (f < nframes) {
     const float wr = w ? w[f] : 1.0f;
     long e = f + 1;
-    while (e < nframes && same_bits(w ? w[e] : 1.0f, wr)) e++;
+    // one launch never adds more than a quarter of the counter range to a cell (saturation guard)
+    const long max_frames = (long)std::max<unsigned long long>(1, (c->clamp_ceiling / 4) / (unsigned long long)std::max(c->gnx, 1));
+    while (e < nframes && e - f < max_frames && same_bits(w ? w[e] : 1.0f, wr)) e++;
     const long n = e - f;
+    const unsigned long long units = (unsigned long long)n * (unsigned long long)c->gnx;
     if (!c->any) { c->any = true; c->w_first = wr; }
     else if (!same_bits(wr, c->w_first)) c->uniform = false;
 
@@ -1341,12 +1379,18 @@ int bin_device_batch(gcb_counter *c, const float *d_x, long nframes, const float
       if (c->have_run && !continues) { rc = fold_pending(c); if (rc) return rc; }
       c->have_run = true;
       c->w_cur = wr;
+      rc = ensure_headroom(c, c->d_runcnt, c->bound_run, units);
+      if (rc) return rc;
+      c->bound_run += units;
       rc = launch_bin_pbc<MODE_COUNT>(c, xs, n, wr, bs, d_hits + f);
     } else {
       rc = fold_pending(c);
       if (rc) return rc;
       rc = ensure_acc(c);
       if (rc) return rc;
+      rc = ensure_headroom(c, c->d_total, c->bound_total, units);
+      if (rc) return rc;
+      c->bound_total += units;
       rc = launch_bin_pbc<MODE_FLOAT>(c, xs, n, wr, bs, d_hits + f);
     }
     if (rc) return rc;
@@ -1559,6 +1603,11 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
     if (getenv("GCB_NO_ROUTE")) c->route_mode = 0;
     // narrow path: the bytes must stay L2-resident next to the coordinate stream (random returning atomics
     // hold 128 G/s up to a 96 MB window, profiles/atomic_peak_r01e.json)
+    if (const char *e = getenv("GCB_CLAMP_AT")) c->clamp_at = strtoull(e, nullptr, 10);
+    if (const char *e = getenv("GCB_CLAMP_CEILING")) c->clamp_ceiling = strtoull(e, nullptr, 10);
+    if (c->clamp_at < 1 || c->clamp_ceiling > 0xffffffffull || c->clamp_at * 2 > c->clamp_ceiling) {
+      c->clamp_at = 1ull << 27; c->clamp_ceiling = 0xffffffffull;
+    }
     const char *nenv = getenv("GCB_NARROW_UNITS");
     c->narrow_units = nenv ? atoll(nenv) : (256LL << 20);
     if (c->narrow_units < 4096) c->narrow_units = 4096;
@@ -1606,6 +1655,7 @@ int gcb_counter_reset(gcb_counter *c)
   }
   GCB_CUDA(cudaMemsetAsync(c->d_diag, 0, sizeof(unsigned long long) * 4, c->compute));
   c->narrow_rounds = 0; c->narrow_redone = 0;
+  c->bound_run = 0; c->bound_total = 0;
   c->reduced = false; c->global_frames = 0;
   c->have_run = false; c->any = false; c->uniform = true; c->w_cur = 0; c->w_first = 0;
   c->hits_per_frame.clear(); c->weight_per_frame.clear();
@@ -1805,11 +1855,12 @@ int gcb_counter_sync(gcb_counter *c)
     cudaFree(h.d_box3);
   }
   c->devhits.clear();
-  if (!c->reduced) {                  // after an all-reduce the statistics are the global ones
+  {
     unsigned long long diag[4];
     GCB_CUDA(cudaMemcpy(diag, c->d_diag, sizeof(diag), cudaMemcpyDeviceToHost));
-    c->edge_overflow = diag[0];
+    if (!c->reduced) c->edge_overflow = diag[0];      // after an all-reduce the statistic is the global one
     c->narrow_redone = diag[2];
+    c->saturated = diag[3] != 0;
   }
   // sumP: `sumP += (double)weight` once per hit, frame by frame (g_ri3Dc.c:151,426)
   for (; c->sumP_frames < c->hits_per_frame.size(); c->sumP_frames++) {
@@ -1835,6 +1886,7 @@ int gcb_counter_stats(gcb_counter *c, gcb_stats *out)
   out->kernel_launches = c->launches;
   out->narrow_rounds = c->narrow_rounds;
   out->narrow_redone = c->narrow_redone;
+  out->saturated = c->saturated ? 1 : 0;
   return GCB_OK;
 }
 
@@ -2155,27 +2207,32 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops 
   //    {has frames, weight bits, uniform, has f32 accumulator, frame count}: host-side knowledge, so it
   //    travels while the binning kernels are still running
   const size_t R = (size_t)c->nranks;
-  rc = scratch(R * 5);
+  constexpr size_t TW = 7;                 // table words per rank
+  rc = scratch(R * TW);
   if (rc) return rc;
   uint32_t wb; memcpy(&wb, &c->w_first, 4);
-  memset(c->h_scr, 0, sizeof(unsigned long long) * R * 5);
-  c->h_scr[(size_t)c->rank * 5 + 0] = c->any ? 1ull : 0ull;
-  c->h_scr[(size_t)c->rank * 5 + 1] = wb;
-  c->h_scr[(size_t)c->rank * 5 + 2] = c->uniform ? 1ull : 0ull;
-  c->h_scr[(size_t)c->rank * 5 + 3] = (c->d_acc != nullptr) ? 1ull : 0ull;
-  c->h_scr[(size_t)c->rank * 5 + 4] = c->hits_per_frame.size();
-  GCB_CUDA(cudaMemcpyAsync(c->d_scr, c->h_scr, sizeof(unsigned long long) * R * 5, cudaMemcpyHostToDevice, c->comm_stream));
-  rc = ops->allreduce(c->d_scr, c->d_scr, R * 5, U64, c->nccl, c->comm_stream);
+  memset(c->h_scr, 0, sizeof(unsigned long long) * R * TW);
+  c->h_scr[(size_t)c->rank * TW + 0] = c->any ? 1ull : 0ull;
+  c->h_scr[(size_t)c->rank * TW + 1] = wb;
+  c->h_scr[(size_t)c->rank * TW + 2] = c->uniform ? 1ull : 0ull;
+  c->h_scr[(size_t)c->rank * TW + 3] = (c->d_acc != nullptr) ? 1ull : 0ull;
+  c->h_scr[(size_t)c->rank * TW + 4] = c->hits_per_frame.size();
+  c->h_scr[(size_t)c->rank * TW + 5] = c->bound_run;          // saturation guard: what this rank's fullest cell may hold
+  c->h_scr[(size_t)c->rank * TW + 6] = c->bound_total;
+  GCB_CUDA(cudaMemcpyAsync(c->d_scr, c->h_scr, sizeof(unsigned long long) * R * TW, cudaMemcpyHostToDevice, c->comm_stream));
+  rc = ops->allreduce(c->d_scr, c->d_scr, R * TW, U64, c->nccl, c->comm_stream);
   if (rc) return rc;
-  GCB_CUDA(cudaMemcpyAsync(c->h_scr, c->d_scr, sizeof(unsigned long long) * R * 5, cudaMemcpyDeviceToHost, c->comm_stream));
+  GCB_CUDA(cudaMemcpyAsync(c->h_scr, c->d_scr, sizeof(unsigned long long) * R * TW, cudaMemcpyDeviceToHost, c->comm_stream));
   GCB_CUDA(cudaStreamSynchronize(c->comm_stream));
   bool global_uniform = true, any_acc = false, have_w = false;
   uint32_t w0 = 0;
   size_t total_frames = 0, my_off = 0;
+  unsigned long long sum_bound_run = 0, sum_bound_total = 0;
   for (int r = 0; r < c->nranks; r++) {
-    const unsigned long long *o = c->h_scr + (size_t)r * 5;
+    const unsigned long long *o = c->h_scr + (size_t)r * TW;
     if (r == c->rank) my_off = total_frames;
     total_frames += (size_t)o[4];
+    sum_bound_run += o[5]; sum_bound_total += o[6];
     if (!o[0]) continue;
     if (!o[2]) global_uniform = false;
     if (o[3]) any_acc = true;
@@ -2214,6 +2271,23 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops 
     if (rc) return rc;
     rc = ensure_acc(c);
     if (rc) return rc;
+    sum_bound_total += sum_bound_run;            // every rank has folded its run into the totals by now
+    sum_bound_run = 0;
+  }
+  {
+    // saturation guard across ranks: if the ranks' bounds could add up beyond the counter range, every rank
+    // clamps its cells to an equal share first (the same decision everywhere: it rests on the exchanged table)
+    const unsigned long long share = std::min<unsigned long long>(c->clamp_at, c->clamp_ceiling / R);
+    uint32_t *grid_cnt = (global_uniform && !any_acc) ? c->d_runcnt : c->d_total;
+    unsigned long long &sum_bound = (global_uniform && !any_acc) ? sum_bound_run : sum_bound_total;
+    if (sum_bound > c->clamp_ceiling) {
+      clamp_counts_kernel<<<elementwise_grid(c, c->ncells), 256, 0, c->compute>>>(grid_cnt, c->ncells, (uint32_t)share, c->d_diag + 3);
+      c->launches++;
+      GCB_CUDA(cudaGetLastError());
+      sum_bound = share * R;
+    }
+    c->bound_run = sum_bound_run;                 // bounds of the reduced grids
+    c->bound_total = sum_bound_total;
   }
   rc = ops->group_start();
   if (rc) return rc;

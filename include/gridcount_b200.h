@@ -117,6 +117,9 @@ typedef struct {
   int64_t kernel_launches; /* CUDA kernels launched by this counter so far */
   uint64_t narrow_rounds;  /* rounds binned into packed 8-bit counters (GCB_KERNEL_NARROW) ... */
   uint64_t narrow_redone;  /* ... of which a carry alarm had redone by the uint32 kernel (this rank) */
+  int saturated;           /* 1 if some cell reached the saturation guard (2^27 hits and the counter range was about
+                              to run out): its count is a lower bound; occupancy and density are still the reference's
+                              bits, because the reference's f32 accumulator stops moving long before (this rank) */
 } gcb_stats;
 
 int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex, int gnx,
@@ -171,8 +174,8 @@ int gcb_counter_timer_stop(gcb_counter *c, float *ms);
  * gcb_counter_allreduce returns once the collectives are queued behind the binning
  * kernels (device-side consumers such as gcb_counter_density are ordered on the
  * stream); the gathered per-frame statistics are waited for by the first getter that
- * needs them (gcb_counter_stats, _hits_per_frame, _sync).  The uint32 cells are summed
- * without an overflow check: 2^32 hits on one cell across all ranks wrap. */
+ * needs them (gcb_counter_stats, _hits_per_frame, _sync).  Before the sum the cells are clamped
+ * if the ranks' bounds could add up to 2^32 (see gcb_stats.saturated). */
 int gcb_nccl_unique_id(char id_out[128]);
 int gcb_counter_comm_init(gcb_counter *c, const char id[128], int rank, int nranks);
 int gcb_counter_allreduce(gcb_counter *c);

@@ -501,3 +501,42 @@ def test_empty_and_degenerate_inputs(kernel):
     np.testing.assert_array_equal(ctr.counts(), oc)
     np.testing.assert_array_equal(ctr.hits_per_frame(), oh)
     ctr.close()
+
+
+# ----------------------------------------------------------------------------- saturation guard of the uint32 cells
+def test_saturation_guard_with_lowered_thresholds(monkeypatch):
+    """The library clamps cell counts at 2^27 whenever the uint32 range could otherwise run out (the reference's f32
+    accumulator has stopped moving long before, so densities keep the reference's bits).  With the thresholds lowered
+    through the environment the mechanism is visible: a cell that keeps collecting hits is held between the clamp
+    value and the ceiling and flagged, every other cell stays exact; a well-spread run is never touched."""
+    monkeypatch.setenv("GCB_CLAMP_AT", "1000")
+    monkeypatch.setenv("GCB_CLAMP_CEILING", "40000")
+    L = (2.0, 2.0, 2.0)
+    geom = g.setup_geometry(L, 0.1)
+    natoms, nframes = 4096, 40
+    rng = np.random.default_rng(5)
+    x = (rng.random((nframes, natoms, 3)) * 2.0).astype(np.float32)
+    gindex = np.arange(natoms, dtype=np.int32)
+    for kernel in (K.KERNEL_STREAM, K.KERNEL_GATHER, K.KERNEL_ROUTED):
+        # (a) spread out: bounds force clamp passes (4096 possible hits per frame against a ceiling of 40 000), no cell is near 1000
+        ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel, frames_per_batch=4)
+        ctr.add_frames(x, np.ones(nframes, np.float32))
+        oc, oh, _ = oracle_counts(geom, x, gindex)
+        np.testing.assert_array_equal(ctr.counts(), oc)
+        assert ctr.stats().saturated == 0 and oc.max() < 1000
+        ctr.close()
+        # (b) a quarter of the atoms parked in one cell: 1024 hits per frame on it
+        y = x.copy()
+        y[:, ::4] = np.asarray([0.55, 0.65, 0.75], np.float32)
+        ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel, frames_per_batch=4)
+        ctr.add_frames(y, np.ones(nframes, np.float32))
+        oc, oh, _ = oracle_counts(geom, y, gindex)
+        got = ctr.counts()
+        hot = np.unravel_index(np.argmax(oc), oc.shape)
+        assert oc[hot] == 1024 * nframes
+        assert 1000 <= got[hot] <= 40000, got[hot]
+        mask = np.ones(oc.shape, bool); mask[hot] = False
+        np.testing.assert_array_equal(got[mask], oc[mask])
+        np.testing.assert_array_equal(ctr.hits_per_frame(), oh)      # per-frame statistics are 64-bit and unaffected
+        assert ctr.stats().saturated == 1
+        ctr.close()
