@@ -249,7 +249,7 @@ __global__ void an_slice_finish_kernel(const float *__restrict__ raw, int mz, Sl
 // One block per radial bin r: rdf[r][1] chains the occupied cells over k, then bin r's cells in (j,i)
 // order (a_ri3Dc.c:627-645); hrdf[r][1] is a chain of +1.0f over the other cells, i.e. min(count, 2^24).
 // bin_xy[] lists each bin's cells as j*mx + i.
-constexpr int RDF_THREADS = 256;
+constexpr int RDF_THREADS = 1024;
 __global__ void __launch_bounds__(RDF_THREADS)
 an_rdf_scan_kernel(const float *__restrict__ gx, Dims d, const int *__restrict__ bin_start,
                    const int *__restrict__ bin_xy, float min_occ, float *__restrict__ rdf, float *__restrict__ hrdf,
