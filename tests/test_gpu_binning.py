@@ -318,7 +318,7 @@ def test_reset_and_slot_interface():
 
 
 # ----------------------------------------------------------------------------- full-size properties
-def test_full_size_c2_properties():
+def test_c2_shape_512_frames_all_kernels_agree():
     """BASELINE config 2 shape (60k atoms, 20k OW, 80x80x134) on 512 generated frames: size-independent
     invariants + a replayable prefix against the oracle."""
     L = (8.0, 8.0, 13.4)
