@@ -15,6 +15,11 @@ the number density (K2).  `value` is binned atom-frames per second with the fram
 CUDA streams inside the timed region, density grid read back).  N > 1 is frame sharding: every
 rank gets its own 10 000 frames (weak scaling).
 
+Beside the contract's keys the line carries, at N = 1: `a_ri3Dc` (K3, gcb_analyse over the job's density: wall time
+from a host grid and from the density left in HBM, the oracle's single-thread time, bit-equality), `xtc` (host
+decode rate, GPU decode rate, the job driven from compressed bytes) and, in `roofline`, the DRAM fraction the
+kernel really reaches (36 B of traffic per unit) and the fraction of the fitted L2 ceiling.
+
 --impl reference times the reference's own CPU implementation of the path (the compiled,
 unmodified gridcount() loop in oracle/_ref/libgcref.so; the oracle's C port if that binary is
 absent) on all host threads, on bounded samples of the same workload.
