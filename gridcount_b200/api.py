@@ -430,7 +430,8 @@ def analyse(tg, grid_zfast, unit="unity", min_occ=0.0, radius=None, z1=None, z2=
             out[name] = (np.ctypeslib.as_array(p, shape=(n,)).reshape(shape).copy() if n
                          else np.zeros(shape, np.float32))
         n = a.tg.cells
-        out["grid"] = np.ctypeslib.as_array(a.grid, shape=(n,)).reshape(a.tg.shape).copy() if a.grid else None
+        # the cropped grid, else the grid that was passed in (None for a device-resident one)
+        out["grid"] = np.ctypeslib.as_array(a.grid, shape=(n,)).reshape(a.tg.shape).copy() if a.grid else grid
         tg2 = K.TGrid.from_buffer_copy(a.tg)
         cav = K.Cavity.from_buffer_copy(a.geometry)
         out.update(tg=tg2, geometry=cav, DeltaR=a.DeltaR, dV=a.dV, iradNR=a.iradNR, unit_value=a.unit_value,

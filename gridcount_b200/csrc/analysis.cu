@@ -547,19 +547,6 @@ struct Streams {
   ~Streams() { if (owned) for (auto &s : st) if (s) cudaStreamDestroy(s); }
 };
 
-// the caller's grid copied into out->grid by a helper thread while the GPU works (uncropped analyses)
-struct HostGridCopy {
-  std::thread th;
-  float *dst = nullptr;
-  void start(const float *src, size_t n)
-  {
-    dst = (float *)malloc(std::max<size_t>(n, 1) * sizeof(float));
-    if (dst) th = std::thread([d = dst, src, n] { memcpy(d, src, n * sizeof(float)); });
-  }
-  float *finish() { if (th.joinable()) th.join(); float *r = dst; dst = nullptr; return r; }
-  ~HostGridCopy() { if (th.joinable()) th.join(); free(dst); }
-};
-
 #define AN_CUDA(call)                                                                            \
   do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                                          \
       gcb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
@@ -581,8 +568,8 @@ int blocks_for(size_t n, int threads) { return (int)std::max<size_t>(1, (n + thr
 
 }  // namespace
 
-// `on_device`: grid_zfast is device memory on opts->device (a counter's density, gcb_counter_device_density) and
-// out->grid stays NULL unless the analysis crops; otherwise host memory in, out->grid always filled.
+// `on_device`: grid_zfast is device memory on opts->device (a counter's density, gcb_counter_device_density),
+// otherwise host memory.  out->grid is filled only when the analysis crops.
 static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on_device, const gcb_analysis_opts *opts,
                         gcb_analysis *out)
 {
@@ -684,11 +671,6 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
   DevBuf d_in, d_g, d_gx, d_c2, d_flags, d_bs, d_bc, d_bxy, d_fbuf, d_sraw, d_xyp, d_hxyp, d_xzp, d_yzp, d_zdf, d_lzdf, d_prof, d_nocc,
       d_rzp, d_hrzp, d_rdf, d_hrdf, d_rw, d_scal;
   Arena arena;
-  HostGridCopy host_grid;
-  if (!cropped && !on_device) {
-    host_grid.start(grid_zfast, ncells);
-    if (!host_grid.dst) return gcb::fail(GCB_ERR_NOMEM, "out of memory");
-  }
   const size_t nrz = (size_t)iradNR * d.mz;
   const size_t maxseg = (ncells + (size_t)SCAN_THREADS * SCAN_T - 1) / ((size_t)SCAN_THREADS * SCAN_T) + 1;
   if (!on_device) arena.want(d_in, ocells * 4);
@@ -840,7 +822,7 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
   const auto t_kern = now();
   // ---- results back; the O(iradNR*mz) normalisations (a_ri3Dc.c:717-762) on the host ----------
   int rc = GCB_OK;
-  out->grid = cropped ? host_copy<float>(d_g, ncells, &rc) : (on_device ? nullptr : host_grid.finish());
+  out->grid = cropped ? host_copy<float>(d_g, ncells, &rc) : nullptr;    // uncropped: the caller's grid IS the analysed grid
   // everything else was laid out contiguously in the arena (d_xyp ... d_scal): one copy, then cut up on the host
   const char *span0 = d_xyp.as<char>();
   const size_t span = (size_t)(d_scal.as<char>() + 32 - span0);

@@ -195,13 +195,13 @@ int main(int argc, char **argv)
 
   if (gh_fn_set(fnm, NFILE, "-dump")) {
     gh_msg("Dumping the 3D grid into ascii file %s...[Unit is %s]", gh_fn(fnm, NFILE, "-dump"), unit_names[nunit]);
-    CHECK(gcb_ascii_write(gh_fn(fnm, NFILE, "-dump"), &an.tg, an.grid, U));
+    CHECK(gcb_ascii_write(gh_fn(fnm, NFILE, "-dump"), &an.tg, an.grid ? an.grid : grid, U));
     gh_msg(".. done!\n");
   }
   if (gh_fn_set(fnm, NFILE, "-plt")) {
     gh_msg("Dumping the 3D grid into gOpenMol density file %s... (rename to xxx.plt)\n[Unit is %s]", gh_fn(fnm, NFILE, "-plt"),
            unit_names[nunit]);
-    CHECK(gcb_plt_write(gh_fn(fnm, NFILE, "-plt"), &an.tg, an.grid, U));
+    CHECK(gcb_plt_write(gh_fn(fnm, NFILE, "-plt"), &an.tg, an.grid ? an.grid : grid, U));
     gh_msg("... done!\n");
   }
   gh_xf_write_resource();

@@ -262,7 +262,8 @@ typedef struct {
   float DeltaR; double dV; int iradNR; float unit_value;
   double sumP, sumH;       /* a_ri3Dc.c:499-512 */
   float volume, reff, average, height; int ivol;    /* a_ri3Dc.c:759-762 */
-  float *grid;             /* cropped grid, z fastest [mx][my][mz] */
+  float *grid;             /* the cropped grid, z fastest [mx][my][mz]; NULL when the analysis did not crop
+                              (no -R/-z1/-z2): the grid that was passed in is the grid that was analysed */
   float *xyp, *xzp, *yzp, *hxyp;        /* [mx][my] [mx][mz] [my][mz] [mx][my] */
   float *zdf, *lzdf, *profile;          /* [mz][2] */
   float *rweight;                       /* [iradNR] */
@@ -275,7 +276,7 @@ float gcb_dens_unit(int unit, const gcb_tgrid *tg);      /* DensUnit[] (count.c:
 int gcb_analyse(const gcb_tgrid *tg, const float *grid_zfast, const gcb_analysis_opts *opts,
                 gcb_analysis *out);
 /* the same over a grid that already sits in device memory on opts->device (gcb_counter_device_density):
- * K1 -> K2 -> K3 without the grid crossing PCIe.  out->grid is NULL unless the analysis crops. */
+ * K1 -> K2 -> K3 without the grid crossing PCIe. */
 int gcb_analyse_device(const gcb_tgrid *tg, const float *grid_zfast_dev, const gcb_analysis_opts *opts,
                        gcb_analysis *out);
 void gcb_analysis_free(gcb_analysis *a);
