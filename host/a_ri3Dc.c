@@ -127,8 +127,7 @@ int main(int argc, char **argv)
                (gh_opt_set(pa, NPA, "-z2") ? GCB_SET_Z2 : 0);
   ao.radius = geometry.radius; ao.z1 = geometry.z1; ao.z2 = geometry.z2;
   gcb_analysis an;
-  CHECK(gcb_analyse(&tg, grid, &ao, &an));
-  gcb_free(grid);
+  CHECK(gcb_analyse(&tg, grid, &ao, &an));     /* an.grid is NULL unless the analysis cropped: `grid` is needed until the end */
   if (ao.setmask & GCB_SET_Z1) gh_msg("Readjusted: z1 = %g nm (supplied: %g)\n", an.tg.a[2], geometry.z1);
   if (ao.setmask & GCB_SET_Z2) gh_msg("Readjusted: z2 = %g nm (supplied: %g)\n", an.tg.b[2], geometry.z2);
   if (ao.setmask & GCB_SET_R) gh_msg("Readjusted: R = %g nm (supplied: %g)\n", an.geometry.radius, geometry.radius);
@@ -206,6 +205,7 @@ int main(int argc, char **argv)
   }
   gh_xf_write_resource();
   gcb_analysis_free(&an);
+  gcb_free(grid);
   gh_msg("\n");
   return 0;
 }
