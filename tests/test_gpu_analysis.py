@@ -182,3 +182,31 @@ def test_analysis_of_an_empty_grid_and_tiny_grids(shape_L, delta):
             u.assert_bits_equal(np.float32(r[k]), np.float32(scal[k]), k)
         for k in ("sumP", "sumH"):
             u.assert_bits_equal(np.float64(r[k]), np.float64(scal[k]), k)
+
+
+@pytest.mark.parametrize("name,run", [(n, r) for n, r in ANALYSES
+                                      if gc.parse_aargs(gc.CASES[n]["analyses"][r])["setmask"]][:3])
+def test_device_resident_grid_with_crop_equals_host_path(name, run):
+    """gcb_analyse_device on a grid that already sits in HBM, with -R/-z1/-z2 cropping (readjust_tgrid on the
+    device): same cropped grid and same profiles as the host-grid call"""
+    aa = gc.parse_aargs(gc.CASES[name]["analyses"][run])
+    tg, hdr, grid = g.grid_read(os.path.join(u.GOLDEN_DIR, name, "grid.dat"))
+    r, _ = gpu_analysis(tg, grid, aa)
+    lib = g._cabi.lib
+    p = C.c_void_p()
+    g._cabi.check(lib.gcb_device_malloc(C.byref(p), grid.nbytes, 0), "gcb_device_malloc")
+    try:
+        g._cabi.check(lib.gcb_memcpy_h2d(p, grid.ctypes.data, grid.nbytes, 0), "gcb_memcpy_h2d")
+        kw = {}
+        if aa["setmask"] & u.SET_R: kw["radius"] = aa["R"]
+        if aa["setmask"] & u.SET_Z1: kw["z1"] = aa["z1"]
+        if aa["setmask"] & u.SET_Z2: kw["z2"] = aa["z2"]
+        rd = g.analyse(tg, None, unit=aa["unit"], min_occ=aa["minocc"], rad_ba_nr=aa["radnr"], rad_ba_step=aa["radstep"],
+                       grid_dev=p, **kw)
+    finally:
+        lib.gcb_device_free(p, 0)
+    assert rd["grid"] is not None and rd["grid"].shape == r["grid"].shape
+    u.assert_bits_equal(rd["grid"], r["grid"], "cropped grid")
+    for k in ARRAYS:
+        u.assert_bits_equal(rd[k], r[k], k)
+    assert bytes(rd["tg"]) == bytes(r["tg"])
