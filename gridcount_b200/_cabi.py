@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgridcount_b200.so")
+LIB_PATH = os.environ.get("GCB_LIB") or os.path.join(HERE, "libgridcount_b200.so")   # GCB_LIB: tools/sweep_k1.sh variants
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int)
@@ -20,7 +20,7 @@ c_long_p = C.POINTER(C.c_long)
 HEADER_MAX = 256
 SET_CPOINT, SET_R, SET_Z1, SET_Z2 = 1, 2, 4, 8
 PBC_NONE, PBC_RECT = 0, 1
-KERNEL_AUTO, KERNEL_GATHER, KERNEL_STREAM, KERNEL_STREAM_INDEXED, KERNEL_ROUTED, KERNEL_NARROW = 0, 1, 2, 3, 4, 5
+KERNEL_AUTO, KERNEL_GATHER, KERNEL_STREAM, KERNEL_STREAM_INDEXED, KERNEL_ROUTED, KERNEL_PACKED = 0, 1, 2, 3, 4, 5
 UNITS = {"unity": 0, "SPC": 1, "molar": 2, "Angstrom": 3, "Voxel": 4}
 GEN_UNIFORM, GEN_QUANTISED, GEN_PORE, GEN_CLUSTER = 0, 1, 2, 3
 
@@ -51,8 +51,8 @@ class CounterOpts(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("atom_frames", C.c_uint64), ("hits", C.c_uint64),
                 ("edge_overflow", C.c_uint64), ("sumP", C.c_double), ("uniform_weight", C.c_int),
-                ("weight", C.c_float), ("kernel_launches", C.c_int64), ("narrow_rounds", C.c_uint64),
-                ("narrow_redone", C.c_uint64), ("saturated", C.c_int)]
+                ("weight", C.c_float), ("kernel_launches", C.c_int64), ("packed_rounds", C.c_uint64),
+                ("packed_redone", C.c_uint64), ("saturated", C.c_int)]
 
 
 class AnalysisOpts(C.Structure):

@@ -156,7 +156,11 @@ bin_gather_kernel(const float *__restrict__ x, int natoms, const int *__restrict
 constexpr int CONSUMER_WARPS = GCB_CONSUMER_WARPS;
 constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
 constexpr int STREAM_THREADS = CONSUMER_THREADS + 32;     // + producer warp
-constexpr int TILE_ATOMS = 3072;                          // 1024 selected per tile for 3-site water
+#ifndef GCB_TILE_ATOMS
+#define GCB_TILE_ATOMS 3072
+#endif
+constexpr int TILE_ATOMS = GCB_TILE_ATOMS;                // 3072: 1024 selected per tile for 3-site water
+static_assert(TILE_ATOMS % 4 == 0, "tiles must start 16-byte aligned");
 constexpr int TILE_FLOATS = TILE_ATOMS * 3;                  // 36 KiB per tile
 constexpr int STAGES = GCB_STAGES;
 constexpr int UNROLL = GCB_UNROLL;
@@ -294,57 +298,46 @@ template <int MODE>
 struct DirectSink {
   static constexpr int NSTAGES = STAGES;
   static constexpr size_t EXTRA_SMEM = 0;
-  static constexpr bool SETTLES = false;
   uint32_t *counts; float *acc; float w;
   // `smem` is the sink's share of the dynamic shared memory (unused here)
   __device__ __forceinline__ void init(void *, unsigned) const {}
-  __device__ __forceinline__ uint32_t hit(void *, int cell) const { deposit<MODE>(counts, acc, cell, w); return 0u; }
-  __device__ __forceinline__ void settle(int, uint32_t) const {}
+  __device__ __forceinline__ void hit(void *, int cell) const { deposit<MODE>(counts, acc, cell, w); }
   __device__ __forceinline__ void tile_end(void *, unsigned) const {}
   __device__ __forceinline__ void finish(void *, unsigned) const {}
 };
 
-// NarrowSink: L2-resident atomics for grids whose uint32 counters do not fit the L2 but whose BYTES do
-// (BASELINE config 3: 400^3 cells = 256 MB of uint32, 64 MB of bytes).  Four 8-bit counters share a word; a hit
-// is one returning atomic add of 1 << 8*(cell & 3).  The thread that takes a byte from 127 to 128 owes the
-// cell a spill: it subtracts the 128 again and logs the cell (128 hits, applied to the uint32 grid at the end
-// of the round), so a byte only ever exceeds 128 transiently.  A byte observed at 255 means a carry into the
-// neighbouring counter has happened or is about to: the round raises `alarm`, its packed counters and log are
-// thrown away and the round is redone by the direct uint32 kernel (narrow_resolve_kernel, `run_if`).  Exact
-// for every input; the alarm needs > 127 hits on one cell inside the few hundred nanoseconds between a
-// thread's add and its subtract.
-struct NarrowSink {
+// PackedSink: L2-resident atomics for grids whose uint32 counters do not fit the L2 but whose packed counters do
+// (BASELINE config 3: 400^3 cells = 256 MB of uint32, 64 MB as bytes; config 4: 500^3 = 500 MB, 62.5 MB as nibbles).
+// 32/W counters of W bits share a word; a hit is ONE NON-RETURNING add (RED) of 1 << W*(cell mod 32/W) on the word,
+// so it runs at the L2's RED rate and nothing comes back to the SM.  Overflow of a W-bit lane is not looked for per
+// hit but once per round: every carry out of a lane lowers the word's digit sum (base 2^W) by at least 2^W - 1 and
+// nothing can raise it, so "sum of all digits == hits the round reported" holds iff no lane overflowed and no RED
+// was lost (packed_verify_kernel).  A round that fails is thrown away and redone by the direct uint32 kernel.
+template <int W>
+struct PackedSink {
   static constexpr int NSTAGES = STAGES;
   static constexpr size_t EXTRA_SMEM = 0;
-  static constexpr bool SETTLES = true;
-  uint32_t *g8;                            // packed counters, (ncells + 3) / 4 words
-  uint32_t *log;                           // [gridDim][seg_cap] spilled cells
-  unsigned *log_n;                         // [gridDim]
-  unsigned seg_cap;
-  int *alarm;
+  uint32_t *pk;                            // packed counters, all-zero between rounds
   __device__ __forceinline__ void init(void *, unsigned) const {}
-  // hit() only issues the atomic and hands its result back as a token; settle() looks at it.  The streaming
-  // kernel issues a whole unrolled group of hits before it settles any, so the L2 round trips overlap.
-  __device__ __forceinline__ uint32_t hit(void *, int cell) const
+  __device__ __forceinline__ void hit(void *, int cell) const
   {
-    return atomicAdd(g8 + ((unsigned)cell >> 2), 1u << (8u * ((unsigned)cell & 3u)));
-  }
-  __device__ __forceinline__ void settle(int cell, uint32_t old) const
-  {
-    const unsigned sh = 8u * ((unsigned)cell & 3u);
-    uint32_t *w = g8 + ((unsigned)cell >> 2);
-    const uint32_t ob = (old >> sh) & 255u;
-    if (ob == 127u) {
-      atomicSub(w, 128u << sh);
-      const unsigned i = atomicAdd(log_n + blockIdx.x, 1u);
-      if (i < seg_cap) log[(size_t)blockIdx.x * seg_cap + i] = (uint32_t)cell;
-      else *alarm = 1;
-    } else if (ob == 255u) {
-      *alarm = 1;
-    }
+    constexpr unsigned PER = 32u / W, SH = W == 8 ? 2u : 3u;
+    atomicAdd(pk + ((unsigned)cell >> SH), 1u << ((unsigned)W * ((unsigned)cell & (PER - 1u))));      // RED.E.ADD
   }
   __device__ __forceinline__ void tile_end(void *, unsigned) const {}
   __device__ __forceinline__ void finish(void *, unsigned) const {}
+};
+
+// device-resident state of the packed path: the host queues the same kernels every round, they decide here
+struct PackedState {
+  int alarm;                               // this round is binned by the direct uint32 kernel
+  int dirty;                               // the packed pass of this round ran and failed: its side effects are taken back
+  int skip;                                // rounds still to be binned directly (back-off after a failed round)
+  int backoff;
+  unsigned ticket, pad;
+  unsigned long long digits, expect;       // digit sum of the packed counters / hits the packed pass reported
+  unsigned long long diag_snap[2];
+  unsigned long long rounds, redone;       // statistics: rounds queued, rounds that the direct kernel had to bin
 };
 
 constexpr int ROUTE_NB_MAX = 128;          // buckets
@@ -372,7 +365,6 @@ __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %
 struct RouteSink {
   static constexpr int NSTAGES = 2;        // 2 x 36 KiB tile ring + 34 KiB staging: two CTAs per SM
   static constexpr size_t EXTRA_SMEM = sizeof(RouteStage);
-  static constexpr bool SETTLES = false;
   uint32_t *keys_g;                        // [nb][gridDim][seg_cap]
   uint32_t *seg_len;                       // [nb][gridDim]
   uint32_t *counts;                        // the grid, for the overflow fallback only
@@ -386,8 +378,7 @@ struct RouteSink {
     for (unsigned i = ctid; i < ROUTE_NB_MAX; i += CONSUMER_THREADS) { st->tail[i] = 0; st->head[i] = 0; st->pos[i] = 0; }
     consumer_barrier();
   }
-  __device__ __forceinline__ void settle(int, uint32_t) const {}
-  __device__ __forceinline__ uint32_t hit(void *smem, int cell) const
+  __device__ __forceinline__ void hit(void *smem, int cell) const
   {
     RouteStage *st = static_cast<RouteStage *>(smem);
     const unsigned b = map.bucket((unsigned)cell);
@@ -395,7 +386,6 @@ struct RouteSink {
     const unsigned slot = atomicAdd(&st->tail[b], 1u);
     if (slot - h < (unsigned)cap) st->keys[b * cap + (slot & (cap - 1))] = map.local((unsigned)cell);
     else atomicAdd(counts + cell, 1u);     // ring full (pathologically clustered input): counted directly, still exact
-    return 0u;
   }
   // Move the complete 128-byte lines (everything when `all`) of every bucket from the rings to this CTA's
   // segments.  Runs between two consumer barriers: no hit is appended meanwhile.  Warp w owns buckets
@@ -467,7 +457,9 @@ struct RouteSink {
   }
 };
 
-template <class SINK, bool PBC, bool AP, bool GUARDED = false>
+// GUARD: 0 = always run; 1 = run only if *run_if != 0; 2 = run only if *run_if == 0 (the two passes of a packed
+// round, decided on the device; separate instantiations, because the test costs the plain kernel a spill)
+template <class SINK, bool PBC, bool AP, int GUARD = 0>
 __global__ void __launch_bounds__(STREAM_THREADS)
 bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict__ gindex, unsigned gnx,
                   const unsigned *__restrict__ rank, long long ntiles, ApGroup G, GridParamsFast P, SINK sink,
@@ -475,9 +467,8 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
                   unsigned long long *__restrict__ diag, const int *__restrict__ run_if)
 {
   constexpr int NST = SINK::NSTAGES;
-  if constexpr (GUARDED) {                         // the redo of a narrow round: nothing to do unless it raised the alarm
-    if (*run_if == 0) return;                      // (a separate instantiation: the test costs the plain kernel a spill)
-  }
+  if constexpr (GUARD == 1) { if (*run_if == 0) return; }
+  if constexpr (GUARD == 2) { if (*run_if != 0) return; }
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StreamSmem<NST> &S = *reinterpret_cast<StreamSmem<NST> *>(smem_raw);
   const int tid = threadIdx.x;
@@ -534,11 +525,6 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
   const int lane = tid & 31;
   void *const sink_smem = smem_raw + ((sizeof(StreamSmem<NST>) + 15) & ~(size_t)15);
   sink.init(sink_smem, ctid);
-  unsigned pend_went = 0;               // SETTLES sinks: hits issued one step ago, results not looked at yet
-  int pend_cells[UNROLL];
-  uint32_t pend_tok[UNROLL];
-#pragma unroll
-  for (int k = 0; k < UNROLL; k++) { pend_cells[k] = 0; pend_tok[k] = 0u; }
   int it = 0;
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
     const int stage = it % NST;
@@ -561,35 +547,6 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
           px[k] = lds_f32(p); py[k] = lds_f32(p + 4); pz[k] = lds_f32(p + 8);
         }
         unsigned rare = 0;
-        if constexpr (SINK::SETTLES) {
-          // sinks whose atomics return a value: the group of this step is issued before the group of the
-          // previous step is settled, so two groups of L2 round trips are in flight per thread
-          unsigned went = 0;
-          int cells[UNROLL];
-          uint32_t tok[UNROLL];
-#pragma unroll
-          for (int k = 0; k < UNROLL; k++) {
-            if (PBC) {
-              const float *L = box3 + 3 * (m.f0 + (inB[k] ? 1 : 0));
-              px[k] = wrap1(px[k], __ldg(L)); py[k] = wrap1(py[k], __ldg(L + 1)); pz[k] = wrap1(pz[k], __ldg(L + 2));
-            }
-            const FastCell fc = cell_of_fast(P, px[k], py[k], pz[k]);
-            const bool go = valid[k] & fc.inside & fc.sure;
-            cells[k] = fc.cell;
-            tok[k] = 0u;
-            if (go) tok[k] = sink.hit(sink_smem, fc.cell);
-            went |= go ? (1u << k) : 0u;
-            c0 += (go & !inB[k]) ? 1u : 0u;
-            c1 += (go & inB[k]) ? 1u : 0u;
-            rare |= (valid[k] & fc.inside & !fc.sure) ? (1u << k) : 0u;
-          }
-#pragma unroll
-          for (int k = 0; k < UNROLL; k++) {
-            if ((pend_went >> k) & 1u) sink.settle(pend_cells[k], pend_tok[k]);
-            pend_cells[k] = cells[k]; pend_tok[k] = tok[k];
-          }
-          pend_went = went;
-        } else {
 #pragma unroll
         for (int k = 0; k < UNROLL; k++) {
           if (PBC) {
@@ -603,14 +560,13 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
           c1 += (go & inB[k]) ? 1u : 0u;
           rare |= (valid[k] & fc.inside & !fc.sure) ? (1u << k) : 0u;
         }
-        }
         if (rare) {                                  // atoms within a few ulp of a cell boundary
 #pragma unroll
           for (int k = 0; k < UNROLL; k++) {
             if (!((rare >> k) & 1u)) continue;
             const int cell = cell_of_exact(P, px[k], py[k], pz[k]);
             if (cell >= 0) {
-              sink.settle(cell, sink.hit(sink_smem, cell));
+              sink.hit(sink_smem, cell);
               if (inB[k]) c1++; else c0++;
             } else {
               atomicAdd(diag, 1ull);
@@ -649,7 +605,7 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
         const FastCell fc = cell_of_fast(P, px[k], py[k], pz[k]);
         const int cell = !fc.inside ? -1 : fc.sure ? fc.cell : cell_of_exact(P, px[k], py[k], pz[k]);
         if (cell >= 0) {
-          sink.settle(cell, sink.hit(sink_smem, cell));
+          sink.hit(sink_smem, cell);
           if (df[k] == 0) c0++;
           else if (df[k] == 1) c1++;
           else atomicAdd(hits + m.f0 + df[k], 1ull);
@@ -666,11 +622,6 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
       mbar_arrive(&S.empty[stage]);     // this warp is done with the stage (its LDS results are in registers)
     }
     sink.tile_end(sink_smem, ctid);
-  }
-  if constexpr (SINK::SETTLES) {
-#pragma unroll
-    for (int k = 0; k < UNROLL; k++)
-      if ((pend_went >> k) & 1u) sink.settle(pend_cells[k], pend_tok[k]);
   }
   sink.finish(sink_smem, ctid);
 }
@@ -761,51 +712,110 @@ __device__ float seq_add_dev(float v, float w, unsigned long long n)
   return v;
 }
 
-// fold a finished weight run into the f32 accumulator: acc = acc (+)= w, runcnt times
-// End of a narrow round.  No alarm: the packed counters are added to the uint32 grid (every word is owned by
-// one thread, nothing else touches the grid meanwhile) and zeroed.  Alarm: they are zeroed only, and what the
-// round's streaming kernel added to the per-frame hit counters and the diagnostics is taken back, because the
-// guarded uint32 kernel behind this one redoes the round.  narrow_log_kernel then applies the spills.
-__global__ void __launch_bounds__(256)
-narrow_resolve_kernel(uint4 *__restrict__ g8, size_t nquads, uint32_t *__restrict__ counts, size_t ncells,
-                      const int *__restrict__ alarm, unsigned long long *__restrict__ hits, long nhits,
-                      unsigned long long *__restrict__ diag, const unsigned long long *__restrict__ diag_snap)
+// ---------------------------------------------------------------------------
+// The three small kernels around the packed pass of a round (see PackedSink).
+// ---------------------------------------------------------------------------
+__global__ void packed_begin_kernel(PackedState *__restrict__ st, const unsigned long long *__restrict__ diag)
 {
-  const bool bad = *alarm != 0;
+  st->alarm = st->skip > 0 ? 1 : 0;         // backing off: the packed pass returns at once, the direct kernel bins the round
+  st->dirty = 0;
+  st->ticket = 0;
+  st->digits = 0; st->expect = 0;
+  st->diag_snap[0] = diag[0]; st->diag_snap[1] = diag[1];
+  st->rounds++;
+}
+
+template <int W>
+__device__ __forceinline__ unsigned digit_sum(uint32_t w)
+{
+  if (W == 8) return __dp4a(w, 0x01010101u, 0u);
+  return __dp4a(w & 0x0F0F0F0Fu, 0x01010101u, __dp4a((w >> 4) & 0x0F0F0F0Fu, 0x01010101u, 0u));
+}
+
+// digit sum of all packed counters against the hits the packed pass reported for the round's frames; the last
+// block to finish writes the verdict and runs the back-off (a failed round is followed by `backoff` rounds that
+// go straight to the direct kernel; the back-off doubles on every failure and halves on every success)
+template <int W>
+__global__ void __launch_bounds__(256)
+packed_verify_kernel(const uint4 *__restrict__ pk, size_t nquads, const unsigned long long *__restrict__ hits, long nhits,
+                     PackedState *__restrict__ st)
+{
+  __shared__ unsigned long long red[2][8];
+  if (st->alarm) {                                   // skipped round
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->skip--; st->redone++; }
+    return;
+  }
+  unsigned long long dsum = 0, hsum = 0;
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += (size_t)gridDim.x * blockDim.x) {
-    const uint4 v = g8[q];
+    const uint4 v = pk[q];
+    dsum += digit_sum<W>(v.x) + digit_sum<W>(v.y) + digit_sum<W>(v.z) + digit_sum<W>(v.w);
+  }
+  for (long f = (long)blockIdx.x * blockDim.x + threadIdx.x; f < nhits; f += (long)gridDim.x * blockDim.x) hsum += hits[f];
+  for (int o = 16; o > 0; o >>= 1) { dsum += __shfl_down_sync(0xffffffffu, dsum, o); hsum += __shfl_down_sync(0xffffffffu, hsum, o); }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = dsum; red[1][threadIdx.x >> 5] = hsum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) { dsum += red[0][w]; hsum += red[1][w]; }
+    if (dsum) atomicAdd(&st->digits, dsum);
+    if (hsum) atomicAdd(&st->expect, hsum);
+    __threadfence();
+    if (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) {
+      __threadfence();
+      const unsigned long long d = *(volatile unsigned long long *)&st->digits, e = *(volatile unsigned long long *)&st->expect;
+      if (d != e) {
+        st->alarm = 1; st->dirty = 1; st->redone++;
+        st->backoff = st->backoff < 1 ? 1 : (st->backoff >= 32 ? 64 : 2 * st->backoff);
+        st->skip = st->backoff;
+      } else {
+        st->backoff >>= 1;
+      }
+    }
+  }
+}
+
+// End of the packed pass.  Verified: the packed counters are added to the uint32 grid (every word is owned by one
+// thread, nothing else touches the grid meanwhile) and zeroed.  Failed: they are zeroed only, and what the pass
+// added to the per-frame hit counters and the diagnostics is taken back, because the guarded uint32 kernel behind
+// this one redoes the round.  Skipped round: nothing to do.
+template <int W>
+__global__ void __launch_bounds__(256)
+packed_apply_kernel(uint4 *__restrict__ pk, size_t nquads, uint32_t *__restrict__ counts, size_t ncells,
+                    const PackedState *__restrict__ st, unsigned long long *__restrict__ hits, long nhits,
+                    unsigned long long *__restrict__ diag)
+{
+  const bool bad = st->alarm != 0;
+  if (bad && !st->dirty) return;
+  constexpr int PER = 32 / W;                      // cells per word
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = pk[q];
     if (!(v.x | v.y | v.z | v.w)) continue;
-    g8[q] = make_uint4(0u, 0u, 0u, 0u);
+    pk[q] = make_uint4(0u, 0u, 0u, 0u);
     if (bad) continue;
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       if (!w[k]) continue;
-      const size_t c0 = q * 16 + (size_t)k * 4;
-      if (c0 + 3 < ncells) {
-        uint4 *dst = reinterpret_cast<uint4 *>(counts + c0);
-        uint4 t = *dst;
-        t.x += w[k] & 255u; t.y += (w[k] >> 8) & 255u; t.z += (w[k] >> 16) & 255u; t.w += w[k] >> 24;
-        *dst = t;
+      const size_t c0 = (q * 4 + (size_t)k) * PER;
+      if (c0 + PER <= ncells) {
+#pragma unroll
+        for (int h = 0; h < PER / 4; h++) {
+          uint4 *dst = reinterpret_cast<uint4 *>(counts + c0) + h;
+          const uint32_t part = w[k] >> (4 * W * h);
+          if (W == 4 && !(part & 0xFFFFu)) continue;
+          uint4 t = *dst;
+          constexpr uint32_t M = (1u << W) - 1u;
+          t.x += part & M; t.y += (part >> W) & M; t.z += (part >> (2 * W)) & M; t.w += (part >> (3 * W)) & M;
+          *dst = t;
+        }
       } else {
-        for (int b = 0; b < 4; b++) if (c0 + b < ncells) counts[c0 + b] += (w[k] >> (8 * b)) & 255u;
+        for (int b = 0; b < PER; b++) if (c0 + b < ncells) counts[c0 + b] += (w[k] >> (W * b)) & ((1u << W) - 1u);
       }
     }
   }
   if (bad) {
     for (long f = (long)blockIdx.x * blockDim.x + threadIdx.x; f < nhits; f += (long)gridDim.x * blockDim.x) hits[f] = 0;
-    if (blockIdx.x == 0 && threadIdx.x < 2) diag[threadIdx.x] = diag_snap[threadIdx.x];
-    if (blockIdx.x == 0 && threadIdx.x == 2) diag[2] += 1ull;
+    if (blockIdx.x == 0 && threadIdx.x < 2) diag[threadIdx.x] = st->diag_snap[threadIdx.x];
   }
-}
-
-__global__ void __launch_bounds__(256)
-narrow_log_kernel(const uint32_t *__restrict__ log, const unsigned *__restrict__ log_n, unsigned seg_cap,
-                  uint32_t *__restrict__ counts, const int *__restrict__ alarm)
-{
-  if (*alarm != 0) return;
-  const unsigned n = min(log_n[blockIdx.x], seg_cap);
-  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(counts + log[(size_t)blockIdx.x * seg_cap + i], 128u);
 }
 
 // Saturation guard of the uint32 cells.  The reference accumulates in f32, which stops moving after at most
@@ -820,6 +830,7 @@ __global__ void clamp_counts_kernel(uint32_t *__restrict__ cnt, size_t n, uint32
   if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(flag, 1ull);
 }
 
+// fold a finished weight run into the f32 accumulator: acc = acc (+)= w, runcnt times
 __global__ void fold_run_kernel(uint32_t *__restrict__ runcnt, uint32_t *__restrict__ total,
                                 float *__restrict__ acc, float w, size_t n)
 {
@@ -1002,15 +1013,13 @@ struct gcb_counter {
   uint32_t *d_keys = nullptr, *d_seglen = nullptr;
   unsigned route_seg_cap = 0;
   int route_grid = 0;                 // streaming CTAs the key buffer is laid out for
-  // narrow (packed 8-bit, L2-resident) path
-  bool narrow_ok = false;             // AUTO takes it: uint32 grid beyond L2, one byte per cell inside it
-  long long narrow_units = 0;         // atom-frames per round
-  uint32_t *d_g8 = nullptr;           // packed counters, always all-zero between rounds
-  uint32_t *d_nlog = nullptr;         // [narrow_grid][narrow_seg_cap]
-  unsigned char *d_nctl = nullptr;    // int alarm | u64 diag_snap[2] (at 8) | unsigned log_n[narrow_grid] (at 32)
-  unsigned narrow_seg_cap = 0;
-  int narrow_grid = 0;
-  uint64_t narrow_rounds = 0, narrow_redone = 0;
+  // packed (W-bit lanes, L2-resident) path
+  int packed_bits = 0;                // 0: not available for this grid; 8 or 4
+  bool packed_auto = false;           // AUTO takes it: uint32 grid beyond L2, packed counters inside it
+  long long packed_units = 0;         // atom-frames per round
+  uint32_t *d_pk = nullptr;           // packed counters, always all-zero between rounds
+  PackedState *d_pstate = nullptr;
+  uint64_t packed_rounds = 0, packed_redone = 0;
   bool saturated = false;             // some cell was clamped (diag[3])
   // xtc path: two sets of {compressed bytes, frame table, status, decoded frames}, copy stream + events
   struct XtcSet {
@@ -1125,7 +1134,7 @@ int fold_pending(gcb_counter *c)
 template <class SINK>
 size_t stream_smem_bytes() { return ((sizeof(StreamSmem<SINK::NSTAGES>) + 15) & ~(size_t)15) + SINK::EXTRA_SMEM; }
 
-template <class SINK, bool PBC, bool AP, bool GUARDED = false>
+template <class SINK, bool PBC, bool AP, int GUARD = 0>
 int launch_stream(gcb_counter *c, const float *d_x, long long ntiles, const SINK &sink, int grid_cap,
                   const float *d_box3, unsigned long long *d_hits, int *grid_out, const int *run_if = nullptr)
 {
@@ -1133,13 +1142,13 @@ int launch_stream(gcb_counter *c, const float *d_x, long long ntiles, const SINK
   const size_t smem = stream_smem_bytes<SINK>();
   const int dv = c->opts.device & 63;
   if (!attr_done[dv]) {
-    GCB_CUDA(cudaFuncSetAttribute(bin_stream_kernel<SINK, PBC, AP, GUARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GCB_CUDA(cudaFuncSetAttribute(bin_stream_kernel<SINK, PBC, AP, GUARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[dv] = true;
   }
   const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
   long long grid = std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
   if (grid_cap > 0) grid = std::min<long long>(grid, grid_cap);
-  bin_stream_kernel<SINK, PBC, AP, GUARDED><<<(unsigned)grid, STREAM_THREADS, smem, c->compute>>>(
+  bin_stream_kernel<SINK, PBC, AP, GUARD><<<(unsigned)grid, STREAM_THREADS, smem, c->compute>>>(
       d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, c->ap, c->PF, sink, d_box3, d_hits, c->d_diag, run_if);
   c->launches++;
   GCB_CUDA(cudaGetLastError());
@@ -1233,38 +1242,25 @@ int launch_routed(gcb_counter *c, const float *d_x, long nframes, const float *d
   return GCB_OK;
 }
 
-// Narrow path: rounds of ~narrow_units atom-frames; per round the streaming kernel into the packed counters,
-// the resolve + log kernels, the guarded uint32 redo (returns at once unless the round raised the alarm), and
-// the gather kernel for the sub-tile tail (straight into the uint32 grid).
-template <bool PBC>
-int launch_narrow(gcb_counter *c, const float *d_x, long nframes, const float *d_box3, unsigned long long *d_hits)
+// Packed path: rounds of ~packed_units atom-frames; per round the streaming kernel into the packed counters
+// (returns at once while backing off), verify + apply, the guarded uint32 kernel (returns at once unless the round
+// failed or is skipped), and the gather kernel for the sub-tile tail (straight into the uint32 grid).
+template <int W, bool PBC>
+int launch_packed(gcb_counter *c, const float *d_x, long nframes, const float *d_box3, unsigned long long *d_hits)
 {
   const bool ap = c->ap_ok && c->opts.kernel != GCB_KERNEL_STREAM_INDEXED;
   const int tile_atoms = ap ? c->ap.tile_atoms : TILE_ATOMS;
-  const size_t smem = stream_smem_bytes<NarrowSink>();
-  const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
-  const int G = c->sm_count * per_sm;
-  long fpr = (long)std::max<long long>(4, (c->narrow_units / std::max(c->gnx, 1)) & ~3LL);   // multiple of 4 frames:
+  long fpr = (long)std::max<long long>(4, (c->packed_units / std::max(c->gnx, 1)) & ~3LL);   // multiple of 4 frames:
   fpr = std::min<long>(fpr, (nframes + 3) & ~3L);                                              // rounds start 16-byte aligned
-  const long long round_units = (long long)fpr * c->gnx;
-  const unsigned seg_cap = (unsigned)std::max<long long>(1024, 2 * (round_units / 128) / G + 64);
-  const size_t nquads = (c->ncells + 15) / 16;
-  if (!c->d_g8) {
-    GCB_CUDA(cudaMalloc(&c->d_g8, nquads * 16));
-    GCB_CUDA(cudaMemsetAsync(c->d_g8, 0, nquads * 16, c->compute));
+  const size_t nwords = (c->ncells + (32 / W) - 1) / (32 / W), nquads = (nwords + 3) / 4;
+  if (!c->d_pk) {
+    GCB_CUDA(cudaMalloc(&c->d_pk, nquads * 16));
+    GCB_CUDA(cudaMemsetAsync(c->d_pk, 0, nquads * 16, c->compute));
+    GCB_CUDA(cudaMalloc(&c->d_pstate, sizeof(PackedState)));
+    GCB_CUDA(cudaMemsetAsync(c->d_pstate, 0, sizeof(PackedState), c->compute));
   }
-  if (!c->d_nlog || seg_cap > c->narrow_seg_cap || G != c->narrow_grid) {
-    GCB_CUDA(cudaStreamSynchronize(c->compute));
-    cudaFree(c->d_nlog); cudaFree(c->d_nctl);
-    c->d_nlog = nullptr; c->d_nctl = nullptr;
-    GCB_CUDA(cudaMalloc(&c->d_nlog, sizeof(uint32_t) * (size_t)G * seg_cap));
-    GCB_CUDA(cudaMalloc(&c->d_nctl, 32 + sizeof(unsigned) * (size_t)G));
-    c->narrow_seg_cap = seg_cap;
-    c->narrow_grid = G;
-  }
-  int *alarm = reinterpret_cast<int *>(c->d_nctl);
-  unsigned long long *diag_snap = reinterpret_cast<unsigned long long *>(c->d_nctl + 8);
-  unsigned *log_n = reinterpret_cast<unsigned *>(c->d_nctl + 32);
+  PackedState *st = c->d_pstate;
+  const int aux_grid = (int)std::max<size_t>(1, std::min<size_t>((nquads + 255) / 256, (size_t)c->sm_count * 8));
   for (long f0 = 0; f0 < nframes; f0 += fpr) {
     const long n = std::min(fpr, nframes - f0);
     const float *xs = d_x + (size_t)f0 * c->natoms * 3;
@@ -1273,24 +1269,21 @@ int launch_narrow(gcb_counter *c, const float *d_x, long nframes, const float *d
     const long long ntiles = total_atoms / tile_atoms;
     long long e_begin = 0;
     if (ntiles > 0) {
-      GCB_CUDA(cudaMemsetAsync(c->d_nctl, 0, 32 + sizeof(unsigned) * (size_t)G, c->compute));
-      GCB_CUDA(cudaMemcpyAsync(diag_snap, c->d_diag, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->compute));
-      c->narrow_rounds++;
-      NarrowSink sink;
-      sink.g8 = c->d_g8; sink.log = c->d_nlog; sink.log_n = log_n; sink.seg_cap = c->narrow_seg_cap; sink.alarm = alarm;
-      int grid = 0;
-      int rc = ap ? launch_stream<NarrowSink, PBC, true>(c, xs, ntiles, sink, G, bs, d_hits + f0, &grid)
-                  : launch_stream<NarrowSink, PBC, false>(c, xs, ntiles, sink, G, bs, d_hits + f0, &grid);
+      packed_begin_kernel<<<1, 1, 0, c->compute>>>(st, c->d_diag);
+      PackedSink<W> sink;
+      sink.pk = c->d_pk;
+      int rc = ap ? launch_stream<PackedSink<W>, PBC, true, 2>(c, xs, ntiles, sink, 0, bs, d_hits + f0, nullptr, &st->alarm)
+                  : launch_stream<PackedSink<W>, PBC, false, 2>(c, xs, ntiles, sink, 0, bs, d_hits + f0, nullptr, &st->alarm);
       if (rc) return rc;
-      narrow_resolve_kernel<<<c->sm_count * 8, 256, 0, c->compute>>>(reinterpret_cast<uint4 *>(c->d_g8), nquads, c->d_runcnt, c->ncells,
-                                                                     alarm, d_hits + f0, n, c->d_diag, diag_snap);
-      narrow_log_kernel<<<grid, 256, 0, c->compute>>>(c->d_nlog, log_n, c->narrow_seg_cap, c->d_runcnt, alarm);
-      c->launches += 2;
+      packed_verify_kernel<W><<<aux_grid, 256, 0, c->compute>>>(reinterpret_cast<const uint4 *>(c->d_pk), nquads, d_hits + f0, n, st);
+      packed_apply_kernel<W><<<aux_grid, 256, 0, c->compute>>>(reinterpret_cast<uint4 *>(c->d_pk), nquads, c->d_runcnt, c->ncells, st,
+                                                               d_hits + f0, n, c->d_diag);
+      c->launches += 3;
       GCB_CUDA(cudaGetLastError());
       DirectSink<MODE_COUNT> redo;
       redo.counts = c->d_runcnt; redo.acc = c->d_acc; redo.w = 1.0f;
-      rc = ap ? launch_stream<DirectSink<MODE_COUNT>, PBC, true, true>(c, xs, ntiles, redo, 0, bs, d_hits + f0, nullptr, alarm)
-              : launch_stream<DirectSink<MODE_COUNT>, PBC, false, true>(c, xs, ntiles, redo, 0, bs, d_hits + f0, nullptr, alarm);
+      rc = ap ? launch_stream<DirectSink<MODE_COUNT>, PBC, true, 1>(c, xs, ntiles, redo, 0, bs, d_hits + f0, nullptr, &st->alarm)
+              : launch_stream<DirectSink<MODE_COUNT>, PBC, false, 1>(c, xs, ntiles, redo, 0, bs, d_hits + f0, nullptr, &st->alarm);
       if (rc) return rc;
       const long long g1 = ntiles * tile_atoms, f1 = g1 / c->natoms;
       e_begin = f1 * c->gnx + rank_host(c, (int)(g1 - f1 * c->natoms));
@@ -1313,11 +1306,14 @@ int launch_bin(gcb_counter *c, const float *d_x, long nframes, float w, const fl
   const int k = c->opts.kernel;
   const bool use_stream = aligned && k != GCB_KERNEL_GATHER &&
                           (c->stream_ok || k == GCB_KERNEL_STREAM || k == GCB_KERNEL_STREAM_INDEXED || k == GCB_KERNEL_ROUTED ||
-                           k == GCB_KERNEL_NARROW);
-  // AUTO takes the routed path for grids beyond L2 (slabs: 1.2-1.3x the direct kernel, profiles/perf_r01.md); for
-  // shared-memory sized buckets the two-kernel round still loses to direct L2 REDs and is only used on request
-  if (use_stream && MODE == MODE_COUNT && (k == GCB_KERNEL_NARROW || (k == GCB_KERNEL_AUTO && c->narrow_ok && total_e >= (1LL << 20))))
-    return launch_narrow<PBC>(c, d_x, nframes, d_box3, d_hits);
+                           k == GCB_KERNEL_PACKED);
+  // AUTO: grids beyond L2 whose packed counters fit it take the packed path (PackedSink); grids beyond even that
+  // take the routed slabs.  For shared-memory sized buckets the two-kernel routed round loses to direct L2 REDs
+  // and is only used on request.
+  if (use_stream && MODE == MODE_COUNT && c->packed_bits != 0 &&
+      (k == GCB_KERNEL_PACKED || (k == GCB_KERNEL_AUTO && c->packed_auto && total_e >= (1LL << 20))))
+    return c->packed_bits == 8 ? launch_packed<8, PBC>(c, d_x, nframes, d_box3, d_hits)
+                               : launch_packed<4, PBC>(c, d_x, nframes, d_box3, d_hits);
   if (use_stream && MODE == MODE_COUNT && c->route_mode != 0 && k != GCB_KERNEL_STREAM && k != GCB_KERNEL_STREAM_INDEXED &&
       (k == GCB_KERNEL_ROUTED || (c->route_mode == 2 && total_e >= (1LL << 20))))
     return launch_routed<PBC>(c, d_x, nframes, d_box3, d_hits);
@@ -1481,7 +1477,7 @@ void free_counter(gcb_counter *c)
   for (auto &p : c->hit_pool) cudaFree(p.second);
   cudaFree(c->d_gindex); cudaFree(c->d_rank); cudaFree(c->d_runcnt); cudaFree(c->d_total); cudaFree(c->d_acc);
   cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2); cudaFree(c->d_keys); cudaFree(c->d_seglen);
-  cudaFree(c->d_g8); cudaFree(c->d_nlog); cudaFree(c->d_nctl);
+  cudaFree(c->d_pk); cudaFree(c->d_pstate);
   for (auto &x : c->xtc) {
     cudaFree(x.d_buf); cudaFree(x.d_meta); cudaFree(x.d_status); cudaFree(x.d_x); cudaFree(x.d_work); cudaFreeHost(x.h_meta); cudaFreeHost(x.h_status);
     if (x.copied) cudaEventDestroy(x.copied);
@@ -1601,25 +1597,30 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
       c->route_map = RouteMap{23, 0xFFu, 31, 23, (1u << 23) - 1};
     }
     if (getenv("GCB_NO_ROUTE")) c->route_mode = 0;
-    // narrow path: the bytes must stay L2-resident next to the coordinate stream (random returning atomics
-    // hold 128 G/s up to a 96 MB window, profiles/atomic_peak_r01e.json)
     if (const char *e = getenv("GCB_CLAMP_AT")) c->clamp_at = strtoull(e, nullptr, 10);
     if (const char *e = getenv("GCB_CLAMP_CEILING")) c->clamp_ceiling = strtoull(e, nullptr, 10);
     if (c->clamp_at < 1 || c->clamp_ceiling > 0xffffffffull || c->clamp_at * 2 > c->clamp_ceiling) {
       c->clamp_at = 1ull << 27; c->clamp_ceiling = 0xffffffffull;
     }
-    const char *nenv = getenv("GCB_NARROW_UNITS");
-    c->narrow_units = nenv ? atoll(nenv) : (256LL << 20);
-    if (c->narrow_units < 4096) c->narrow_units = 4096;
-    // Measured (profiles/perf_r01e.txt): 36.9 G/s on C3 against 68.7 for the routed slabs, 66.9 on C2 against 111
-    // for plain REDs -- the returning atomics' replies share the L2->SM path with the coordinate stream.  AUTO
-    // therefore never takes this path; it stays selectable (GCB_KERNEL_NARROW, or GCB_NARROW=1 for AUTO).
-    c->narrow_ok = c->route_mode == 2 && c->ncells <= ((size_t)80 << 20) && getenv("GCB_NARROW") != nullptr;
+    // Packed path: bytes while they fit ~80 MB of the 126 MB L2 next to the coordinate stream, nibbles up to twice
+    // as many cells (500^3, and every grid the XDR format can hold: 512^3 cells = 64 MB of nibbles).  A round is
+    // sized so that a uniform density stays far below the lane range: mean 3 hits per byte cell (P[>255] = 0),
+    // 1.25 per nibble cell (P[>15] ~ 5e-13 per cell); denser spots fail verification and are binned directly.
+    {
+      const char *benv = getenv("GCB_PACKED_BITS");
+      const int want = benv ? atoi(benv) : 0;
+      c->packed_bits = want == 4 ? 4 : want == 8 ? 8 : (c->ncells <= ((size_t)80 << 20) ? 8 : 4);
+      c->packed_auto = c->ncells * sizeof(uint32_t) > ((size_t)48 << 20) && c->ncells / (c->packed_bits == 8 ? 1 : 2) <= ((size_t)80 << 20) &&
+                       !getenv("GCB_NO_PACKED");
+      const char *uenv = getenv("GCB_PACKED_UNITS");
+      c->packed_units = uenv ? atoll(uenv) : (long long)((double)c->ncells * (c->packed_bits == 8 ? 3.0 : 1.25));
+      if (c->packed_units < 4096) c->packed_units = 4096;
+    }
   }
   GCB_CREATE_CUDA(cudaMalloc(&c->d_gindex, sizeof(int) * std::max(gnx, 1)));
   GCB_CREATE_CUDA(cudaMalloc(&c->d_rank, sizeof(unsigned) * rank.size()));
   GCB_CREATE_CUDA(cudaMalloc(&c->d_runcnt, sizeof(uint32_t) * c->ncells));
-  GCB_CREATE_CUDA(cudaMalloc(&c->d_diag, sizeof(unsigned long long) * 4));   // [0] edge overflow, [2] narrow rounds redone
+  GCB_CREATE_CUDA(cudaMalloc(&c->d_diag, sizeof(unsigned long long) * 4));   // [0] edge overflow, [3] saturation flag
   if (gnx) GCB_CREATE_CUDA(cudaMemcpy(c->d_gindex, c->h_gindex.data(), sizeof(int) * gnx, cudaMemcpyHostToDevice));
   GCB_CREATE_CUDA(cudaMemcpy(c->d_rank, rank.data(), sizeof(unsigned) * rank.size(), cudaMemcpyHostToDevice));
   // on the compute stream: it is non-blocking, a legacy-stream cudaMemset could still be
@@ -1654,7 +1655,8 @@ int gcb_counter_reset(gcb_counter *c)
     GCB_CUDA(cudaMemsetAsync(c->d_total, 0, sizeof(uint32_t) * c->ncells, c->compute));
   }
   GCB_CUDA(cudaMemsetAsync(c->d_diag, 0, sizeof(unsigned long long) * 4, c->compute));
-  c->narrow_rounds = 0; c->narrow_redone = 0;
+  if (c->d_pstate) GCB_CUDA(cudaMemsetAsync(&c->d_pstate->rounds, 0, 2 * sizeof(unsigned long long), c->compute));
+  c->packed_rounds = 0; c->packed_redone = 0;
   c->bound_run = 0; c->bound_total = 0;
   c->reduced = false; c->global_frames = 0;
   c->have_run = false; c->any = false; c->uniform = true; c->w_cur = 0; c->w_first = 0;
@@ -1859,8 +1861,12 @@ int gcb_counter_sync(gcb_counter *c)
     unsigned long long diag[4];
     GCB_CUDA(cudaMemcpy(diag, c->d_diag, sizeof(diag), cudaMemcpyDeviceToHost));
     if (!c->reduced) c->edge_overflow = diag[0];      // after an all-reduce the statistic is the global one
-    c->narrow_redone = diag[2];
     c->saturated = diag[3] != 0;
+    if (c->d_pstate) {
+      PackedState ps;
+      GCB_CUDA(cudaMemcpy(&ps, c->d_pstate, sizeof(ps), cudaMemcpyDeviceToHost));
+      c->packed_rounds = ps.rounds; c->packed_redone = ps.redone;
+    }
   }
   // sumP: `sumP += (double)weight` once per hit, frame by frame (g_ri3Dc.c:151,426)
   for (; c->sumP_frames < c->hits_per_frame.size(); c->sumP_frames++) {
@@ -1884,8 +1890,8 @@ int gcb_counter_stats(gcb_counter *c, gcb_stats *out)
   out->uniform_weight = c->uniform ? 1 : 0;
   out->weight = c->w_first;
   out->kernel_launches = c->launches;
-  out->narrow_rounds = c->narrow_rounds;
-  out->narrow_redone = c->narrow_redone;
+  out->packed_rounds = c->packed_rounds;
+  out->packed_redone = c->packed_redone;
   out->saturated = c->saturated ? 1 : 0;
   return GCB_OK;
 }

@@ -94,8 +94,9 @@ enum {                     /* kernel selection (GCB_KERNEL_AUTO picks by index-g
   GCB_KERNEL_AUTO = 0, GCB_KERNEL_GATHER = 1, GCB_KERNEL_STREAM = 2,
   GCB_KERNEL_STREAM_INDEXED = 3,  /* streaming kernel without the arithmetic-progression shortcut */
   GCB_KERNEL_ROUTED = 4,          /* streaming kernel + shared-memory privatised counting (two kernels per round) */
-  GCB_KERNEL_NARROW = 5           /* streaming kernel into packed 8-bit L2-resident counters, folded per round;
-                                     exact, but slower than ROUTED on B200: never picked by AUTO */
+  GCB_KERNEL_PACKED = 5           /* streaming kernel with non-returning REDs into packed 8- or 4-bit L2-resident
+                                     counters, verified (digit sum == hits) and folded into the uint32 grid once per
+                                     round; AUTO picks it for grids whose uint32 cells exceed the L2 */
 };
 
 typedef struct {
@@ -115,8 +116,8 @@ typedef struct {
   int uniform_weight;      /* 1 while every frame so far had the same weight */
   float weight;            /* that weight */
   int64_t kernel_launches; /* CUDA kernels launched by this counter so far */
-  uint64_t narrow_rounds;  /* rounds binned into packed 8-bit counters (GCB_KERNEL_NARROW) ... */
-  uint64_t narrow_redone;  /* ... of which a carry alarm had redone by the uint32 kernel (this rank) */
+  uint64_t packed_rounds;  /* rounds queued on the packed-counter path (GCB_KERNEL_PACKED) ... */
+  uint64_t packed_redone;  /* ... of which the direct uint32 kernel binned (lane overflow, or backing off after one; this rank) */
   int saturated;           /* 1 if some cell reached the saturation guard (2^27 hits and the counter range was about
                               to run out): its count is a lower bound; occupancy and density are still the reference's
                               bits, because the reference's f32 accumulator stops moving long before (this rank) */

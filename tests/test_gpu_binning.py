@@ -13,7 +13,7 @@ from gridcount_b200 import _cabi as K
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [K.KERNEL_GATHER, K.KERNEL_STREAM, K.KERNEL_STREAM_INDEXED, K.KERNEL_ROUTED, K.KERNEL_NARROW]
+KERNELS = [K.KERNEL_GATHER, K.KERNEL_STREAM, K.KERNEL_STREAM_INDEXED, K.KERNEL_ROUTED, K.KERNEL_PACKED]
 
 
 def to_ogeom(geom):
@@ -417,41 +417,68 @@ def test_full_size_c2_properties():
     p.close(); dev.free()
 
 
-# ----------------------------------------------------------------------------- packed 8-bit counters under pressure
-@pytest.mark.parametrize("kind", ["one cell", "64 sites", "warm + background"])
-def test_narrow_counters_spill_and_alarm_paths_stay_exact(kind):
-    """GCB_KERNEL_NARROW keeps four 8-bit counters per word: cells that collect more than 127 hits in a round go
-    through the spill log, and hits piling onto one cell faster than its spills are taken back raise the carry
-    alarm, after which the round is redone by the uint32 kernel.  Counts and per-frame hits must be exact either way."""
+# ----------------------------------------------------------------------------- packed counters under pressure
+@pytest.mark.parametrize("bits", [8, 4])
+@pytest.mark.parametrize("kind", ["one cell", "64 sites", "warm + background", "uniform"])
+def test_packed_counters_overflow_and_backoff_stay_exact(kind, bits, monkeypatch):
+    """GCB_KERNEL_PACKED keeps 8- or 4-bit counters packed into words and updates them with non-returning REDs; a
+    round is accepted only if the digit sum of the packed counters equals the hits it reported, otherwise it is
+    thrown away and redone by the uint32 kernel, and the next round(s) go straight there (back-off).  Counts and
+    per-frame hits must be exact whichever way every round went; a spread-out input must never take the redo."""
+    monkeypatch.setenv("GCB_PACKED_BITS", str(bits))
+    monkeypatch.setenv("GCB_PACKED_UNITS", str(8192 * 8))           # 8 frames per round: six rounds per call
     L, delta = (4.0, 4.0, 4.0), 0.1
     geom = g.setup_geometry(L, delta)
     natoms, nframes = 8192, 48
     rng = np.random.default_rng(11)
     x = (rng.random((nframes, natoms, 3)) * np.asarray(L)).astype(np.float32)
-    if kind == "one cell":                       # 393 216 hits on a single byte: the alarm must fire
+    if kind == "one cell":                       # 65 536 hits on a single lane per round: every packed pass must fail
         x[:] = np.asarray([1.234, 2.345, 3.456], np.float32)
-    elif kind == "64 sites":                     # ~6 000 hits per cell, all atoms of a frame on 64 cells
+    elif kind == "64 sites":                     # ~1 000 hits per cell and round, all atoms of a frame on 64 cells
         sites = (rng.random((64, 3)) * np.asarray(L)).astype(np.float32)
         x[:] = sites[rng.integers(0, 64, (nframes, natoms))]
-    else:                                        # every 16th atom sits on one of 64 sites: ~8 hits per frame, ~380 in all
+    elif kind == "warm + background":            # every 16th atom sits on one of 64 sites: ~8 hits per frame and site
         sites = (rng.random((64, 3)) * np.asarray(L)).astype(np.float32)
         x[:, ::16] = sites[rng.integers(0, 64, (nframes, natoms // 16))]
     gindex = np.arange(natoms, dtype=np.int32)
-    ctr = g.GridCounter(geom, gindex, natoms, kernel=K.KERNEL_NARROW)
+    ctr = g.GridCounter(geom, gindex, natoms, kernel=K.KERNEL_PACKED)
     ctr.add_frames(x, np.ones(nframes, np.float32))
     ocounts, ohits, _ = oracle_counts(geom, x, gindex)
     np.testing.assert_array_equal(ctr.counts(), ocounts)
     np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
     st = ctr.stats()
-    assert st.narrow_rounds >= 1 and st.hits == int(ohits.sum())
-    if kind == "one cell":
-        assert st.narrow_redone >= 1, "393 216 simultaneous hits on one byte did not raise the carry alarm"
-    if kind == "warm + background":
-        assert ocounts.max() > 127               # spill log in use (the alarm may or may not fire: it is a race by design)
-    # a second batch on top: the packed counters must have been left all-zero
+    assert st.packed_rounds == 6 and st.hits == int(ohits.sum())
+    if kind in ("one cell", "64 sites"):
+        assert st.packed_redone == 6, "overflowing lanes were not caught by the digit-sum check"
+    if kind == "uniform":                        # 64 000 cells, 65 536 hits per round: mean 1 per cell
+        assert st.packed_redone == 0
+    # a second batch on top: the packed counters must have been left all-zero, the statistics keep counting
     ctr.add_frames(x[:8], np.ones(8, np.float32))
     o2, _, _ = oracle_counts(geom, x[:8], gindex)
     np.testing.assert_array_equal(ctr.counts(), ocounts + o2)
+    assert ctr.stats().packed_rounds == 7
+    ctr.close()
+
+
+def test_packed_backoff_recovers(monkeypatch):
+    """Dense frames followed by spread-out ones: the dense rounds fail verification and switch the following rounds
+    to the direct kernel; the back-off halves on every verified round, so the packed path comes back."""
+    monkeypatch.setenv("GCB_PACKED_UNITS", str(8192 * 4))
+    L = (4.0, 4.0, 4.0)
+    geom = g.setup_geometry(L, 0.1)
+    natoms, nframes = 8192, 128
+    rng = np.random.default_rng(12)
+    x = (rng.random((nframes, natoms, 3)) * np.asarray(L)).astype(np.float32)
+    x[:16] = np.asarray([0.5, 0.5, 0.5], np.float32)
+    gindex = np.arange(natoms, dtype=np.int32)
+    ctr = g.GridCounter(geom, gindex, natoms, kernel=K.KERNEL_PACKED)
+    ctr.add_frames(x, np.ones(nframes, np.float32))
+    ocounts, ohits, _ = oracle_counts(geom, x, gindex)
+    np.testing.assert_array_equal(ctr.counts(), ocounts)
+    np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
+    st = ctr.stats()
+    assert st.packed_rounds == 32
+    assert 4 <= st.packed_redone < 16, st.packed_redone      # the four dense rounds and a few skipped ones, not the rest
     ctr.close()
 
 

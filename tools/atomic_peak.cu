@@ -84,6 +84,49 @@ __global__ void __launch_bounds__(256) stream_read(const float4 *x, size_t n, fl
   if (acc == 1234.5f) *sink = acc;
 }
 
+// The mix K1 really sends to the L2: a coalesced evict-first stream of coordinate bytes plus random REDs, NUM REDs
+// per DEN float4 loads (1-of-3 water: 1 RED per 36 B = 4 per 9 loads; all atoms: 1 per 12 B = 4 per 3 loads).
+// No conversion work, no shared memory: what the memory system sustains for this mix, whatever the kernel around it.
+template <int NUM, int DEN>
+__global__ void __launch_bounds__(256) stream_plus_red(const float4 *x, size_t n, uint32_t *grid, uint32_t ncells, float *sink)
+{
+  float acc = 0;
+  uint32_t s = mix(blockIdx.x * blockDim.x + threadIdx.x + 1);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i + (DEN - 1) * stride < n; i += DEN * stride) {
+    float4 v[DEN];
+#pragma unroll
+    for (int k = 0; k < DEN; k++) v[k] = __ldcs(x + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < DEN; k++) acc += v[k].x + v[k].y + v[k].z + v[k].w;
+#pragma unroll
+    for (int k = 0; k < NUM; k++) {
+      s = s * 1664525u + 1013904223u;
+      atomicAdd(grid + (uint32_t)(((uint64_t)mix(s ^ __float_as_uint(acc)) * ncells) >> 32), 1u);
+    }
+  }
+  if (acc == 1234.5f) *sink = acc;
+}
+
+template <int NUM, int DEN>
+static void run_mix(const float4 *x, size_t bytes, uint32_t *g, uint32_t ncells, float *sink, int sms, cudaEvent_t a, cudaEvent_t b,
+                    size_t window_mb, bool &first)
+{
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(a));
+    stream_plus_red<NUM, DEN><<<sms * 16, 256>>>(x, bytes / 16, g, ncells, sink);
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    float ms; CK(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  const double loads = (double)(bytes / 16);
+  printf("%s{\"window_mb\": %zu, \"reds_per_36B\": %.3f, \"read_gbs\": %.1f, \"red_gops\": %.2f}", first ? "" : ",\n  ", window_mb,
+         (double)NUM / DEN * 2.25, bytes / best * 1e-6, loads * NUM / DEN / best * 1e-6);
+  first = false;
+}
+
 int main()
 {
   cudaDeviceProp prop;
@@ -172,7 +215,22 @@ int main()
       float ms; CK(cudaEventElapsedTime(&ms, a, b));
       if (rep > 0 && ms < best) best = ms;
     }
-    printf(" \"hbm_read_gbs\": %.1f}\n", bytes / best * 1e-6);
+    printf(" \"hbm_read_gbs\": %.1f,\n \"stream_plus_red\": [", bytes / best * 1e-6);
+    bool f2 = true;
+    for (size_t mb : {4, 64}) {
+      uint32_t *g;
+      CK(cudaMalloc(&g, mb << 20));
+      CK(cudaMemset(g, 0, mb << 20));
+      const uint32_t nc = (uint32_t)((mb << 20) / 4);
+      run_mix<0, 9>(x, bytes, g, nc, sink, sms, a, b, mb, f2);
+      run_mix<1, 9>(x, bytes, g, nc, sink, sms, a, b, mb, f2);
+      run_mix<2, 9>(x, bytes, g, nc, sink, sms, a, b, mb, f2);
+      run_mix<4, 9>(x, bytes, g, nc, sink, sms, a, b, mb, f2);
+      run_mix<8, 9>(x, bytes, g, nc, sink, sms, a, b, mb, f2);
+      run_mix<4, 3>(x, bytes, g, nc, sink, sms, a, b, mb, f2);
+      CK(cudaFree(g));
+    }
+    printf("]}\n");
   }
   return 0;
 }

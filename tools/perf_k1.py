@@ -14,9 +14,10 @@ SHAPES = {
     "c1": ((3.0, 3.0, 3.0), 0.05, 2700, 3, 20000),
     "c2": ((8.0, 8.0, 13.4), 0.1, 60000, 3, 4000),
     "c2all": ((8.0, 8.0, 13.4), 0.1, 60000, 1, 2000),
-    "c3": ((20.0, 20.0, 20.0), 0.05, 1000000, 3, 256),
-    "c4": ((10.0, 10.0, 10.0), 0.02, 100000, 3, 2048),
-    "c4k": ((10.0, 10.0, 10.0), 0.02, 100000, 3, 2048),     # clustered: Gaussians (sigma 0.1 nm) around 256 sites (SURVEY 8d "K")
+    "c3": ((20.0, 20.0, 20.0), 0.05, 1000000, 3, 1152),
+    "c3all": ((20.0, 20.0, 20.0), 0.05, 1000000, 1, 384),
+    "c4": ((10.0, 10.0, 10.0), 0.02, 100000, 3, 9600),
+    "c4k": ((10.0, 10.0, 10.0), 0.02, 100000, 3, 9600),     # clustered: Gaussians (sigma 0.1 nm) around 256 sites (SURVEY 8d "K")
 }
 
 
@@ -30,7 +31,7 @@ def main():
     gen = g.make_gen(1, L, K.GEN_CLUSTER, nsites=256, sigma=0.1) if name.endswith("k") else g.make_gen(1, L)
     dev = g.DeviceFrames(nframes, natoms).generate(gen)
     kernels = (("gather", K.KERNEL_GATHER), ("stream", K.KERNEL_STREAM), ("routed", K.KERNEL_ROUTED),
-               ("narrow", K.KERNEL_NARROW), ("auto", K.KERNEL_AUTO))
+               ("packed", K.KERNEL_PACKED), ("auto", K.KERNEL_AUTO))
     only = os.environ.get("PERF_KERNELS")
     for kname, kernel in kernels:
         if only and kname not in only.split(","):
@@ -50,8 +51,8 @@ def main():
         print("%s %s grid=%s atom-frames=%.3g  best %.3f ms (%.1f G/s, %.1f GB/s algorithmic)  median %.3f ms (%.1f G/s)"
               % (name, kname, geom.shape, af, best, af / best * 1e-6, af * 12 / best * 1e-6, med, af / med * 1e-6))
         st = ctr.stats()
-        if st.narrow_rounds:
-            print("    narrow rounds %d, redone %d" % (st.narrow_rounds, st.narrow_redone))
+        if st.packed_rounds:
+            print("    packed rounds %d, redone %d" % (st.packed_rounds, st.packed_redone))
         ctr.close()
     dev.free()
 

@@ -1,9 +1,9 @@
 #!/bin/bash
-# compile-time parameter sweep of the streaming kernel, run on the GPU box: tools/sweep_k1.sh "shape" "cfg1" "cfg2" ...
-SHAPES=$1; shift
-for cfg in "$@"; do
-  rm -f gridcount_b200/csrc/binning.o
-  make -s -C gridcount_b200/csrc EXTRA_NVFLAGS="$cfg" > /dev/null 2>&1 || { echo "build failed: $cfg"; continue; }
-  for s in $SHAPES; do echo "[$cfg] $(timeout 200 python tools/perf_k1.py $s 2>&1 | grep -E 'stream|routed' | sed 's/grid=.*best/best/' | tr '\n' ' ')"; done
+# run on the GPU box: tools/sweep_k1.sh "shapes" "kernels" -> one line per (variant, shape) for every variants/libgcb_*.so
+SHAPES=$1; KERN=${2:-stream}
+for lib in gridcount_b200/libgridcount_b200.so variants/libgcb_*.so; do
+  [ -f "$lib" ] || continue
+  for s in $SHAPES; do
+    echo "[$(basename $lib)] $(GCB_LIB=$PWD/$lib PERF_KERNELS=$KERN timeout 200 python tools/perf_k1.py $s 2>&1 | grep -E 'best' | sed 's/grid=.*best/best/' | tr '\n' ' ')"
+  done
 done
-rm -f gridcount_b200/csrc/binning.o; make -s -C gridcount_b200/csrc > /dev/null 2>&1
