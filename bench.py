@@ -1,28 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the gridcount hot path on B200.
+"""bench.py -- benchmark of the gridcount hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): hydrophobic-nanopore membrane system,
-60 000 atoms of which the 20 000 water oxygens (every third atom) are counted, 10 000 frames,
-0.1 nm grid -> 80 x 80 x 134 cells.  Synthetic pore-shaped positions from the counter-based
-generator (bit-reproducible on the CPU oracle).
+Headline workload (BASELINE.json configs[2], SURVEY.md 8d "C3" -- the largest single-GPU configuration):
+1M-atom solvated box of 20 nm, the 333 334 water oxygens (every third atom) counted, 0.05 nm grid = 400^3 cells
+(256 MB of uint32 counters, beyond the L2).  Synthetic uniform positions from the counter-based generator
+(bit-reproducible on the CPU oracle).  Each rank keeps RESIDENT (1152) frames in HBM, 13.8 GB, far beyond the L2.
 
-One STEP is one complete g_ri3Dc job over the rank's 10 000-frame shard: zero the grid, bin all
-frames (K1), combine the per-GPU grids with one NCCL integer all-reduce when N > 1, normalise to
-the number density (K2).  `value` is binned atom-frames per second with the frames resident in HBM;
-`e2e` is the same job driven through the C ABI from pinned HOST frames (H2D staging in batches on
-CUDA streams inside the timed region, density grid read back).  N > 1 is frame sharding: every
-rank gets its own 10 000 frames (weak scaling).
+One STEP = one batch of the job on every rank: zero the grid, bin PASSES x RESIDENT frames (K1), combine the per-GPU
+grids with one NCCL integer all-reduce when N > 1, normalise to the number density (K2).  `value` is binned
+atom-frames per second with the frames resident in HBM; `e2e` is the same path driven through the C ABI from
+pinned HOST frames (H2D staging in batches on CUDA streams inside the timed region, density grid read back).
+N > 1 is frame sharding: every rank gets its own frames (weak scaling).
 
-Beside the contract's keys the line carries, at N = 1: `a_ri3Dc` (K3, gcb_analyse over the job's density: wall time
-from a host grid and from the density left in HBM, the oracle's single-thread time, bit-equality), `xtc` (host
-decode rate, GPU decode rate, the job driven from compressed bytes) and, in `roofline`, the DRAM fraction the
-kernel really reaches (36 B of traffic per unit) and the fraction of the fitted L2 ceiling.
+Beside the contract's keys the line carries
+  roofline      K1's dominant kernel: achieved = 12 B x atom-frames / summed launch durations, measured live with CUDA
+                events around every launch; the memory-system ceilings for K1's traffic mix measured in the same run
+                by gcb_selftest_l2 (random-RED peak, and a read stream with one RED per 36 bytes)
+  per_config    (N = 1) the other named shapes C1, C2, C4 (uniform and clustered), each with value, roofline, the
+                kernel that ran and a bit-exact oracle check of a prefix of its frames
+  c5            (N > 1) the C5 shape: breathing box, 256 MB NCCL all-reduce, with its own oracle parity check
+  parity_checked / parity   counts and per-frame hits of a frame prefix (of every rank's shard) equal the CPU oracle's
+  a_ri3Dc, xtc  (N = 1) K3 over the job's density; XTC decode rates
 
---impl reference times the reference's own CPU implementation of the path (the compiled,
-unmodified gridcount() loop in oracle/_ref/libgcref.so; the oracle's C port if that binary is
-absent) on all host threads, on bounded samples of the same workload.
+--impl reference times the reference's own CPU implementation of the path (the compiled, unmodified gridcount()
+loop in oracle/_ref/libgcref.so; the oracle's C port if that binary is absent) on all host threads, on bounded
+samples of the same workload.
 """
 import argparse
 import ctypes as C
@@ -39,12 +43,58 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-WORKLOAD = dict(name="C2 nanopore: 60000 atoms, 20000 OW counted, 10000 frames, 0.1 nm grid 80x80x134",
-                L=(8.0, 8.0, 13.4), delta=0.1, natoms=60000, stride=3, nframes=10000,
-                slab=(4.7, 8.7), pore_r=0.8, seed=20261019 + 2, dt=1.0)
-ALGO_BYTES_PER_UNIT = 12          # three f32 coordinates of one selected atom
+SEED = 20261019
+CONFIGS = {
+    "C1": dict(title="C1 SPC water box 3 nm: 2700 atoms, 900 OW counted, 0.05 nm grid 60x60x60",
+               L=(3.0, 3.0, 3.0), delta=0.05, natoms=2700, stride=3, named_frames=1000, resident=20000, gen="uniform",
+               grid=(60, 60, 60), seed=SEED + 1, prefix=64,
+               note="the named job (1000 frames, 32 MB) would be L2-resident and launch-bound; measured over 20000 "
+                    "distinct frames (648 MB)"),
+    "C2": dict(title="C2 nanopore: 60000 atoms, 20000 OW counted, 10000 frames, 0.1 nm grid 80x80x134",
+               L=(8.0, 8.0, 13.4), delta=0.1, natoms=60000, stride=3, named_frames=10000, resident=10000, gen="pore",
+               slab=(4.7, 8.7), pore_r=0.8, grid=(80, 80, 134), seed=SEED + 2, prefix=64),
+    "C3": dict(title="C3 1M-atom solvated box 20 nm: 333334 OW counted, 0.05 nm grid 400x400x400 (grid beyond L2)",
+               L=(20.0, 20.0, 20.0), delta=0.05, natoms=1000000, stride=3, named_frames=100000, resident=1152,
+               gen="uniform", grid=(400, 400, 400), seed=SEED + 3, prefix=8),
+    "C4": dict(title="C4 fine grid: 10 nm box, 100000 atoms, 33334 OW counted, 0.02 nm grid 500x500x500",
+               L=(10.0, 10.0, 10.0), delta=0.02, natoms=100000, stride=3, named_frames=50000, resident=9600,
+               gen="uniform", grid=(500, 500, 500), seed=SEED + 4, prefix=32),
+    "C4K": dict(title="C4 clustered (atomic-contention stress): as C4, Gaussians of sigma 0.1 nm around 256 sites",
+                L=(10.0, 10.0, 10.0), delta=0.02, natoms=100000, stride=3, named_frames=50000, resident=9600,
+                gen="cluster", nsites=256, sigma=0.1, grid=(500, 500, 500), seed=SEED + 4, prefix=32),
+    "C5": dict(title="C5 frame-sharded run: 1M atoms per frame, 333334 OW counted, pressure-coupled (breathing) box, "
+                     "400x400x400 grid, NCCL uint32 grid all-reduce",
+               L=(20.0, 20.0, 20.0), delta=0.05, natoms=1000000, stride=3, named_frames=1000000, resident=1152,
+               gen="uniform", box_period=1000, box_amp=0.002, grid=(400, 400, 400), seed=SEED + 5, prefix=4),
+}
+HEADLINE = "C3"
+PASSES = 8                         # passes over the resident frames per step: 9216 frames per rank and step
+ALGO_BYTES_PER_UNIT = 12           # three f32 coordinates of one selected atom
 METRIC = "binned atom-frames/sec"
 UNIT = "G atom-frames/s"
+GEN_MODES = {"uniform": 0, "quantised": 1, "pore": 2, "cluster": 3}
+
+
+def cfg_gindex(cfg):
+    return np.arange(0, cfg["natoms"], cfg["stride"], dtype=np.int32)
+
+
+def cfg_gen(mod, cfg):
+    """mod: gridcount_b200 (device generator) or gcutil (the oracle's generator); same bits"""
+    return mod.make_gen(cfg["seed"], cfg["L"], GEN_MODES[cfg["gen"]], slab=cfg.get("slab", (0.0, 0.0)),
+                        pore_r=cfg.get("pore_r", 0.0), nsites=cfg.get("nsites", 1), sigma=cfg.get("sigma", 0.0),
+                        box_period=cfg.get("box_period", 0), box_amp=cfg.get("box_amp", 0.0))
+
+
+def headline_config(world):
+    """the `config` object of the JSON line: identical in both arms"""
+    cfg = CONFIGS[HEADLINE]
+    return {"workload": cfg["title"], "grid": list(cfg["grid"]), "atoms_per_frame": cfg["natoms"],
+            "counted_per_frame": len(cfg_gindex(cfg)), "distribution": cfg["gen"] + " (counter-based generator)",
+            "frames_per_step_per_gpu": cfg["resident"] * PASSES,
+            "step": "zero the grid + bin %d x %d frames (K1) + grid all-reduce if N > 1 + density (K2)"
+                    % (PASSES, cfg["resident"]),
+            "parallelism": "frame-sharded x%d" % world}
 
 
 def read_peaks():
@@ -54,15 +104,14 @@ def read_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def read_traffic():
-    """per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any"""
+def read_traffic(kernel_key):
+    """per-launch DRAM bytes of a kernel from the committed ncu --set full capture of this round, if any
+    (profiles/k1_traffic.json: {kernel_key: {dram_bytes_per_launch, atom_frames_per_launch, source}})"""
     p = os.path.join(ROOT, "profiles", "k1_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p))
-        except Exception:
-            return None
-    return None
+    try:
+        return json.load(open(p)).get(kernel_key)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -120,6 +169,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+
 # --------------------------------------------------------------------------------------------
 # CPU reference arm
 # --------------------------------------------------------------------------------------------
@@ -150,41 +200,37 @@ def cpu_reference(sample_frames, repeats, threads, frames_host, gindex, L, delta
     return sample_frames * len(gi) * repeats / total, kind
 
 
-def host_sample_frames(nframes, wl):
-    import gcutil as u
-    gen = u.make_gen(wl["seed"], wl["L"], 2, slab=wl["slab"], pore_r=wl["pore_r"])
-    return u.gen_frames(gen, 0, nframes, wl["natoms"])
-
-
 def run_reference_arm(args, rank, world):
-    wl = WORKLOAD
+    """the reference's gridcount() loop on all host threads over a bounded sample of the headline workload"""
+    import gcutil as u
+    cfg = CONFIGS[HEADLINE]
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    gindex = np.arange(0, wl["natoms"], wl["stride"], dtype=np.int32)
-    sample = 256                                   # frames held in memory (18 MB), re-binned `repeats` times
-    x = host_sample_frames(sample, wl)
-    # size a step to ~2 s of wall time on this host
-    rate, kind = cpu_reference(sample, 1, threads, x, gindex, wl["L"], wl["delta"], wl["natoms"])
+    gindex = cfg_gindex(cfg)
+    sample = 2 * threads                           # frames held in memory (12 MB each), one or two per thread
+    x = u.gen_frames(cfg_gen(u, cfg), 0, sample, cfg["natoms"])
+    # size a step to ~3 s of binning on this host
+    rate, kind = cpu_reference(sample, 1, threads, x, gindex, cfg["L"], cfg["delta"], cfg["natoms"])
     per_rep = sample * len(gindex) / rate
-    repeats = int(max(1, min(200, round(2.0 / max(per_rep, 1e-6)))))
-    for _ in range(args.warmup):
-        cpu_reference(sample, 1, threads, x, gindex, wl["L"], wl["delta"], wl["natoms"])
+    repeats = int(max(1, min(50, round(3.0 / max(per_rep, 1e-6)))))
+    for _ in range(min(args.warmup, 2)):
+        cpu_reference(sample, 1, threads, x, gindex, cfg["L"], cfg["delta"], cfg["natoms"])
     t_units = 0.0
     t_secs = 0.0
     for _ in range(args.steps):
-        r, kind = cpu_reference(sample, repeats, threads, x, gindex, wl["L"], wl["delta"], wl["natoms"])
+        r, kind = cpu_reference(sample, repeats, threads, x, gindex, cfg["L"], cfg["delta"], cfg["natoms"])
         units = sample * len(gindex) * repeats
         t_units += units
         t_secs += units / r
     value = t_units / t_secs * 1e-9
-    sample_txt = ("%d generated frames of the workload held in host memory, binned %d times per step by %d threads "
-                  "with private grids (decode excluded)" % (sample, repeats, threads))
+    sample_txt = ("%d generated frames of the workload (%d MB) held in host memory, binned %d times per step by %d threads, "
+                  "each into a private 256 MB grid and a contiguous frame range; grid allocation and trajectory decode "
+                  "excluded from the timed region" % (sample, sample * cfg["natoms"] * 12 >> 20, repeats, threads))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_secs / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "grid": [80, 80, 134], "distribution": "pore",
-                       "inputs": "host memory"},
+            "config": headline_config(args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample_txt},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -243,10 +289,11 @@ def xtc_section(g, ctr, dev, wl, geom, gindex):
     return res
 
 
-def k3_section(g, ctr, T_tot):
+
+def k3_section(g, ctr, T_tot, oracle_too=True):
     """a_ri3Dc's reductions (K3, gcb_analyse) over the job's density: wall time through the C ABI from a HOST grid
-    (H2D of the grid, all kernels, D2H of every output), with the oracle's single-thread time beside it.
-    Reported on its own line, not folded into the metric."""
+    (H2D of the grid, all kernels, D2H of every output) and from the density left in HBM, with the oracle's
+    single-thread time beside it.  Reported on its own line, not folded into the metric."""
     import gcutil as u
     tg, dens, _ = ctr.density(T_tot)
     g.analyse(tg, dens, unit="SPC")                       # warm-up
@@ -255,7 +302,6 @@ def k3_section(g, ctr, T_tot):
         t0 = time.perf_counter()
         r = g.analyse(tg, dens, unit="SPC")
         ts.append(time.perf_counter() - t0)
-    # the same with the density left in HBM (gcb_counter_device_density -> gcb_analyse_device): no grid over PCIe
     dptr = ctr.density_device(T_tot)
     ctr.sync()
     g.analyse(tg, None, unit="SPC", grid_dev=dptr)
@@ -264,24 +310,149 @@ def k3_section(g, ctr, T_tot):
         t0 = time.perf_counter()
         g.analyse(tg, None, unit="SPC", grid_dev=dptr)
         td.append(time.perf_counter() - t0)
-    og = u.Geom.from_buffer_copy(bytes(tg))
-    u.oracle().gco_update_b(C.byref(og))
-    an = u.Analysis()
-    an.unit = u.UNITS["SPC"]; an.rad_ba_step = 1
-    t0 = time.perf_counter()
-    u.oracle().gco_analyse(C.byref(og), u.fptr(dens), C.byref(an))
-    cpu_s = time.perf_counter() - t0
-    arrs = u.analysis_arrays(an, og)
-    def _same(p, q):
-        return np.array_equal(np.isnan(p), np.isnan(q)) and bool(((p.view(np.uint32) == q.view(np.uint32)) | np.isnan(p)).all())
-    same = all(_same(arrs[k], r[k]) for k in ("rzp", "zdf", "rdf", "xyp"))
-    same = same and np.float32(an.average).view(np.uint32) == np.float32(r["average"]).view(np.uint32) and an.sumP == r["sumP"]
-    u.oracle().gco_analysis_free(C.byref(an))
     cells = int(np.prod(dens.shape))
-    return {"grid": list(dens.shape), "ms": float(np.median(ts)) * 1e3, "cells_per_s": cells / float(np.median(ts)),
-            "ms_device_resident_grid": float(np.median(td)) * 1e3,
-            "kernel_launches": int(r["kernel_launches"]), "oracle_ms_1_thread": cpu_s * 1e3, "bit_equal_to_oracle": bool(same),
-            "note": "host grid in, all profiles out; every sum is the reference's sequential f32/f64 chain, evaluated in parallel"}
+    out = {"grid": list(dens.shape), "ms": float(np.median(ts)) * 1e3, "cells_per_s": cells / float(np.median(ts)),
+           "ms_device_resident_grid": float(np.median(td)) * 1e3,
+           "roofline_frac_device_resident": cells * 4 / float(np.median(td)) * 1e-9 / read_peaks()[0],
+           "kernel_launches": int(r["kernel_launches"]),
+           "note": "host grid in, all profiles out; every sum is the reference's sequential f32/f64 chain, evaluated in "
+                   "parallel; roofline: 4 B per cell read once"}
+    if oracle_too:
+        og = u.Geom.from_buffer_copy(bytes(tg))
+        u.oracle().gco_update_b(C.byref(og))
+        an = u.Analysis()
+        an.unit = u.UNITS["SPC"]; an.rad_ba_step = 1
+        t0 = time.perf_counter()
+        u.oracle().gco_analyse(C.byref(og), u.fptr(dens), C.byref(an))
+        cpu_s = time.perf_counter() - t0
+        arrs = u.analysis_arrays(an, og)
+
+        def _same(p, q):
+            return np.array_equal(np.isnan(p), np.isnan(q)) and bool(((p.view(np.uint32) == q.view(np.uint32)) | np.isnan(p)).all())
+        same = all(_same(arrs[k], r[k]) for k in ("rzp", "zdf", "rdf", "xyp", "xzp", "yzp", "lzdf"))
+        same = same and np.float32(an.average).view(np.uint32) == np.float32(r["average"]).view(np.uint32) and an.sumP == r["sumP"]
+        u.oracle().gco_analysis_free(C.byref(an))
+        out["oracle_ms_1_thread"] = cpu_s * 1e3
+        out["bit_equal_to_oracle"] = bool(same)
+    return out
+
+
+def oracle_counts(tg, x, gindex):
+    """the CPU oracle's integer counts and per-frame hits for host frames x (checker only)"""
+    import gcutil as u
+    og = u.Geom.from_buffer_copy(bytes(tg))
+    shape = (tg.mx[0], tg.mx[1], tg.mx[2])
+    want = np.zeros(shape, np.uint32)
+    hits = np.zeros(x.shape[0], np.uint64)
+    u.oracle().gco_count_frames(C.byref(og), want.ctypes.data_as(u.c_u32_p), u.fptr(x), x.shape[0], x.shape[1],
+                                u.iptr(gindex), len(gindex), hits.ctypes.data_as(u.c_u64_p), None)
+    return want, hits
+
+
+def prefix_parity(g, cfg, geom, gindex, dev, device):
+    """Bit-exactness inside the bench: a prefix of the resident frames is binned by a fresh counter with the kernel
+    AUTO picks for this shape and compared, cell by cell and frame by frame, with the CPU oracle on the same frames."""
+    n = min(cfg["prefix"], dev.nframes)
+    ctr = g.GridCounter(geom, gindex, cfg["natoms"], device=device)
+    ctr.add_device_frames(dev, first=0, count=n)
+    got = ctr.counts()
+    hits = ctr.hits_per_frame()
+    st = ctr.stats()
+    ctr.close()
+    want, whits = oracle_counts(geom.tg, dev.download(0, n), gindex)
+    ok = bool(np.array_equal(got, want) and np.array_equal(hits, whits))
+    return {"ok": ok, "frames": int(n), "hits": int(whits.sum()), "packed_rounds": int(st.packed_rounds),
+            "packed_redone": int(st.packed_redone), "against": "CPU oracle (oracle/gc_oracle.c), counts and per-frame hits"}
+
+
+def l2_ceilings(g, window_bytes, stride, device):
+    """the memory system's ceilings for K1's traffic on this shape, measured now (gcb_selftest_l2)"""
+    red_peak, _ = g.selftest_l2(window_bytes, 0, device)
+    mix, rd = g.selftest_l2(window_bytes, 1 if stride == 3 else 2, device)
+    return {"window_mb": window_bytes / 2.0 ** 20, "red_peak_gops": red_peak,
+            "stream_plus_red_gops": mix, "stream_plus_red_read_gbs": rd,
+            "mix": "one random RED per %d streamed bytes" % (36 if stride == 3 else 12)}
+
+
+def roofline_of(g, ctr, stride, cells, peak, peak_src, device, kernel_key, l2=None):
+    """K1's dominant kernel from the event pairs gcb_counter_profile put around its launches"""
+    k1_ms, nl, units = ctr.profile_read()
+    st = ctr.stats()
+    packed = st.packed_rounds > 0
+    bits = 8 if cells <= (80 << 20) else 4
+    kernel = ("bin_stream_kernel<PackedSink<%d>> (non-returning REDs into %d-bit L2-resident counters)" % (bits, bits)
+              if packed else "bin_stream_kernel<DirectSink> (one RED per hit into the uint32 grid)")
+    gps = units / (k1_ms * 1e-3) * 1e-9
+    achieved = ALGO_BYTES_PER_UNIT * gps
+    tr = read_traffic(kernel_key)
+    out = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+           "peak_source": peak_src, "launch_ms_avg": k1_ms / max(nl, 1), "launches_timed": int(nl),
+           "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UNIT * units / max(nl, 1),
+           "kernel_g_atom_frames_per_s": gps,
+           "traffic": None, "hbm_ceiling_note": "one atom in %d is counted out of x[atom][3]: every 32 B sector of a frame "
+                                                "holds part of a counted atom, so DRAM moves %d B per unit and frac <= %.2f"
+                                                % (stride, 12 * stride, 1.0 / stride) if stride > 1 else None}
+    if tr:
+        out["traffic"] = tr["dram_bytes_per_launch"]
+        out["traffic_source"] = tr.get("source")
+        out["traffic_bytes_per_unit"] = tr["dram_bytes_per_launch"] / tr["atom_frames_per_launch"]
+    if l2:
+        out["l2"] = dict(l2)
+        out["l2"]["frac_of_red_peak"] = gps / l2["red_peak_gops"]
+        out["l2"]["frac_of_stream_plus_red"] = gps / l2["stream_plus_red_gops"]
+    return out
+
+
+def measure_config(g, name, cfg, device, peak, peak_src, reps=10, extra=None):
+    """device-resident throughput of one named shape on one GPU, with roofline and oracle parity"""
+    geom = g.setup_geometry(cfg["L"], cfg["delta"])
+    assert geom.shape == tuple(cfg["grid"]), (geom.shape, cfg["grid"])
+    gindex = cfg_gindex(cfg)
+    gnx, F = len(gindex), cfg["resident"]
+    dev = g.DeviceFrames(F, cfg["natoms"], device).generate(cfg_gen(g, cfg))
+    ctr = g.GridCounter(geom, gindex, cfg["natoms"], device=device)
+    w = np.ones(F, np.float32)
+    for _ in range(3):
+        ctr.add_device_frames(dev, weights=w)
+    ctr.sync()
+    ctr.reset_grid()
+    ctr.event_record(0)
+    for _ in range(reps):
+        ctr.add_device_frames(dev, weights=w)
+    ctr.event_record(1)
+    ms = ctr.event_elapsed(0, 1)
+    st = ctr.stats()
+    lost = st.hits != st.atom_frames
+    ctr.profile(True)
+    for _ in range(2):
+        ctr.add_device_frames(dev, weights=w)
+    packed_bytes = geom.cells if geom.cells <= (80 << 20) else geom.cells // 2
+    window = packed_bytes if st.packed_rounds > 0 else geom.cells * 4
+    rl = roofline_of(g, ctr, cfg["stride"], geom.cells, peak, peak_src, device, name)
+    ctr.profile(False)
+    res = {"workload": cfg["title"], "grid": list(geom.shape), "frames_resident": F,
+           "frames_resident_gb": F * cfg["natoms"] * 12 / 1e9, "passes_timed": reps,
+           "value": float(gnx) * F * reps / (ms * 1e-3) * 1e-9, "unit": UNIT,
+           "ms_per_pass": ms / reps, "all_hits_in_grid": not lost,
+           "packed_rounds": int(st.packed_rounds), "packed_redone": int(st.packed_redone)}
+    if cfg.get("note"):
+        res["note"] = cfg["note"]
+    if extra:
+        try:
+            res.update(extra(ctr, dev, geom, gindex))
+        except Exception as e:
+            res["extra_error"] = str(e)[:200]
+    ctr.close()
+    par = prefix_parity(g, cfg, geom, gindex, dev, device)
+    dev.free()
+    l2 = l2_ceilings(g, window, cfg["stride"], device)        # after the counters are gone: it borrows the L2 set-aside
+    rl["l2"] = dict(l2)
+    rl["l2"]["frac_of_red_peak"] = rl["kernel_g_atom_frames_per_s"] / l2["red_peak_gops"]
+    rl["l2"]["frac_of_stream_plus_red"] = rl["kernel_g_atom_frames_per_s"] / l2["stream_plus_red_gops"]
+    res["roofline"] = rl
+    res["parity_checked"] = par["ok"]
+    res["parity"] = par
+    return res
 
 
 def bind_to_gpu_numa_node(device):
@@ -313,16 +484,17 @@ def bind_to_gpu_numa_node(device):
         return None
 
 
+
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
 def run_gpu_arm(args, rank, local_rank, world):
     import torch
+    import gcutil as u
     import gridcount_b200 as g
-    from gridcount_b200 import _cabi as K
     from gridcount_b200.api import nccl_unique_id
 
-    wl = WORKLOAD
+    cfg = CONFIGS[HEADLINE]
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -338,15 +510,25 @@ def run_gpu_arm(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    natoms, F = wl["natoms"], wl["nframes"]
-    gindex = np.arange(0, natoms, wl["stride"], dtype=np.int32)
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        tt = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    peak, peak_src = read_peaks()
+    natoms, F = cfg["natoms"], cfg["resident"]
+    gindex = cfg_gindex(cfg)
     gnx = len(gindex)
-    geom = g.setup_geometry(wl["L"], wl["delta"])
-    assert geom.shape == (80, 80, 134)
-    gen = g.make_gen(wl["seed"], wl["L"], K.GEN_PORE, slab=wl["slab"], pore_r=wl["pore_r"])
-    dev = g.DeviceFrames(F, natoms, device).generate(gen, frame0=rank * F)       # 7.2 GB resident in HBM
-    weights = np.full(F, wl["dt"], np.float32)
-    T_tot = float(F * world) * wl["dt"]
+    geom = g.setup_geometry(cfg["L"], cfg["delta"])
+    assert geom.shape == tuple(cfg["grid"])
+    packed_bytes = geom.cells                         # 8-bit lanes for 400^3
+    # the memory system's ceilings for this traffic mix, measured before the counter takes the L2 set-aside
+    l2 = l2_ceilings(g, packed_bytes, cfg["stride"], device) if rank == 0 else None
+    dev = g.DeviceFrames(F, natoms, device).generate(cfg_gen(g, cfg), frame0=rank * F)       # 13.8 GB resident in HBM
+    weights = np.ones(F, np.float32)
+    T_tot = float(F * PASSES * world)
 
     ctr = g.GridCounter(geom, gindex, natoms, device=device)
     if world > 1:
@@ -354,19 +536,17 @@ def run_gpu_arm(args, rank, local_rank, world):
         dist.broadcast_object_list(uid, src=0)
         ctr.comm_init(uid[0], rank, world)
 
-    def step_device(ev=None):
+    def step_device():
         ctr.reset_grid()
-        if ev is not None:
-            ctr.event_record(ev)
-        ctr.add_device_frames(dev, weights=weights)
-        if ev is not None:
-            ctr.event_record(ev + 1)
+        for _ in range(PASSES):
+            ctr.add_device_frames(dev, weights=weights)
         if world > 1:
             ctr.allreduce()
         ctr.density_device(T_tot)
 
     # ---- device-resident value -----------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_device()
     ctr.sync()
     launches0 = ctr.stats().kernel_launches
@@ -376,151 +556,221 @@ def run_gpu_arm(args, rank, local_rank, world):
         sampler.start()
     ctr.event_record(2)
     for s in range(args.steps):
-        step_device(ev=4 + 2 * s)
+        step_device()
     ctr.event_record(3)
     ctr.sync()
     barrier()
-    # the device-timed region lasts tens of milliseconds; the sampler keeps running through the end-to-end region
-    # below (the same kernels fed over PCIe) so that the clocks line rests on more than one or two samples
-    ms_total = ctr.event_elapsed(2, 3)
-    k1_ms = [ctr.event_elapsed(4 + 2 * s, 5 + 2 * s) for s in range(args.steps)]
-    launches = ctr.stats().kernel_launches - launches0
+    ms_total = max_over_ranks(ctr.event_elapsed(2, 3))
+    st = ctr.stats()
+    launches = st.kernel_launches - launches0
     if dist is not None:
-        tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total = float(tt.item())
         ll = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(ll)
         launches = int(ll.item())
-    units_per_step = float(gnx) * F * world
+    units_per_step = float(gnx) * F * PASSES * world
     value = units_per_step * args.steps / (ms_total * 1e-3) * 1e-9
+    # size-independent property of the full-size run: every generated atom lies in the grid, none was lost
+    assert st.hits == st.atom_frames == int(gnx) * F * PASSES * world, "bench grid lost hits"
+    packed_info = {"rounds": int(st.packed_rounds), "redone_by_direct_kernel": int(st.packed_redone)}
 
-    # parity spot check inside the bench: global hit count equals frames*gnx (all generated atoms are in-grid)
-    st = ctr.stats()
-    assert st.hits == st.atom_frames, "bench grid lost hits"
-
-    # ---- roofline of the dominant kernel (K1, the streaming binning kernel) -----------------
-    peak, peak_src = read_peaks()
-    k1_avg_ms = float(np.mean(k1_ms))
-    achieved = ALGO_BYTES_PER_UNIT * float(gnx) * F / (k1_avg_ms * 1e-3) * 1e-9      # GB/s, this rank's launch
-    traffic = read_traffic()
-    roofline = {"bound": "hbm", "kernel": "bin_stream_kernel (K1)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UNIT * gnx * F,
-                "launch_ms_avg": k1_avg_ms,
-                "l2_atomic_peak_gops": (traffic or {}).get("l2_atomic_peak_gops"),
-                "frac_of_l2_atomic_peak": ((float(gnx) * F / (k1_avg_ms * 1e-3) * 1e-9) /
-                                           traffic["l2_atomic_peak_gops"]) if traffic and
-                traffic.get("l2_atomic_peak_gops") else None}
-    if traffic:
-        # what the kernel really moves: every 32-byte sector of a frame holds part of a counted atom when one atom in
-        # three is counted, so DRAM traffic is 36 B per unit whatever the kernel does
-        roofline["dram_frac"] = traffic["dram_bytes_per_launch"] / (k1_avg_ms * 1e-3) * 1e-9 / peak
-        roofline["dram_bytes_per_unit"] = traffic["dram_bytes_per_launch"] / (float(gnx) * F)
-    # L2 work model fitted to three measurements: a RED costs 1.625 read sectors, the L2
-    # sustains 310 G sector-equivalents/s; this workload needs 36/32 read sectors + 1 RED per unit
-    l2_ceiling = 310.0 / (36.0 / 32.0 + 1.625)
-    roofline["l2_model_ceiling_g_units_s"] = l2_ceiling
-    roofline["frac_of_l2_model"] = (float(gnx) * F / (k1_avg_ms * 1e-3) * 1e-9) / l2_ceiling
+    # ---- roofline of the dominant kernel: event pairs around every launch of one more step ----------
+    ctr.profile(True)
+    step_device()
+    roofline = roofline_of(g, ctr, cfg["stride"], geom.cells, peak, peak_src, device, HEADLINE, l2)
+    ctr.profile(False)
 
     # ---- end to end: pinned host frames through the C ABI ----------------------------------
-    HOSTF = 1000                                     # distinct frames kept in pinned memory (720 MB)
+    HOSTF = 96                                        # distinct frames kept in pinned memory (1.15 GB)
     pin = g.PinnedFrames(HOSTF, natoms)
-    chunk = 250
-    for f0 in range(0, HOSTF, chunk):
-        pin.array[f0:f0 + chunk] = dev.download(f0, chunk)
-    wh = np.full(HOSTF, wl["dt"], np.float32)
+    for f0 in range(0, HOSTF, 32):
+        pin.array[f0:f0 + 32] = dev.download(f0, 32)
+    wh = np.ones(HOSTF, np.float32)
     dens_host = np.zeros(geom.shape, np.float32)
+    E2E_CALLS = F // HOSTF                            # 12 calls: the resident batch's 1152 frames, once
 
     def step_e2e():
         ctr.reset_grid()
-        for _ in range(F // HOSTF):
+        for _ in range(E2E_CALLS):
             ctr.add_host_ptr(pin.ptr, HOSTF, wh)        # H2D in batches on copy streams, overlapped with K1
         if world > 1:
             ctr.allreduce()
-        ctr.density_into(T_tot, dens_host)              # K2 + D2H of the density grid
+        ctr.density_into(float(HOSTF * E2E_CALLS * world), dens_host)     # K2 + D2H of the density grid
 
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 3))
     step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_e2e()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
-        clocks["window"] = "device-timed steps + end-to-end steps"
-    e2e = {"value": units_per_step * e2e_steps / e2e_s * 1e-9, "unit": UNIT,
-           "h2d_bytes_per_step": int(F) * natoms * 12 * world,
-           "d2h_bytes_per_step": int(geom.cells * 4 + F * 8) * world, "steps": e2e_steps,
-           "ms_per_step": e2e_s / e2e_steps * 1e3,
+        clocks["window"] = "device-timed steps + roofline step + end-to-end steps"
+    e2e_units = float(gnx) * HOSTF * E2E_CALLS * world
+    e2e = {"value": e2e_units * e2e_steps / e2e_s * 1e-9, "unit": UNIT,
+           "h2d_bytes_per_step": int(HOSTF * E2E_CALLS) * natoms * 12 * world,
+           "d2h_bytes_per_step": int(geom.cells * 4 + HOSTF * E2E_CALLS * 8) * world, "steps": e2e_steps,
+           "frames_per_step_per_gpu": HOSTF * E2E_CALLS, "ms_per_step": e2e_s / e2e_steps * 1e3,
            "path": "gcb_counter_add_frames(pinned host x[F][natoms][3]) -> gcb_counter_density(host grid)"}
     pin.free()
+
+    # ---- parity inside the bench ---------------------------------------------------------------
+    parity = None
+    c5 = None
+    if world == 1:
+        parity = prefix_parity(g, cfg, geom, gindex, dev, device)
+    else:
+        c5, parity = c5_section(g, u, torch, dist, ctr, dev, geom, rank, world, device, barrier, max_over_ranks)
 
     # ---- a_ri3Dc's reductions over the job's density (K3), on its own line -----------------------
     k3 = None
     if rank == 0 and world == 1:
         try:
-            k3 = k3_section(g, ctr, T_tot)
+            ctr.reset_grid()
+            ctr.add_device_frames(dev, weights=weights)
+            k3 = k3_section(g, ctr, float(F))
         except Exception as e:
             k3 = {"error": str(e)[:200]}
 
-    # ---- XTC decode, timed separately (north star): host decoder vs GPU decoder on the same frames ----
-    xtc = None
-    if rank == 0 and world == 1:
-        try:
-            xtc = xtc_section(g, ctr, dev, wl, geom, gindex)
-        except Exception as e:          # the section is informative; never let it take the headline down
-            xtc = {"error": str(e)[:200]}
-
-    # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's loop on this box's cores --------
     cpu = None
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1
-        sample = 256
+        sample = 2 * threads
         xh = dev.download(0, sample)
-        r1, kind = cpu_reference(sample, 2, 1, xh, gindex, wl["L"], wl["delta"], natoms)
-        per = sample * gnx / r1
-        rep1 = int(max(1, min(20, round(4.0 / per))))
-        r1, kind = cpu_reference(sample, rep1, 1, xh, gindex, wl["L"], wl["delta"], natoms)
-        rp, kind = cpu_reference(sample, 4, threads, xh, gindex, wl["L"], wl["delta"], natoms)
-        repp = int(max(1, min(400, round(6.0 * rp / (sample * gnx)))))
-        rp, kind = cpu_reference(sample, repp, threads, xh, gindex, wl["L"], wl["delta"], natoms)
-        cpu = {"value": rp * 1e-9, "unit": UNIT, "cores": threads, "kind": kind,
-               "single_core_value": r1 * 1e-9,
-               "sample": "%d frames of the workload (from the same generator) in host memory; 1 thread x %d passes "
-                         "and %d threads x %d passes with private grids; trajectory decode excluded"
-                         % (sample, rep1, threads, repp)}
+        r1, kind = cpu_reference(4, 1, 1, xh, gindex, cfg["L"], cfg["delta"], natoms)
+        rep1 = int(max(1, min(8, round(4.0 * r1 / (4 * gnx)))))
+        r1, kind = cpu_reference(4, rep1, 1, xh, gindex, cfg["L"], cfg["delta"], natoms)
+        rp, kind = cpu_reference(sample, 1, threads, xh, gindex, cfg["L"], cfg["delta"], natoms)
+        repp = int(max(1, min(40, round(8.0 * rp / (sample * gnx)))))
+        rp, kind = cpu_reference(sample, repp, threads, xh, gindex, cfg["L"], cfg["delta"], natoms)
+        cpu = {"value": rp * 1e-9, "unit": UNIT, "cores": threads, "kind": kind, "single_core_value": r1 * 1e-9,
+               "sample": "frames of the workload (from the same generator) in host memory, binned into private 256 MB "
+                         "grids: 1 thread x 4 frames x %d passes, and %d threads x %d frames x %d passes; grid "
+                         "allocation and trajectory decode excluded" % (rep1, threads, sample, repp)}
+    ctr.close()
+    dev.free()
+
+    # ---- the other named shapes (N = 1): C1, C2 (+ its a_ri3Dc and XTC sections), C4 uniform and clustered ----
+    per_config = None
+    xtc = None
+    k3_c2 = None
+    if rank == 0 and world == 1:
+        per_config = {}
+        for name in ("C1", "C2", "C4", "C4K"):
+            c = CONFIGS[name]
+            extra = None
+            if name == "C2":
+                def extra(cc, dd, gg, gi, c=c):
+                    out = {}
+                    cc.reset_grid()
+                    cc.add_device_frames(dd, weights=np.ones(dd.nframes, np.float32))
+                    out["a_ri3Dc"] = k3_section(g, cc, float(dd.nframes))
+                    out["xtc"] = xtc_section(g, cc, dd, c, gg, gi)
+                    return out
+            try:
+                per_config[name] = measure_config(g, name, c, device, peak, peak_src, extra=extra)
+            except Exception as e:
+                per_config[name] = {"error": str(e)[:300]}
+        xtc = per_config.get("C2", {}).pop("xtc", None)
+        k3_c2 = per_config.get("C2", {}).pop("a_ri3Dc", None)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": wl["name"], "grid": list(geom.shape), "distribution": "pore (generator mode 2)",
-                           "frames_resident_gb": F * natoms * 12 / 1e9, "l2_policy": "inputs (7.2 GB) larger than L2",
-                           "parallelism": "frame-sharded x%d, one NCCL u32 all-reduce per job" % world,
-                           "host_binding": numa,
-                           "step": "reset + K1 bin 10000 frames + (all-reduce) + K2 density"},
+                "config": headline_config(world),
+                "timing": {"frames_resident_gb_per_gpu": F * natoms * 12 / 1e9,
+                           "l2_policy": "inputs (13.8 GB per GPU) larger than L2", "host_binding": numa,
+                           "clock": "CUDA events on the launching stream, max over ranks"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu, "a_ri3Dc": k3, "xtc": xtc}
+                "packed_counters": packed_info,
+                "parity_checked": bool(parity and parity["ok"]), "parity": parity,
+                "cpu_baseline": cpu, "a_ri3Dc": {"C3": k3, "C2": k3_c2} if world == 1 else None, "xtc": xtc,
+                "per_config": per_config, "c5": c5}
         print(json.dumps(line), flush=True)
-    ctr.close()
-    dev.free()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def c5_section(g, u, torch, dist, ctr, dev, geom, rank, world, device, barrier, max_over_ranks):
+    """N > 1: the C5 shape on the same counter -- every rank's frames come from a breathing box (the grid stays the
+    first frame's, atoms that end up outside are dropped as the reference drops them), one 256 MB NCCL uint32
+    all-reduce per job.  First a parity job: a short prefix of EVERY rank's shard is binned and all-reduced, and rank 0
+    compares the reduced counts with the CPU oracle run over the same frames; then the timed jobs."""
+    cfg = CONFIGS["C5"]
+    natoms, F = cfg["natoms"], cfg["resident"]
+    gindex = cfg_gindex(cfg)
+    gnx = len(gindex)
+    dev.generate(cfg_gen(g, cfg), frame0=rank * F)
+    npre = cfg["prefix"]
+    ctr.reset_grid()
+    ctr.add_device_frames(dev, first=0, count=npre)
+    ctr.allreduce()
+    st = ctr.stats()
+    parity = None
+    if rank == 0:
+        got = ctr.counts()
+        want = np.zeros(geom.shape, np.uint32)
+        nh = 0
+        for r in range(world):
+            x = u.gen_frames(cfg_gen(u, cfg), r * F, npre, natoms)
+            wr, hr = oracle_counts(geom.tg, x, gindex)
+            want += wr
+            nh += int(hr.sum())
+        parity = {"ok": bool(np.array_equal(got, want) and st.hits == nh and st.frames == npre * world),
+                  "frames": npre * world, "hits": nh, "atom_frames": npre * world * gnx,
+                  "against": "CPU oracle over the first %d frames of every rank's shard (breathing box): NCCL-reduced "
+                             "uint32 grid, global hit count and frame count" % npre}
+    else:
+        ctr.counts()
+    barrier()
+    REPS, JOBS = 4, 3
+    w = np.ones(F, np.float32)
+
+    def job(ev=None):
+        ctr.reset_grid()
+        if ev is not None:
+            ctr.event_record(ev)
+        for _ in range(REPS):
+            ctr.add_device_frames(dev, weights=w)
+        if ev is not None:
+            ctr.event_record(ev + 1)
+        ctr.allreduce()
+        if ev is not None:
+            ctr.event_record(ev + 2)
+        ctr.density_device(float(F * REPS * world))
+
+    job()
+    ctr.sync()
+    barrier()
+    ctr.event_record(2)
+    for j in range(JOBS):
+        job(ev=10 + 4 * j)
+    ctr.event_record(3)
+    ctr.sync()
+    barrier()
+    ms = max_over_ranks(ctr.event_elapsed(2, 3) / JOBS)
+    bin_ms = max_over_ranks(float(np.mean([ctr.event_elapsed(10 + 4 * j, 11 + 4 * j) for j in range(JOBS)])))
+    red_ms = max_over_ranks(float(np.mean([ctr.event_elapsed(11 + 4 * j, 12 + 4 * j) for j in range(JOBS)])))
+    st = ctr.stats()
+    c5 = None
+    if rank == 0:
+        c5 = {"workload": cfg["title"], "n_gpus": world, "frames_per_job": F * REPS * world,
+              "value": float(gnx) * F * REPS * world / (ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_job": ms,
+              "binning_ms": bin_ms, "allreduce_256MB_ms": red_ms, "hits": int(st.hits), "atom_frames": int(st.atom_frames),
+              "note": "a job here is %d frames per rank; the named job is 125000 per rank, so the all-reduce's share is "
+                      "overstated %dx" % (F * REPS, 125000 // (F * REPS)),
+              "parity_checked": bool(parity["ok"])}
+    return c5, parity
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()

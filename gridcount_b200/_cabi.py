@@ -115,6 +115,9 @@ SIGNATURES = {
     "gcb_counter_event_elapsed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "gcb_counter_timer_start": (C.c_int, [C.c_void_p]),
     "gcb_counter_timer_stop": (C.c_int, [C.c_void_p, c_float_p]),
+    "gcb_counter_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "gcb_counter_profile_read": (C.c_int, [C.c_void_p, c_double_p, c_long_p, c_double_p]),
+    "gcb_selftest_l2": (C.c_int, [C.c_int, C.c_size_t, C.c_int, C.c_size_t, c_double_p, c_double_p]),
     "gcb_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "gcb_counter_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "gcb_counter_allreduce": (C.c_int, [C.c_void_p]),

@@ -370,6 +370,16 @@ class GridCounter:
         check(lib.gcb_counter_event_elapsed(self.h, i, j, C.byref(ms)), "gcb_counter_event_elapsed")
         return ms.value
 
+    def profile(self, enable=True):
+        """event pairs around every launch of the streaming kernel from now on (gcb_counter_profile)"""
+        check(lib.gcb_counter_profile(self.h, int(bool(enable))), "gcb_counter_profile")
+
+    def profile_read(self):
+        """-> (summed launch durations in ms, launches, atom-frames those launches covered)"""
+        ms, n, units = C.c_double(0), C.c_long(0), C.c_double(0)
+        check(lib.gcb_counter_profile_read(self.h, C.byref(ms), C.byref(n), C.byref(units)), "gcb_counter_profile_read")
+        return ms.value, n.value, units.value
+
     def timer_start(self):
         check(lib.gcb_counter_timer_start(self.h), "gcb_counter_timer_start")
 
@@ -383,6 +393,14 @@ class GridCounter:
 
     def allreduce(self):
         check(lib.gcb_counter_allreduce(self.h), "gcb_counter_allreduce")
+
+
+def selftest_l2(window_bytes, mix, device=0, stream_bytes=0):
+    """gcb_selftest_l2: what the memory system sustains for K1's traffic mix -> (G REDs/s, GB/s streamed).
+    mix 0: random REDs only; 1: + one RED per 36 streamed bytes; 2: per 12 bytes; 3: the stream alone."""
+    red, rd = C.c_double(0), C.c_double(0)
+    check(lib.gcb_selftest_l2(device, window_bytes, mix, stream_bytes, C.byref(red), C.byref(rd)), "gcb_selftest_l2")
+    return red.value, rd.value
 
 
 def nccl_unique_id():

@@ -1020,6 +1020,7 @@ struct gcb_counter {
   uint32_t *d_pk = nullptr;           // packed counters, always all-zero between rounds
   PackedState *d_pstate = nullptr;
   uint64_t packed_rounds = 0, packed_redone = 0;
+  bool l2_window = false;             // persisting-L2 window over d_pk set on the compute stream
   bool saturated = false;             // some cell was clamped (diag[3])
   // xtc path: two sets of {compressed bytes, frame table, status, decoded frames}, copy stream + events
   struct XtcSet {
@@ -1070,6 +1071,11 @@ struct gcb_counter {
   void *nccl = nullptr;               // ncclComm_t, see nccl_reduce.cpp
   int nranks = 1, rank = 0;
   std::vector<cudaEvent_t> events;
+  // gcb_counter_profile: an event pair around every launch of the streaming kernel (K1's dominant kernel)
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_used = 0;
+  double prof_units = 0;
   bool reduced = false;               // statistics below are global after gcb_counter_allreduce
   uint64_t global_frames = 0;
 };
@@ -1148,10 +1154,24 @@ int launch_stream(gcb_counter *c, const float *d_x, long long ntiles, const SINK
   const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
   long long grid = std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
   if (grid_cap > 0) grid = std::min<long long>(grid, grid_cap);
+  const bool timed = c->prof && GUARD != 1;         // (the redo pass of a packed round normally returns at once)
+  if (timed) {
+    if (c->prof_used + 2 > c->prof_ev.size()) {
+      c->prof_ev.resize(c->prof_used + 2, nullptr);
+      GCB_CUDA(cudaEventCreate(&c->prof_ev[c->prof_used]));
+      GCB_CUDA(cudaEventCreate(&c->prof_ev[c->prof_used + 1]));
+    }
+    GCB_CUDA(cudaEventRecord(c->prof_ev[c->prof_used], c->compute));
+  }
   bin_stream_kernel<SINK, PBC, AP, GUARD><<<(unsigned)grid, STREAM_THREADS, smem, c->compute>>>(
       d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, c->ap, c->PF, sink, d_box3, d_hits, c->d_diag, run_if);
   c->launches++;
   GCB_CUDA(cudaGetLastError());
+  if (timed) {
+    GCB_CUDA(cudaEventRecord(c->prof_ev[c->prof_used + 1], c->compute));
+    c->prof_used += 2;
+    c->prof_units += (double)ntiles * (AP ? c->ap.tile_atoms : TILE_ATOMS) / (double)c->natoms * (double)c->gnx;
+  }
   if (grid_out) *grid_out = (int)grid;
   return GCB_OK;
 }
@@ -1250,14 +1270,38 @@ int launch_packed(gcb_counter *c, const float *d_x, long nframes, const float *d
 {
   const bool ap = c->ap_ok && c->opts.kernel != GCB_KERNEL_STREAM_INDEXED;
   const int tile_atoms = ap ? c->ap.tile_atoms : TILE_ATOMS;
-  long fpr = (long)std::max<long long>(4, (c->packed_units / std::max(c->gnx, 1)) & ~3LL);   // multiple of 4 frames:
-  fpr = std::min<long>(fpr, (nframes + 3) & ~3L);                                              // rounds start 16-byte aligned
+  // frames per round: as many as packed_units allows, the call cut into equal rounds, a multiple of 4 frames
+  // (every round starts 16-byte aligned)
+  long fpr = (long)std::max<long long>(4, (c->packed_units / std::max(c->gnx, 1)) & ~3LL);
+  {
+    const long nrounds = (nframes + fpr - 1) / fpr;
+    fpr = std::max<long>(4, (((nframes + nrounds - 1) / nrounds) + 3) & ~3L);
+  }
   const size_t nwords = (c->ncells + (32 / W) - 1) / (32 / W), nquads = (nwords + 3) / 4;
   if (!c->d_pk) {
     GCB_CUDA(cudaMalloc(&c->d_pk, nquads * 16));
     GCB_CUDA(cudaMemsetAsync(c->d_pk, 0, nquads * 16, c->compute));
     GCB_CUDA(cudaMalloc(&c->d_pstate, sizeof(PackedState)));
     GCB_CUDA(cudaMemsetAsync(c->d_pstate, 0, sizeof(PackedState), c->compute));
+    // Keep the packed counters L2-resident next to the coordinate stream: a persisting-L2 set-aside with an
+    // access-policy window over them on the compute stream.  Measured (tools/l2_window.cu, profiles/l2_window_r02.txt):
+    // one RED per 36 streamed bytes into a 64 MB window runs at 83 G/s without it (the stream evicts the window,
+    // whatever evict-first hints the loads carry) and at 123 G/s with it -- the rate of a 4 MB window.
+    if (!getenv("GCB_NO_L2_PERSIST") && nquads * 16 > ((size_t)32 << 20)) {
+      cudaDeviceProp prop;
+      GCB_CUDA(cudaGetDeviceProperties(&prop, c->opts.device));
+      const size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, nquads * 16 + ((size_t)2 << 20));
+      if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+        cudaStreamAttrValue av = {};
+        av.accessPolicyWindow.base_ptr = c->d_pk;
+        av.accessPolicyWindow.num_bytes = std::min<size_t>(nquads * 16, (size_t)prop.accessPolicyMaxWindowSize);
+        av.accessPolicyWindow.hitRatio = std::min(1.0f, (float)((double)want / (double)(nquads * 16)));
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(c->compute, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess) c->l2_window = true;
+      }
+      cudaGetLastError();
+    }
   }
   PackedState *st = c->d_pstate;
   const int aux_grid = (int)std::max<size_t>(1, std::min<size_t>((nquads + 255) / 256, (size_t)c->sm_count * 8));
@@ -1466,6 +1510,11 @@ void free_counter(gcb_counter *c)
   cudaSetDevice(c->opts.device);
   if (c->compute) cudaStreamSynchronize(c->compute);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+  if (c->l2_window) {                  // give the set-aside lines back
+    cudaStreamAttrValue av = {};
+    cudaStreamSetAttribute(c->compute, cudaStreamAttributeAccessPolicyWindow, &av);
+    cudaCtxResetPersistingL2Cache();
+  }
   for (auto &s : c->slots) {
     if (s.copy) { cudaStreamSynchronize(s.copy); cudaStreamDestroy(s.copy); }
     if (s.copied) cudaEventDestroy(s.copied);
@@ -1486,6 +1535,7 @@ void free_counter(gcb_counter *c)
   if (c->xtc_copy) cudaStreamDestroy(c->xtc_copy);
   cudaFree(c->d_scr); cudaFreeHost(c->h_scr);
   for (auto e : c->events) if (e) cudaEventDestroy(e);
+  for (auto e : c->prof_ev) if (e) cudaEventDestroy(e);
   if (c->compute) cudaStreamDestroy(c->compute);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->reduce_done) cudaEventDestroy(c->reduce_done);
@@ -2099,6 +2149,34 @@ int gcb_counter_event_elapsed(gcb_counter *c, int id0, int id1, float *ms)
   GCB_CUDA(cudaSetDevice(c->opts.device));
   GCB_CUDA(cudaEventSynchronize(c->events[id1]));
   GCB_CUDA(cudaEventElapsedTime(ms, c->events[id0], c->events[id1]));
+  return GCB_OK;
+}
+
+int gcb_counter_profile(gcb_counter *c, int enable)
+{
+  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  GCB_CUDA(cudaStreamSynchronize(c->compute));
+  c->prof = enable != 0;
+  c->prof_used = 0;
+  c->prof_units = 0;
+  return GCB_OK;
+}
+
+int gcb_counter_profile_read(gcb_counter *c, double *k1_ms, long *k1_launches, double *k1_atom_frames)
+{
+  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  GCB_CUDA(cudaStreamSynchronize(c->compute));
+  double total = 0;
+  for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+    float ms = 0;
+    GCB_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]));
+    total += ms;
+  }
+  if (k1_ms) *k1_ms = total;
+  if (k1_launches) *k1_launches = (long)(c->prof_used / 2);
+  if (k1_atom_frames) *k1_atom_frames = c->prof_units;
   return GCB_OK;
 }
 

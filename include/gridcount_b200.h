@@ -168,6 +168,12 @@ int gcb_counter_event_record(gcb_counter *c, int id);
 int gcb_counter_event_elapsed(gcb_counter *c, int id0, int id1, float *ms);
 int gcb_counter_timer_start(gcb_counter *c);
 int gcb_counter_timer_stop(gcb_counter *c, float *ms);
+/* Per-launch timing of K1's dominant kernel (the streaming binning kernel that replaces the atom loop
+ * g_ri3Dc.c:425-426): while enabled, every launch is bracketed by a CUDA event pair on the launching stream.
+ * _profile_read waits for the stream and returns the summed launch durations, the number of launches and the
+ * atom-frames those launches covered (everything but the sub-tile tails).  Measurement aid: bench.py's roofline. */
+int gcb_counter_profile(gcb_counter *c, int enable);
+int gcb_counter_profile_read(gcb_counter *c, double *k1_ms, long *k1_launches, double *k1_atom_frames);
 
 /* Frame-sharded multi-GPU: one counter per rank; integer sum of the private
  * grids and of the statistics over NCCL (the reference's manual equivalent is
@@ -305,6 +311,15 @@ int gcb_host_free_pinned(void *p);
 int gcb_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, int device);
 int gcb_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, int device);
 int gcb_device_count(void);
+
+/* ------------------------------------------------------------------------
+ * Memory-system self-test: the measured denominators of K1's roofline next to the HBM copy bandwidth
+ * ("the L2-atomic peak ... the builder must measure it").  mix 0: random-address
+ * red.global.add.u32 over a window of window_bytes (the L2-atomic peak for that window); mix 1 / 2: a coalesced
+ * evict-first read stream with one such RED per 36 / 12 streamed bytes (one atom in three counted / every atom
+ * counted: the traffic K1 sends the L2, without K1); mix 3: the stream alone.  stream_bytes 0: 2 GiB.
+ * ---------------------------------------------------------------------- */
+int gcb_selftest_l2(int device, size_t window_bytes, int mix, size_t stream_bytes, double *red_gops, double *read_gbs);
 
 #ifdef __cplusplus
 }
