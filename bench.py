@@ -412,7 +412,7 @@ def measure_config(g, name, cfg, device, peak, peak_src, reps=10, extra=None):
     dev = g.DeviceFrames(F, cfg["natoms"], device).generate(cfg_gen(g, cfg))
     ctr = g.GridCounter(geom, gindex, cfg["natoms"], device=device)
     w = np.ones(F, np.float32)
-    for _ in range(3):
+    for _ in range(max(3, reps)):                 # also sizes the counter's per-call buffers for `reps` calls in flight
         ctr.add_device_frames(dev, weights=w)
     ctr.sync()
     ctr.reset_grid()

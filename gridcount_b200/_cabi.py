@@ -20,7 +20,7 @@ c_long_p = C.POINTER(C.c_long)
 HEADER_MAX = 256
 SET_CPOINT, SET_R, SET_Z1, SET_Z2 = 1, 2, 4, 8
 PBC_NONE, PBC_RECT = 0, 1
-KERNEL_AUTO, KERNEL_GATHER, KERNEL_STREAM, KERNEL_STREAM_INDEXED, KERNEL_ROUTED, KERNEL_PACKED = 0, 1, 2, 3, 4, 5
+KERNEL_AUTO, KERNEL_GATHER, KERNEL_STREAM, KERNEL_STREAM_INDEXED, KERNEL_PACKED = 0, 1, 2, 3, 5
 UNITS = {"unity": 0, "SPC": 1, "molar": 2, "Angstrom": 3, "Voxel": 4}
 GEN_UNIFORM, GEN_QUANTISED, GEN_PORE, GEN_CLUSTER = 0, 1, 2, 3
 

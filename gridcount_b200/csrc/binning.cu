@@ -281,18 +281,14 @@ __device__ __forceinline__ int cell_of_exact(const GridParamsFast &P, float x, f
 // ---------------------------------------------------------------------------
 // Where a hit goes.
 //
-// DirectSink: one RED per hit into the global grid (L2-resident when the grid is small).  On B200
-// that is bounded by the L2 tag/atomic rate, not by HBM: every hit is its own 32-byte-sector
-// request, and half of them cross to the other die's L2 partition (profiles/k1_r01c_summary.json).
+// DirectSink: one RED per hit into the global uint32 grid (L2-resident when the grid is small).  On B200
+// that is bounded by what the L2 sustains for the mix "coordinate stream + one scattered RED per unit"
+// (gcb_selftest_l2 measures it: ~120 G units/s for one atom in three, ~175 for every atom), not by HBM.
+// PackedSink: the same for grids whose uint32 cells exceed the L2 (below).
 //
-// RouteSink: the shared-memory privatisation.  The grid is cut into `nb` buckets, each small
-// enough to be counted in one CTA's shared memory (or, for grids beyond L2, into 32 MB slabs that
-// stay L2-resident).  The streaming kernel does not touch the grid: it converts a hit into a
-// (bucket, local cell) key, stages keys per bucket in shared memory and writes them out in whole
-// 128-byte lines into this CTA's private segment of the bucket's key buffer (no global atomics,
-// no cursors).  A second kernel (route_count_*) then owns one bucket per CTA, counts its keys with
-// shared-memory atomics and adds the tile to the grid with plain coalesced stores.  L2 sees 4 bytes
-// of coalesced traffic per hit each way instead of a scattered sector request.
+// Tried and removed (numbers in DESIGN.md section 3): routing hits as keys to shared-memory sized buckets or
+// L2-sized slabs and counting them in a second kernel (round 1: 92 G/s against 111 on the nanopore shape,
+// 72 against 82+ on 400^3), and packed counters with returning atomics (37 G/s on 400^3).
 // ---------------------------------------------------------------------------
 template <int MODE>
 struct DirectSink {
@@ -338,123 +334,6 @@ struct PackedState {
   unsigned long long digits, expect;       // digit sum of the packed counters / hits the packed pass reported
   unsigned long long diag_snap[2];
   unsigned long long rounds, redone;       // statistics: rounds queued, rounds that the direct kernel had to bin
-};
-
-constexpr int ROUTE_NB_MAX = 128;          // buckets
-constexpr int ROUTE_STAGE_KEYS = 8192;     // staged keys per CTA, split evenly over the buckets in use
-
-struct RouteMap {                          // cell <-> (bucket, local cell)
-  int sh_b; unsigned mask_b; int sh_hi, sh_lo; unsigned mask_lo;
-  __host__ __device__ __forceinline__ unsigned bucket(unsigned cell) const { return (cell >> sh_b) & mask_b; }
-  __host__ __device__ __forceinline__ unsigned local(unsigned cell) const { return ((cell >> sh_hi) << sh_lo) | (cell & mask_lo); }
-  __host__ __device__ __forceinline__ unsigned cell(unsigned b, unsigned l) const
-  {
-    return ((l >> sh_lo) << sh_hi) | (b << sh_b) | (l & mask_lo);
-  }
-};
-
-struct RouteStage {
-  uint32_t keys[ROUTE_STAGE_KEYS];         // one ring of `cap` keys per bucket
-  uint32_t tail[ROUTE_NB_MAX];             // keys appended so far (slots handed out)
-  uint32_t head[ROUTE_NB_MAX];             // keys that have left the ring; always a multiple of 32 until the end
-  uint32_t pos[ROUTE_NB_MAX];              // keys written to this CTA's segment (== head unless the segment filled up)
-};
-
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_THREADS) : "memory"); }
-
-struct RouteSink {
-  static constexpr int NSTAGES = 2;        // 2 x 36 KiB tile ring + 34 KiB staging: two CTAs per SM
-  static constexpr size_t EXTRA_SMEM = sizeof(RouteStage);
-  uint32_t *keys_g;                        // [nb][gridDim][seg_cap]
-  uint32_t *seg_len;                       // [nb][gridDim]
-  uint32_t *counts;                        // the grid, for the overflow fallback only
-  unsigned seg_cap;                        // multiple of 32
-  int nb, cap;                             // buckets in use; ring size per bucket (power of two, >= 64)
-  RouteMap map;
-
-  __device__ __forceinline__ void init(void *smem, unsigned ctid) const
-  {
-    RouteStage *st = static_cast<RouteStage *>(smem);
-    for (unsigned i = ctid; i < ROUTE_NB_MAX; i += CONSUMER_THREADS) { st->tail[i] = 0; st->head[i] = 0; st->pos[i] = 0; }
-    consumer_barrier();
-  }
-  __device__ __forceinline__ void hit(void *smem, int cell) const
-  {
-    RouteStage *st = static_cast<RouteStage *>(smem);
-    const unsigned b = map.bucket((unsigned)cell);
-    const unsigned h = st->head[b];        // only flush() changes it, and never while hits are appended
-    const unsigned slot = atomicAdd(&st->tail[b], 1u);
-    if (slot - h < (unsigned)cap) st->keys[b * cap + (slot & (cap - 1))] = map.local((unsigned)cell);
-    else atomicAdd(counts + cell, 1u);     // ring full (pathologically clustered input): counted directly, still exact
-  }
-  // Move the complete 128-byte lines (everything when `all`) of every bucket from the rings to this CTA's
-  // segments.  Runs between two consumer barriers: no hit is appended meanwhile.  Warp w owns buckets
-  // w, w+W, ...: each lane inspects one of them and updates its ring state; the copies are then done by
-  // groups of 8 lanes, one bucket per group, 16 bytes per lane (a line never wraps: heads are multiples of 32),
-  // so a warp moves four lines per step instead of walking its buckets one after the other.
-  __device__ __forceinline__ void flush(void *smem, unsigned ctid, bool all) const
-  {
-    RouteStage *st = static_cast<RouteStage *>(smem);
-    const unsigned warp = ctid >> 5, lane = ctid & 31, grp = lane >> 3, sub = lane & 7;
-    for (unsigned base = warp; base < (unsigned)nb; base += CONSUMER_WARPS * 32) {
-      const unsigned mine = base + CONSUMER_WARPS * lane;
-      unsigned nout_mine = 0, h_mine = 0, pos_mine = 0;
-      bool fits_mine = true;
-      if (mine < (unsigned)nb) {
-        h_mine = st->head[mine];
-        pos_mine = st->pos[mine];
-        const unsigned t = st->tail[mine];
-        const unsigned n = min(t - h_mine, (unsigned)cap);          // valid keys in the ring
-        if (t - h_mine > (unsigned)cap) st->tail[mine] = h_mine + cap;     // the excess was counted directly
-        nout_mine = all ? n : (n & ~31u);
-        fits_mine = pos_mine + nout_mine <= seg_cap;
-        if (nout_mine) {
-          st->head[mine] = h_mine + nout_mine;
-          if (fits_mine) st->pos[mine] = pos_mine + nout_mine;
-        }
-      }
-      unsigned todo = __ballot_sync(0xffffffffu, nout_mine > 0u);
-      while (todo) {
-        const unsigned src = __fns(todo, 0, (int)grp + 1);            // the grp-th bucket still to do (or none)
-        const bool have = src < 32u;
-        const unsigned sl = have ? src : 0u;
-        const unsigned b = base + CONSUMER_WARPS * sl;
-        const unsigned nout = __shfl_sync(0xffffffffu, nout_mine, sl);
-        const unsigned h = __shfl_sync(0xffffffffu, h_mine, sl);
-        const unsigned pos = __shfl_sync(0xffffffffu, pos_mine, sl);
-        const bool fits = __shfl_sync(0xffffffffu, (int)fits_mine, sl) != 0;
-        if (have) {
-          const uint32_t *ring = st->keys + b * cap;
-          if (fits) {
-            uint32_t *dst = keys_g + ((size_t)b * gridDim.x + blockIdx.x) * seg_cap + pos;
-            const unsigned n4 = nout & ~3u;
-            for (unsigned k = sub * 4; k < n4; k += 32)
-              *reinterpret_cast<uint4 *>(dst + k) = *reinterpret_cast<const uint4 *>(ring + ((h + k) & (cap - 1)));
-            for (unsigned k = n4 + sub; k < nout; k += 8) dst[k] = ring[(h + k) & (cap - 1)];     // final flush only
-          } else {                         // segment full: count these keys directly
-            for (unsigned k = sub; k < nout; k += 8) atomicAdd(counts + map.cell(b, ring[(h + k) & (cap - 1)]), 1u);
-          }
-        }
-        // drop the (up to) four buckets just handled
-        todo &= todo - 1; todo &= todo - 1; todo &= todo - 1; todo &= todo - 1;
-      }
-    }
-  }
-  __device__ __forceinline__ void tile_end(void *smem, unsigned ctid) const
-  {
-    consumer_barrier();                    // every hit of the tile is staged
-    flush(smem, ctid, false);
-    consumer_barrier();                    // heads advanced before the next tile appends
-  }
-  __device__ __forceinline__ void finish(void *smem, unsigned ctid) const
-  {
-    RouteStage *st = static_cast<RouteStage *>(smem);
-    consumer_barrier();
-    flush(smem, ctid, true);
-    consumer_barrier();
-    for (unsigned b = ctid; b < (unsigned)nb; b += CONSUMER_THREADS)
-      seg_len[(size_t)b * gridDim.x + blockIdx.x] = st->pos[b];
-  }
 };
 
 // GUARD: 0 = always run; 1 = run only if *run_if != 0; 2 = run only if *run_if == 0 (the two passes of a packed
@@ -627,66 +506,6 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
 }
 
 // ---------------------------------------------------------------------------
-// Second phase of the routed path.
-// route_count_smem_kernel: CTA b owns bucket b.  Its slice of the grid (cells whose 32-cell run
-// number is b mod nb) lives in shared memory for the duration of the kernel; the keys of all the
-// streaming CTAs' segments are read once, coalesced, and counted with shared-memory atomics; the
-// tile is then added to the grid with plain stores (no other CTA touches these cells).
-// route_count_slab_kernel: buckets are contiguous 32 MB slabs of a grid that does not fit L2;
-// all CTAs work through the buckets in the same order so the REDs of one slab stay L2-resident.
-// ---------------------------------------------------------------------------
-constexpr int COUNT_THREADS = 1024;
-
-__global__ void __launch_bounds__(COUNT_THREADS)
-route_count_smem_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ seg_len, int nseg,
-                        unsigned seg_cap, unsigned tile_cells, RouteMap map, uint32_t *__restrict__ counts,
-                        unsigned ncells)
-{
-  extern __shared__ uint32_t tile_sh[];
-  const unsigned b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (unsigned l = tid; l < tile_cells; l += COUNT_THREADS) tile_sh[l] = 0;
-  __syncthreads();
-  for (int seg = (int)warp; seg < nseg; seg += COUNT_THREADS / 32) {
-    const unsigned len = __ldg(seg_len + (size_t)b * nseg + seg);
-    const uint32_t *p = keys + ((size_t)b * nseg + seg) * seg_cap;
-    unsigned k = lane;
-    for (; k + 96 < len; k += 128) {
-      const uint32_t k0 = __ldcs(p + k), k1 = __ldcs(p + k + 32), k2 = __ldcs(p + k + 64), k3 = __ldcs(p + k + 96);
-      atomicAdd(&tile_sh[k0], 1u); atomicAdd(&tile_sh[k1], 1u); atomicAdd(&tile_sh[k2], 1u); atomicAdd(&tile_sh[k3], 1u);
-    }
-    for (; k < len; k += 32) atomicAdd(&tile_sh[__ldcs(p + k)], 1u);
-  }
-  __syncthreads();
-  for (unsigned l = tid; l < tile_cells; l += COUNT_THREADS) {
-    const uint32_t n = tile_sh[l];
-    if (n) {
-      const unsigned cell = map.cell(b, l);
-      if (cell < ncells) counts[cell] += n;
-    }
-  }
-}
-
-constexpr unsigned SLAB_CHUNK = 2048;
-__global__ void __launch_bounds__(256)
-route_count_slab_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ seg_len, int nseg,
-                        unsigned seg_cap, int b, RouteMap map, uint32_t *__restrict__ counts)
-{
-  // one launch per slab: the launches are ordered on the stream, so exactly one 32 MB slab is being
-  // updated at any time and its REDs stay in L2 (CTAs of one long kernel drift apart and thrash it)
-  const unsigned nchunk = (seg_cap + SLAB_CHUNK - 1) / SLAB_CHUNK;
-  const unsigned nitems = (unsigned)nseg * nchunk;
-  {
-    for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const unsigned seg = item / nchunk, k0 = (item - seg * nchunk) * SLAB_CHUNK;
-      const unsigned len = __ldg(seg_len + (size_t)b * nseg + seg);
-      const unsigned k1 = min(len, k0 + SLAB_CHUNK);
-      const uint32_t *p = keys + ((size_t)b * nseg + seg) * seg_cap;
-      for (unsigned k = k0 + threadIdx.x; k < k1; k += 256) atomicAdd(counts + map.cell((unsigned)b, __ldcs(p + k)), 1u);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
 // n sequential f32 additions of w to v (see gcb::seq_add_f32)
 // ---------------------------------------------------------------------------
 __device__ float seq_add_dev(float v, float w, unsigned long long n)
@@ -779,37 +598,34 @@ packed_verify_kernel(const uint4 *__restrict__ pk, size_t nquads, const unsigned
 // this one redoes the round.  Skipped round: nothing to do.
 template <int W>
 __global__ void __launch_bounds__(256)
-packed_apply_kernel(uint4 *__restrict__ pk, size_t nquads, uint32_t *__restrict__ counts, size_t ncells,
+packed_apply_kernel(uint32_t *__restrict__ pk, size_t nwords, uint32_t *__restrict__ counts, size_t ncells,
                     const PackedState *__restrict__ st, unsigned long long *__restrict__ hits, long nhits,
                     unsigned long long *__restrict__ diag)
 {
   const bool bad = st->alarm != 0;
   if (bad && !st->dirty) return;
   constexpr int PER = 32 / W;                      // cells per word
-  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += (size_t)gridDim.x * blockDim.x) {
-    const uint4 v = pk[q];
-    if (!(v.x | v.y | v.z | v.w)) continue;
-    pk[q] = make_uint4(0u, 0u, 0u, 0u);
+  constexpr uint32_t M = (1u << W) - 1u;
+  // one thread per packed word: a warp reads 128 contiguous bytes of packed counters and updates 32 * PER
+  // contiguous uint32 cells (16 or 32 bytes per lane)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t w = pk[i];
+    if (!w) continue;
+    pk[i] = 0u;
     if (bad) continue;
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const size_t c0 = i * PER;
+    if (c0 + PER <= ncells) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (!w[k]) continue;
-      const size_t c0 = (q * 4 + (size_t)k) * PER;
-      if (c0 + PER <= ncells) {
-#pragma unroll
-        for (int h = 0; h < PER / 4; h++) {
-          uint4 *dst = reinterpret_cast<uint4 *>(counts + c0) + h;
-          const uint32_t part = w[k] >> (4 * W * h);
-          if (W == 4 && !(part & 0xFFFFu)) continue;
-          uint4 t = *dst;
-          constexpr uint32_t M = (1u << W) - 1u;
-          t.x += part & M; t.y += (part >> W) & M; t.z += (part >> (2 * W)) & M; t.w += (part >> (3 * W)) & M;
-          *dst = t;
-        }
-      } else {
-        for (int b = 0; b < PER; b++) if (c0 + b < ncells) counts[c0 + b] += (w[k] >> (W * b)) & ((1u << W) - 1u);
+      for (int h = 0; h < PER / 4; h++) {
+        const uint32_t part = w >> (4 * W * h);
+        if (W == 4 && !(part & 0xFFFFu)) continue;
+        uint4 *dst = reinterpret_cast<uint4 *>(counts + c0) + h;
+        uint4 t = *dst;
+        t.x += part & M; t.y += (part >> W) & M; t.z += (part >> (2 * W)) & M; t.w += (part >> (3 * W)) & M;
+        *dst = t;
       }
+    } else {
+      for (int b = 0; b < PER; b++) if (c0 + b < ncells) counts[c0 + b] += (w >> (W * b)) & M;
     }
   }
   if (bad) {
@@ -984,8 +800,7 @@ struct Slot {
 };
 
 struct DevHits {                      // hit counters of an add_device_frames call awaiting collection
-  unsigned long long *d = nullptr;
-  size_t cap = 0;
+  unsigned long long *d = nullptr;    // inside one of the counter's hit arenas
   float *d_box3 = nullptr;
   long n = 0;
   size_t frame0 = 0;
@@ -1004,21 +819,14 @@ struct gcb_counter {
   bool stream_ok = false;             // index group dense enough for the streaming kernel
   bool ap_ok = false;                 // index group is g0 + i*step: arithmetic selection inside the tile
   ApGroup ap{0, 1, TILE_ATOMS};
-  // routed (shared-memory privatised) path
-  int route_mode = 0;                 // 0 none, 1 interleaved buckets counted in shared memory, 2 L2-sized slabs
-  RouteMap route_map{};
-  int route_nb = 0;
-  unsigned route_tile_cells = 0;
-  long long route_units = 0;          // atom-frames per routing round
-  uint32_t *d_keys = nullptr, *d_seglen = nullptr;
-  unsigned route_seg_cap = 0;
-  int route_grid = 0;                 // streaming CTAs the key buffer is laid out for
   // packed (W-bit lanes, L2-resident) path
   int packed_bits = 0;                // 0: not available for this grid; 8 or 4
   bool packed_auto = false;           // AUTO takes it: uint32 grid beyond L2, packed counters inside it
   long long packed_units = 0;         // atom-frames per round
   uint32_t *d_pk = nullptr;           // packed counters, always all-zero between rounds
   PackedState *d_pstate = nullptr;
+  PackedState *h_pstate = nullptr;    // pinned mirror, refreshed (asynchronously) behind every call's rounds
+  int packed_pause = 0;               // calls still to be binned without the packed pass (see launch_packed)
   uint64_t packed_rounds = 0, packed_redone = 0;
   bool l2_window = false;             // persisting-L2 window over d_pk set on the compute stream
   bool saturated = false;             // some cell was clamped (diag[3])
@@ -1060,7 +868,11 @@ struct gcb_counter {
   std::vector<Slot> slots;
   int next_slot = 0;
   std::vector<DevHits> devhits;
-  std::vector<std::pair<size_t, unsigned long long *>> hit_pool;
+  // per-frame hit counters of device-resident batches are carved out of a few large device buffers (no allocation
+  // per call in steady state, however many calls lie between two collections); `used` goes back to zero whenever
+  // no batch is waiting for collection (later launches that reuse the memory are ordered on the compute stream)
+  struct HitArena { unsigned long long *d; size_t cap, used; };
+  std::vector<HitArena> hit_arenas;
 
   std::vector<uint64_t> hits_per_frame;
   std::vector<float> weight_per_frame;
@@ -1192,76 +1004,6 @@ int launch_gather(gcb_counter *c, const float *d_x, long long e_begin, long long
   return GCB_OK;
 }
 
-// Routed path: frames are processed in rounds of ~route_units atom-frames; per round one streaming
-// kernel that only writes keys, the gather kernel for the sub-tile tail, one counting kernel.
-template <bool PBC>
-int launch_routed(gcb_counter *c, const float *d_x, long nframes, const float *d_box3, unsigned long long *d_hits)
-{
-  const bool ap = c->ap_ok && c->opts.kernel != GCB_KERNEL_STREAM_INDEXED;
-  const int tile_atoms = ap ? c->ap.tile_atoms : TILE_ATOMS;
-  const size_t smem = stream_smem_bytes<RouteSink>();
-  const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
-  const int G = c->sm_count * per_sm;
-  long fpr = (long)std::max<long long>(4, (c->route_units / std::max(c->gnx, 1)) & ~3LL);   // frames per round, multiple of 4:
-  fpr = std::min<long>(fpr, (nframes + 3) & ~3L);                                             // every round starts 16-byte aligned
-  // key buffer: [nb][G][seg_cap]; twice the even share per segment, anything beyond goes straight to the grid
-  const long long round_units = (long long)fpr * c->gnx;
-  const unsigned seg_cap = (unsigned)(((2 * round_units / ((long long)G * c->route_nb) + 96) + 31) & ~31LL);
-  if (!c->d_keys || seg_cap > c->route_seg_cap || G != c->route_grid) {
-    GCB_CUDA(cudaStreamSynchronize(c->compute));
-    cudaFree(c->d_keys); cudaFree(c->d_seglen);
-    c->d_keys = nullptr; c->d_seglen = nullptr;
-    GCB_CUDA(cudaMalloc(&c->d_keys, sizeof(uint32_t) * (size_t)c->route_nb * G * seg_cap));
-    GCB_CUDA(cudaMalloc(&c->d_seglen, sizeof(uint32_t) * (size_t)c->route_nb * G));
-    c->route_seg_cap = seg_cap;
-    c->route_grid = G;
-  }
-  if (c->route_mode == 1) {
-    static bool attr_done[64] = {false};
-    if (!attr_done[c->opts.device & 63]) {
-      GCB_CUDA(cudaFuncSetAttribute(route_count_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_done[c->opts.device & 63] = true;
-    }
-  }
-  for (long f0 = 0; f0 < nframes; f0 += fpr) {
-    const long n = std::min(fpr, nframes - f0);
-    const float *xs = d_x + (size_t)f0 * c->natoms * 3;
-    const float *bs = d_box3 ? d_box3 + 3 * f0 : nullptr;
-    const long long total_e = (long long)n * c->gnx, total_atoms = (long long)n * c->natoms;
-    const long long ntiles = total_atoms / tile_atoms;
-    long long e_begin = 0;
-    if (ntiles > 0) {
-      RouteSink sink;
-      sink.keys_g = c->d_keys; sink.seg_len = c->d_seglen; sink.counts = c->d_runcnt; sink.seg_cap = c->route_seg_cap;
-      sink.nb = c->route_nb; sink.map = c->route_map;
-      sink.cap = 64;
-      while (sink.cap * 2 * c->route_nb <= ROUTE_STAGE_KEYS) sink.cap *= 2;
-      int grid = 0;
-      int rc = ap ? launch_stream<RouteSink, PBC, true>(c, xs, ntiles, sink, G, bs, d_hits + f0, &grid)
-                  : launch_stream<RouteSink, PBC, false>(c, xs, ntiles, sink, G, bs, d_hits + f0, &grid);
-      if (rc) return rc;
-      if (c->route_mode == 1) {
-        route_count_smem_kernel<<<c->route_nb, COUNT_THREADS, c->route_tile_cells * sizeof(uint32_t), c->compute>>>(
-            c->d_keys, c->d_seglen, grid, c->route_seg_cap, c->route_tile_cells, c->route_map, c->d_runcnt, (unsigned)c->ncells);
-      } else {
-        for (int b = 0; b < c->route_nb; b++) {
-          route_count_slab_kernel<<<c->sm_count * 8, 256, 0, c->compute>>>(c->d_keys, c->d_seglen, grid, c->route_seg_cap, b,
-                                                                           c->route_map, c->d_runcnt);
-          c->launches++;
-        }
-        c->launches--;
-      }
-      c->launches++;
-      GCB_CUDA(cudaGetLastError());
-      const long long g1 = ntiles * tile_atoms, f1 = g1 / c->natoms;
-      e_begin = f1 * c->gnx + rank_host(c, (int)(g1 - f1 * c->natoms));
-    }
-    int rc = launch_gather<MODE_COUNT, PBC>(c, xs, e_begin, total_e, c->d_runcnt, 1.0f, bs, d_hits + f0);
-    if (rc) return rc;
-  }
-  return GCB_OK;
-}
-
 // Packed path: rounds of ~packed_units atom-frames; per round the streaming kernel into the packed counters
 // (returns at once while backing off), verify + apply, the guarded uint32 kernel (returns at once unless the round
 // failed or is skipped), and the gather kernel for the sub-tile tail (straight into the uint32 grid).
@@ -1283,6 +1025,8 @@ int launch_packed(gcb_counter *c, const float *d_x, long nframes, const float *d
     GCB_CUDA(cudaMemsetAsync(c->d_pk, 0, nquads * 16, c->compute));
     GCB_CUDA(cudaMalloc(&c->d_pstate, sizeof(PackedState)));
     GCB_CUDA(cudaMemsetAsync(c->d_pstate, 0, sizeof(PackedState), c->compute));
+    GCB_CUDA(cudaHostAlloc((void **)&c->h_pstate, sizeof(PackedState), cudaHostAllocDefault));
+    memset(c->h_pstate, 0, sizeof(PackedState));
     // Keep the packed counters L2-resident next to the coordinate stream: a persisting-L2 set-aside with an
     // access-policy window over them on the compute stream.  Measured (tools/l2_window.cu, profiles/l2_window_r02.txt):
     // one RED per 36 streamed bytes into a 64 MB window runs at 83 G/s without it (the stream evicts the window,
@@ -1305,6 +1049,7 @@ int launch_packed(gcb_counter *c, const float *d_x, long nframes, const float *d
   }
   PackedState *st = c->d_pstate;
   const int aux_grid = (int)std::max<size_t>(1, std::min<size_t>((nquads + 255) / 256, (size_t)c->sm_count * 8));
+  const int apply_grid = (int)std::max<size_t>(1, std::min<size_t>((nwords + 255) / 256, (size_t)c->sm_count * 16));
   for (long f0 = 0; f0 < nframes; f0 += fpr) {
     const long n = std::min(fpr, nframes - f0);
     const float *xs = d_x + (size_t)f0 * c->natoms * 3;
@@ -1320,8 +1065,7 @@ int launch_packed(gcb_counter *c, const float *d_x, long nframes, const float *d
                   : launch_stream<PackedSink<W>, PBC, false, 2>(c, xs, ntiles, sink, 0, bs, d_hits + f0, nullptr, &st->alarm);
       if (rc) return rc;
       packed_verify_kernel<W><<<aux_grid, 256, 0, c->compute>>>(reinterpret_cast<const uint4 *>(c->d_pk), nquads, d_hits + f0, n, st);
-      packed_apply_kernel<W><<<aux_grid, 256, 0, c->compute>>>(reinterpret_cast<uint4 *>(c->d_pk), nquads, c->d_runcnt, c->ncells, st,
-                                                               d_hits + f0, n, c->d_diag);
+      packed_apply_kernel<W><<<apply_grid, 256, 0, c->compute>>>(c->d_pk, nwords, c->d_runcnt, c->ncells, st, d_hits + f0, n, c->d_diag);
       c->launches += 3;
       GCB_CUDA(cudaGetLastError());
       DirectSink<MODE_COUNT> redo;
@@ -1335,7 +1079,25 @@ int launch_packed(gcb_counter *c, const float *d_x, long nframes, const float *d
     int rc = launch_gather<MODE_COUNT, PBC>(c, xs, e_begin, total_e, c->d_runcnt, 1.0f, bs, d_hits + f0);
     if (rc) return rc;
   }
+  // the host learns how the rounds went without waiting for them: the state is copied to a pinned mirror behind the
+  // call's kernels and read (possibly one call late) by packed_paused() before the next call is queued
+  GCB_CUDA(cudaMemcpyAsync(c->h_pstate, c->d_pstate, sizeof(PackedState), cudaMemcpyDeviceToHost, c->compute));
   return GCB_OK;
+}
+
+// Input that keeps overflowing the packed lanes (atoms piled onto a few cells) is binned faster by the direct
+// kernel alone -- its hot cells stay L2-resident by themselves -- than by a packed pass that is thrown away every
+// other round.  Once the device-side back-off has reached 8 rounds the host stops queueing packed passes for 32
+// calls, then probes again.
+bool packed_paused(gcb_counter *c)
+{
+  if (c->packed_pause > 0) { c->packed_pause--; return true; }
+  if (c->h_pstate && ((volatile PackedState *)c->h_pstate)->backoff >= 8) {
+    c->h_pstate->backoff = 0;                    // (the mirror only: the next copy brings the device's value back)
+    c->packed_pause = 32;
+    return true;
+  }
+  return false;
 }
 
 template <int MODE, bool PBC>
@@ -1349,18 +1111,12 @@ int launch_bin(gcb_counter *c, const float *d_x, long nframes, float w, const fl
   const bool aligned = ((uintptr_t)d_x & 15u) == 0;
   const int k = c->opts.kernel;
   const bool use_stream = aligned && k != GCB_KERNEL_GATHER &&
-                          (c->stream_ok || k == GCB_KERNEL_STREAM || k == GCB_KERNEL_STREAM_INDEXED || k == GCB_KERNEL_ROUTED ||
-                           k == GCB_KERNEL_PACKED);
-  // AUTO: grids beyond L2 whose packed counters fit it take the packed path (PackedSink); grids beyond even that
-  // take the routed slabs.  For shared-memory sized buckets the two-kernel routed round loses to direct L2 REDs
-  // and is only used on request.
+                          (c->stream_ok || k == GCB_KERNEL_STREAM || k == GCB_KERNEL_STREAM_INDEXED || k == GCB_KERNEL_PACKED);
+  // AUTO: grids beyond L2 whose packed counters fit it take the packed path (PackedSink)
   if (use_stream && MODE == MODE_COUNT && c->packed_bits != 0 &&
-      (k == GCB_KERNEL_PACKED || (k == GCB_KERNEL_AUTO && c->packed_auto && total_e >= (1LL << 20))))
+      (k == GCB_KERNEL_PACKED || (k == GCB_KERNEL_AUTO && c->packed_auto && total_e >= (1LL << 20) && !packed_paused(c))))
     return c->packed_bits == 8 ? launch_packed<8, PBC>(c, d_x, nframes, d_box3, d_hits)
                                : launch_packed<4, PBC>(c, d_x, nframes, d_box3, d_hits);
-  if (use_stream && MODE == MODE_COUNT && c->route_mode != 0 && k != GCB_KERNEL_STREAM && k != GCB_KERNEL_STREAM_INDEXED &&
-      (k == GCB_KERNEL_ROUTED || (c->route_mode == 2 && total_e >= (1LL << 20))))
-    return launch_routed<PBC>(c, d_x, nframes, d_box3, d_hits);
   if (use_stream) {
     const bool ap = c->ap_ok && k != GCB_KERNEL_STREAM_INDEXED;
     const int tile_atoms = ap ? c->ap.tile_atoms : TILE_ATOMS;
@@ -1523,10 +1279,10 @@ void free_counter(gcb_counter *c)
     cudaFree(s.d_box3); cudaFreeHost(s.h_box3);
   }
   for (auto &d : c->devhits) { cudaFree(d.d); cudaFree(d.d_box3); }
-  for (auto &p : c->hit_pool) cudaFree(p.second);
+  for (auto &a : c->hit_arenas) cudaFree(a.d);
   cudaFree(c->d_gindex); cudaFree(c->d_rank); cudaFree(c->d_runcnt); cudaFree(c->d_total); cudaFree(c->d_acc);
-  cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2); cudaFree(c->d_keys); cudaFree(c->d_seglen);
-  cudaFree(c->d_pk); cudaFree(c->d_pstate);
+  cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2);
+  cudaFree(c->d_pk); cudaFree(c->d_pstate); cudaFreeHost(c->h_pstate);
   for (auto &x : c->xtc) {
     cudaFree(x.d_buf); cudaFree(x.d_meta); cudaFree(x.d_status); cudaFree(x.d_x); cudaFree(x.d_work); cudaFreeHost(x.h_meta); cudaFreeHost(x.h_status);
     if (x.copied) cudaEventDestroy(x.copied);
@@ -1627,26 +1383,6 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
   }
 
   {
-    // routed path geometry.  Interleaved: bucket = (cell / 32) mod 128, the bucket's cells fit one CTA's
-    // shared memory.  Slabs (grid well beyond what stays L2-resident next to the coordinate stream):
-    // bucket = cell / 2^23 (32 MB of counters each).
-    const char *env = getenv("GCB_ROUTE_UNITS");
-    c->route_units = env ? atoll(env) : (16LL << 20);
-    if (c->route_units < 4096) c->route_units = 4096;
-    const size_t tile_cells = ((c->ncells + 32 * ROUTE_NB_MAX - 1) / (32 * ROUTE_NB_MAX)) * 32;
-    if (tile_cells * sizeof(uint32_t) <= 192 * 1024) {
-      c->route_mode = 1;
-      c->route_nb = ROUTE_NB_MAX;
-      c->route_tile_cells = (unsigned)tile_cells;
-      c->route_map = RouteMap{5, ROUTE_NB_MAX - 1, 12, 5, 31u};
-    } else if (c->ncells * sizeof(uint32_t) > ((size_t)48 << 20)) {
-      c->route_mode = 2;
-      // every round turns the whole grid over in L2 once (read + write-back of each slab): long rounds amortise it
-      if (!env) c->route_units = 192LL << 20;
-      c->route_nb = (int)((c->ncells + (1u << 23) - 1) >> 23);
-      c->route_map = RouteMap{23, 0xFFu, 31, 23, (1u << 23) - 1};
-    }
-    if (getenv("GCB_NO_ROUTE")) c->route_mode = 0;
     if (const char *e = getenv("GCB_CLAMP_AT")) c->clamp_at = strtoull(e, nullptr, 10);
     if (const char *e = getenv("GCB_CLAMP_CEILING")) c->clamp_ceiling = strtoull(e, nullptr, 10);
     if (c->clamp_at < 1 || c->clamp_ceiling > 0xffffffffull || c->clamp_at * 2 > c->clamp_ceiling) {
@@ -1654,7 +1390,7 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
     }
     // Packed path: bytes while they fit ~80 MB of the 126 MB L2 next to the coordinate stream, nibbles up to twice
     // as many cells (500^3, and every grid the XDR format can hold: 512^3 cells = 64 MB of nibbles).  A round is
-    // sized so that a uniform density stays far below the lane range: mean 3 hits per byte cell (P[>255] = 0),
+    // sized so that a uniform density stays far below the lane range: mean 8 hits per byte cell (P[>255] = 0),
     // 1.25 per nibble cell (P[>15] ~ 5e-13 per cell); denser spots fail verification and are binned directly.
     {
       const char *benv = getenv("GCB_PACKED_BITS");
@@ -1663,7 +1399,7 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
       c->packed_auto = c->ncells * sizeof(uint32_t) > ((size_t)48 << 20) && c->ncells / (c->packed_bits == 8 ? 1 : 2) <= ((size_t)80 << 20) &&
                        !getenv("GCB_NO_PACKED");
       const char *uenv = getenv("GCB_PACKED_UNITS");
-      c->packed_units = uenv ? atoll(uenv) : (long long)((double)c->ncells * (c->packed_bits == 8 ? 3.0 : 1.25));
+      c->packed_units = uenv ? atoll(uenv) : (long long)((double)c->ncells * (c->packed_bits == 8 ? 8.0 : 1.25));
       if (c->packed_units < 4096) c->packed_units = 4096;
     }
   }
@@ -1694,11 +1430,10 @@ int gcb_counter_reset(gcb_counter *c)
   // pool; later launches that reuse them are ordered on the same stream).
   for (auto &s : c->slots) s.pending = 0;
   c->reduce_pending = false;          // statistics of a reduce nobody collected are dropped with the rest
-  for (auto &h : c->devhits) {
-    c->hit_pool.emplace_back(h.cap, h.d);
+  for (auto &h : c->devhits)
     if (h.d_box3) { GCB_CUDA(cudaStreamSynchronize(c->compute)); cudaFree(h.d_box3); }
-  }
   c->devhits.clear();
+  for (auto &a : c->hit_arenas) a.used = 0;
   GCB_CUDA(cudaMemsetAsync(c->d_runcnt, 0, sizeof(uint32_t) * c->ncells, c->compute));
   if (c->d_acc) {
     GCB_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(float) * c->ncells, c->compute));
@@ -1780,17 +1515,20 @@ int gcb_counter_add_device_frames(gcb_counter *c, const float *x_dev, long nfram
   GCB_CUDA(cudaSetDevice(c->opts.device));
   DevHits h;
   h.n = nframes;
-  // per-frame hit counters: taken from the pool of buffers earlier calls have returned (no allocation in steady state)
-  for (size_t k = 0; k < c->hit_pool.size(); k++)
-    if (c->hit_pool[k].first >= (size_t)nframes + 2) {
-      h.d = c->hit_pool[k].second; h.cap = c->hit_pool[k].first;
-      c->hit_pool.erase(c->hit_pool.begin() + (long)k);
-      break;
+  {
+    const size_t need = ((size_t)nframes + 2 + 15) & ~(size_t)15;
+    for (auto &a : c->hit_arenas)
+      if (a.cap - a.used >= need) { h.d = a.d + a.used; a.used += need; break; }
+    if (!h.d) {
+      gcb_counter::HitArena a{nullptr, std::max<size_t>(need * 4, c->hit_arenas.empty() ? (size_t)1 << 16 : c->hit_arenas.back().cap * 2), need};
+      GCB_CUDA(cudaMalloc(&a.d, sizeof(unsigned long long) * a.cap));
+      c->hit_arenas.push_back(a);
+      h.d = a.d;
     }
-  if (!h.d) { h.cap = (size_t)nframes + 2; GCB_CUDA(cudaMalloc(&h.d, sizeof(unsigned long long) * h.cap)); }
+  }
   GCB_CUDA(cudaMemsetAsync(h.d, 0, sizeof(unsigned long long) * (nframes + 2), c->compute));
   if (c->opts.pbc == GCB_PBC_RECT) {
-    if (!box) { c->hit_pool.emplace_back(h.cap, h.d); return gcb::fail(GCB_ERR_ARG, "GCB_PBC_RECT needs the per-frame box"); }
+    if (!box) return gcb::fail(GCB_ERR_ARG, "GCB_PBC_RECT needs the per-frame box");
     std::vector<float> b3((size_t)nframes * 3);
     for (long f = 0; f < nframes; f++) { b3[3 * f] = box[9 * f]; b3[3 * f + 1] = box[9 * f + 4]; b3[3 * f + 2] = box[9 * f + 8]; }
     GCB_CUDA(cudaMalloc(&h.d_box3, sizeof(float) * 3 * nframes));
@@ -1903,10 +1641,10 @@ int gcb_counter_sync(gcb_counter *c)
     std::vector<unsigned long long> tmp((size_t)h.n);
     GCB_CUDA(cudaMemcpy(tmp.data(), h.d, sizeof(unsigned long long) * h.n, cudaMemcpyDeviceToHost));
     for (long f = 0; f < h.n; f++) c->hits_per_frame[h.frame0 + f] = tmp[f];
-    c->hit_pool.emplace_back(h.cap, h.d);
     cudaFree(h.d_box3);
   }
   c->devhits.clear();
+  for (auto &a : c->hit_arenas) a.used = 0;
   {
     unsigned long long diag[4];
     GCB_CUDA(cudaMemcpy(diag, c->d_diag, sizeof(diag), cudaMemcpyDeviceToHost));
@@ -2422,10 +2160,10 @@ static int finish_reduce(gcb_counter *c)
   for (size_t i = 0; i < ndev; i++) {
     DevHits &h = c->devhits[i];
     for (long f = 0; f < h.n; f++) c->hits_per_frame[h.frame0 + f] = fr[my_off + h.frame0 + f];
-    c->hit_pool.emplace_back(h.cap, h.d);
     cudaFree(h.d_box3);
   }
   c->devhits.erase(c->devhits.begin(), c->devhits.begin() + (long)ndev);
+  if (c->devhits.empty()) for (auto &a : c->hit_arenas) a.used = 0;
   c->sumP_frames = c->pend_nlocal;            // frames added after the reduce continue the chain from the global sum
   // consecutive frames of equal weight are one run of identical additions: one closed-form call per run
   double sp = 0;

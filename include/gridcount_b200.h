@@ -93,7 +93,8 @@ enum {
 enum {                     /* kernel selection (GCB_KERNEL_AUTO picks by index-group density and regularity) */
   GCB_KERNEL_AUTO = 0, GCB_KERNEL_GATHER = 1, GCB_KERNEL_STREAM = 2,
   GCB_KERNEL_STREAM_INDEXED = 3,  /* streaming kernel without the arithmetic-progression shortcut */
-  GCB_KERNEL_ROUTED = 4,          /* streaming kernel + shared-memory privatised counting (two kernels per round) */
+  /* 4 was GCB_KERNEL_ROUTED (keys routed to buckets, counted by a second kernel): removed in round 2, it lost to
+     both kernels below on every shape */
   GCB_KERNEL_PACKED = 5           /* streaming kernel with non-returning REDs into packed 8- or 4-bit L2-resident
                                      counters, verified (digit sum == hits) and folded into the uint32 grid once per
                                      round; AUTO picks it for grids whose uint32 cells exceed the L2 */

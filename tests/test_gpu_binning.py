@@ -13,7 +13,7 @@ from gridcount_b200 import _cabi as K
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [K.KERNEL_GATHER, K.KERNEL_STREAM, K.KERNEL_STREAM_INDEXED, K.KERNEL_ROUTED, K.KERNEL_PACKED]
+KERNELS = [K.KERNEL_GATHER, K.KERNEL_STREAM, K.KERNEL_STREAM_INDEXED, K.KERNEL_PACKED]
 
 
 def to_ogeom(geom):
@@ -379,7 +379,7 @@ def test_large_grids(cfg):
 def test_full_size_c2_properties():
     """BASELINE config 2 at FULL size (60 000 atoms, 20 000 OW, 10 000 frames, 80x80x134): too large for the oracle,
     so size-independent properties: every generated atom lies in the grid (total = frames*gnx, per-frame hits = gnx);
-    direct, routed and gather kernels agree cell for cell; counting is additive over frame ranges; and the first
+    direct, packed and gather kernels agree cell for cell; counting is additive over frame ranges; and the first
     64 frames match the oracle."""
     L, natoms, F = (8.0, 8.0, 13.4), 60000, 10000
     geom = g.setup_geometry(L, 0.1)
@@ -388,7 +388,7 @@ def test_full_size_c2_properties():
     gen = g.make_gen(20261021, L, K.GEN_PORE, slab=(4.7, 8.7), pore_r=0.8)
     dev = g.DeviceFrames(F, natoms).generate(gen)
     ref = None
-    for kernel in (K.KERNEL_STREAM, K.KERNEL_ROUTED, K.KERNEL_GATHER):
+    for kernel in (K.KERNEL_STREAM, K.KERNEL_PACKED, K.KERNEL_GATHER):
         ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel)
         ctr.add_device_frames(dev)
         c = ctr.counts()
@@ -415,6 +415,39 @@ def test_full_size_c2_properties():
     p.add_device_frames(dev, first=0, count=64)
     assert np.array_equal(p.counts(), oc)
     p.close(); dev.free()
+
+
+@pytest.mark.parametrize("name", ["C3", "C4"])
+def test_named_large_shapes_with_the_kernel_auto_picks(name):
+    """BASELINE configs 3 and 4 at their named frame size (1 M atoms on 400^3; 100 k atoms on 500^3) through
+    GCB_KERNEL_AUTO, i.e. the packed-counter path with its persisting-L2 window: counts and per-frame hits against the
+    oracle for a uniform box (no round may need the redo) and for atoms piled onto eight small clusters (every packed
+    round overflows its lanes: the digit-sum check must catch it, the uint32 kernel redoes it, the host pauses the
+    packed passes) -- and a uniform batch afterwards still comes out exact."""
+    L, delta, shape, natoms, nframes = {"C3": ((20.0, 20.0, 20.0), 0.05, (400, 400, 400), 1000000, 16),
+                                        "C4": ((10.0, 10.0, 10.0), 0.02, (500, 500, 500), 100000, 96)}[name]
+    geom = g.setup_geometry(L, delta)
+    assert geom.shape == shape
+    gindex = np.arange(0, natoms, 3, dtype=np.int32)
+    ctr = g.GridCounter(geom, gindex, natoms)
+    dev = g.DeviceFrames(nframes, natoms).generate(g.make_gen(31, L))
+    ctr.add_device_frames(dev)
+    want, whits, _ = oracle_counts(geom, dev.download(), gindex)
+    np.testing.assert_array_equal(ctr.counts(), want)
+    np.testing.assert_array_equal(ctr.hits_per_frame(), whits)
+    st = ctr.stats()
+    assert st.packed_rounds >= 1 and st.packed_redone == 0
+    dev.generate(g.make_gen(32, L, K.GEN_CLUSTER, nsites=8, sigma=0.01))
+    total = want
+    for rep in range(16):                              # enough calls for the back-off to reach the host-side pause
+        ctr.add_device_frames(dev)
+    w2, h2, _ = oracle_counts(geom, dev.download(), gindex)
+    total = total + 16 * w2
+    np.testing.assert_array_equal(ctr.counts(), total)
+    st2 = ctr.stats()
+    assert st2.packed_redone >= 1 and st2.hits == int(whits.sum()) + 16 * int(h2.sum())
+    assert st2.packed_rounds < st.packed_rounds + 16, "the host never paused the packed passes"
+    ctr.close(); dev.free()
 
 
 # ----------------------------------------------------------------------------- packed counters under pressure
@@ -544,7 +577,7 @@ def test_saturation_guard_with_lowered_thresholds(monkeypatch):
     rng = np.random.default_rng(5)
     x = (rng.random((nframes, natoms, 3)) * 2.0).astype(np.float32)
     gindex = np.arange(natoms, dtype=np.int32)
-    for kernel in (K.KERNEL_STREAM, K.KERNEL_GATHER, K.KERNEL_ROUTED):
+    for kernel in (K.KERNEL_STREAM, K.KERNEL_GATHER, K.KERNEL_PACKED):
         # (a) spread out: bounds force clamp passes (4096 possible hits per frame against a ceiling of 40 000), no cell is near 1000
         ctr = g.GridCounter(geom, gindex, natoms, kernel=kernel, frames_per_batch=4)
         ctr.add_frames(x, np.ones(nframes, np.float32))

@@ -30,8 +30,7 @@ def main():
     gindex = np.arange(0, natoms, stride, dtype=np.int32)
     gen = g.make_gen(1, L, K.GEN_CLUSTER, nsites=256, sigma=0.1) if name.endswith("k") else g.make_gen(1, L)
     dev = g.DeviceFrames(nframes, natoms).generate(gen)
-    kernels = (("gather", K.KERNEL_GATHER), ("stream", K.KERNEL_STREAM), ("routed", K.KERNEL_ROUTED),
-               ("packed", K.KERNEL_PACKED), ("auto", K.KERNEL_AUTO))
+    kernels = (("gather", K.KERNEL_GATHER), ("stream", K.KERNEL_STREAM), ("packed", K.KERNEL_PACKED), ("auto", K.KERNEL_AUTO))
     only = os.environ.get("PERF_KERNELS")
     for kname, kernel in kernels:
         if only and kname not in only.split(","):
