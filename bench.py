@@ -375,26 +375,35 @@ def l2_ceilings(g, window_bytes, stride, device):
 
 
 def roofline_of(g, ctr, stride, cells, peak, peak_src, device, kernel_key, l2=None):
-    """K1's dominant kernel from the event pairs gcb_counter_profile put around its launches"""
-    k1_ms, nl, units = ctr.profile_read()
-    st = ctr.stats()
-    packed = st.packed_rounds > 0
+    """K1's dominant kernel from the event pairs gcb_counter_profile put around every K1 launch: the kind of
+    binning kernel (direct uint32 REDs, packed-counter pass, or the guarded uint32 pass that redoes a failed packed
+    round) with the largest summed duration; the other K1 launches of the same frames are listed beside it"""
+    kinds = ctr.profile_kinds()
+    dom = max(("direct", "packed", "redo"), key=lambda k: kinds[k][0])
+    k1_ms, nl, units = kinds[dom]
     bits = 8 if cells <= (80 << 20) else 4
-    kernel = ("bin_stream_kernel<PackedSink<%d>> (non-returning REDs into %d-bit L2-resident counters)" % (bits, bits)
-              if packed else "bin_stream_kernel<DirectSink> (one RED per hit into the uint32 grid)")
+    names = {"direct": "bin_stream_kernel<DirectSink> (one RED per hit into the uint32 grid)",
+             "packed": "bin_stream_kernel<PackedSink<%d>> (non-returning REDs into %d-bit L2-resident counters)" % (bits, bits),
+             "redo": "bin_stream_kernel<DirectSink>, guarded pass (one RED per hit into the uint32 grid, after a packed "
+                     "round failed its digit-sum verification)"}
     gps = units / (k1_ms * 1e-3) * 1e-9
     achieved = ALGO_BYTES_PER_UNIT * gps
-    tr = read_traffic(kernel_key)
-    out = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    tr = read_traffic(kernel_key) if dom != "redo" else None
+    all_ms = sum(v[0] for v in kinds.values())
+    out = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
            "peak_source": peak_src, "launch_ms_avg": k1_ms / max(nl, 1), "launches_timed": int(nl),
            "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UNIT * units / max(nl, 1),
-           "kernel_g_atom_frames_per_s": gps,
+           "kernel_g_atom_frames_per_s": gps, "share_of_k1_time": k1_ms / all_ms if all_ms else None,
+           "k1_launch_kinds_ms": {k: round(v[0], 4) for k, v in kinds.items()},
            "traffic": None, "hbm_ceiling_note": "one atom in %d is counted out of x[atom][3]: every 32 B sector of a frame "
                                                 "holds part of a counted atom, so DRAM moves %d B per unit and frac <= %.2f"
                                                 % (stride, 12 * stride, 1.0 / stride) if stride > 1 else None}
+    if tr and tr.get("kernel", "").find("Packed") >= 0 and dom != "packed":
+        tr = None                                  # the committed capture is of the other kernel
     if tr:
-        out["traffic"] = tr["dram_bytes_per_launch"]
-        out["traffic_source"] = tr.get("source")
+        out["traffic"] = tr["dram_bytes_per_launch"] * (units / max(nl, 1)) / tr["atom_frames_per_launch"]
+        out["traffic_source"] = "%s: %.2f B of DRAM traffic per atom-frame, scaled to this launch size" % (
+            tr.get("source"), tr["dram_bytes_per_launch"] / tr["atom_frames_per_launch"])
         out["traffic_bytes_per_unit"] = tr["dram_bytes_per_launch"] / tr["atom_frames_per_launch"]
     if l2:
         out["l2"] = dict(l2)
@@ -427,8 +436,8 @@ def measure_config(g, name, cfg, device, peak, peak_src, reps=10, extra=None):
     for _ in range(2):
         ctr.add_device_frames(dev, weights=w)
     packed_bytes = geom.cells if geom.cells <= (80 << 20) else geom.cells // 2
-    window = packed_bytes if st.packed_rounds > 0 else geom.cells * 4
     rl = roofline_of(g, ctr, cfg["stride"], geom.cells, peak, peak_src, device, name)
+    window = packed_bytes if "PackedSink" in rl["kernel"] else geom.cells * 4       # what the dominant kernel's REDs address
     ctr.profile(False)
     res = {"workload": cfg["title"], "grid": list(geom.shape), "frames_resident": F,
            "frames_resident_gb": F * cfg["natoms"] * 12 / 1e9, "passes_timed": reps,

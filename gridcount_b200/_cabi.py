@@ -117,10 +117,17 @@ SIGNATURES = {
     "gcb_counter_timer_stop": (C.c_int, [C.c_void_p, c_float_p]),
     "gcb_counter_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "gcb_counter_profile_read": (C.c_int, [C.c_void_p, c_double_p, c_long_p, c_double_p]),
+    "gcb_counter_profile_kinds": (C.c_int, [C.c_void_p, c_double_p, c_long_p, c_double_p]),
     "gcb_selftest_l2": (C.c_int, [C.c_int, C.c_size_t, C.c_int, C.c_size_t, c_double_p, c_double_p]),
     "gcb_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "gcb_counter_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "gcb_counter_allreduce": (C.c_int, [C.c_void_p]),
+    "gcb_ctl_open": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gcb_ctl_allgather": (C.c_int, [C.c_void_p, c_u64_p, c_u64_p, C.c_int]),
+    "gcb_ctl_close": (None, [C.c_void_p]),
+    "gcb_local_comm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "gcb_counter_comm_init_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "gcb_local_comm_destroy": (None, [C.c_void_p]),
     "gcb_xtc_scan": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(XtcFrame), C.c_long, c_long_p, C.POINTER(C.c_size_t)]),
     "gcb_xtc_decode_device": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(XtcFrame), C.c_long, C.c_int, C.c_void_p, C.c_int]),
     "gcb_counter_add_xtc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(XtcFrame), C.c_long, c_float_p]),

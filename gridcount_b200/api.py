@@ -380,6 +380,13 @@ class GridCounter:
         check(lib.gcb_counter_profile_read(self.h, C.byref(ms), C.byref(n), C.byref(units)), "gcb_counter_profile_read")
         return ms.value, n.value, units.value
 
+    def profile_kinds(self):
+        """-> {kind: (summed ms, launches, atom-frames)} for 'direct', 'packed', 'redo' (the guarded uint32 pass
+        behind a packed pass) and 'other' (verify/apply passes, gather tails)"""
+        ms, n, units = (C.c_double * 4)(), (C.c_long * 4)(), (C.c_double * 4)()
+        check(lib.gcb_counter_profile_kinds(self.h, ms, n, units), "gcb_counter_profile_kinds")
+        return {k: (ms[i], n[i], units[i]) for i, k in enumerate(("direct", "packed", "redo", "other"))}
+
     def timer_start(self):
         check(lib.gcb_counter_timer_start(self.h), "gcb_counter_timer_start")
 

@@ -846,13 +846,16 @@ struct gcb_counter {
   cudaEvent_t reduce_done = nullptr;  // behind the D2H of the gathered statistics
   cudaEvent_t scr_up = nullptr, grp_done = nullptr;   // scratch uploaded / NCCL group finished
   bool reduce_pending = false;        // host half of the last all-reduce still to do (finish_reduce)
-  size_t pend_total = 0, pend_off = 0, pend_ndev = 0, pend_nlocal = 0;
+  size_t pend_total = 0, pend_off = 0, pend_ndev = 0, pend_nlocal = 0, pend_blk = 0;
+  std::vector<size_t> pend_frames;    // frames each rank contributed to the pending reduce
+  gcb_ctl *ctl = nullptr;             // shared-memory control plane between the ranks of this node (may be absent)
 
   std::vector<int> h_gindex;          // sorted copy of the index group
   int *d_gindex = nullptr;
   unsigned *d_rank = nullptr;         // rank[r] = number of group entries < r, r in [0, natoms]
   uint32_t *d_runcnt = nullptr, *d_total = nullptr;
   float *d_acc = nullptr;
+  bool acc_used = false;              // d_acc / d_total hold something since the last reset (they stay allocated)
   unsigned long long *d_diag = nullptr;
   float *d_out = nullptr, *d_out2 = nullptr;   // density / transpose outputs
 
@@ -880,14 +883,16 @@ struct gcb_counter {
   size_t sumP_frames = 0;
   uint64_t hits_total = 0, edge_overflow = 0;
   int64_t launches = 0;
-  void *nccl = nullptr;               // ncclComm_t, see nccl_reduce.cpp
+  void *nccl = nullptr;               // the communicator: an ncclComm_t (nccl_reduce.cpp) or an in-process rank (local_reduce.cu)
+  const gcb_reduce_ops *ops = nullptr;
   int nranks = 1, rank = 0;
   std::vector<cudaEvent_t> events;
   // gcb_counter_profile: an event pair around every launch of the streaming kernel (K1's dominant kernel)
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
-  double prof_units = 0;
+  std::vector<int> prof_kind;         // per event pair: GCB_PROF_*
+  std::vector<double> prof_units;     // per event pair: atom-frames the launch covered
   bool reduced = false;               // statistics below are global after gcb_counter_allreduce
   uint64_t global_frames = 0;
 };
@@ -903,6 +908,7 @@ unsigned rank_host(const gcb_counter *c, int r)
 
 int ensure_acc(gcb_counter *c)
 {
+  c->acc_used = true;
   if (c->d_acc) return GCB_OK;
   GCB_CUDA(cudaMalloc(&c->d_acc, c->ncells * sizeof(float)));
   GCB_CUDA(cudaMalloc(&c->d_total, c->ncells * sizeof(uint32_t)));
@@ -949,6 +955,28 @@ int fold_pending(gcb_counter *c)
   return GCB_OK;
 }
 
+// gcb_counter_profile: an event pair on the compute stream around one launch (or a short run of launches)
+int prof_begin(gcb_counter *c)
+{
+  if (!c->prof) return GCB_OK;
+  if (c->prof_used + 2 > c->prof_ev.size()) {
+    c->prof_ev.resize(c->prof_used + 2, nullptr);
+    GCB_CUDA(cudaEventCreate(&c->prof_ev[c->prof_used]));
+    GCB_CUDA(cudaEventCreate(&c->prof_ev[c->prof_used + 1]));
+  }
+  GCB_CUDA(cudaEventRecord(c->prof_ev[c->prof_used], c->compute));
+  return GCB_OK;
+}
+int prof_end(gcb_counter *c, int kind, double units)
+{
+  if (!c->prof) return GCB_OK;
+  GCB_CUDA(cudaEventRecord(c->prof_ev[c->prof_used + 1], c->compute));
+  c->prof_used += 2;
+  c->prof_kind.push_back(kind);
+  c->prof_units.push_back(units);
+  return GCB_OK;
+}
+
 template <class SINK>
 size_t stream_smem_bytes() { return ((sizeof(StreamSmem<SINK::NSTAGES>) + 15) & ~(size_t)15) + SINK::EXTRA_SMEM; }
 
@@ -966,24 +994,15 @@ int launch_stream(gcb_counter *c, const float *d_x, long long ntiles, const SINK
   const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
   long long grid = std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
   if (grid_cap > 0) grid = std::min<long long>(grid, grid_cap);
-  const bool timed = c->prof && GUARD != 1;         // (the redo pass of a packed round normally returns at once)
-  if (timed) {
-    if (c->prof_used + 2 > c->prof_ev.size()) {
-      c->prof_ev.resize(c->prof_used + 2, nullptr);
-      GCB_CUDA(cudaEventCreate(&c->prof_ev[c->prof_used]));
-      GCB_CUDA(cudaEventCreate(&c->prof_ev[c->prof_used + 1]));
-    }
-    GCB_CUDA(cudaEventRecord(c->prof_ev[c->prof_used], c->compute));
-  }
+  const int kind = GUARD == 2 ? GCB_PROF_PACKED : GUARD == 1 ? GCB_PROF_REDO : GCB_PROF_DIRECT;
+  int rc = prof_begin(c);
+  if (rc) return rc;
   bin_stream_kernel<SINK, PBC, AP, GUARD><<<(unsigned)grid, STREAM_THREADS, smem, c->compute>>>(
       d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, c->ap, c->PF, sink, d_box3, d_hits, c->d_diag, run_if);
   c->launches++;
   GCB_CUDA(cudaGetLastError());
-  if (timed) {
-    GCB_CUDA(cudaEventRecord(c->prof_ev[c->prof_used + 1], c->compute));
-    c->prof_used += 2;
-    c->prof_units += (double)ntiles * (AP ? c->ap.tile_atoms : TILE_ATOMS) / (double)c->natoms * (double)c->gnx;
-  }
+  rc = prof_end(c, kind, (double)ntiles * (AP ? c->ap.tile_atoms : TILE_ATOMS) / (double)c->natoms * (double)c->gnx);
+  if (rc) return rc;
   if (grid_out) *grid_out = (int)grid;
   return GCB_OK;
 }
@@ -997,11 +1016,13 @@ int launch_gather(gcb_counter *c, const float *d_x, long long e_begin, long long
   const long long chunk = (long long)GATHER_THREADS * GATHER_ITEMS;
   const long long nchunks = (e_end - e_begin + chunk - 1) / chunk;
   const long long grid = std::min<long long>(nchunks, (long long)c->sm_count * 8);
+  int rc = prof_begin(c);
+  if (rc) return rc;
   bin_gather_kernel<MODE, PBC><<<(unsigned)grid, GATHER_THREADS, 0, c->compute>>>(
       d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, e_begin, e_end, c->P, cnt, c->d_acc, w, d_box3, d_hits, c->d_diag);
   c->launches++;
   GCB_CUDA(cudaGetLastError());
-  return GCB_OK;
+  return prof_end(c, GCB_PROF_OTHER, (double)(e_end - e_begin));
 }
 
 // Packed path: rounds of ~packed_units atom-frames; per round the streaming kernel into the packed counters
@@ -1064,10 +1085,14 @@ int launch_packed(gcb_counter *c, const float *d_x, long nframes, const float *d
       int rc = ap ? launch_stream<PackedSink<W>, PBC, true, 2>(c, xs, ntiles, sink, 0, bs, d_hits + f0, nullptr, &st->alarm)
                   : launch_stream<PackedSink<W>, PBC, false, 2>(c, xs, ntiles, sink, 0, bs, d_hits + f0, nullptr, &st->alarm);
       if (rc) return rc;
+      rc = prof_begin(c);
+      if (rc) return rc;
       packed_verify_kernel<W><<<aux_grid, 256, 0, c->compute>>>(reinterpret_cast<const uint4 *>(c->d_pk), nquads, d_hits + f0, n, st);
       packed_apply_kernel<W><<<apply_grid, 256, 0, c->compute>>>(c->d_pk, nwords, c->d_runcnt, c->ncells, st, d_hits + f0, n, c->d_diag);
       c->launches += 3;
       GCB_CUDA(cudaGetLastError());
+      rc = prof_end(c, GCB_PROF_OTHER, 0.0);
+      if (rc) return rc;
       DirectSink<MODE_COUNT> redo;
       redo.counts = c->d_runcnt; redo.acc = c->d_acc; redo.w = 1.0f;
       rc = ap ? launch_stream<DirectSink<MODE_COUNT>, PBC, true, 1>(c, xs, ntiles, redo, 0, bs, d_hits + f0, nullptr, &st->alarm)
@@ -1168,7 +1193,7 @@ int bin_device_batch(gcb_counter *c, const float *d_x, long nframes, const float
     const float *xs = d_x + (size_t)f * c->natoms * 3;
     const float *bs = d_box3 ? d_box3 + 3 * f : nullptr;
     const bool continues = c->have_run && same_bits(wr, c->w_cur);
-    const bool fresh = !c->have_run && !c->d_acc;
+    const bool fresh = !c->have_run && !c->acc_used;
     const bool long_run = (double)n * c->gnx >= (double)c->ncells / 8.0;
     int rc;
     if (continues || fresh || long_run) {
@@ -1266,6 +1291,8 @@ void free_counter(gcb_counter *c)
   cudaSetDevice(c->opts.device);
   if (c->compute) cudaStreamSynchronize(c->compute);
   if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+  if (c->nccl && c->ops && c->ops->destroy) c->ops->destroy(c->nccl);
+  if (c->ctl) gcb_ctl_close(c->ctl);
   if (c->l2_window) {                  // give the set-aside lines back
     cudaStreamAttrValue av = {};
     cudaStreamSetAttribute(c->compute, cudaStreamAttributeAccessPolicyWindow, &av);
@@ -1278,7 +1305,7 @@ void free_counter(gcb_counter *c)
     cudaFreeHost(s.h_x); cudaFree(s.d_x); cudaFree(s.d_hits); cudaFreeHost(s.h_hits);
     cudaFree(s.d_box3); cudaFreeHost(s.h_box3);
   }
-  for (auto &d : c->devhits) { cudaFree(d.d); cudaFree(d.d_box3); }
+  for (auto &d : c->devhits) cudaFree(d.d_box3);           // (d.d lives in a hit arena)
   for (auto &a : c->hit_arenas) cudaFree(a.d);
   cudaFree(c->d_gindex); cudaFree(c->d_rank); cudaFree(c->d_runcnt); cudaFree(c->d_total); cudaFree(c->d_acc);
   cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2);
@@ -1297,6 +1324,7 @@ void free_counter(gcb_counter *c)
   if (c->reduce_done) cudaEventDestroy(c->reduce_done);
   if (c->scr_up) cudaEventDestroy(c->scr_up);
   if (c->grp_done) cudaEventDestroy(c->grp_done);
+  cudaGetLastError();                  // nothing above may leave an error behind for the next counter's launch checks
   delete c;
 }
 
@@ -1391,7 +1419,8 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
     // Packed path: bytes while they fit ~80 MB of the 126 MB L2 next to the coordinate stream, nibbles up to twice
     // as many cells (500^3, and every grid the XDR format can hold: 512^3 cells = 64 MB of nibbles).  A round is
     // sized so that a uniform density stays far below the lane range: mean 8 hits per byte cell (P[>255] = 0),
-    // 1.25 per nibble cell (P[>15] ~ 5e-13 per cell); denser spots fail verification and are binned directly.
+    // 1.5 per nibble cell (P[>15] ~ 7e-12 per cell, about one failed round in a thousand on 500^3, which costs that
+    // round and the next a pass of the direct kernel); denser spots fail verification and are binned directly.
     {
       const char *benv = getenv("GCB_PACKED_BITS");
       const int want = benv ? atoi(benv) : 0;
@@ -1399,7 +1428,7 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
       c->packed_auto = c->ncells * sizeof(uint32_t) > ((size_t)48 << 20) && c->ncells / (c->packed_bits == 8 ? 1 : 2) <= ((size_t)80 << 20) &&
                        !getenv("GCB_NO_PACKED");
       const char *uenv = getenv("GCB_PACKED_UNITS");
-      c->packed_units = uenv ? atoll(uenv) : (long long)((double)c->ncells * (c->packed_bits == 8 ? 8.0 : 1.25));
+      c->packed_units = uenv ? atoll(uenv) : (long long)((double)c->ncells * (c->packed_bits == 8 ? 8.0 : 1.5));
       if (c->packed_units < 4096) c->packed_units = 4096;
     }
   }
@@ -1435,9 +1464,10 @@ int gcb_counter_reset(gcb_counter *c)
   c->devhits.clear();
   for (auto &a : c->hit_arenas) a.used = 0;
   GCB_CUDA(cudaMemsetAsync(c->d_runcnt, 0, sizeof(uint32_t) * c->ncells, c->compute));
-  if (c->d_acc) {
+  if (c->acc_used) {
     GCB_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(float) * c->ncells, c->compute));
     GCB_CUDA(cudaMemsetAsync(c->d_total, 0, sizeof(uint32_t) * c->ncells, c->compute));
+    c->acc_used = false;
   }
   GCB_CUDA(cudaMemsetAsync(c->d_diag, 0, sizeof(unsigned long long) * 4, c->compute));
   if (c->d_pstate) GCB_CUDA(cudaMemsetAsync(&c->d_pstate->rounds, 0, 2 * sizeof(unsigned long long), c->compute));
@@ -1503,6 +1533,10 @@ int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes, const f
     if (rc) return rc;
     done += n;
   }
+  // Pinned x is DMA-ed straight out of the caller's memory: the call returns when the last of those copies has
+  // left it (the kernels behind them keep running), so the caller may refill x at once, as with pageable memory.
+  if (pinned)
+    for (auto &s : c->slots) GCB_CUDA(cudaEventSynchronize(s.copied));
   return GCB_OK;
 }
 
@@ -1711,7 +1745,7 @@ int gcb_counter_device_counts(gcb_counter *c, uint32_t **counts_dev)
 {
   if (!c || !counts_dev) return gcb::fail(GCB_ERR_ARG, "null argument");
   GCB_CUDA(cudaSetDevice(c->opts.device));
-  if (!c->d_total) { *counts_dev = c->d_runcnt; return GCB_OK; }
+  if (!c->acc_used) { *counts_dev = c->d_runcnt; return GCB_OK; }
   int rc = ensure_out(c);
   if (rc) return rc;
   add_u32_kernel<<<elementwise_grid(c, c->ncells), 256, 0, c->compute>>>(c->d_total, c->have_run ? c->d_runcnt : nullptr,
@@ -1737,7 +1771,7 @@ static int density_to_device(gcb_counter *c, double denom)
 {
   int rc = ensure_out(c);
   if (rc) return rc;
-  density_kernel<<<elementwise_grid(c, c->ncells), 256, 0, c->compute>>>(c->d_runcnt, c->d_acc, c->w_cur,
+  density_kernel<<<elementwise_grid(c, c->ncells), 256, 0, c->compute>>>(c->d_runcnt, c->acc_used ? c->d_acc : nullptr, c->w_cur,
                                                                           c->have_run ? 1 : 0, denom, c->d_out, c->ncells);
   c->launches++;
   GCB_CUDA(cudaGetLastError());
@@ -1897,24 +1931,39 @@ int gcb_counter_profile(gcb_counter *c, int enable)
   GCB_CUDA(cudaStreamSynchronize(c->compute));
   c->prof = enable != 0;
   c->prof_used = 0;
-  c->prof_units = 0;
+  c->prof_kind.clear();
+  c->prof_units.clear();
   return GCB_OK;
 }
 
-int gcb_counter_profile_read(gcb_counter *c, double *k1_ms, long *k1_launches, double *k1_atom_frames)
+int gcb_counter_profile_kinds(gcb_counter *c, double ms[GCB_PROF_KINDS], long launches[GCB_PROF_KINDS], double atom_frames[GCB_PROF_KINDS])
 {
-  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
+  if (!c || !ms || !launches || !atom_frames) return gcb::fail(GCB_ERR_ARG, "gcb_counter_profile_kinds: null argument");
   GCB_CUDA(cudaSetDevice(c->opts.device));
   GCB_CUDA(cudaStreamSynchronize(c->compute));
-  double total = 0;
+  for (int k = 0; k < GCB_PROF_KINDS; k++) { ms[k] = 0; launches[k] = 0; atom_frames[k] = 0; }
   for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
-    float ms = 0;
-    GCB_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]));
-    total += ms;
+    float t = 0;
+    GCB_CUDA(cudaEventElapsedTime(&t, c->prof_ev[i], c->prof_ev[i + 1]));
+    const int k = c->prof_kind[i / 2];
+    ms[k] += t; launches[k]++; atom_frames[k] += c->prof_units[i / 2];
   }
-  if (k1_ms) *k1_ms = total;
-  if (k1_launches) *k1_launches = (long)(c->prof_used / 2);
-  if (k1_atom_frames) *k1_atom_frames = c->prof_units;
+  return GCB_OK;
+}
+
+// the kind of binning kernel that took the most time (direct, packed pass or its redo pass)
+int gcb_counter_profile_read(gcb_counter *c, double *k1_ms, long *k1_launches, double *k1_atom_frames)
+{
+  double ms[GCB_PROF_KINDS], units[GCB_PROF_KINDS];
+  long n[GCB_PROF_KINDS];
+  int rc = gcb_counter_profile_kinds(c, ms, n, units);
+  if (rc) return rc;
+  int best = GCB_PROF_DIRECT;
+  if (ms[GCB_PROF_PACKED] > ms[best]) best = GCB_PROF_PACKED;
+  if (ms[GCB_PROF_REDO] > ms[best]) best = GCB_PROF_REDO;
+  if (k1_ms) *k1_ms = ms[best];
+  if (k1_launches) *k1_launches = n[best];
+  if (k1_atom_frames) *k1_atom_frames = units[best];
   return GCB_OK;
 }
 
@@ -1983,28 +2032,36 @@ int gcb_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, int device
 // ---------------------------------------------------------------------------
 // multi-GPU reduce (the NCCL binding lives in nccl_reduce.cpp)
 // ---------------------------------------------------------------------------
-extern "C" int gcb_counter_comm_attach_(gcb_counter *c, void *comm, int rank, int nranks)
+extern "C" int gcb_counter_comm_attach_(gcb_counter *c, void *comm, const gcb_reduce_ops *ops, int rank, int nranks, gcb_ctl *ctl)
 {
   GCB_CUDA(cudaSetDevice(c->opts.device));
-  if (comm) { c->nccl = comm; c->rank = rank; c->nranks = nranks; }
+  if (comm) {
+    if (c->nccl) return gcb::fail(GCB_ERR_STATE, "the counter already has a communicator");
+    c->nccl = comm; c->ops = ops; c->rank = rank; c->nranks = nranks; c->ctl = ctl;
+  }
   return GCB_OK;
 }
 
 // After this call every rank holds the global integer counts and statistics.
 // Counts are an integer sum, so the result is independent of the rank count.
 // Exact f32 occupancy needs one weight for the whole job (checked); with
-// differing weights per rank the f32 accumulators are summed instead, which is
-// no longer the reference's sequential order (documented in DESIGN.md).
+// differing weights the ranks' f32 accumulators are summed instead, which is
+// not the reference's frame-ordered chain (see gridcount_b200.h).
 //
-// Two host synchronisations per call, only the second one behind the binning kernels:
-//   1. the ranks' {weight, uniformity, frame count} table is exchanged on a separate stream, so it
-//      does not queue behind the binning work still running on the compute stream;
-//   2. the per-frame hit counters never visit the host on their way: they are copied device to device
-//      into the gather buffer, and the grid all-reduce and the gather go out as ONE NCCL group.
-extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops *ops)
+// What the call costs the host:
+//   1. the ranks' {weight, uniformity, frame count, saturation bounds} table is host-side knowledge.  On one node it
+//      is exchanged through shared memory (shm_ctl.cpp): no kernel, no stream, nothing that has to find an SM while
+//      the persistent binning CTAs hold them all.  Ranks on several nodes fall back to a small NCCL all-reduce on a
+//      side stream.
+//   2. the per-frame hit counters never visit the host on their way: they are copied device to device into this
+//      rank's block of the gather buffer, and the grid all-reduce and the (in-place) all-gather of the blocks go
+//      out as ONE NCCL group behind the binning kernels.  The call returns after queueing.
+extern "C" int gcb_counter_allreduce(gcb_counter *c)
 {
   enum { U32 = 3, U64 = 5, F32 = 7, F64 = 8 };
+  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
   if (c->nranks <= 1 || !c->nccl) return gcb_counter_sync(c);
+  const gcb_reduce_ops *ops = c->ops;
   GCB_CUDA(cudaSetDevice(c->opts.device));
   static const bool trace = getenv("GCB_TRACE") != nullptr;
   auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
@@ -2025,35 +2082,41 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops 
     c->scr_words = cap;
     return GCB_OK;
   };
-  // 1. all-gather (written as a sum of disjoint slots: one collective type for everything) of each rank's
-  //    {has frames, weight bits, uniform, has f32 accumulator, frame count}: host-side knowledge, so it
-  //    travels while the binning kernels are still running
+  // 1. each rank's {has frames, weight bits, uniform, f32 accumulator in use, frame count, saturation bounds}
   const size_t R = (size_t)c->nranks;
-  constexpr size_t TW = 7;                 // table words per rank
-  rc = scratch(R * TW);
-  if (rc) return rc;
-  uint32_t wb; memcpy(&wb, &c->w_first, 4);
-  memset(c->h_scr, 0, sizeof(unsigned long long) * R * TW);
-  c->h_scr[(size_t)c->rank * TW + 0] = c->any ? 1ull : 0ull;
-  c->h_scr[(size_t)c->rank * TW + 1] = wb;
-  c->h_scr[(size_t)c->rank * TW + 2] = c->uniform ? 1ull : 0ull;
-  c->h_scr[(size_t)c->rank * TW + 3] = (c->d_acc != nullptr) ? 1ull : 0ull;
-  c->h_scr[(size_t)c->rank * TW + 4] = c->hits_per_frame.size();
-  c->h_scr[(size_t)c->rank * TW + 5] = c->bound_run;          // saturation guard: what this rank's fullest cell may hold
-  c->h_scr[(size_t)c->rank * TW + 6] = c->bound_total;
-  GCB_CUDA(cudaMemcpyAsync(c->d_scr, c->h_scr, sizeof(unsigned long long) * R * TW, cudaMemcpyHostToDevice, c->comm_stream));
-  rc = ops->allreduce(c->d_scr, c->d_scr, R * TW, U64, c->nccl, c->comm_stream);
-  if (rc) return rc;
-  GCB_CUDA(cudaMemcpyAsync(c->h_scr, c->d_scr, sizeof(unsigned long long) * R * TW, cudaMemcpyDeviceToHost, c->comm_stream));
-  GCB_CUDA(cudaStreamSynchronize(c->comm_stream));
+  constexpr size_t TW = GCB_CTL_WORDS;
+  std::vector<unsigned long long> table(R * TW, 0ull);
+  {
+    uint32_t wb; memcpy(&wb, &c->w_first, 4);
+    unsigned long long mine[TW] = {c->any ? 1ull : 0ull, wb, c->uniform ? 1ull : 0ull, c->acc_used ? 1ull : 0ull,
+                                   c->hits_per_frame.size(), c->bound_run, c->bound_total, 0ull};
+    if (c->ctl) {
+      rc = gcb_ctl_allgather(c->ctl, (const uint64_t *)mine, (uint64_t *)table.data(), 120000);
+      if (rc) return rc;
+    } else {
+      rc = scratch(R * TW);
+      if (rc) return rc;
+      memset(c->h_scr, 0, sizeof(unsigned long long) * R * TW);
+      memcpy(c->h_scr + (size_t)c->rank * TW, mine, sizeof(mine));
+      GCB_CUDA(cudaMemcpyAsync(c->d_scr, c->h_scr, sizeof(unsigned long long) * R * TW, cudaMemcpyHostToDevice, c->comm_stream));
+      rc = ops->allreduce(c->d_scr, c->d_scr, R * TW, U64, c->nccl, c->comm_stream);     // disjoint slots: a sum is a gather
+      if (rc) return rc;
+      GCB_CUDA(cudaMemcpyAsync(c->h_scr, c->d_scr, sizeof(unsigned long long) * R * TW, cudaMemcpyDeviceToHost, c->comm_stream));
+      GCB_CUDA(cudaStreamSynchronize(c->comm_stream));
+      memcpy(table.data(), c->h_scr, sizeof(unsigned long long) * R * TW);
+    }
+  }
   bool global_uniform = true, any_acc = false, have_w = false;
   uint32_t w0 = 0;
-  size_t total_frames = 0, my_off = 0;
+  size_t total_frames = 0, my_off = 0, max_frames = 0;
   unsigned long long sum_bound_run = 0, sum_bound_total = 0;
+  c->pend_frames.assign(R, 0);
   for (int r = 0; r < c->nranks; r++) {
-    const unsigned long long *o = c->h_scr + (size_t)r * TW;
+    const unsigned long long *o = table.data() + (size_t)r * TW;
     if (r == c->rank) my_off = total_frames;
     total_frames += (size_t)o[4];
+    max_frames = std::max(max_frames, (size_t)o[4]);
+    c->pend_frames[(size_t)r] = (size_t)o[4];
     sum_bound_run += o[5]; sum_bound_total += o[6];
     if (!o[0]) continue;
     if (!o[2]) global_uniform = false;
@@ -2062,31 +2125,32 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops 
     else if (w0 != (uint32_t)o[1]) global_uniform = false;
   }
   const double t_gather = now();
-  // 2. Statistics buffer [hits | weight bits | edge overflow] over ALL frames.  Ranks hold contiguous frame
-  //    shards in rank order, so gathering the per-frame hit counts and weights lets every rank redo the
-  //    reference's frame-ordered `sumP += (double)weight` chain (g_ri3Dc.c:151,426): bit-identical to a
-  //    single-GPU run.  Host-known parts go up from the pinned mirror; counters of device-resident batches
-  //    and the overflow counter are copied in on the device, behind the kernels that produce them.
-  const size_t nfr_words = 2 * total_frames + 1;
-  rc = scratch(nfr_words);
+  // 2. Statistics: one block [hits(max_frames) | weight bits(max_frames) | edge overflow] per rank, all-gathered in
+  //    place.  Ranks hold contiguous frame shards in rank order, so with every rank's per-frame hit counts and
+  //    weights each rank redoes the reference's frame-ordered `sumP += (double)weight` chain (g_ri3Dc.c:151,426):
+  //    bit-identical to a single-GPU run.  Host-known parts of this rank's block go up from the pinned mirror;
+  //    counters of device-resident batches and the overflow counter are copied in on the device, behind the kernels
+  //    that produce them.
+  const size_t blk = 2 * max_frames + 1;
+  rc = scratch(R * blk);
   if (rc) return rc;
-  unsigned long long *fr = c->h_scr;
-  memset(fr, 0, sizeof(unsigned long long) * nfr_words);
+  unsigned long long *mine_h = c->h_scr + (size_t)c->rank * blk, *mine_d = c->d_scr + (size_t)c->rank * blk;
+  memset(mine_h, 0, sizeof(unsigned long long) * blk);
   for (size_t f = 0; f < c->hits_per_frame.size(); f++) {
-    fr[my_off + f] = c->hits_per_frame[f];
+    mine_h[f] = c->hits_per_frame[f];
     uint32_t wbits; memcpy(&wbits, &c->weight_per_frame[f], 4);
-    fr[total_frames + my_off + f] = wbits;
+    mine_h[max_frames + f] = wbits;
   }
-  for (auto &h : c->devhits) for (long f = 0; f < h.n; f++) fr[my_off + h.frame0 + f] = 0;
+  for (auto &h : c->devhits) for (long f = 0; f < h.n; f++) mine_h[h.frame0 + f] = 0;
   // the host-known part goes up on the side stream while the binning kernels are still running
   if (!c->scr_up) GCB_CUDA(cudaEventCreateWithFlags(&c->scr_up, cudaEventDisableTiming));
   if (!c->grp_done) GCB_CUDA(cudaEventCreateWithFlags(&c->grp_done, cudaEventDisableTiming));
-  GCB_CUDA(cudaMemcpyAsync(c->d_scr, fr, sizeof(unsigned long long) * nfr_words, cudaMemcpyHostToDevice, c->comm_stream));
+  GCB_CUDA(cudaMemcpyAsync(mine_d, mine_h, sizeof(unsigned long long) * blk, cudaMemcpyHostToDevice, c->comm_stream));
   GCB_CUDA(cudaEventRecord(c->scr_up, c->comm_stream));
   GCB_CUDA(cudaStreamWaitEvent(c->compute, c->scr_up, 0));
   for (auto &h : c->devhits)
-    GCB_CUDA(cudaMemcpyAsync(c->d_scr + my_off + h.frame0, h.d, sizeof(unsigned long long) * h.n, cudaMemcpyDeviceToDevice, c->compute));
-  GCB_CUDA(cudaMemcpyAsync(c->d_scr + 2 * total_frames, c->d_diag, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->compute));
+    GCB_CUDA(cudaMemcpyAsync(mine_d + h.frame0, h.d, sizeof(unsigned long long) * h.n, cudaMemcpyDeviceToDevice, c->compute));
+  GCB_CUDA(cudaMemcpyAsync(mine_d + 2 * max_frames, c->d_diag, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->compute));
   // 3. the grids and the statistics, one NCCL group
   if (!(global_uniform && !any_acc)) {
     rc = fold_pending(c);
@@ -2120,7 +2184,7 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops 
     rc = ops->allreduce(c->d_acc, c->d_acc, c->ncells, F32, c->nccl, c->compute);
     if (!rc) rc = ops->allreduce(c->d_total, c->d_total, c->ncells, U32, c->nccl, c->compute);
   }
-  if (!rc) rc = ops->allreduce(c->d_scr, c->d_scr, nfr_words, U64, c->nccl, c->compute);
+  if (!rc) rc = ops->allgather(mine_d, c->d_scr, blk, U64, c->nccl, c->compute);
   const int rc_end = ops->group_end();
   if (rc) return rc;
   if (rc_end) return rc_end;
@@ -2132,18 +2196,18 @@ extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops 
   // the gathered statistics come back on the side stream: the next job's kernels do not queue behind the copy
   GCB_CUDA(cudaEventRecord(c->grp_done, c->compute));
   GCB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->grp_done, 0));
-  GCB_CUDA(cudaMemcpyAsync(fr, c->d_scr, sizeof(unsigned long long) * nfr_words, cudaMemcpyDeviceToHost, c->comm_stream));
+  GCB_CUDA(cudaMemcpyAsync(c->h_scr, c->d_scr, sizeof(unsigned long long) * R * blk, cudaMemcpyDeviceToHost, c->comm_stream));
   // The grids are reduced in stream order; the host half (per-frame counters -> sumP chain) is finished when
   // somebody asks for it (finish_reduce), so the caller can queue the density and the next job meanwhile.
   if (!c->reduce_done) GCB_CUDA(cudaEventCreateWithFlags(&c->reduce_done, cudaEventDisableTiming));
   GCB_CUDA(cudaEventRecord(c->reduce_done, c->comm_stream));
   c->reduce_pending = true; c->pend_total = total_frames; c->pend_off = my_off; c->pend_ndev = c->devhits.size();
-  c->pend_nlocal = c->hits_per_frame.size();
+  c->pend_nlocal = c->hits_per_frame.size(); c->pend_blk = blk;
   c->global_frames = total_frames;
   c->reduced = true;
   if (trace && c->rank == 0)
-    fprintf(stderr, "[gcb allreduce] rank table (beside the binning) %.3f ms, queueing the grid/statistics group %.3f ms\n",
-            t_gather - t_begin, now() - t_gather);
+    fprintf(stderr, "[gcb allreduce] rank table (%s) %.3f ms, queueing the grid/statistics group %.3f ms\n",
+            c->ctl ? "shared memory" : "NCCL, beside the binning", t_gather - t_begin, now() - t_gather);
   return GCB_OK;
 }
 
@@ -2153,13 +2217,13 @@ static int finish_reduce(gcb_counter *c)
   if (!c->reduce_pending) return GCB_OK;
   GCB_CUDA(cudaEventSynchronize(c->reduce_done));
   c->reduce_pending = false;
-  const size_t total_frames = c->pend_total, my_off = c->pend_off;
-  const unsigned long long *fr = c->h_scr;
+  const size_t blk = c->pend_blk, max_frames = (blk - 1) / 2;
+  const unsigned long long *mine = c->h_scr + (size_t)c->rank * blk;
   // local bookkeeping that gcb_counter_sync would have done, for the batches the reduce covered
   const size_t ndev = std::min(c->pend_ndev, c->devhits.size());
   for (size_t i = 0; i < ndev; i++) {
     DevHits &h = c->devhits[i];
-    for (long f = 0; f < h.n; f++) c->hits_per_frame[h.frame0 + f] = fr[my_off + h.frame0 + f];
+    for (long f = 0; f < h.n; f++) c->hits_per_frame[h.frame0 + f] = mine[h.frame0 + f];
     cudaFree(h.d_box3);
   }
   c->devhits.erase(c->devhits.begin(), c->devhits.begin() + (long)ndev);
@@ -2167,20 +2231,24 @@ static int finish_reduce(gcb_counter *c)
   c->sumP_frames = c->pend_nlocal;            // frames added after the reduce continue the chain from the global sum
   // consecutive frames of equal weight are one run of identical additions: one closed-form call per run
   double sp = 0;
-  unsigned long long hits = 0, run_hits = 0;
+  unsigned long long hits = 0, run_hits = 0, edge = 0;
   uint32_t run_w = 0;
-  for (size_t f = 0; f < total_frames; f++) {
-    const uint32_t wbits = (uint32_t)fr[total_frames + f];
-    if (wbits != run_w && run_hits) {
-      float wf; memcpy(&wf, &run_w, 4);
-      sp = gcb::seq_add_f64(sp, (double)wf, run_hits);
-      run_hits = 0;
+  for (size_t r = 0; r < c->pend_frames.size(); r++) {
+    const unsigned long long *fr = c->h_scr + r * blk;
+    for (size_t f = 0; f < c->pend_frames[r]; f++) {
+      const uint32_t wbits = (uint32_t)fr[max_frames + f];
+      if (wbits != run_w && run_hits) {
+        float wf; memcpy(&wf, &run_w, 4);
+        sp = gcb::seq_add_f64(sp, (double)wf, run_hits);
+        run_hits = 0;
+      }
+      run_w = wbits;
+      run_hits += fr[f];
+      hits += fr[f];
     }
-    run_w = wbits;
-    run_hits += fr[f];
-    hits += fr[f];
+    edge += fr[2 * max_frames];
   }
   if (run_hits) { float wf; memcpy(&wf, &run_w, 4); sp = gcb::seq_add_f64(sp, (double)wf, run_hits); }
-  c->hits_total = hits; c->edge_overflow = fr[2 * total_frames]; c->sumP = sp;
+  c->hits_total = hits; c->edge_overflow = edge; c->sumP = sp;
   return GCB_OK;
 }

@@ -20,12 +20,21 @@ double seq_add_f64(double v, double w, uint64_t n);
 
 }  // namespace gcb
 
-// the collective operations gcb_counter_allreduce needs; bound to NCCL in nccl_reduce.cpp
+// The collective operations gcb_counter_allreduce needs, stream-ordered like NCCL's (dtype: ncclUint32 = 3,
+// ncclUint64 = 5, ncclFloat32 = 7).  Bound to NCCL in nccl_reduce.cpp (one process per GPU) and to the in-process
+// transport of local_reduce.cu (one host thread per counter, any devices).
 struct gcb_reduce_ops {
   int (*allreduce)(const void *send, void *recv, size_t count, int nccl_dtype, void *comm, void *stream);
+  int (*allgather)(const void *send, void *recv, size_t count_per_rank, int nccl_dtype, void *comm, void *stream);
   int (*group_start)(void);
   int (*group_end)(void);
+  void (*destroy)(void *comm);
 };
+// binning.cu: selects the counter's device (comm == NULL) / attaches a communicator, its operations and control plane
+extern "C" int gcb_counter_comm_attach_(gcb_counter *c, void *comm, const gcb_reduce_ops *ops, int rank, int nranks, gcb_ctl *ctl);
+
+// host control plane between the ranks of one node (shm_ctl.cpp); declared in gridcount_b200.h
+#define GCB_CTL_WORDS 8
 
 #define GCB_CUDA(call)                                                                          \
   do {                                                                                          \

@@ -4,6 +4,7 @@
 #include "gcb_internal.h"
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <cstdlib>
 
 // minimal NCCL declarations (stable C ABI of libnccl.so.2)
 typedef struct ncclComm *ncclComm_t;
@@ -20,6 +21,7 @@ struct Nccl {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -39,10 +41,11 @@ int load_nccl()
   g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(g_nccl.lib, "ncclAllGather");
   g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(g_nccl.lib, "ncclGroupStart");
   g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(g_nccl.lib, "ncclGroupEnd");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.GroupStart || !g_nccl.GroupEnd)
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.GroupStart || !g_nccl.GroupEnd)
     return gcb::fail(GCB_ERR_NCCL, "libnccl.so.2 lacks the expected symbols");
   return GCB_OK;
 }
@@ -55,18 +58,27 @@ int load_nccl()
       return gcb::fail(GCB_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
   } while (0)
 
-// implemented in binning.cu (they need the counter's internals)
-extern "C" int gcb_counter_comm_attach_(gcb_counter *c, void *comm, int rank, int nranks);
-extern "C" int gcb_counter_allreduce_impl_(gcb_counter *c, const gcb_reduce_ops *ops);
-
 static int do_allreduce(const void *send, void *recv, size_t count, int dtype, void *comm, void *stream)
 {
   GCB_NCCL(g_nccl.AllReduce(send, recv, count, (ncclDataType_t)dtype, ncclSum, (ncclComm_t)comm, (cudaStream_t)stream));
   return GCB_OK;
 }
 
+static int do_allgather(const void *send, void *recv, size_t count_per_rank, int dtype, void *comm, void *stream)
+{
+  GCB_NCCL(g_nccl.AllGather(send, recv, count_per_rank, (ncclDataType_t)dtype, (ncclComm_t)comm, (cudaStream_t)stream));
+  return GCB_OK;
+}
+
+// called by the counter's destructor
+static void do_destroy(void *comm)
+{
+  if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)comm);
+}
+
 static int do_group_start() { GCB_NCCL(g_nccl.GroupStart()); return GCB_OK; }
 static int do_group_end() { GCB_NCCL(g_nccl.GroupEnd()); return GCB_OK; }
+static const gcb_reduce_ops nccl_ops = {do_allreduce, do_allgather, do_group_start, do_group_end, do_destroy};
 
 extern "C" {
 
@@ -85,20 +97,25 @@ int gcb_counter_comm_init(gcb_counter *c, const char id[128], int rank, int nran
   if (!c || !id || rank < 0 || rank >= nranks) return gcb::fail(GCB_ERR_ARG, "gcb_counter_comm_init: bad argument");
   int rc = load_nccl();
   if (rc) return rc;
-  rc = gcb_counter_comm_attach_(c, nullptr, rank, nranks);   // selects the device
+  rc = gcb_counter_comm_attach_(c, nullptr, nullptr, rank, nranks, nullptr);   // selects the device
   if (rc) return rc;
   ncclUniqueId uid;
   memcpy(uid.internal, id, 128);
   ncclComm_t comm;
   GCB_NCCL(g_nccl.CommInitRank(&comm, nranks, uid, rank));
-  return gcb_counter_comm_attach_(c, comm, rank, nranks);
-}
-
-int gcb_counter_allreduce(gcb_counter *c)
-{
-  if (!c) return gcb::fail(GCB_ERR_ARG, "null counter");
-  static const gcb_reduce_ops ops = {do_allreduce, do_group_start, do_group_end};
-  return gcb_counter_allreduce_impl_(c, &ops);
+  // control plane: a shared-memory all-gather between the ranks of this node (shm_ctl.cpp).  The communicator is up,
+  // so every rank is alive; ranks that cannot attach within the timeout (other nodes) leave every rank without it,
+  // and the rank table then travels over NCCL as a small all-reduce.
+  gcb_ctl *ctl = nullptr;
+  if (!getenv("GCB_NO_SHM_CTL") && nranks > 1) {
+    if (gcb_ctl_open(&ctl, id, rank, nranks, GCB_CTL_WORDS, 20000) == GCB_OK) {
+      uint64_t mine[GCB_CTL_WORDS] = {1}, all[GCB_CTL_WORDS * 64];
+      if (nranks > 64 || gcb_ctl_allgather(ctl, mine, all, 20000) != GCB_OK) { gcb_ctl_close(ctl); ctl = nullptr; }
+    } else {
+      ctl = nullptr;
+    }
+  }
+  return gcb_counter_comm_attach_(c, comm, &nccl_ops, rank, nranks, ctl);
 }
 
 }  // extern "C"

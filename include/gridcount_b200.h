@@ -132,7 +132,11 @@ int gcb_counter_reset(gcb_counter *c);
 /* Host frames x[nframes][natoms][3]; weight[f] is the reference's per-frame
  * `weight` (NULL: 1); box[f][9] is only read with GCB_PBC_RECT.  Frames are
  * staged through pinned buffers in batches on CUDA streams and binned
- * asynchronously; the call returns when all of x has been consumed. */
+ * asynchronously; the call returns when all of x has been consumed: pageable x has been copied to the staging
+ * buffers, pinned x (which is DMA-ed in place) has been read by the last copy, so the caller may refill x at once.
+ * Frames whose weight differs from frame to frame in short runs are accumulated with global f32 atomics
+ * (RED.ADD.F32), which flush subnormal sums to zero whatever -ftz says; weights are time steps, many orders of
+ * magnitude above 1e-38, so this never shows. */
 int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes,
                            const float *weight, const float *box);
 /* Same for frames already resident in device memory (16-byte aligned). */
@@ -175,6 +179,11 @@ int gcb_counter_timer_stop(gcb_counter *c, float *ms);
  * atom-frames those launches covered (everything but the sub-tile tails).  Measurement aid: bench.py's roofline. */
 int gcb_counter_profile(gcb_counter *c, int enable);
 int gcb_counter_profile_read(gcb_counter *c, double *k1_ms, long *k1_launches, double *k1_atom_frames);
+/* The same split by what the launch was: [0] the direct uint32 kernel, [1] the packed-counter pass of a round,
+ * [2] the guarded uint32 pass behind it (returns at once unless the round failed verification or was skipped),
+ * [3] everything else K1 queued for those frames (verify/apply passes, gather tails). */
+enum { GCB_PROF_DIRECT = 0, GCB_PROF_PACKED = 1, GCB_PROF_REDO = 2, GCB_PROF_OTHER = 3, GCB_PROF_KINDS = 4 };
+int gcb_counter_profile_kinds(gcb_counter *c, double ms[GCB_PROF_KINDS], long launches[GCB_PROF_KINDS], double atom_frames[GCB_PROF_KINDS]);
 
 /* Frame-sharded multi-GPU: one counter per rank; integer sum of the private
  * grids and of the statistics over NCCL (the reference's manual equivalent is
@@ -187,6 +196,27 @@ int gcb_counter_profile_read(gcb_counter *c, double *k1_ms, long *k1_launches, d
 int gcb_nccl_unique_id(char id_out[128]);
 int gcb_counter_comm_init(gcb_counter *c, const char id[128], int rank, int nranks);
 int gcb_counter_allreduce(gcb_counter *c);
+/* With frame weights that differ between frames the reduce adds the ranks' f32 accumulators (ncclSum), which is
+ * not the reference's frame-ordered `grid += weight` chain (g_ri3Dc.c:149,413-416): occupancy and density then
+ * agree with a single-process run to f32 accumulation error (the order of an f32 sum), not bit for bit; counts,
+ * per-frame hits and sumP stay exact.  One weight for the whole job (constant dt) is exact for any rank count.
+ *
+ * The control plane under gcb_counter_comm_init: what the ranks must agree on before the grid reduce (one weight
+ * or not, frame counts, saturation bounds) is host-side knowledge and is exchanged through a shared-memory
+ * all-gather between the ranks of one node, not through a second NCCL collective.  Exposed for tests: */
+typedef struct gcb_ctl gcb_ctl;
+int gcb_ctl_open(gcb_ctl **out, const char id[128], int rank, int nranks, int words, int timeout_ms);
+int gcb_ctl_allgather(gcb_ctl *h, const uint64_t *mine /* [words] */, uint64_t *all /* [nranks][words] */, int timeout_ms);
+void gcb_ctl_close(gcb_ctl *h);
+/* The same reduce between counters of ONE process (one host thread per counter, on one GPU or several): an
+ * in-process transport behind the same protocol, for host programs that drive their GPUs from threads and for
+ * exercising the frame-sharded path on a single-GPU box (NCCL refuses two ranks on one device).
+ * gcb_counter_comm_init_local is called once per rank from `nranks` threads at the same time, gcb_counter_allreduce
+ * likewise; gcb_local_comm_destroy after the counters are destroyed. */
+typedef struct gcb_local_comm gcb_local_comm;
+int gcb_local_comm_create(gcb_local_comm **out, int nranks);
+int gcb_counter_comm_init_local(gcb_counter *c, gcb_local_comm *lc, int rank);
+void gcb_local_comm_destroy(gcb_local_comm *lc);
 
 /* ------------------------------------------------------------------------
  * XTC trajectories decoded on the GPU.  Replaces, for .xtc input, the frames that

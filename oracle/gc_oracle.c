@@ -181,6 +181,25 @@ void gco_bin_frames(const gco_geom *g, float *grid, const float *x, long nframes
   if (edge_overflow) *edge_overflow += ovf;
 }
 
+/* The same accumulation with `real = double` (a Gromacs -DDOUBLE build of g_ri3Dc.c:149: `grid[i][j][k] += dt`
+ * in f64; bins from the same f32 coordinates).  The f32 chain above carries its own summation error (SURVEY.md
+ * section 0: 1.5e-4 after 15 625 additions of 0.1); this is the value that error is measured against, and the
+ * yardstick for results whose f32 additions happen in another order (several ranks with differing weights). */
+void gco_bin_frames_f64(const gco_geom *g, double *grid, const float *x, long nframes,
+                        int natoms, const int *gindex, int gnx, const float *weight)
+{
+  long f;
+  int i;
+  for (f = 0; f < nframes; f++) {
+    const float *xf = x + (size_t)f * natoms * 3;
+    const double w = weight ? (double)weight[f] : 1.0;
+    for (i = 0; i < gnx; i++) {
+      long c = cell_of(g, xf + 3 * (size_t)gindex[i]);
+      if (c >= 0) grid[c] += w;
+    }
+  }
+}
+
 void gco_count_frames(const gco_geom *g, uint32_t *counts, const float *x, long nframes,
                       int natoms, const int *gindex, int gnx,
                       uint64_t *hits_per_frame, uint64_t *edge_overflow)

@@ -58,6 +58,9 @@ void gco_frame_weights(const float *t, long nframes, int dtweight,
 void gco_bin_frames(const gco_geom *g, float *grid, const float *x, long nframes,
                     int natoms, const int *gindex, int gnx, const float *weight,
                     double *sumP, uint64_t *hits_per_frame, uint64_t *edge_overflow);
+/* the same with `real = double` (a -DDOUBLE build): f64 accumulation, the yardstick for f32 summation error */
+void gco_bin_frames_f64(const gco_geom *g, double *grid, const float *x, long nframes,
+                        int natoms, const int *gindex, int gnx, const float *weight);
 /* integer hit counts (what the CUDA path accumulates) */
 void gco_count_frames(const gco_geom *g, uint32_t *counts, const float *x, long nframes,
                       int natoms, const int *gindex, int gnx,

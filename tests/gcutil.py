@@ -92,6 +92,7 @@ def oracle():
     L.gco_frame_weights.argtypes = [c_float_p, C.c_long, C.c_int, c_float_p, c_double_p]
     L.gco_bin_frames.argtypes = [C.POINTER(Geom), c_float_p, c_float_p, C.c_long, C.c_int, c_int_p, C.c_int,
                                  c_float_p, c_double_p, c_u64_p, c_u64_p]
+    L.gco_bin_frames_f64.argtypes = [C.POINTER(Geom), c_double_p, c_float_p, C.c_long, C.c_int, c_int_p, C.c_int, c_float_p]
     L.gco_count_frames.argtypes = [C.POINTER(Geom), c_u32_p, c_float_p, C.c_long, C.c_int, c_int_p, C.c_int,
                                    c_u64_p, c_u64_p]
     L.gco_wrap_frames.argtypes = [c_float_p, C.c_long, C.c_int, c_float_p]

@@ -441,6 +441,7 @@ def test_named_large_shapes_with_the_kernel_auto_picks(name):
     total = want
     for rep in range(16):                              # enough calls for the back-off to reach the host-side pause
         ctr.add_device_frames(dev)
+        ctr.sync()                                     # (the host learns of the back-off from a mirror copied behind each call)
     w2, h2, _ = oracle_counts(geom, dev.download(), gindex)
     total = total + 16 * w2
     np.testing.assert_array_equal(ctr.counts(), total)

@@ -11,6 +11,6 @@ for spec in "$@"; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -fmad=false -prec-div=true \
     -prec-sqrt=true -ftz=false -Xcompiler -fPIC,-ffp-contract=off -I../../include $flags -c binning.cu -o /tmp/binning_$tag.o
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants/libgcb_$tag.so \
-    host_geometry.o grid_io.o /tmp/binning_$tag.o analysis.o xtc_decode.o nccl_reduce.o selftest.o -ldl
+    host_geometry.o grid_io.o /tmp/binning_$tag.o analysis.o xtc_decode.o nccl_reduce.o selftest.o shm_ctl.o local_reduce.o -ldl -lrt
   echo "built variants/libgcb_$tag.so  [$flags]"
 done
