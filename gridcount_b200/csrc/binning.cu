@@ -15,6 +15,7 @@
 //   acc      f32 same shape, only materialised when frame weights change
 //   gindex   i32 sorted copy of the index group, rank[] = prefix count per atom
 #include "gcb_internal.h"
+#include "xtc_device.cuh"
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
@@ -129,6 +130,77 @@ bin_gather_kernel(const float *__restrict__ x, int natoms, const int *__restrict
       count_hits(hits, cell >= 0, f);
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// K1x  XTC frames binned straight out of the segment decoder (xtc_device.cuh): one thread per (frame, 256-atom
+// segment) decodes its atoms and bins the selected ones at once -- the reference's read_next_x + gridcount() for
+// .xtc input (g_ri3Dc.c:425-428) without the decoded coordinates ever being stored.  Same f32 products as the
+// decoder that writes x, same exact conversion as the gather kernel, so counts equal the two-step path bit for bit.
+// Selection: arithmetic for groups g0 + i*step; otherwise the multiplicity rank[atom + 1] - rank[atom].
+// ---------------------------------------------------------------------------
+template <bool PBC, bool AP>
+struct XtcBinEmit {
+  const GridParams &P;
+  uint32_t *__restrict__ counts;
+  const unsigned *__restrict__ rank;
+  unsigned long long *__restrict__ diag;
+  int next_sel, step, sel_end;       // AP: the next selected atom, the group's stride, one past its last atom
+  float L0, L1, L2;                  // PBC: this frame's box
+  unsigned nh;
+  __device__ __forceinline__ void operator()(int atom, float x, float y, float z)
+  {
+    unsigned mult = 1u;
+    if (AP) {
+      if (atom != next_sel) return;
+      next_sel += step;
+      if (next_sel >= sel_end) next_sel = 0x7fffffff;
+    } else {
+      mult = __ldg(rank + atom + 1) - __ldg(rank + atom);
+      if (!mult) return;
+    }
+    if (PBC) { x = wrap1(x, L0); y = wrap1(y, L1); z = wrap1(z, L2); }
+    const int cell = cell_of(P, x, y, z);
+    if (cell >= 0) { atomicAdd(counts + cell, mult); nh += mult; }
+    else if (cell == -2) atomicAdd(diag, (unsigned long long)mult);
+  }
+};
+
+template <bool PBC, bool AP>
+__global__ void __launch_bounds__(128)
+xtc_bin_kernel(const uint8_t *__restrict__ buf, const xtcdev::FrameDev *__restrict__ meta, long nframes, int natoms,
+               const xtcdev::Checkpoint *__restrict__ ckpt, const int *__restrict__ nseg, const int *__restrict__ status,
+               GridParams P, uint32_t *__restrict__ counts, int g0, int step, int gnx, const unsigned *__restrict__ rank,
+               const float *__restrict__ box3, unsigned long long *__restrict__ hits, unsigned long long *__restrict__ diag)
+{
+  const int msegs = xtcdev::max_segments(natoms);
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long f = t / msegs;
+  const int sg = (int)(t - f * msegs);
+  if (f >= nframes || status[f] != 0 || sg >= nseg[f]) return;      // (a damaged frame bins nothing: the call fails)
+  const xtcdev::FrameDev m = meta[f];
+  XtcBinEmit<PBC, AP> emit{P, counts, rank, diag, 0x7fffffff, step, g0 + gnx * step, 0.f, 0.f, 0.f, 0u};
+  if (PBC) { emit.L0 = __ldg(box3 + 3 * f); emit.L1 = __ldg(box3 + 3 * f + 1); emit.L2 = __ldg(box3 + 3 * f + 2); }
+  int a0 = 0, a1 = natoms;
+  xtcdev::Checkpoint cp{0u, 0u, 0, 0};
+  if (natoms > 9) {
+    cp = ckpt[(size_t)f * msegs + sg];
+    a0 = (int)cp.atom;
+    a1 = sg + 1 < nseg[f] ? (int)ckpt[(size_t)f * msegs + sg + 1].atom : natoms;
+  }
+  if (AP) {
+    const int k = a0 <= g0 ? 0 : (a0 - g0 + step - 1) / step;
+    if (k < gnx) emit.next_sel = g0 + k * step;
+  }
+  if (natoms <= 9) {                 // tiny frames are stored as plain big-endian floats
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(buf + m.offset);
+    for (int i = 0; i < natoms; i++)
+      emit(i, __uint_as_float(__byte_perm(__ldg(w + 3 * i), 0, 0x0123)), __uint_as_float(__byte_perm(__ldg(w + 3 * i + 1), 0, 0x0123)),
+           __uint_as_float(__byte_perm(__ldg(w + 3 * i + 2), 0, 0x0123)));
+  } else {
+    xtcdev::decode_segment(buf, m, cp, a1, emit);
+  }
+  if (emit.nh) atomicAdd(hits + f, (unsigned long long)emit.nh);
 }
 
 // ---------------------------------------------------------------------------
@@ -808,6 +880,8 @@ struct DevHits {                      // hit counters of an add_device_frames ca
 
 }  // namespace
 
+constexpr int GCB_XTC_SETS = 6;
+
 struct gcb_counter {
   gcb_tgrid tg{};
   GridParams P{};
@@ -830,15 +904,15 @@ struct gcb_counter {
   uint64_t packed_rounds = 0, packed_redone = 0;
   bool l2_window = false;             // persisting-L2 window over d_pk set on the compute stream
   bool saturated = false;             // some cell was clamped (diag[3])
-  // xtc path: two sets of {compressed bytes, frame table, status, decoded frames}, copy stream + events
+  // xtc path: GCB_XTC_SETS sets of {compressed bytes, frame table, status, decoded frames}, copy stream + events
   struct XtcSet {
     uint8_t *d_buf = nullptr; size_t buf_cap = 0;
     void *d_meta = nullptr, *h_meta = nullptr, *d_work = nullptr; int *d_status = nullptr, *h_status = nullptr; long frames_cap = 0;
     float *d_x = nullptr; size_t x_cap = 0;
-    cudaEvent_t copied = nullptr, consumed = nullptr;
+    cudaStream_t stream = nullptr;                      // H2D of the compressed bytes + frame table + skim
+    cudaEvent_t skimmed = nullptr, consumed = nullptr;  // skim done (set stream) / segment kernels done (compute stream)
     long nframes = 0; long first = 0;
-  } xtc[2];
-  cudaStream_t xtc_copy = nullptr;
+  } xtc[GCB_XTC_SETS];
   // multi-GPU statistics scratch
   unsigned long long *d_scr = nullptr, *h_scr = nullptr;
   size_t scr_words = 0;
@@ -1312,10 +1386,10 @@ void free_counter(gcb_counter *c)
   cudaFree(c->d_pk); cudaFree(c->d_pstate); cudaFreeHost(c->h_pstate);
   for (auto &x : c->xtc) {
     cudaFree(x.d_buf); cudaFree(x.d_meta); cudaFree(x.d_status); cudaFree(x.d_x); cudaFree(x.d_work); cudaFreeHost(x.h_meta); cudaFreeHost(x.h_status);
-    if (x.copied) cudaEventDestroy(x.copied);
+    if (x.skimmed) cudaEventDestroy(x.skimmed);
     if (x.consumed) cudaEventDestroy(x.consumed);
+    if (x.stream) { cudaStreamSynchronize(x.stream); cudaStreamDestroy(x.stream); }
   }
-  if (c->xtc_copy) cudaStreamDestroy(c->xtc_copy);
   cudaFree(c->d_scr); cudaFreeHost(c->h_scr);
   for (auto e : c->events) if (e) cudaEventDestroy(e);
   for (auto e : c->prof_ev) if (e) cudaEventDestroy(e);
@@ -1540,13 +1614,10 @@ int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes, const f
   return GCB_OK;
 }
 
-int gcb_counter_add_device_frames(gcb_counter *c, const float *x_dev, long nframes, const float *weight,
-                                  const float *box)
+// per-frame hit counters (and boxes) of a batch of device-resident frames: carved out of the hit arenas, zeroed on
+// the compute stream, registered for collection
+static int reserve_devhits(gcb_counter *c, long nframes, const float *box, DevHits *out)
 {
-  if (!c || (!x_dev && nframes > 0) || nframes < 0)
-    return gcb::fail(GCB_ERR_ARG, "gcb_counter_add_device_frames: bad argument");
-  if (nframes == 0) return GCB_OK;
-  GCB_CUDA(cudaSetDevice(c->opts.device));
   DevHits h;
   h.n = nframes;
   {
@@ -1571,16 +1642,84 @@ int gcb_counter_add_device_frames(gcb_counter *c, const float *x_dev, long nfram
   h.frame0 = c->hits_per_frame.size();
   c->hits_per_frame.resize(h.frame0 + (size_t)nframes, 0);
   c->devhits.push_back(h);
-  int rc = bin_device_batch(c, x_dev, nframes, weight, h.d_box3, h.d);
+  *out = h;
+  return GCB_OK;
+}
+
+int gcb_counter_add_device_frames(gcb_counter *c, const float *x_dev, long nframes, const float *weight,
+                                  const float *box)
+{
+  if (!c || (!x_dev && nframes > 0) || nframes < 0)
+    return gcb::fail(GCB_ERR_ARG, "gcb_counter_add_device_frames: bad argument");
+  if (nframes == 0) return GCB_OK;
+  GCB_CUDA(cudaSetDevice(c->opts.device));
+  DevHits h;
+  int rc = reserve_devhits(c, nframes, box, &h);
+  if (rc) return rc;
+  rc = bin_device_batch(c, x_dev, nframes, weight, h.d_box3, h.d);
   if (rc) return rc;
   for (long f = 0; f < nframes; f++) c->weight_per_frame.push_back(weight ? weight[f] : 1.0f);
   return GCB_OK;
 }
 
-extern "C" int gcb_xtc_decode_on_stream_(const uint8_t *buf_dev, const gcb_xtc_frame *frames, long nframes, int natoms,
-                                         float *x_dev, void *meta_dev, int *status_dev, void *stream, void *meta_host_pinned, void *work_dev);
+extern "C" int gcb_xtc_skim_on_stream_(const uint8_t *buf_dev, const gcb_xtc_frame *frames, long nframes, int natoms, void *meta_dev,
+                                       int *status_dev, void *stream, void *meta_host_pinned, void *work_dev);
+extern "C" int gcb_xtc_segments_on_stream_(const uint8_t *buf_dev, long nframes, int natoms, float *x_dev, const void *meta_dev,
+                                           int *status_dev, void *stream, const void *work_dev);
 extern "C" size_t gcb_xtc_work_bytes_(long nframes, int natoms);
 extern "C" size_t gcb_xtc_meta_bytes_(long nframes);
+
+// A batch of xtc frames can be binned straight out of the decoder (xtc_bin_kernel) when it is one run of integer
+// counts: one weight for the whole batch that continues the current run (or starts one under the rules of
+// bin_device_batch), the uint32 grid as the target (grids on the packed-counter path take the two-step route),
+// and not more frames than one launch may add to a cell.  Prepares the run exactly as bin_device_batch would.
+static bool xtc_batch_fusable(gcb_counter *c, long n, const float *w)
+{
+  const bool off = getenv("GCB_XTC_UNFUSED") != nullptr;
+  if (off || c->opts.kernel != GCB_KERNEL_AUTO) return false;
+  if (c->packed_bits != 0 && c->packed_auto) return false;
+  const float wr = w ? w[0] : 1.0f;
+  for (long f = 1; f < n; f++) if (!same_bits(w ? w[f] : 1.0f, wr)) return false;
+  const long max_frames = (long)std::max<unsigned long long>(1, (c->clamp_ceiling / 4) / (unsigned long long)std::max(c->gnx, 1));
+  if (n > max_frames) return false;
+  const bool continues = c->have_run && same_bits(wr, c->w_cur);
+  const bool fresh = !c->have_run && !c->acc_used;
+  const bool long_run = (double)n * c->gnx >= (double)c->ncells / 8.0;
+  return continues || fresh || long_run;
+}
+
+static int xtc_bin_batch(gcb_counter *c, const uint8_t *d_buf, const void *d_meta, const void *d_work, const int *d_status,
+                         long n, const float *w, const float *d_box3, unsigned long long *d_hits)
+{
+  const float wr = w ? w[0] : 1.0f;
+  const unsigned long long units = (unsigned long long)n * (unsigned long long)c->gnx;
+  if (!c->any) { c->any = true; c->w_first = wr; }
+  else if (!same_bits(wr, c->w_first)) c->uniform = false;
+  int rc;
+  if (c->have_run && !same_bits(wr, c->w_cur)) { rc = fold_pending(c); if (rc) return rc; }
+  c->have_run = true;
+  c->w_cur = wr;
+  rc = ensure_headroom(c, c->d_runcnt, c->bound_run, units);
+  if (rc) return rc;
+  c->bound_run += units;
+  const int *nseg = static_cast<const int *>(d_work);
+  const xtcdev::Checkpoint *ckpt = reinterpret_cast<const xtcdev::Checkpoint *>(static_cast<const char *>(d_work) + xtcdev::work_ckpt_offset(n));
+  const long long nthreads = (long long)n * xtcdev::max_segments(c->natoms);
+  const unsigned grid = (unsigned)((nthreads + 127) / 128);
+  const xtcdev::FrameDev *meta = static_cast<const xtcdev::FrameDev *>(d_meta);
+  const bool pbc = c->opts.pbc == GCB_PBC_RECT;
+  rc = prof_begin(c);
+  if (rc) return rc;
+#define GCB_XTC_BIN(PBC_, AP_)                                                                                              \
+  xtc_bin_kernel<PBC_, AP_><<<grid, 128, 0, c->compute>>>(d_buf, meta, n, c->natoms, ckpt, nseg, d_status, c->P, c->d_runcnt, \
+                                                          c->ap.g0, c->ap.step, c->gnx, c->d_rank, d_box3, d_hits, c->d_diag)
+  if (c->ap_ok) { if (pbc) GCB_XTC_BIN(true, true); else GCB_XTC_BIN(false, true); }
+  else          { if (pbc) GCB_XTC_BIN(true, false); else GCB_XTC_BIN(false, false); }
+#undef GCB_XTC_BIN
+  c->launches++;
+  GCB_CUDA(cudaGetLastError());
+  return prof_end(c, GCB_PROF_OTHER, (double)units);
+}
 
 int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gcb_xtc_frame *frames, long nframes,
                         const float *weight)
@@ -1588,18 +1727,32 @@ int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gc
   if (!c || !buf || !frames || nframes < 0) return gcb::fail(GCB_ERR_ARG, "gcb_counter_add_xtc: bad argument");
   if (nframes == 0) return GCB_OK;
   GCB_CUDA(cudaSetDevice(c->opts.device));
-  if (!c->xtc_copy) {
-    GCB_CUDA(cudaStreamCreateWithFlags(&c->xtc_copy, cudaStreamNonBlocking));
+  if (!c->xtc[0].stream) {
     for (auto &x : c->xtc) {
-      GCB_CUDA(cudaEventCreateWithFlags(&x.copied, cudaEventDisableTiming));
+      GCB_CUDA(cudaStreamCreateWithFlags(&x.stream, cudaStreamNonBlocking));
+      GCB_CUDA(cudaEventCreateWithFlags(&x.skimmed, cudaEventDisableTiming));
       GCB_CUDA(cudaEventCreateWithFlags(&x.consumed, cudaEventDisableTiming));
     }
   }
+  static const bool trace = getenv("GCB_TRACE") != nullptr;
+  auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+  const double t_begin = now();
   const size_t frame_bytes = (size_t)c->natoms * 12;
-  // frames per batch: hundreds to thousands (one warp per frame walks the stream); decoded frames <= 4 GiB per set
+  // The pipeline.  A batch goes through: H2D of its compressed bytes -> skim -> segment kernel(s).  The skim walks
+  // each frame's control bits as one chain of dependent steps: ~2 ms for a 60 000-atom frame whether the batch has 64
+  // frames or 1024.  So every batch has its own set of buffers and its own stream for copy + skim (GCB_XTC_SETS of them
+  // in flight: the skims of several batches overlap each other and the copies), and only the segment kernels, which
+  // are short and wide, queue on the compute stream.  Batches of ~64 MB of compressed bytes (1.2 ms of PCIe), at
+  // least 16 frames, decoded frames <= 1 GiB per set.
   const char *env = getenv("GCB_XTC_BATCH");
-  long per = env ? atol(env) : (long)std::min<size_t>(16384, std::max<size_t>(64, ((size_t)4 << 30) / frame_bytes));
-  if (!env) per = std::min(per, std::max<long>(512, (nframes + 3) / 4));   // a few batches, so that copies overlap decoding
+  long per;
+  if (env) per = atol(env);
+  else {
+    const double bytes_per_frame = (double)(frames[nframes - 1].payload_offset + frames[nframes - 1].payload_bytes - frames[0].payload_offset) / (double)nframes;
+    per = (long)(((size_t)64 << 20) / std::max(bytes_per_frame, 1.0));
+    per = std::max<long>(16, std::min<long>(per, 16384));
+    per = std::min<long>(per, (long)std::max<size_t>(4, ((size_t)1 << 30) / frame_bytes));
+  }
   per = std::max<long>(4, per & ~3L);                         // batches start 16-byte aligned in the decoded array
   std::vector<float> box3;
   int set = 0;
@@ -1607,11 +1760,16 @@ int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gc
     if (x.nframes == 0) return GCB_OK;
     GCB_CUDA(cudaEventSynchronize(x.consumed));
     for (long f = 0; f < x.nframes; f++)
-      if (x.h_status[f]) { x.nframes = 0; return gcb::fail(GCB_ERR_FORMAT, "xtc frame %ld: damaged compressed stream", x.first + f); }
+      if (x.h_status[f]) {
+        x.nframes = 0;
+        return gcb::fail(GCB_ERR_FORMAT, "xtc frame %ld: damaged compressed stream (frames of its batch that were decoded before the "
+                                         "damage may have been binned: reset the counter)", x.first + f);
+      }
     x.nframes = 0;
     return GCB_OK;
   };
-  for (long f0 = 0; f0 < nframes; f0 += per, set ^= 1) {
+  long nfused = 0;
+  for (long f0 = 0; f0 < nframes; f0 += per, set = (set + 1) % GCB_XTC_SETS) {
     const long n = std::min(per, nframes - f0);
     gcb_counter::XtcSet &x = c->xtc[set];
     int rc = check_set(x);
@@ -1625,6 +1783,8 @@ int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gc
       lo = std::min(lo, b); hi = std::max(hi, b + nb);
     }
     lo &= ~(size_t)3;
+    const float *wb = weight ? weight + f0 : nullptr;
+    const bool fused = xtc_batch_fusable(c, n, wb);
     if (hi - lo + 16 > x.buf_cap) { cudaFree(x.d_buf); x.d_buf = nullptr; x.buf_cap = (hi - lo) + (hi - lo) / 8 + 16; GCB_CUDA(cudaMalloc(&x.d_buf, x.buf_cap)); }
     if (n > x.frames_cap) {
       cudaFree(x.d_meta); cudaFree(x.d_status); cudaFree(x.d_work); cudaFreeHost(x.h_meta); cudaFreeHost(x.h_status);
@@ -1636,29 +1796,48 @@ int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gc
       GCB_CUDA(cudaHostAlloc(&x.h_meta, gcb_xtc_meta_bytes_(n), cudaHostAllocDefault));
       GCB_CUDA(cudaHostAlloc((void **)&x.h_status, sizeof(int) * (size_t)n, cudaHostAllocDefault));
     }
-    if ((size_t)n * frame_bytes + 16 > x.x_cap) { cudaFree(x.d_x); x.d_x = nullptr; x.x_cap = (size_t)n * frame_bytes + 16; GCB_CUDA(cudaMalloc(&x.d_x, x.x_cap)); }
-    // compressed bytes on the copy stream, everything else on the compute stream
-    GCB_CUDA(cudaMemcpyAsync(x.d_buf, buf + lo, hi - lo, cudaMemcpyHostToDevice, c->xtc_copy));
-    GCB_CUDA(cudaEventRecord(x.copied, c->xtc_copy));
-    GCB_CUDA(cudaStreamWaitEvent(c->compute, x.copied, 0));
+    if (!fused && (size_t)n * frame_bytes + 16 > x.x_cap) { cudaFree(x.d_x); x.d_x = nullptr; x.x_cap = (size_t)n * frame_bytes + 16; GCB_CUDA(cudaMalloc(&x.d_x, x.x_cap)); }
+    // compressed bytes, frame table and skim on the set's stream; the segment kernels on the compute stream
+    GCB_CUDA(cudaMemcpyAsync(x.d_buf, buf + lo, hi - lo, cudaMemcpyHostToDevice, x.stream));
     std::vector<gcb_xtc_frame> rel(frames + f0, frames + f0 + n);
     for (auto &r : rel) r.payload_offset -= lo;
-    rc = gcb_xtc_decode_on_stream_(x.d_buf, rel.data(), n, c->natoms, x.d_x, x.d_meta, x.d_status, c->compute, x.h_meta, x.d_work);
-    if (rc) return rc;
-    GCB_CUDA(cudaMemcpyAsync(x.h_status, x.d_status, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->compute));
     const float *boxarg = nullptr;
     if (c->opts.pbc == GCB_PBC_RECT) {
       box3.resize((size_t)n * 9);
       for (long f = 0; f < n; f++) memcpy(&box3[(size_t)f * 9], frames[f0 + f].box, sizeof(float) * 9);
       boxarg = box3.data();
     }
-    rc = gcb_counter_add_device_frames(c, x.d_x, n, weight ? weight + f0 : nullptr, boxarg);
+    rc = gcb_xtc_skim_on_stream_(x.d_buf, rel.data(), n, c->natoms, x.d_meta, x.d_status, x.stream, x.h_meta, x.d_work);
     if (rc) return rc;
+    GCB_CUDA(cudaEventRecord(x.skimmed, x.stream));
+    GCB_CUDA(cudaStreamWaitEvent(c->compute, x.skimmed, 0));
+    if (!fused) {
+      rc = gcb_xtc_segments_on_stream_(x.d_buf, n, c->natoms, x.d_x, x.d_meta, x.d_status, c->compute, x.d_work);
+      if (rc) return rc;
+    }
+    GCB_CUDA(cudaMemcpyAsync(x.h_status, x.d_status, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->compute));
+    if (fused) {
+      DevHits h;
+      rc = reserve_devhits(c, n, boxarg, &h);
+      if (rc) return rc;
+      rc = xtc_bin_batch(c, x.d_buf, x.d_meta, x.d_work, x.d_status, n, wb, h.d_box3, h.d);
+      if (rc) return rc;
+      for (long f = 0; f < n; f++) c->weight_per_frame.push_back(wb ? wb[f] : 1.0f);
+      nfused += n;
+    } else {
+      rc = gcb_counter_add_device_frames(c, x.d_x, n, wb, boxarg);
+      if (rc) return rc;
+    }
+    // (the next copy into this set is queued only after the host has waited for this event in check_set: no wait on
+    // the copy stream here, it would hold back the copy of the NEXT batch, which goes into another set)
     GCB_CUDA(cudaEventRecord(x.consumed, c->compute));
-    GCB_CUDA(cudaStreamWaitEvent(c->xtc_copy, x.consumed, 0));      // the next copy into this set waits for its kernels
     x.nframes = n; x.first = f0;
   }
+  const double t_queued = now();
   for (auto &x : c->xtc) { int rc = check_set(x); if (rc) return rc; }
+  if (trace)
+    fprintf(stderr, "[gcb add_xtc] %ld frames in batches of %ld (%ld binned out of the decoder): queued after %.3f ms, done after %.3f ms\n",
+            nframes, per, nfused, t_queued - t_begin, now() - t_begin);
   return GCB_OK;
 }
 

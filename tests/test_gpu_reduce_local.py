@@ -145,7 +145,7 @@ def test_jittered_weights_across_ranks_stay_within_the_f32_summation_bound(world
     both are measured against the `real = double` accumulation: the multi-rank result must stay inside the standard
     bound of sequential f32 summation of n positive terms, (n - 1) * 2^-24 relative, and is reported next to the
     reference chain's own error."""
-    natoms, F = 6000, 1024                       # per rank; a coarse grid, so cells collect thousands of hits
+    natoms, F = 6000, 1536                       # per rank; a coarse grid, so cells collect thousands of hits
     Lc = (2.0, 2.0, 2.0)
     geom = g.setup_geometry(Lc, 0.25)            # 8 x 8 x 8 cells
     gindex = np.arange(0, natoms, 3, dtype=np.int32)

@@ -9,6 +9,7 @@ import pytest
 
 import gcutil as u
 import gridcount_b200 as g
+from gridcount_b200 import _cabi as K
 from test_host_tools_cpu import FrameInfo, water_like, HOST
 
 pytestmark = pytest.mark.gpu
@@ -132,3 +133,85 @@ def test_damaged_stream_is_reported(host):
     bad[2] ^= 0x40
     with pytest.raises(g._cabi.GcbError):
         g.XtcBuffer(bytes(bad))
+
+
+@pytest.mark.parametrize("case", ["stride3", "all", "indexed+duplicates", "pbc", "jittered weights", "tiny frames"])
+def test_binning_out_of_the_decoder_equals_the_two_step_path(host, case, monkeypatch):
+    """gcb_counter_add_xtc bins a batch straight out of the segment decoder (xtc_bin_kernel) when the batch is one run
+    of integer counts; otherwise, and with GCB_XTC_UNFUSED, it decodes to x[frame][atom][3] first and runs the
+    binning kernels.  Both must give the oracle's counts, per-frame hits, sumP and occupancy, bit for bit."""
+    L, natoms, nframes = (3.0, 3.0, 3.0), 2700, 70
+    if case == "tiny frames":
+        natoms = 9
+    rng = np.random.default_rng(11)
+    if case == "pbc":           # atoms outside the box on both sides: the single-image wrap of count.c:88-92 must act
+        x = (np.stack([water_like(natoms // 3, 3.0, rng) for _ in range(nframes)]) + rng.normal(0, 0.6, (nframes, 1, 3))).astype(np.float32)
+    elif case == "tiny frames":
+        x = (rng.random((nframes, natoms, 3)) * 3.0).astype(np.float32)
+    else:
+        x = np.stack([np.mod(water_like(natoms // 3, 3.0, rng), 3.0).astype(np.float32) for _ in range(nframes)])
+    t = (np.arange(nframes + 1, dtype=np.float64) * 0.1 + 100.0).astype(np.float32)[1:]
+    data = encode_traj(host, x, t)
+    xd = host_decode(host, data, natoms, nframes)
+    geom = g.setup_geometry(L, 0.05)
+    if case == "indexed+duplicates":
+        gindex = np.concatenate([rng.choice(natoms, 900, replace=False), [5, 5, 17]]).astype(np.int32)
+    elif case in ("all", "tiny frames"):
+        gindex = np.arange(natoms, dtype=np.int32)
+    else:
+        gindex = np.arange(0, natoms, 3, dtype=np.int32)
+    if case == "jittered weights":
+        w, T = g.frame_weights(t)              # dt in f32: several distinct weights
+        assert len(np.unique(w)) > 1
+    else:
+        w = np.full(nframes, 0.1, np.float32)
+    pbc = K.PBC_RECT if case == "pbc" else K.PBC_NONE
+    xo = xd.copy()
+    b9 = np.tile(u.box9(L), (nframes, 1)).astype(np.float32)
+    og = u.Geom.from_buffer_copy(bytes(geom.tg))
+    if case == "pbc":
+        u.oracle().gco_wrap_frames(u.fptr(xo), nframes, natoms, u.fptr(b9))
+    want = np.zeros(geom.shape, np.uint32)
+    hits = np.zeros(nframes, np.uint64)
+    u.oracle().gco_count_frames(C.byref(og), want.ctypes.data_as(u.c_u32_p), u.fptr(xo), nframes, natoms, u.iptr(gindex),
+                                len(gindex), hits.ctypes.data_as(u.c_u64_p), None)
+    occ = np.zeros(geom.shape, np.float32)
+    sp = C.c_double(0)
+    u.oracle().gco_bin_frames(C.byref(og), u.fptr(occ), u.fptr(xo), nframes, natoms, u.iptr(gindex), len(gindex), u.fptr(w),
+                              C.byref(sp), None, None)
+    assert int(hits.sum()) > 0
+    xb = g.XtcBuffer(data, pinned=True)
+    for unfused in (False, True):
+        for batch in ("12", None):
+            if unfused:
+                monkeypatch.setenv("GCB_XTC_UNFUSED", "1")
+            else:
+                monkeypatch.delenv("GCB_XTC_UNFUSED", raising=False)
+            if batch:
+                monkeypatch.setenv("GCB_XTC_BATCH", batch)
+            else:
+                monkeypatch.delenv("GCB_XTC_BATCH", raising=False)
+            ctr = g.GridCounter(geom, gindex, natoms, pbc=pbc)
+            ctr.add_xtc(xb, w)
+            np.testing.assert_array_equal(ctr.counts(), want)
+            np.testing.assert_array_equal(ctr.hits_per_frame(), hits)
+            st = ctr.stats()
+            assert st.hits == int(hits.sum()) and st.sumP == sp.value
+            np.testing.assert_array_equal(ctr.occupancy().view(np.uint32), occ.view(np.uint32))
+            ctr.close()
+    xb.free()
+
+
+def test_a_damaged_frame_fails_the_binning_call(host):
+    natoms, nframes = 600, 6
+    x = make_frames("water", natoms, nframes, 1)
+    data = bytearray(encode_traj(host, x, np.arange(nframes, dtype=np.float32)))
+    fr = g.XtcBuffer(bytes(data)).frames[3]
+    for k in range(fr.payload_offset, fr.payload_offset + 64):
+        data[k] = 0xFF
+    xb = g.XtcBuffer(bytes(data))
+    geom = g.setup_geometry((3.0, 3.0, 3.0), 0.1)
+    ctr = g.GridCounter(geom, np.arange(0, natoms, 3, dtype=np.int32), natoms)
+    with pytest.raises(g._cabi.GcbError, match="damaged"):
+        ctr.add_xtc(xb, np.ones(nframes, np.float32))
+    ctr.close()
