@@ -193,7 +193,10 @@ __global__ void an_rdf_kernel(const float *__restrict__ g, Dims d, const int *__
 // ---------------------------------------------------------------------------------------------------
 // One block per (slice k, chain): chain 0 = zdf, 1 = lzdf (and the count nocc), 2 = Rgyr2; raw sums go to
 // raw[chain][k], an_slice_finish_kernel turns them into the three profiles.
-constexpr int SLICE_THREADS = 256;
+#ifndef GCB_SLICE_THREADS
+#define GCB_SLICE_THREADS 256
+#endif
+constexpr int SLICE_THREADS = GCB_SLICE_THREADS;
 __global__ void __launch_bounds__(SLICE_THREADS)
 an_slice_scan_kernel(const float *__restrict__ gx, Dims d, const float *__restrict__ c2tab,
                      const unsigned char *__restrict__ flags, float min_occ, float *__restrict__ raw,
@@ -249,7 +252,10 @@ __global__ void an_slice_finish_kernel(const float *__restrict__ raw, int mz, Sl
 // One block per radial bin r: rdf[r][1] chains the occupied cells over k, then bin r's cells in (j,i)
 // order (a_ri3Dc.c:627-645); hrdf[r][1] is a chain of +1.0f over the other cells, i.e. min(count, 2^24).
 // bin_xy[] lists each bin's cells as j*mx + i.
-constexpr int RDF_THREADS = 1024;
+#ifndef GCB_RDF_THREADS
+#define GCB_RDF_THREADS 1024
+#endif
+constexpr int RDF_THREADS = GCB_RDF_THREADS;
 __global__ void __launch_bounds__(RDF_THREADS)
 an_rdf_scan_kernel(const float *__restrict__ gx, Dims d, const int *__restrict__ bin_start,
                    const int *__restrict__ bin_xy, float min_occ, float *__restrict__ rdf, float *__restrict__ hrdf,
@@ -288,7 +294,10 @@ an_rdf_scan_kernel(const float *__restrict__ gx, Dims d, const int *__restrict__
 // block 0: sumP += (double)g (a_ri3Dc.c:499-508) and the count behind sumH
 // block 1: average += g for cells with irad < iradNR (a_ri3Dc.c:633); masked cells add +0.0f,
 //          which leaves any partial sum that started at +0 unchanged bit for bit
-constexpr int SCAN_THREADS = 1024;
+#ifndef GCB_SCAN_THREADS
+#define GCB_SCAN_THREADS 1024
+#endif
+constexpr int SCAN_THREADS = GCB_SCAN_THREADS;
 constexpr int SCAN_T = 8;
 __global__ void __launch_bounds__(SCAN_THREADS)
 an_chain_scan_kernel(const float *__restrict__ gx, size_t ncells, int nxy, const unsigned char *__restrict__ flags,
@@ -482,17 +491,41 @@ struct DevBuf {
 };
 
 // all device buffers of one gcb_analyse call in a single allocation
-// Per device: one allocation of up to 64 MB and four streams are kept between calls (a C2-sized analysis is
-// 1 ms of kernels; cudaMalloc/cudaFree and stream creation cost as much again).  A second thread analysing on
-// the same device at the same time simply allocates its own.
+// Per device: one allocation (up to CACHE_MAX: a 500^3 grid with its x-fastest copy), four streams, pinned staging
+// buffers and the per-(i,j) tables of the last geometry are kept between calls: a C2-sized analysis is 1 ms of
+// kernels and a C3-sized one a few ms, while cudaMalloc/cudaFree of the grid copies, stream creation, rebuilding the
+// tables and pageable copies cost several times that.  gcb_analyse_release_cache() gives everything back.  A second
+// thread analysing on the same device at the same time simply allocates its own.
+struct TableKey {
+  int mx = 0, my = 0, mz = 0, iradNR = -1;
+  uint32_t radius_bits = 0, deltaR_bits = 0;
+  bool operator==(const TableKey &o) const
+  {
+    return mx == o.mx && my == o.my && mz == o.mz && iradNR == o.iradNR && radius_bits == o.radius_bits && deltaR_bits == o.deltaR_bits;
+  }
+};
 struct DeviceCache {
   std::mutex m;
   char *base = nullptr;
   size_t cap = 0;
   cudaStream_t st[4] = {nullptr, nullptr, nullptr, nullptr};
+  // tables of the last geometry: valid while `base` has not been reallocated (they sit at the front of the arena)
+  bool tables_valid = false;
+  TableKey key;
+  std::vector<int> bin_start;
+  std::vector<float> rweight;
+  // pinned staging: results on their way back, tables on their way up
+  char *h_stage = nullptr;
+  size_t h_stage_cap = 0;
+  // pinned chunks for the upload of a pageable host grid
+  static constexpr int NCHUNK = 16;
+  static constexpr size_t CHUNK = (size_t)16 << 20;
+  char *h_chunk[NCHUNK] = {nullptr};
+  cudaEvent_t chunk_done[NCHUNK] = {nullptr};
+  cudaStream_t chunk_st[NCHUNK] = {nullptr};
 };
 DeviceCache g_cache[64];
-constexpr size_t CACHE_MAX = (size_t)64 << 20;
+constexpr size_t CACHE_MAX = (size_t)1536 << 20;
 
 struct Arena {
   char *base = nullptr;
@@ -512,7 +545,7 @@ struct Arena {
       cache = &dc;
       if (dc.cap < total) {
         if (dc.base) cudaFree(dc.base);
-        dc.base = nullptr; dc.cap = 0;
+        dc.base = nullptr; dc.cap = 0; dc.tables_valid = false;
         e = cudaMalloc(&dc.base, total);
         if (e == cudaSuccess) dc.cap = total;
       }
@@ -546,6 +579,73 @@ struct Streams {
   }
   ~Streams() { if (owned) for (auto &s : st) if (s) cudaStreamDestroy(s); }
 };
+
+// pinned staging of at least `bytes` (cached), or NULL: the caller then uses pageable memory
+char *stage_pinned(DeviceCache *cache, size_t bytes)
+{
+  if (!cache) return nullptr;
+  if (cache->h_stage_cap < bytes) {
+    if (cache->h_stage) cudaFreeHost(cache->h_stage);
+    cache->h_stage = nullptr; cache->h_stage_cap = 0;
+    const size_t cap = bytes + bytes / 4 + 4096;
+    if (cudaHostAlloc((void **)&cache->h_stage, cap, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); cache->h_stage = nullptr; return nullptr; }
+    cache->h_stage_cap = cap;
+  }
+  return cache->h_stage;
+}
+
+// Host grid -> device.  Pinned memory goes in one DMA.  Pageable memory would be staged by the driver at ~8 GB/s
+// (32 ms for a 400^3 grid, six times the kernels): instead up to 8 threads copy 16 MB chunks into cached pinned
+// buffers and queue their DMA themselves, so host copies and DMA of different chunks overlap.
+int upload_grid(DeviceCache *cache, int device, void *dst, const float *src, size_t bytes)
+{
+  cudaPointerAttributes attr;
+  bool pinned = false;
+  if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+  else cudaGetLastError();
+  if (pinned || !cache || bytes < 4 * DeviceCache::CHUNK) {
+    if (cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+      return gcb::fail(GCB_ERR_CUDA, "copying the grid to the device failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return GCB_OK;
+  }
+  for (int i = 0; i < DeviceCache::NCHUNK; i++) {
+    if (!cache->h_chunk[i]) {
+      if (cudaHostAlloc((void **)&cache->h_chunk[i], DeviceCache::CHUNK, cudaHostAllocDefault) != cudaSuccess ||
+          cudaEventCreateWithFlags(&cache->chunk_done[i], cudaEventDisableTiming) != cudaSuccess ||
+          cudaStreamCreateWithFlags(&cache->chunk_st[i], cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        if (cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+          return gcb::fail(GCB_ERR_CUDA, "copying the grid to the device failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return GCB_OK;
+      }
+    }
+  }
+  const size_t nchunks = (bytes + DeviceCache::CHUNK - 1) / DeviceCache::CHUNK;
+  const int nthreads = (int)std::min<size_t>(DeviceCache::NCHUNK / 2, std::min<size_t>(nchunks, std::max(1u, std::thread::hardware_concurrency() / 2)));
+  std::vector<int> rcs((size_t)nthreads, 0);
+  auto work = [&](int t) {
+    if (cudaSetDevice(device) != cudaSuccess) { rcs[(size_t)t] = 1; return; }
+    const int slots[2] = {t, t + DeviceCache::NCHUNK / 2};   // thread t owns two pinned buffers (nthreads <= NCHUNK / 2)
+    int turn = 0;
+    for (size_t c = (size_t)t; c < nchunks; c += (size_t)nthreads, turn++) {
+      const int slot = slots[turn & 1];
+      if (turn >= 2 && cudaEventSynchronize(cache->chunk_done[slot]) != cudaSuccess) { rcs[(size_t)t] = 1; return; }
+      const size_t off = c * DeviceCache::CHUNK, n = std::min(DeviceCache::CHUNK, bytes - off);
+      memcpy(cache->h_chunk[slot], reinterpret_cast<const char *>(src) + off, n);
+      if (cudaMemcpyAsync(static_cast<char *>(dst) + off, cache->h_chunk[slot], n, cudaMemcpyHostToDevice, cache->chunk_st[slot]) != cudaSuccess ||
+          cudaEventRecord(cache->chunk_done[slot], cache->chunk_st[slot]) != cudaSuccess) { rcs[(size_t)t] = 1; return; }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; t++) th.emplace_back(work, t);
+  work(0);
+  for (auto &x : th) x.join();
+  bool bad = false;
+  for (int r : rcs) bad |= r != 0;
+  for (int i = 0; i < DeviceCache::NCHUNK; i++) if (cudaStreamSynchronize(cache->chunk_st[i]) != cudaSuccess) bad = true;
+  if (bad) return gcb::fail(GCB_ERR_CUDA, "copying the grid to the device failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return GCB_OK;
+}
 
 #define AN_CUDA(call)                                                                            \
   do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                                          \
@@ -625,62 +725,24 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
   int iradNR = (int)floor((double)(geometry.radius / DeltaR));                  // :544
   if (iradNR < 0) iradNR = 0;
 
-  // ---- per-(i,j) tables (a_ri3Dc.c:586-592, 625), [j][i] order = the traversal order -----------
-  std::vector<float> c2tab((size_t)nxy);
-  std::vector<unsigned char> flags((size_t)nxy);
-  std::vector<int> irad((size_t)nxy);
-  {
-    const float rcirc = geometry.radius / DeltaR;
-    const float cx = (float)((double)fmx / 2.0), cy = (float)((double)fmy / 2.0);
-    for (int j = 0; j < d.my; j++) {
-      const float cj = (float)(((double)(float)j + 0.5) - (double)fmy / 2.0);
-      for (int i = 0; i < d.mx; i++) {
-        const float ci = (float)(((double)(float)i + 0.5) - (double)fmx / 2.0);
-        const float c2 = ci * ci + cj * cj;
-        const float ex = (float)i - cx, ey = (float)j - cy;
-        const int ir = (int)floor(sqrt((double)c2));
-        const size_t t = (size_t)j * d.mx + i;
-        c2tab[t] = c2;
-        irad[t] = ir;
-        flags[t] = (unsigned char)((ex * ex + ey * ey <= rcirc * rcirc ? 1 : 0) | (ir < iradNR ? 2 : 0));
-      }
-    }
-  }
-  // cells of each radial bin in (j,i) order, as z-fastest row numbers i*my + j
-  std::vector<int> bin_start((size_t)iradNR + 1, 0), bin_cells, bin_xy;
-  {
-    for (size_t t = 0; t < (size_t)nxy; t++) if (irad[t] < iradNR) bin_start[(size_t)irad[t] + 1]++;
-    for (int r = 0; r < iradNR; r++) bin_start[(size_t)r + 1] += bin_start[r];
-    bin_cells.resize((size_t)bin_start[iradNR]);
-    bin_xy.resize((size_t)bin_start[iradNR]);
-    std::vector<int> fill(bin_start.begin(), bin_start.end() - 1);
-    for (int j = 0; j < d.my; j++)
-      for (int i = 0; i < d.mx; i++) {
-        const int r = irad[(size_t)j * d.mx + i];
-        if (r < iradNR) { bin_xy[(size_t)fill[r]] = j * d.mx + i; bin_cells[(size_t)fill[r]++] = i * d.my + j; }
-      }
-  }
-  const long long ncyl = iradNR > 0 ? bin_start[iradNR] : 0;
-
   static const bool trace = getenv("GCB_TRACE") != nullptr;
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
     return std::chrono::duration<double, std::milli>(b - a).count(); };
   const auto t_start = now();
-  // ---- device buffers --------------------------------------------------------------------------
+  const double rw_inc = 1.0 / (double)fmz;                                 // a_ri3Dc.c:637
+  // ---- device buffers: the tables first, so that they stay where they are from call to call --------
   DevBuf d_in, d_g, d_gx, d_c2, d_flags, d_bs, d_bc, d_bxy, d_fbuf, d_sraw, d_xyp, d_hxyp, d_xzp, d_yzp, d_zdf, d_lzdf, d_prof, d_nocc,
       d_rzp, d_hrzp, d_rdf, d_hrdf, d_rw, d_scal;
   Arena arena;
   const size_t nrz = (size_t)iradNR * d.mz;
   const size_t maxseg = (ncells + (size_t)SCAN_THREADS * SCAN_T - 1) / ((size_t)SCAN_THREADS * SCAN_T) + 1;
-  if (!on_device) arena.want(d_in, ocells * 4);
-  if (cropped) arena.want(d_g, ncells * 4);
-  arena.want(d_gx, ncells * 4);
   arena.want(d_c2, (size_t)nxy * 4);
   arena.want(d_flags, (size_t)nxy);
-  arena.want(d_bs, bin_start.size() * 4);
-  arena.want(d_bc, bin_cells.size() * 4);
-  arena.want(d_bxy, bin_xy.size() * 4);
+  arena.want(d_bs, ((size_t)iradNR + 1) * 4);
+  arena.want(d_bc, (size_t)nxy * 4);              // (at most every (i,j) column lies in a radial bin)
+  arena.want(d_bxy, (size_t)nxy * 4);
+  const size_t table_span = arena.total;
   arena.want(d_xyp, (size_t)nxy * 4);
   arena.want(d_hxyp, (size_t)nxy * 4);
   arena.want(d_xzp, (size_t)d.mx * d.mz * 4);
@@ -692,31 +754,100 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
   arena.want(d_sraw, (size_t)d.mz * 12);
   arena.want(d_rzp, nrz * 4);
   arena.want(d_hrzp, nrz * 4);
-  arena.want(d_rdf, ((size_t)iradNR + 1) * 8);
-  arena.want(d_hrdf, ((size_t)iradNR + 1) * 8);
   arena.want(d_rw, ((size_t)iradNR + 1) * 4);
+  arena.want(d_rdf, ((size_t)iradNR + 1) * 8);    // d_rdf .. the head of d_fbuf are zeroed in one go
+  arena.want(d_hrdf, ((size_t)iradNR + 1) * 8);
   arena.want(d_scal, 32);
   arena.want(d_fbuf, 16 + 4 * maxseg * sizeof(seqsum::Fn));
+  arena.want(d_gx, ncells * 4);
+  if (cropped) arena.want(d_g, ncells * 4);
+  if (!on_device) arena.want(d_in, ocells * 4);
   AN_CUDA(arena.commit(opts->device));
-  if (!on_device) AN_CUDA(cudaMemcpy(d_in.p, grid_zfast, ocells * 4, cudaMemcpyHostToDevice));
-  else AN_CUDA(cudaDeviceSynchronize());          // whatever stream is still producing the grid
+  DeviceCache *cache = arena.cache;
+
+  // ---- per-(i,j) tables (a_ri3Dc.c:586-592, 625), [j][i] order = the traversal order; kept per device for the
+  //      last geometry (host: bin_start, rweight; device: all five tables) ------------------------------
+  TableKey key;
+  key.mx = d.mx; key.my = d.my; key.mz = d.mz; key.iradNR = iradNR;
+  memcpy(&key.radius_bits, &geometry.radius, 4); memcpy(&key.deltaR_bits, &DeltaR, 4);
+  std::vector<int> bin_start_local;
+  std::vector<float> rweight_local;
+  const bool tables_hit = cache && cache->tables_valid && cache->key == key;
+  if (!tables_hit) {
+    std::vector<float> c2tab((size_t)nxy);
+    std::vector<unsigned char> flags((size_t)nxy);
+    std::vector<int> irad((size_t)nxy);
+    {
+      const float rcirc = geometry.radius / DeltaR;
+      const float cx = (float)((double)fmx / 2.0), cy = (float)((double)fmy / 2.0);
+      for (int j = 0; j < d.my; j++) {
+        const float cj = (float)(((double)(float)j + 0.5) - (double)fmy / 2.0);
+        for (int i = 0; i < d.mx; i++) {
+          const float ci = (float)(((double)(float)i + 0.5) - (double)fmx / 2.0);
+          const float c2 = ci * ci + cj * cj;
+          const float ex = (float)i - cx, ey = (float)j - cy;
+          const int ir = (int)floor(sqrt((double)c2));
+          const size_t t = (size_t)j * d.mx + i;
+          c2tab[t] = c2;
+          irad[t] = ir;
+          flags[t] = (unsigned char)((ex * ex + ey * ey <= rcirc * rcirc ? 1 : 0) | (ir < iradNR ? 2 : 0));
+        }
+      }
+    }
+    // cells of each radial bin in (j,i) order, as z-fastest row numbers i*my + j and as x-fastest j*mx + i
+    std::vector<int> bin_start((size_t)iradNR + 1, 0), bin_cells, bin_xy;
+    {
+      for (size_t t = 0; t < (size_t)nxy; t++) if (irad[t] < iradNR) bin_start[(size_t)irad[t] + 1]++;
+      for (int r = 0; r < iradNR; r++) bin_start[(size_t)r + 1] += bin_start[r];
+      bin_cells.resize((size_t)bin_start[iradNR]);
+      bin_xy.resize((size_t)bin_start[iradNR]);
+      std::vector<int> fill(bin_start.begin(), bin_start.end() - 1);
+      for (int j = 0; j < d.my; j++)
+        for (int i = 0; i < d.mx; i++) {
+          const int r = irad[(size_t)j * d.mx + i];
+          if (r < iradNR) { bin_xy[(size_t)fill[r]] = j * d.mx + i; bin_cells[(size_t)fill[r]++] = i * d.my + j; }
+        }
+    }
+    // rweight[r] is a chain of cells(r)*mz constant increments: data-independent, closed form per exponent
+    std::vector<float> rweight_host((size_t)iradNR);
+    for (int r = 0; r < iradNR; r++)
+      rweight_host[(size_t)r] = seqsum::inc_chain_f32(0.0f, rw_inc, (long long)(bin_start[(size_t)r + 1] - bin_start[r]) * d.mz);
+    // one upload of the table span (through pinned staging when there is a cache)
+    std::vector<char> pageable;
+    char *stg = stage_pinned(cache, table_span);
+    if (!stg) { pageable.resize(table_span); stg = pageable.data(); }
+    const char *t0 = d_c2.as<char>();
+    memcpy(stg + (d_c2.as<char>() - t0), c2tab.data(), (size_t)nxy * 4);
+    memcpy(stg + (d_flags.as<char>() - t0), flags.data(), (size_t)nxy);
+    memcpy(stg + (d_bs.as<char>() - t0), bin_start.data(), bin_start.size() * 4);
+    if (!bin_cells.empty()) memcpy(stg + (d_bc.as<char>() - t0), bin_cells.data(), bin_cells.size() * 4);
+    if (!bin_xy.empty()) memcpy(stg + (d_bxy.as<char>() - t0), bin_xy.data(), bin_xy.size() * 4);
+    AN_CUDA(cudaMemcpy(d_c2.p, stg, table_span, cudaMemcpyHostToDevice));
+    if (cache) {
+      cache->key = key; cache->tables_valid = true;
+      cache->bin_start.swap(bin_start); cache->rweight.swap(rweight_host);
+    } else {
+      bin_start_local.swap(bin_start); rweight_local.swap(rweight_host);
+    }
+  }
+  const std::vector<int> &bin_start = cache ? cache->bin_start : bin_start_local;
+  const std::vector<float> &rweight_host = cache ? cache->rweight : rweight_local;
+  const long long ncyl = iradNR > 0 ? bin_start[(size_t)iradNR] : 0;
+
+  if (!on_device) {
+    const int rcu = upload_grid(cache, opts->device, d_in.p, grid_zfast, ocells * 4);
+    if (rcu) return rcu;
+  }
   int64_t launches = 0;
   const float *g_in = on_device ? grid_zfast : d_in.as<float>();
   const float *g = g_in;
+  // d_rdf, d_hrdf, d_scal and the two flag words in front of the segment maps: one memset
+  AN_CUDA(cudaMemset(d_rdf.p, 0, (size_t)(d_fbuf.as<char>() + 16 - d_rdf.as<char>())));
   if (cropped) {
     an_crop_kernel<<<std::min(blocks_for(ncells, 256), 148 * 16), 256>>>(g_in, od, d_g.as<float>(), d, base[0], base[1], base[2]);
     launches++;
     g = d_g.as<float>();
   }
-  AN_CUDA(cudaMemset(d_fbuf.p, 0, 16));
-  AN_CUDA(cudaMemcpy(d_c2.p, c2tab.data(), (size_t)nxy * 4, cudaMemcpyHostToDevice));
-  AN_CUDA(cudaMemcpy(d_flags.p, flags.data(), (size_t)nxy, cudaMemcpyHostToDevice));
-  AN_CUDA(cudaMemcpy(d_bs.p, bin_start.data(), bin_start.size() * 4, cudaMemcpyHostToDevice));
-  if (!bin_cells.empty()) AN_CUDA(cudaMemcpy(d_bc.p, bin_cells.data(), bin_cells.size() * 4, cudaMemcpyHostToDevice));
-  if (!bin_xy.empty()) AN_CUDA(cudaMemcpy(d_bxy.p, bin_xy.data(), bin_xy.size() * 4, cudaMemcpyHostToDevice));
-  AN_CUDA(cudaMemset(d_rdf.p, 0, ((size_t)iradNR + 1) * 8));
-  AN_CUDA(cudaMemset(d_hrdf.p, 0, ((size_t)iradNR + 1) * 8));
-  AN_CUDA(cudaMemset(d_scal.p, 0, 32));
 
   // ---- kernels: independent chains on independent streams --------------------------------------
   Streams streams;
@@ -734,7 +865,6 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
   AN_CUDA(cudaEventRecord(gx_ready, st[0]));
   const float d_xy = fmz * U, d_xz = fmy * U, d_yz = fmx * U;               // a_ri3Dc.c:573-578 divisors
   const double h_inc = 1.0 / (double)(fmz * Uunity);                       // :580
-  const double rw_inc = 1.0 / (double)fmz;                                 // :637
   an_xy_kernel<<<blocks_for(nxy, 128), 128, 0, st[0]>>>(d_gx.as<float>(), d, d_xy, min_occ, h_inc, d_xyp.as<float>(), d_hxyp.as<float>());
   double *d_sumP = d_scal.as<double>();
   unsigned long long *d_holes = reinterpret_cast<unsigned long long *>(d_scal.as<char>() + 8);
@@ -786,10 +916,6 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
                                                           d_hrdf.as<float>(), d_bad);
     launches += 2;
   }
-  // rweight[r] is a chain of cells(r)*mz constant increments: data-independent, closed form per exponent
-  std::vector<float> rweight_host((size_t)iradNR);
-  for (int r = 0; r < iradNR; r++)
-    rweight_host[(size_t)r] = seqsum::inc_chain_f32(0.0f, rw_inc, (long long)(bin_start[(size_t)r + 1] - bin_start[r]) * d.mz);
   cudaError_t kerr = cudaGetLastError();
   for (auto &s : st) { cudaError_t e = cudaStreamSynchronize(s); if (kerr == cudaSuccess) kerr = e; }
   cudaEventDestroy(gx_ready);
@@ -826,13 +952,15 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
   // everything else was laid out contiguously in the arena (d_xyp ... d_scal): one copy, then cut up on the host
   const char *span0 = d_xyp.as<char>();
   const size_t span = (size_t)(d_scal.as<char>() + 32 - span0);
-  std::vector<char> stage(span);
-  if (cudaMemcpy(stage.data(), span0, span, cudaMemcpyDeviceToHost) != cudaSuccess)
+  std::vector<char> stage_pageable;
+  char *stage = stage_pinned(cache, span);
+  if (!stage) { stage_pageable.resize(span); stage = stage_pageable.data(); }
+  if (cudaMemcpy(stage, span0, span, cudaMemcpyDeviceToHost) != cudaSuccess)
     rc = gcb::fail(GCB_ERR_CUDA, "copying the analysis results back failed: %s", cudaGetErrorString(cudaGetLastError()));
   auto cut = [&](const DevBuf &b, size_t n) -> float * {
     float *h = (float *)malloc(std::max<size_t>(n, 1) * sizeof(float));
     if (!h) { rc = gcb::fail(GCB_ERR_NOMEM, "out of memory"); return nullptr; }
-    if (n) memcpy(h, stage.data() + (b.as<char>() - span0), n * sizeof(float));
+    if (n) memcpy(h, stage + (b.as<char>() - span0), n * sizeof(float));
     return h;
   };
   out->xyp = cut(d_xyp, nxy); out->hxyp = cut(d_hxyp, nxy);
@@ -844,8 +972,8 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
   out->rzp = cut(d_rzp, nrz); out->hrzp = cut(d_hrzp, nrz);
   std::vector<unsigned> nocc((size_t)d.mz);
   char scal[32];
-  memcpy(nocc.data(), stage.data() + (d_nocc.as<char>() - span0), (size_t)d.mz * 4);
-  memcpy(scal, stage.data() + (d_scal.as<char>() - span0), 32);
+  memcpy(nocc.data(), stage + (d_nocc.as<char>() - span0), (size_t)d.mz * 4);
+  memcpy(scal, stage + (d_scal.as<char>() - span0), 32);
   if (rc) { gcb_analysis_free(out); return rc; }
 
   const size_t mz = (size_t)d.mz;
@@ -922,6 +1050,28 @@ int gcb_analyse(const gcb_tgrid *tg, const float *grid_zfast, const gcb_analysis
 int gcb_analyse_device(const gcb_tgrid *tg, const float *grid_zfast_dev, const gcb_analysis_opts *opts, gcb_analysis *out)
 {
   return analyse_impl(tg, grid_zfast_dev, true, opts, out);
+}
+
+// gives back what gcb_analyse keeps per device between calls (device arena, streams, pinned staging, tables)
+void gcb_analyse_release_cache(int device)
+{
+  if (device < 0 || device >= 64) return;
+  DeviceCache &dc = g_cache[device];
+  std::lock_guard<std::mutex> lk(dc.m);
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaDeviceSynchronize();
+  if (dc.base) cudaFree(dc.base);
+  dc.base = nullptr; dc.cap = 0; dc.tables_valid = false;
+  for (auto &s : dc.st) { if (s) cudaStreamDestroy(s); s = nullptr; }
+  if (dc.h_stage) cudaFreeHost(dc.h_stage);
+  dc.h_stage = nullptr; dc.h_stage_cap = 0;
+  for (int i = 0; i < DeviceCache::NCHUNK; i++) {
+    if (dc.h_chunk[i]) cudaFreeHost(dc.h_chunk[i]);
+    if (dc.chunk_done[i]) cudaEventDestroy(dc.chunk_done[i]);
+    if (dc.chunk_st[i]) cudaStreamDestroy(dc.chunk_st[i]);
+    dc.h_chunk[i] = nullptr; dc.chunk_done[i] = nullptr; dc.chunk_st[i] = nullptr;
+  }
+  cudaGetLastError();
 }
 
 void gcb_analysis_free(gcb_analysis *a)
