@@ -149,6 +149,7 @@ SIGNATURES = {
     "gcb_analyse": (C.c_int, [C.POINTER(TGrid), c_float_p, C.POINTER(AnalysisOpts), C.POINTER(Analysis)]),
     "gcb_analyse_device": (C.c_int, [C.POINTER(TGrid), C.c_void_p, C.POINTER(AnalysisOpts), C.POINTER(Analysis)]),
     "gcb_analysis_free": (None, [C.POINTER(Analysis)]),
+    "gcb_analyse_release_cache": (None, [C.c_int]),
     "gcb_gridcalc": (C.c_int, [C.c_int, C.POINTER(c_float_p), c_float_p, C.POINTER(TGrid), c_float_p, c_float_p,
                                C.c_int]),
     "gcb_gen_device_frames": (C.c_int, [C.POINTER(Gen), C.c_long, C.c_long, C.c_int, C.c_void_p, C.c_int]),

@@ -221,8 +221,9 @@ class XtcBuffer:
     def times(self):
         return np.array([self.frames[i].time for i in range(self.nframes)], np.float32)
 
-    def decode_to_device(self, device=0):
-        dev = DeviceFrames(self.nframes, self.natoms, device)
+    def decode_to_device(self, device=0, dev=None):
+        """decoded frames x[nframes][natoms][3] in device memory (`dev`: an existing DeviceFrames to decode into)"""
+        dev = dev if dev is not None else DeviceFrames(self.nframes, self.natoms, device)
         check(lib.gcb_xtc_decode_device(self.ptr, self.nbytes, self.frames, self.nframes, self.natoms, dev.ptr, device),
               "gcb_xtc_decode_device")
         return dev

@@ -1743,15 +1743,17 @@ int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gc
   // frames or 1024.  So every batch has its own set of buffers and its own stream for copy + skim (GCB_XTC_SETS of them
   // in flight: the skims of several batches overlap each other and the copies), and only the segment kernels, which
   // are short and wide, queue on the compute stream.  Batches of ~64 MB of compressed bytes (1.2 ms of PCIe), at
-  // least 16 frames, decoded frames <= 1 GiB per set.
+  // least 64 frames.
   const char *env = getenv("GCB_XTC_BATCH");
   long per;
   if (env) per = atol(env);
   else {
     const double bytes_per_frame = (double)(frames[nframes - 1].payload_offset + frames[nframes - 1].payload_bytes - frames[0].payload_offset) / (double)nframes;
     per = (long)(((size_t)64 << 20) / std::max(bytes_per_frame, 1.0));
-    per = std::max<long>(16, std::min<long>(per, 16384));
-    per = std::min<long>(per, (long)std::max<size_t>(4, ((size_t)1 << 30) / frame_bytes));
+    // at least 64 frames: a frame's skim takes ~30 ns per atom and its compressed bytes ~0.1 ns per atom of PCIe
+    // time, so with GCB_XTC_SETS batches in flight the copies hide the skims from ~55 frames per batch on,
+    // whatever the frame size (large systems simply get large batches: 1 M atoms -> 320 MB of compressed bytes)
+    per = std::max<long>(64, std::min<long>(per, 16384));
   }
   per = std::max<long>(4, per & ~3L);                         // batches start 16-byte aligned in the decoded array
   std::vector<float> box3;

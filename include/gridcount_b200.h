@@ -318,6 +318,10 @@ int gcb_analyse(const gcb_tgrid *tg, const float *grid_zfast, const gcb_analysis
 int gcb_analyse_device(const gcb_tgrid *tg, const float *grid_zfast_dev, const gcb_analysis_opts *opts,
                        gcb_analysis *out);
 void gcb_analysis_free(gcb_analysis *a);
+/* gcb_analyse keeps, per device, what a call needs again at once: its device buffers (up to 1.5 GB: a 500^3 grid and
+ * its x-fastest copy), four streams, pinned staging and the per-(i,j) tables of the last geometry.  This gives
+ * them back. */
+void gcb_analyse_release_cache(int device);
 
 /* a_gridcalc.c:132-189: time-weighted average of n grids of identical shape */
 int gcb_gridcalc(int ngrids, const float *const *grids_zfast, const float *tweights,
