@@ -399,11 +399,13 @@ def roofline_of(g, ctr, stride, cells, peak, peak_src, device, kernel_key, l2=No
     binning kernel (direct uint32 REDs, packed-counter pass, or the guarded uint32 pass that redoes a failed packed
     round) with the largest summed duration; the other K1 launches of the same frames are listed beside it"""
     kinds = ctr.profile_kinds()
-    dom = max(("direct", "packed", "redo"), key=lambda k: kinds[k][0])
+    dom = max(("direct", "packed", "redo", "private"), key=lambda k: kinds[k][0])
     k1_ms, nl, units = kinds[dom]
     bits = 8 if cells <= (80 << 20) else 4
     names = {"direct": "bin_stream_kernel<DirectSink> (one RED per hit into the uint32 grid)",
              "packed": "bin_stream_kernel<PackedSink<%d>> (non-returning REDs into %d-bit L2-resident counters)" % (bits, bits),
+             "private": "bin_stream_kernel<PrivateSink> (shared-memory atomics into per-CTA private copies of the grid, "
+                        "folded into the uint32 grid when it is read)",
              "redo": "bin_stream_kernel<DirectSink>, guarded pass (one RED per hit into the uint32 grid, after a packed "
                      "round failed its digit-sum verification)"}
     gps = units / (k1_ms * 1e-3) * 1e-9

@@ -20,7 +20,7 @@ c_long_p = C.POINTER(C.c_long)
 HEADER_MAX = 256
 SET_CPOINT, SET_R, SET_Z1, SET_Z2 = 1, 2, 4, 8
 PBC_NONE, PBC_RECT = 0, 1
-KERNEL_AUTO, KERNEL_GATHER, KERNEL_STREAM, KERNEL_STREAM_INDEXED, KERNEL_PACKED = 0, 1, 2, 3, 5
+KERNEL_AUTO, KERNEL_GATHER, KERNEL_STREAM, KERNEL_STREAM_INDEXED, KERNEL_PACKED, KERNEL_PRIVATE = 0, 1, 2, 3, 5, 6
 UNITS = {"unity": 0, "SPC": 1, "molar": 2, "Angstrom": 3, "Voxel": 4}
 GEN_UNIFORM, GEN_QUANTISED, GEN_PORE, GEN_CLUSTER = 0, 1, 2, 3
 
@@ -52,7 +52,8 @@ class Stats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("atom_frames", C.c_uint64), ("hits", C.c_uint64),
                 ("edge_overflow", C.c_uint64), ("sumP", C.c_double), ("uniform_weight", C.c_int),
                 ("weight", C.c_float), ("kernel_launches", C.c_int64), ("packed_rounds", C.c_uint64),
-                ("packed_redone", C.c_uint64), ("saturated", C.c_int)]
+                ("packed_redone", C.c_uint64), ("saturated", C.c_int),
+                ("private_launches", C.c_uint64), ("private_redone", C.c_uint64)]
 
 
 class AnalysisOpts(C.Structure):

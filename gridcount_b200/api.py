@@ -383,10 +383,10 @@ class GridCounter:
 
     def profile_kinds(self):
         """-> {kind: (summed ms, launches, atom-frames)} for 'direct', 'packed', 'redo' (the guarded uint32 pass
-        behind a packed pass) and 'other' (verify/apply passes, gather tails)"""
-        ms, n, units = (C.c_double * 4)(), (C.c_long * 4)(), (C.c_double * 4)()
+        behind a packed pass), 'other' (verify/apply passes, gather tails, fused xtc kernel) and 'private'"""
+        ms, n, units = (C.c_double * 5)(), (C.c_long * 5)(), (C.c_double * 5)()
         check(lib.gcb_counter_profile_kinds(self.h, ms, n, units), "gcb_counter_profile_kinds")
-        return {k: (ms[i], n[i], units[i]) for i, k in enumerate(("direct", "packed", "redo", "other"))}
+        return {k: (ms[i], n[i], units[i]) for i, k in enumerate(("direct", "packed", "redo", "other", "private"))}
 
     def timer_start(self):
         check(lib.gcb_counter_timer_start(self.h), "gcb_counter_timer_start")

@@ -251,9 +251,9 @@ struct TileMeta {
 // atoms of a tile follow from arithmetic, no index or rank loads in the inner loop.
 struct ApGroup { int g0, step, tile_atoms; };
 
-template <int NST>
+template <int NST, int TCAP_ATOMS = TILE_ATOMS>
 struct StreamSmem {
-  float tile[NST][TILE_FLOATS];
+  float tile[NST][TCAP_ATOMS * 3];
   unsigned long long full[NST], empty[NST];
   TileMeta meta[NST];
 };
@@ -350,6 +350,36 @@ __device__ __forceinline__ int cell_of_exact(const GridParamsFast &P, float x, f
                            P.fmx[2], P.my, P.mz);
 }
 
+// what the consumers need to know about tile t of the flat frame array (the producer publishes it with the tile)
+template <bool AP>
+__device__ __forceinline__ TileMeta make_tile_meta(long long t, int tile_atoms, int natoms, unsigned gnx,
+                                                   const unsigned *__restrict__ rank, const ApGroup &G)
+{
+  const long long g0 = t * tile_atoms, g1 = g0 + tile_atoms;
+  const long long f0 = g0 / natoms, f1 = g1 / natoms;
+  const int r0 = (int)(g0 - f0 * natoms), r1 = (int)(g1 - f1 * natoms);
+  TileMeta m;
+  m.f0 = f0; m.r0 = r0;
+  if (AP) {
+    // frame f0 contributes atoms [r0, endA), frame f0+1 atoms [0, endB)   (tile_atoms <= natoms)
+    const int endA = min(natoms, r0 + tile_atoms), endB = r0 + tile_atoms - natoms;
+    const int iA0 = r0 <= G.g0 ? 0 : min((int)gnx, (r0 - G.g0 + G.step - 1) / G.step);
+    const int iA1 = endA <= G.g0 ? 0 : min((int)gnx, (endA - G.g0 + G.step - 1) / G.step);
+    const int nB = endB <= G.g0 ? 0 : min((int)gnx, (endB - G.g0 + G.step - 1) / G.step);
+    m.nA = (unsigned)(iA1 - iA0);
+    m.nsel = m.nA + (unsigned)nB;
+    m.baseA = G.g0 + iA0 * G.step - r0;
+    m.baseB = G.g0 + (natoms - r0) - (int)m.nA * G.step;
+    m.rel0 = 0;
+  } else {
+    const unsigned rel0 = __ldg(rank + r0);
+    m.rel0 = rel0;
+    m.nsel = (unsigned)((f1 - f0) * (long long)gnx + (long long)__ldg(rank + r1) - (long long)rel0);
+    m.nA = 0; m.baseA = 0; m.baseB = 0;
+  }
+  return m;
+}
+
 // ---------------------------------------------------------------------------
 // Where a hit goes.
 //
@@ -362,16 +392,20 @@ __device__ __forceinline__ int cell_of_exact(const GridParamsFast &P, float x, f
 // L2-sized slabs and counting them in a second kernel (round 1: 92 G/s against 111 on the nanopore shape,
 // 72 against 82+ on 400^3), and packed counters with returning atomics (37 G/s on 400^3).
 // ---------------------------------------------------------------------------
+// Every sink also fixes the shape of the streaming kernel it is compiled into: consumer warps per CTA, atoms per
+// thread and loop step, tile capacity and ring depth.
 template <int MODE>
 struct DirectSink {
-  static constexpr int NSTAGES = STAGES;
-  static constexpr size_t EXTRA_SMEM = 0;
+  static constexpr int NSTAGES = STAGES, CWARPS = CONSUMER_WARPS, UNROLL_ = UNROLL, TILE_CAP = TILE_ATOMS;
+  static constexpr bool PRIVATE = false;
   uint32_t *counts; float *acc; float w;
+  __host__ __device__ __forceinline__ size_t extra_smem() const { return 0; }
   // `smem` is the sink's share of the dynamic shared memory (unused here)
   __device__ __forceinline__ void init(void *, unsigned) const {}
   __device__ __forceinline__ void hit(void *, int cell) const { deposit<MODE>(counts, acc, cell, w); }
-  __device__ __forceinline__ void tile_end(void *, unsigned) const {}
-  __device__ __forceinline__ void finish(void *, unsigned) const {}
+  __device__ __forceinline__ void tile_hits(void *, unsigned) const {}
+  __device__ __forceinline__ bool finish(void *, unsigned) const { return false; }
+  __device__ __forceinline__ void redo_hit(int) const {}
 };
 
 // PackedSink: L2-resident atomics for grids whose uint32 counters do not fit the L2 but whose packed counters do
@@ -383,17 +417,106 @@ struct DirectSink {
 // was lost (packed_verify_kernel).  A round that fails is thrown away and redone by the direct uint32 kernel.
 template <int W>
 struct PackedSink {
-  static constexpr int NSTAGES = STAGES;
-  static constexpr size_t EXTRA_SMEM = 0;
+  static constexpr int NSTAGES = STAGES, CWARPS = CONSUMER_WARPS, UNROLL_ = UNROLL, TILE_CAP = TILE_ATOMS;
+  static constexpr bool PRIVATE = false;
   uint32_t *pk;                            // packed counters, all-zero between rounds
+  __host__ __device__ __forceinline__ size_t extra_smem() const { return 0; }
   __device__ __forceinline__ void init(void *, unsigned) const {}
   __device__ __forceinline__ void hit(void *, int cell) const
   {
     constexpr unsigned PER = 32u / W, SH = W == 8 ? 2u : 3u;
     atomicAdd(pk + ((unsigned)cell >> SH), 1u << ((unsigned)W * ((unsigned)cell & (PER - 1u))));      // RED.E.ADD
   }
-  __device__ __forceinline__ void tile_end(void *, unsigned) const {}
-  __device__ __forceinline__ void finish(void *, unsigned) const {}
+  __device__ __forceinline__ void tile_hits(void *, unsigned) const {}
+  __device__ __forceinline__ bool finish(void *, unsigned) const { return false; }
+  __device__ __forceinline__ void redo_hit(int) const {}
+};
+
+// PrivateSink: the shared-memory privatisation for grids that fit one CTA's shared memory as W-bit counters next
+// to the tile ring: 8 bits up to ~118 000 cells (a typical pore analysis: 40 x 40 x 60), 4 bits up to ~236 000 (the
+// 60^3 grid of BASELINE config 1).  Every CTA (one per SM) keeps its OWN copy of the whole grid in shared memory; a
+// hit is one non-returning shared-memory atomic, and the L2 sees nothing but the coordinate stream.  Between
+// launches the private grids rest in global memory (loaded at the start of a launch, stored at its end: 2 x ~110 KB
+// per CTA, L2-resident), and they are folded into the uint32 grid only when somebody reads it or when a lane could
+// fill up (flush_private): one streaming pass over the copies per ~32 (8-bit) or ~1.5 (4-bit) hits per private cell
+// instead of one L2 atomic per hit.
+// Exactness does not rest on the density being tame: at the end of a launch the CTA compares the digit sum of its
+// private grid with the hits it holds (every carry out of a lane lowers the digit sum); on a mismatch it leaves the
+// stored copy as it was, bins its tiles of this launch again with plain uint32 REDs (hits and diagnostics were
+// already counted), and raises a flag that sends the next launches straight to the uint32 grid (back-off).
+template <int W> __device__ __forceinline__ unsigned digit_sum(uint32_t w);
+
+struct PrivState {
+  int direct;                              // this launch bins into the uint32 grid (backing off)
+  int skip, backoff, failed;
+  unsigned long long launches, redone;
+};
+
+template <int W>
+struct PrivateSink {
+  // full-size tiles (1024 selected atoms of 3-site water per tile, two per thread of 16 consumer warps), 110 KB of ring
+  static constexpr int NSTAGES = 3, CWARPS = 16, UNROLL_ = 2, TILE_CAP = TILE_ATOMS;
+  static constexpr bool PRIVATE = true;
+  static constexpr unsigned PER = 32u / W, SH = W == 8 ? 2u : 3u;
+  uint32_t *counts;                        // the uint32 grid (direct mode, redo)
+  uint32_t *stage;                         // [CTA][nwords] the private grids between launches
+  unsigned long long *stage_hits;          // [CTA] hits held by stage[CTA]
+  PrivState *st;
+  unsigned nwords;
+  struct Head { unsigned long long hits; int direct, redo; };        // in front of the private grid in shared memory
+  __host__ __device__ __forceinline__ size_t extra_smem() const { return sizeof(Head) + (size_t)nwords * 4; }
+  static __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(CWARPS * 32) : "memory"); }
+  __device__ __forceinline__ void init(void *smem, unsigned ctid) const
+  {
+    Head *h = static_cast<Head *>(smem);
+    uint32_t *g = reinterpret_cast<uint32_t *>(h + 1);
+    const int direct = *(volatile int *)&st->direct;
+    if (ctid == 0) { h->hits = direct ? 0ull : stage_hits[blockIdx.x]; h->direct = direct; h->redo = 0; }
+    if (!direct) {
+      const uint32_t *src = stage + (size_t)blockIdx.x * nwords;
+      for (unsigned i = ctid; i < nwords; i += CWARPS * 32) g[i] = src[i];
+    }
+    consumer_barrier();
+  }
+  __device__ __forceinline__ void hit(void *smem, int cell) const
+  {
+    const Head *h = static_cast<const Head *>(smem);
+    if (h->direct) { atomicAdd(counts + cell, 1u); return; }
+    uint32_t *g = reinterpret_cast<uint32_t *>(const_cast<Head *>(h) + 1);
+    atomicAdd(g + ((unsigned)cell >> SH), 1u << ((unsigned)W * ((unsigned)cell & (PER - 1u))));   // shared-memory atomic, no return value
+  }
+  __device__ __forceinline__ void tile_hits(void *smem, unsigned n) const    // lane 0 of a warp: hits of its share of a tile
+  {
+    Head *h = static_cast<Head *>(smem);
+    if (n && !h->direct) atomicAdd(&h->hits, (unsigned long long)n);
+  }
+  // -> true when this CTA has to bin its tiles again into the uint32 grid (uniform over the CTA's consumers)
+  __device__ __forceinline__ bool finish(void *smem, unsigned ctid) const
+  {
+    Head *h = static_cast<Head *>(smem);
+    if (h->direct) return false;
+    uint32_t *g = reinterpret_cast<uint32_t *>(h + 1);
+    __shared__ unsigned long long digits;
+    if (ctid == 0) digits = 0;
+    consumer_barrier();
+    unsigned long long d = 0;
+    for (unsigned i = ctid; i < nwords; i += CWARPS * 32) {
+      d += digit_sum<W>(g[i]);
+    }
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_down_sync(0xffffffffu, d, o);
+    if ((ctid & 31u) == 0 && d) atomicAdd(&digits, d);
+    consumer_barrier();
+    const bool ok = digits == h->hits;
+    if (ok) {
+      uint32_t *dst = stage + (size_t)blockIdx.x * nwords;
+      for (unsigned i = ctid; i < nwords; i += CWARPS * 32) dst[i] = g[i];
+      if (ctid == 0) stage_hits[blockIdx.x] = h->hits;
+    } else if (ctid == 0) {
+      atomicExch(&st->failed, 1);
+    }
+    return !ok;
+  }
+  __device__ __forceinline__ void redo_hit(int cell) const { atomicAdd(counts + cell, 1u); }
 };
 
 // device-resident state of the packed path: the host queues the same kernels every round, they decide here
@@ -411,21 +534,22 @@ struct PackedState {
 // GUARD: 0 = always run; 1 = run only if *run_if != 0; 2 = run only if *run_if == 0 (the two passes of a packed
 // round, decided on the device; separate instantiations, because the test costs the plain kernel a spill)
 template <class SINK, bool PBC, bool AP, int GUARD = 0>
-__global__ void __launch_bounds__(STREAM_THREADS)
+__global__ void __launch_bounds__((SINK::CWARPS + 1) * 32)
 bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict__ gindex, unsigned gnx,
                   const unsigned *__restrict__ rank, long long ntiles, ApGroup G, GridParamsFast P, SINK sink,
                   const float *__restrict__ box3, unsigned long long *__restrict__ hits,
                   unsigned long long *__restrict__ diag, const int *__restrict__ run_if)
 {
-  constexpr int NST = SINK::NSTAGES;
+  constexpr int NST = SINK::NSTAGES, CTHREADS = SINK::CWARPS * 32, UNR = SINK::UNROLL_;
+  using Smem = StreamSmem<NST, SINK::TILE_CAP>;
   if constexpr (GUARD == 1) { if (*run_if == 0) return; }
   if constexpr (GUARD == 2) { if (*run_if != 0) return; }
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  StreamSmem<NST> &S = *reinterpret_cast<StreamSmem<NST> *>(smem_raw);
+  Smem &S = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x;
 
   if (tid == 0) {
-    for (int s = 0; s < NST; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], CONSUMER_WARPS); }
+    for (int s = 0; s < NST; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], SINK::CWARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -440,28 +564,7 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
         const int stage = it % NST;
         if (it >= NST) mbar_wait(&S.empty[stage], (unsigned)(it / NST - 1) & 1u);
         const int tile_atoms = AP ? G.tile_atoms : TILE_ATOMS;
-        const long long g0 = t * tile_atoms, g1 = g0 + tile_atoms;
-        const long long f0 = g0 / natoms, f1 = g1 / natoms;
-        const int r0 = (int)(g0 - f0 * natoms), r1 = (int)(g1 - f1 * natoms);
-        TileMeta m;
-        m.f0 = f0; m.r0 = r0;
-        if (AP) {
-          // frame f0 contributes atoms [r0, endA), frame f0+1 atoms [0, endB)   (tile_atoms <= natoms)
-          const int endA = min(natoms, r0 + tile_atoms), endB = r0 + tile_atoms - natoms;
-          const int iA0 = r0 <= G.g0 ? 0 : min((int)gnx, (r0 - G.g0 + G.step - 1) / G.step);
-          const int iA1 = endA <= G.g0 ? 0 : min((int)gnx, (endA - G.g0 + G.step - 1) / G.step);
-          const int nB = endB <= G.g0 ? 0 : min((int)gnx, (endB - G.g0 + G.step - 1) / G.step);
-          m.nA = (unsigned)(iA1 - iA0);
-          m.nsel = m.nA + (unsigned)nB;
-          m.baseA = G.g0 + iA0 * G.step - r0;
-          m.baseB = G.g0 + (natoms - r0) - (int)m.nA * G.step;
-          m.rel0 = 0;
-        } else {
-          const unsigned rel0 = __ldg(rank + r0);
-          m.rel0 = rel0;
-          m.nsel = (unsigned)((f1 - f0) * (long long)gnx + (long long)__ldg(rank + r1) - (long long)rel0);
-          m.nA = 0; m.baseA = 0; m.baseB = 0;
-        }
+        const TileMeta m = make_tile_meta<AP>(t, tile_atoms, natoms, gnx, rank, G);
         S.meta[stage] = m;                         // published by the mbarrier's release/acquire
         const unsigned bytes = (unsigned)tile_atoms * 12u;
         mbar_expect_tx(&S.full[stage], bytes);
@@ -474,7 +577,7 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
   // ---------------- consumer warps ----------------
   const unsigned ctid = (unsigned)tid - 32u;
   const int lane = tid & 31;
-  void *const sink_smem = smem_raw + ((sizeof(StreamSmem<NST>) + 15) & ~(size_t)15);
+  void *const sink_smem = smem_raw + ((sizeof(Smem) + 15) & ~(size_t)15);
   sink.init(sink_smem, ctid);
   int it = 0;
   for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
@@ -486,12 +589,12 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
     if (AP) {
       const uint32_t addrA = tile + 12u * (uint32_t)m.baseA, addrB = tile + 12u * (uint32_t)m.baseB;
       const uint32_t step12 = 12u * (uint32_t)G.step;
-      for (unsigned base = ctid; base < m.nsel; base += CONSUMER_THREADS * UNROLL) {
-        float px[UNROLL], py[UNROLL], pz[UNROLL];
-        bool valid[UNROLL], inB[UNROLL];
+      for (unsigned base = ctid; base < m.nsel; base += CTHREADS * UNR) {
+        float px[UNR], py[UNR], pz[UNR];
+        bool valid[UNR], inB[UNR];
 #pragma unroll
-        for (int k = 0; k < UNROLL; k++) {
-          const unsigned j = base + k * CONSUMER_THREADS;
+        for (int k = 0; k < UNR; k++) {
+          const unsigned j = base + k * CTHREADS;
           valid[k] = j < m.nsel;
           inB[k] = j >= m.nA;
           const uint32_t p = valid[k] ? (inB[k] ? addrB : addrA) + j * step12 : tile;
@@ -499,7 +602,7 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
         }
         unsigned rare = 0;
 #pragma unroll
-        for (int k = 0; k < UNROLL; k++) {
+        for (int k = 0; k < UNR; k++) {
           if (PBC) {
             const float *L = box3 + 3 * (m.f0 + (inB[k] ? 1 : 0));
             px[k] = wrap1(px[k], __ldg(L)); py[k] = wrap1(py[k], __ldg(L + 1)); pz[k] = wrap1(pz[k], __ldg(L + 2));
@@ -513,7 +616,7 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
         }
         if (rare) {                                  // atoms within a few ulp of a cell boundary
 #pragma unroll
-          for (int k = 0; k < UNROLL; k++) {
+          for (int k = 0; k < UNR; k++) {
             if (!((rare >> k) & 1u)) continue;
             const int cell = cell_of_exact(P, px[k], py[k], pz[k]);
             if (cell >= 0) {
@@ -526,13 +629,13 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
         }
       }
     } else
-    for (unsigned base = 0; base < m.nsel; base += CONSUMER_THREADS * UNROLL) {
-      int local[UNROLL];
-      unsigned df[UNROLL];
-      bool valid[UNROLL];
+    for (unsigned base = 0; base < m.nsel; base += CTHREADS * UNR) {
+      int local[UNR];
+      unsigned df[UNR];
+      bool valid[UNR];
 #pragma unroll
-      for (int k = 0; k < UNROLL; k++) {
-        const unsigned s = base + k * CONSUMER_THREADS + ctid;
+      for (int k = 0; k < UNR; k++) {
+        const unsigned s = base + k * CTHREADS + ctid;
         valid[k] = s < m.nsel;
         unsigned rel = m.rel0 + s;
         df[k] = 0;
@@ -540,14 +643,14 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
         const int idx = valid[k] ? __ldg(gindex + rel) : m.r0;
         local[k] = (int)((long long)df[k] * natoms + idx - m.r0);
       }
-      float px[UNROLL], py[UNROLL], pz[UNROLL];
+      float px[UNR], py[UNR], pz[UNR];
 #pragma unroll
-      for (int k = 0; k < UNROLL; k++) {
+      for (int k = 0; k < UNR; k++) {
         const uint32_t p = tile + 12u * (uint32_t)(valid[k] ? local[k] : 0);
         px[k] = lds_f32(p); py[k] = lds_f32(p + 4); pz[k] = lds_f32(p + 8);
       }
 #pragma unroll
-      for (int k = 0; k < UNROLL; k++) {
+      for (int k = 0; k < UNR; k++) {
         if (!valid[k]) continue;
         if (PBC) {
           const float *L = box3 + 3 * (m.f0 + df[k]);
@@ -570,12 +673,37 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
     if (lane == 0) {
       if (c0) atomicAdd(hits + m.f0, (unsigned long long)c0);
       if (c1) atomicAdd(hits + m.f0 + 1, (unsigned long long)c1);
+      sink.tile_hits(sink_smem, c0 + c1);
       mbar_arrive(&S.empty[stage]);     // this warp is done with the stage (its LDS results are in registers)
     }
-    sink.tile_end(sink_smem, ctid);
   }
-  sink.finish(sink_smem, ctid);
+  const bool redo = sink.finish(sink_smem, ctid);
+  if constexpr (SINK::PRIVATE && AP) {
+    // the private grid of this CTA overflowed a lane (atoms piled onto a few cells): its tiles again, straight from
+    // global memory into the uint32 grid; hits and diagnostics were counted by the pass above
+    if (redo) {
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const TileMeta m = make_tile_meta<true>(t, G.tile_atoms, natoms, gnx, rank, G);
+        const float *tile = x + (size_t)t * ((size_t)G.tile_atoms * 3);
+        for (unsigned j = ctid; j < m.nsel; j += CTHREADS) {
+          const bool inB = j >= m.nA;
+          const float *p = tile + 3 * ((long long)(inB ? m.baseB : m.baseA) + (long long)j * G.step);
+          float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
+          if (PBC) {
+            const float *L = box3 + 3 * (m.f0 + (inB ? 1 : 0));
+            px = wrap1(px, __ldg(L)); py = wrap1(py, __ldg(L + 1)); pz = wrap1(pz, __ldg(L + 2));
+          }
+          const FastCell fc = cell_of_fast(P, px, py, pz);
+          if (!fc.inside) continue;
+          const int cell = fc.sure ? fc.cell : cell_of_exact(P, px, py, pz);
+          if (cell >= 0) sink.redo_hit(cell);
+        }
+      }
+    }
+  }
 }
+
+
 
 // ---------------------------------------------------------------------------
 // n sequential f32 additions of w to v (see gcb::seq_add_f32)
@@ -704,6 +832,56 @@ packed_apply_kernel(uint32_t *__restrict__ pk, size_t nwords, uint32_t *__restri
     for (long f = (long)blockIdx.x * blockDim.x + threadIdx.x; f < nhits; f += (long)gridDim.x * blockDim.x) hits[f] = 0;
     if (blockIdx.x == 0 && threadIdx.x < 2) diag[threadIdx.x] = st->diag_snap[threadIdx.x];
   }
+}
+
+// In front of every private launch: turn the verdicts of the launches before into this launch's mode.
+__global__ void private_begin_kernel(PrivState *__restrict__ st)
+{
+  if (st->failed) {                                  // some CTA overflowed a lane in the launch before: back off
+    st->backoff = st->backoff < 1 ? 1 : (st->backoff >= 32 ? 64 : 2 * st->backoff);
+    st->skip = st->backoff;
+    st->failed = 0;
+    st->redone++;
+  } else if (st->skip == 0 && st->backoff > 0) {
+    st->backoff >>= 1;
+  }
+  st->direct = st->skip > 0 ? 1 : 0;
+  if (st->skip > 0) st->skip--;
+  st->launches++;
+}
+
+// Fold the private grids into the uint32 grid and clear them: one thread per word position, the CTAs' copies of a
+// word are `nwords` apart (coalesced across the warp); nothing else touches the grid meanwhile (stream order).
+template <int W>
+__global__ void __launch_bounds__(256)
+private_flush_kernel(uint32_t *__restrict__ stage, unsigned long long *__restrict__ stage_hits, unsigned nwords, int nctas,
+                     uint32_t *__restrict__ counts, size_t ncells)
+{
+  constexpr unsigned PER = 32u / W, LANE = (1u << W) - 1u;
+  constexpr int DEPTH = 8;                           // copies read per step: independent loads in flight
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) {
+    unsigned sum[PER];
+#pragma unroll
+    for (unsigned l = 0; l < PER; l++) sum[l] = 0;
+    for (int b0 = 0; b0 < nctas; b0 += DEPTH) {
+      uint32_t w[DEPTH];
+#pragma unroll
+      for (int q = 0; q < DEPTH; q++) w[q] = b0 + q < nctas ? stage[(size_t)(b0 + q) * nwords + i] : 0u;
+#pragma unroll
+      for (int q = 0; q < DEPTH; q++) {
+        if (!w[q]) continue;
+        stage[(size_t)(b0 + q) * nwords + i] = 0u;
+#pragma unroll
+        for (unsigned l = 0; l < PER; l++) sum[l] += (w[q] >> (W * l)) & LANE;
+      }
+    }
+#pragma unroll
+    for (unsigned l = 0; l < PER; l++) {
+      const size_t cell = (size_t)i * PER + l;
+      if (sum[l] && cell < ncells) counts[cell] += sum[l];
+    }
+  }
+  if (blockIdx.x == 0) for (int b = threadIdx.x; b < nctas; b += blockDim.x) stage_hits[b] = 0ull;
 }
 
 // Saturation guard of the uint32 cells.  The reference accumulates in f32, which stops moving after at most
@@ -902,6 +1080,19 @@ struct gcb_counter {
   PackedState *h_pstate = nullptr;    // pinned mirror, refreshed (asynchronously) behind every call's rounds
   int packed_pause = 0;               // calls still to be binned without the packed pass (see launch_packed)
   uint64_t packed_rounds = 0, packed_redone = 0;
+  // privatised path (PrivateSink): per-CTA W-bit copies of the grid, resting in d_priv between launches
+  int priv_bits = 0;                  // 0: grid too large for one CTA's shared memory; 8 or 4
+  unsigned priv_words = 0;            // words per private grid
+  int priv_ctas = 0;                  // CTAs (private grids) of every private launch
+  uint32_t *d_priv = nullptr;         // [priv_ctas][priv_words]
+  unsigned long long *d_priv_hits = nullptr;   // [priv_ctas]
+  PrivState *d_privstate = nullptr;
+  bool priv_dirty = false;            // d_priv holds hits that are not in d_runcnt yet
+  unsigned long long priv_bound = 0;  // upper bound of the hits any one private grid holds
+  unsigned long long priv_limit = 0;  // flush before priv_bound could exceed this
+  long long priv_min_units = 0;       // AUTO takes the private path for launches of at least this many atom-frames
+  uint64_t priv_launches = 0, priv_redone = 0;
+  ApGroup ap_priv{0, 1, TILE_ATOMS};
   bool l2_window = false;             // persisting-L2 window over d_pk set on the compute stream
   bool saturated = false;             // some cell was clamped (diag[3])
   // xtc path: GCB_XTC_SETS sets of {compressed bytes, frame table, status, decoded frames}, copy stream + events
@@ -980,6 +1171,8 @@ unsigned rank_host(const gcb_counter *c, int r)
   return (unsigned)(std::lower_bound(c->h_gindex.begin(), c->h_gindex.end(), r) - c->h_gindex.begin());
 }
 
+int flush_private(gcb_counter *c);
+
 int ensure_acc(gcb_counter *c)
 {
   c->acc_used = true;
@@ -1002,6 +1195,7 @@ int ensure_headroom(gcb_counter *c, uint32_t *cnt, unsigned long long &bound, un
 {
   if (bound + units <= c->clamp_ceiling) return GCB_OK;
   if (bound > c->clamp_at) {
+    if (cnt == c->d_runcnt) { int rc = flush_private(c); if (rc) return rc; }
     clamp_counts_kernel<<<elementwise_grid(c, c->ncells), 256, 0, c->compute>>>(cnt, c->ncells, (uint32_t)c->clamp_at, c->d_diag + 3);
     c->launches++;
     GCB_CUDA(cudaGetLastError());
@@ -1015,7 +1209,9 @@ int ensure_headroom(gcb_counter *c, uint32_t *cnt, unsigned long long &bound, un
 int fold_pending(gcb_counter *c)
 {
   if (!c->have_run) return GCB_OK;
-  int rc = ensure_acc(c);
+  int rc = flush_private(c);
+  if (rc) return rc;
+  rc = ensure_acc(c);
   if (rc) return rc;
   rc = ensure_headroom(c, c->d_total, c->bound_total, c->bound_run);
   if (rc) return rc;
@@ -1052,30 +1248,32 @@ int prof_end(gcb_counter *c, int kind, double units)
 }
 
 template <class SINK>
-size_t stream_smem_bytes() { return ((sizeof(StreamSmem<SINK::NSTAGES>) + 15) & ~(size_t)15) + SINK::EXTRA_SMEM; }
+size_t stream_smem_bytes() { return (sizeof(StreamSmem<SINK::NSTAGES, SINK::TILE_CAP>) + 15) & ~(size_t)15; }
 
 template <class SINK, bool PBC, bool AP, int GUARD = 0>
 int launch_stream(gcb_counter *c, const float *d_x, long long ntiles, const SINK &sink, int grid_cap,
-                  const float *d_box3, unsigned long long *d_hits, int *grid_out, const int *run_if = nullptr)
+                  const float *d_box3, unsigned long long *d_hits, int *grid_out, const int *run_if = nullptr,
+                  const ApGroup *tiles = nullptr)
 {
-  static bool attr_done[64] = {false};           // per instantiation and per device (the attribute is per context)
-  const size_t smem = stream_smem_bytes<SINK>();
+  static size_t attr_done[64] = {0};             // per instantiation and per device (the attribute is per context)
+  const size_t smem = stream_smem_bytes<SINK>() + sink.extra_smem();
   const int dv = c->opts.device & 63;
-  if (!attr_done[dv]) {
+  if (attr_done[dv] < smem) {
     GCB_CUDA(cudaFuncSetAttribute(bin_stream_kernel<SINK, PBC, AP, GUARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done[dv] = true;
+    attr_done[dv] = smem;
   }
+  const ApGroup &G = tiles ? *tiles : c->ap;
   const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
   long long grid = std::min<long long>(ntiles, (long long)c->sm_count * per_sm);
   if (grid_cap > 0) grid = std::min<long long>(grid, grid_cap);
-  const int kind = GUARD == 2 ? GCB_PROF_PACKED : GUARD == 1 ? GCB_PROF_REDO : GCB_PROF_DIRECT;
+  const int kind = SINK::PRIVATE ? GCB_PROF_PRIVATE : GUARD == 2 ? GCB_PROF_PACKED : GUARD == 1 ? GCB_PROF_REDO : GCB_PROF_DIRECT;
   int rc = prof_begin(c);
   if (rc) return rc;
-  bin_stream_kernel<SINK, PBC, AP, GUARD><<<(unsigned)grid, STREAM_THREADS, smem, c->compute>>>(
-      d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, c->ap, c->PF, sink, d_box3, d_hits, c->d_diag, run_if);
+  bin_stream_kernel<SINK, PBC, AP, GUARD><<<(unsigned)grid, (SINK::CWARPS + 1) * 32, smem, c->compute>>>(
+      d_x, c->natoms, c->d_gindex, (unsigned)c->gnx, c->d_rank, ntiles, G, c->PF, sink, d_box3, d_hits, c->d_diag, run_if);
   c->launches++;
   GCB_CUDA(cudaGetLastError());
-  rc = prof_end(c, kind, (double)ntiles * (AP ? c->ap.tile_atoms : TILE_ATOMS) / (double)c->natoms * (double)c->gnx);
+  rc = prof_end(c, kind, (double)ntiles * (AP ? G.tile_atoms : TILE_ATOMS) / (double)c->natoms * (double)c->gnx);
   if (rc) return rc;
   if (grid_out) *grid_out = (int)grid;
   return GCB_OK;
@@ -1199,6 +1397,72 @@ bool packed_paused(gcb_counter *c)
   return false;
 }
 
+// The private grids hold hits that the uint32 grid does not have yet: fold them in.  Called by everything that
+// reads or rescales d_runcnt (density, counts, fold, clamp, all-reduce) and before a lane could fill up.
+int flush_private(gcb_counter *c)
+{
+  if (!c->priv_dirty) return GCB_OK;
+  const int grid = (int)std::max<unsigned>(1u, std::min<unsigned>((c->priv_words + 255u) / 256u, (unsigned)c->sm_count * 8u));
+  if (c->priv_bits == 8)
+    private_flush_kernel<8><<<grid, 256, 0, c->compute>>>(c->d_priv, c->d_priv_hits, c->priv_words, c->priv_ctas, c->d_runcnt, c->ncells);
+  else
+    private_flush_kernel<4><<<grid, 256, 0, c->compute>>>(c->d_priv, c->d_priv_hits, c->priv_words, c->priv_ctas, c->d_runcnt, c->ncells);
+  c->launches++;
+  GCB_CUDA(cudaGetLastError());
+  c->priv_dirty = false;
+  c->priv_bound = 0;
+  return GCB_OK;
+}
+
+// Private path: the streaming kernel with one CTA per SM, each binning into its own shared-memory copy of the grid
+// (PrivateSink); the sub-tile tail goes to the gather kernel and straight into the uint32 grid.
+template <int W, bool PBC>
+int launch_private(gcb_counter *c, const float *d_x, long nframes, const float *d_box3, unsigned long long *d_hits)
+{
+  const int tile_atoms = c->ap_priv.tile_atoms;
+  if (!c->d_priv) {
+    GCB_CUDA(cudaMalloc(&c->d_priv, (size_t)c->priv_ctas * c->priv_words * 4));
+    GCB_CUDA(cudaMalloc(&c->d_priv_hits, sizeof(unsigned long long) * (size_t)c->priv_ctas));
+    GCB_CUDA(cudaMalloc(&c->d_privstate, sizeof(PrivState)));
+    GCB_CUDA(cudaMemsetAsync(c->d_priv, 0, (size_t)c->priv_ctas * c->priv_words * 4, c->compute));
+    GCB_CUDA(cudaMemsetAsync(c->d_priv_hits, 0, sizeof(unsigned long long) * (size_t)c->priv_ctas, c->compute));
+    GCB_CUDA(cudaMemsetAsync(c->d_privstate, 0, sizeof(PrivState), c->compute));
+  }
+  // what one private grid may receive from a tile: its selected atoms
+  const unsigned long long per_tile = (unsigned long long)(tile_atoms / std::max(c->ap.step, 1)) + 2ull;
+  // frames per launch: no private grid may be handed more than the flush threshold allows (a multiple of 4 frames:
+  // every launch starts 16-byte aligned)
+  const unsigned long long tiles_cap = std::max<unsigned long long>(1, c->priv_limit / per_tile) * (unsigned long long)c->priv_ctas;
+  const long fpl = (long)std::max<unsigned long long>(4, (tiles_cap * (unsigned long long)tile_atoms / (unsigned long long)c->natoms) & ~3ull);
+  for (long f0 = 0; f0 < nframes; f0 += fpl) {
+    const long n = std::min(fpl, nframes - f0);
+    const float *xs = d_x + (size_t)f0 * c->natoms * 3;
+    const float *bs = d_box3 ? d_box3 + 3 * f0 : nullptr;
+    const long long total_e = (long long)n * c->gnx, total_atoms = (long long)n * c->natoms;
+    const long long ntiles = total_atoms / tile_atoms;
+    long long e_begin = 0;
+    if (ntiles > 0) {
+      const unsigned long long share = ((unsigned long long)ntiles + (unsigned long long)c->priv_ctas - 1ull) / (unsigned long long)c->priv_ctas * per_tile;
+      if (c->priv_bound + share > c->priv_limit) { int rc = flush_private(c); if (rc) return rc; }
+      private_begin_kernel<<<1, 1, 0, c->compute>>>(c->d_privstate);
+      c->launches++;
+      GCB_CUDA(cudaGetLastError());
+      PrivateSink<W> sink;
+      sink.counts = c->d_runcnt; sink.stage = c->d_priv; sink.stage_hits = c->d_priv_hits; sink.st = c->d_privstate;
+      sink.nwords = c->priv_words;
+      int rc = launch_stream<PrivateSink<W>, PBC, true>(c, xs, ntiles, sink, c->priv_ctas, bs, d_hits + f0, nullptr, nullptr, &c->ap_priv);
+      if (rc) return rc;
+      c->priv_dirty = true;
+      c->priv_bound += share;
+      const long long g1 = ntiles * tile_atoms, f1 = g1 / c->natoms;
+      e_begin = f1 * c->gnx + rank_host(c, (int)(g1 - f1 * c->natoms));
+    }
+    int rc = launch_gather<MODE_COUNT, PBC>(c, xs, e_begin, total_e, c->d_runcnt, 1.0f, bs, d_hits + f0);
+    if (rc) return rc;
+  }
+  return GCB_OK;
+}
+
 template <int MODE, bool PBC>
 int launch_bin(gcb_counter *c, const float *d_x, long nframes, float w, const float *d_box3,
                unsigned long long *d_hits)
@@ -1210,7 +1474,13 @@ int launch_bin(gcb_counter *c, const float *d_x, long nframes, float w, const fl
   const bool aligned = ((uintptr_t)d_x & 15u) == 0;
   const int k = c->opts.kernel;
   const bool use_stream = aligned && k != GCB_KERNEL_GATHER &&
-                          (c->stream_ok || k == GCB_KERNEL_STREAM || k == GCB_KERNEL_STREAM_INDEXED || k == GCB_KERNEL_PACKED);
+                          (c->stream_ok || k == GCB_KERNEL_STREAM || k == GCB_KERNEL_STREAM_INDEXED || k == GCB_KERNEL_PACKED || k == GCB_KERNEL_PRIVATE);
+  // AUTO: grids that fit one CTA's shared memory as 6- or 8-bit counters are binned into per-CTA private copies
+  // (PrivateSink) when the launch is large enough to pay for loading and storing them
+  if (use_stream && MODE == MODE_COUNT && c->priv_bits != 0 && c->ap_ok &&
+      (k == GCB_KERNEL_PRIVATE || (k == GCB_KERNEL_AUTO && total_e >= c->priv_min_units)))
+    return c->priv_bits == 8 ? launch_private<8, PBC>(c, d_x, nframes, d_box3, d_hits)
+                             : launch_private<4, PBC>(c, d_x, nframes, d_box3, d_hits);
   // AUTO: grids beyond L2 whose packed counters fit it take the packed path (PackedSink)
   if (use_stream && MODE == MODE_COUNT && c->packed_bits != 0 &&
       (k == GCB_KERNEL_PACKED || (k == GCB_KERNEL_AUTO && c->packed_auto && total_e >= (1LL << 20) && !packed_paused(c))))
@@ -1384,6 +1654,7 @@ void free_counter(gcb_counter *c)
   cudaFree(c->d_gindex); cudaFree(c->d_rank); cudaFree(c->d_runcnt); cudaFree(c->d_total); cudaFree(c->d_acc);
   cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2);
   cudaFree(c->d_pk); cudaFree(c->d_pstate); cudaFreeHost(c->h_pstate);
+  cudaFree(c->d_priv); cudaFree(c->d_priv_hits); cudaFree(c->d_privstate);
   for (auto &x : c->xtc) {
     cudaFree(x.d_buf); cudaFree(x.d_meta); cudaFree(x.d_status); cudaFree(x.d_x); cudaFree(x.d_work); cudaFreeHost(x.h_meta); cudaFreeHost(x.h_status);
     if (x.skimmed) cudaEventDestroy(x.skimmed);
@@ -1505,6 +1776,29 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
       c->packed_units = uenv ? atoll(uenv) : (long long)((double)c->ncells * (c->packed_bits == 8 ? 8.0 : 1.5));
       if (c->packed_units < 4096) c->packed_units = 4096;
     }
+    // Private path: the grid as 8-bit or 4-bit counters next to the 3 x 36 KB tile ring in one CTA's shared memory.
+    // A private grid is flushed before its mean load could pass 32 hits per cell (8-bit lanes, range 255: densities
+    // that peak at several times their mean stay in range) or 1.5 (4-bit lanes, range 15: P[> 15] ~ 1e-11 per cell
+    // of a uniform density); anything denser fails the digit-sum check, is binned again directly, and backs off.
+    {
+      const size_t optin = (size_t)prop.sharedMemPerBlockOptin, ring = stream_smem_bytes<PrivateSink<8>>();
+      const size_t budget = optin > ring + 4096 ? optin - ring - 1024 : 0;
+      const size_t w8 = (c->ncells + 3) / 4, w4 = (c->ncells + 7) / 8;
+      const char *benv = getenv("GCB_PRIVATE_BITS");
+      const int want = benv ? atoi(benv) : 0;
+      if (w8 * 4 <= budget && want != 4) { c->priv_bits = 8; c->priv_words = (unsigned)w8; }
+      else if (w4 * 4 <= budget) { c->priv_bits = 4; c->priv_words = (unsigned)w4; }
+      if (getenv("GCB_NO_PRIVATE") || natoms < 256) c->priv_bits = 0;
+      c->priv_ctas = c->sm_count;
+      c->priv_limit = c->priv_bits == 8 ? (unsigned long long)c->ncells * 32ull : (unsigned long long)c->ncells * 3ull / 2ull;
+      if (const char *e = getenv("GCB_PRIVATE_LIMIT")) c->priv_limit = strtoull(e, nullptr, 10);
+      // loading and storing the private grids costs 2 x 4 B x words x CTAs of L2 traffic per launch: worth it from
+      // about that many atom-frames on (12 B each would stream in the same time)
+      c->priv_min_units = (long long)c->priv_words * c->priv_ctas * 2;
+      if (const char *e = getenv("GCB_PRIVATE_MIN_UNITS")) c->priv_min_units = atoll(e);
+      c->ap_priv = c->ap;
+      c->ap_priv.tile_atoms = std::min(PrivateSink<8>::TILE_CAP, natoms & ~3);
+    }
   }
   GCB_CREATE_CUDA(cudaMalloc(&c->d_gindex, sizeof(int) * std::max(gnx, 1)));
   GCB_CREATE_CUDA(cudaMalloc(&c->d_rank, sizeof(unsigned) * rank.size()));
@@ -1546,6 +1840,14 @@ int gcb_counter_reset(gcb_counter *c)
   GCB_CUDA(cudaMemsetAsync(c->d_diag, 0, sizeof(unsigned long long) * 4, c->compute));
   if (c->d_pstate) GCB_CUDA(cudaMemsetAsync(&c->d_pstate->rounds, 0, 2 * sizeof(unsigned long long), c->compute));
   c->packed_rounds = 0; c->packed_redone = 0;
+  if (c->d_priv) {
+    if (c->priv_dirty) {
+      GCB_CUDA(cudaMemsetAsync(c->d_priv, 0, (size_t)c->priv_ctas * c->priv_words * 4, c->compute));
+      GCB_CUDA(cudaMemsetAsync(c->d_priv_hits, 0, sizeof(unsigned long long) * (size_t)c->priv_ctas, c->compute));
+    }
+    GCB_CUDA(cudaMemsetAsync(&c->d_privstate->launches, 0, 2 * sizeof(unsigned long long), c->compute));
+  }
+  c->priv_dirty = false; c->priv_bound = 0; c->priv_launches = 0; c->priv_redone = 0;
   c->bound_run = 0; c->bound_total = 0;
   c->reduced = false; c->global_frames = 0;
   c->have_run = false; c->any = false; c->uniform = true; c->w_cur = 0; c->w_first = 0;
@@ -1870,6 +2172,11 @@ int gcb_counter_sync(gcb_counter *c)
       GCB_CUDA(cudaMemcpy(&ps, c->d_pstate, sizeof(ps), cudaMemcpyDeviceToHost));
       c->packed_rounds = ps.rounds; c->packed_redone = ps.redone;
     }
+    if (c->d_privstate) {
+      PrivState ps;
+      GCB_CUDA(cudaMemcpy(&ps, c->d_privstate, sizeof(ps), cudaMemcpyDeviceToHost));
+      c->priv_launches = ps.launches; c->priv_redone = ps.redone + (ps.failed ? 1 : 0);
+    }
   }
   // sumP: `sumP += (double)weight` once per hit, frame by frame (g_ri3Dc.c:151,426)
   for (; c->sumP_frames < c->hits_per_frame.size(); c->sumP_frames++) {
@@ -1895,6 +2202,8 @@ int gcb_counter_stats(gcb_counter *c, gcb_stats *out)
   out->kernel_launches = c->launches;
   out->packed_rounds = c->packed_rounds;
   out->packed_redone = c->packed_redone;
+  out->private_launches = c->priv_launches;
+  out->private_redone = c->priv_redone;
   out->saturated = c->saturated ? 1 : 0;
   return GCB_OK;
 }
@@ -1926,8 +2235,10 @@ int gcb_counter_device_counts(gcb_counter *c, uint32_t **counts_dev)
 {
   if (!c || !counts_dev) return gcb::fail(GCB_ERR_ARG, "null argument");
   GCB_CUDA(cudaSetDevice(c->opts.device));
+  int rc = flush_private(c);
+  if (rc) return rc;
   if (!c->acc_used) { *counts_dev = c->d_runcnt; return GCB_OK; }
-  int rc = ensure_out(c);
+  rc = ensure_out(c);
   if (rc) return rc;
   add_u32_kernel<<<elementwise_grid(c, c->ncells), 256, 0, c->compute>>>(c->d_total, c->have_run ? c->d_runcnt : nullptr,
                                                                           (uint32_t *)c->d_out, c->ncells);
@@ -1951,6 +2262,8 @@ int gcb_counter_counts(gcb_counter *c, uint32_t *counts_zfast)
 static int density_to_device(gcb_counter *c, double denom)
 {
   int rc = ensure_out(c);
+  if (rc) return rc;
+  rc = flush_private(c);
   if (rc) return rc;
   density_kernel<<<elementwise_grid(c, c->ncells), 256, 0, c->compute>>>(c->d_runcnt, c->acc_used ? c->d_acc : nullptr, c->w_cur,
                                                                           c->have_run ? 1 : 0, denom, c->d_out, c->ncells);
@@ -2142,6 +2455,7 @@ int gcb_counter_profile_read(gcb_counter *c, double *k1_ms, long *k1_launches, d
   int best = GCB_PROF_DIRECT;
   if (ms[GCB_PROF_PACKED] > ms[best]) best = GCB_PROF_PACKED;
   if (ms[GCB_PROF_REDO] > ms[best]) best = GCB_PROF_REDO;
+  if (ms[GCB_PROF_PRIVATE] > ms[best]) best = GCB_PROF_PRIVATE;
   if (k1_ms) *k1_ms = ms[best];
   if (k1_launches) *k1_launches = n[best];
   if (k1_atom_frames) *k1_atom_frames = units[best];
@@ -2248,6 +2562,8 @@ extern "C" int gcb_counter_allreduce(gcb_counter *c)
   auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
   const double t_begin = now();
   int rc = finish_reduce(c);                  // a previous reduce whose statistics nobody asked for
+  if (rc) return rc;
+  rc = flush_private(c);                      // the grid that is reduced must hold everything
   if (rc) return rc;
   if (c->reduce_done) GCB_CUDA(cudaEventSynchronize(c->reduce_done));          // (or that a reset dropped): its D2H owns the pinned scratch
   for (auto &s : c->slots) { rc = collect_slot(c, s); if (rc) return rc; }     // host-staged batches report through pinned memory

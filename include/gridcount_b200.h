@@ -98,6 +98,14 @@ enum {                     /* kernel selection (GCB_KERNEL_AUTO picks by index-g
   GCB_KERNEL_PACKED = 5           /* streaming kernel with non-returning REDs into packed 8- or 4-bit L2-resident
                                      counters, verified (digit sum == hits) and folded into the uint32 grid once per
                                      round; AUTO picks it for grids whose uint32 cells exceed the L2 */
+  ,
+  GCB_KERNEL_PRIVATE = 6          /* streaming kernel, one CTA per SM, every CTA binning with shared-memory atomics
+                                     into its own 8- or 4-bit copy of the whole grid (grids up to ~118 000 / ~236 000
+                                     cells: 60^3); the copies rest in global memory between launches and are folded into
+                                     the uint32 grid when it is read or a lane could fill up; verified by digit sum
+                                     per CTA and launch.  AUTO picks it for such grids when a launch is large
+                                     enough to pay for loading and storing the copies; on larger grids this value
+                                     means GCB_KERNEL_STREAM */
 };
 
 typedef struct {
@@ -122,6 +130,8 @@ typedef struct {
   int saturated;           /* 1 if some cell reached the saturation guard (2^27 hits and the counter range was about
                               to run out): its count is a lower bound; occupancy and density are still the reference's
                               bits, because the reference's f32 accumulator stops moving long before (this rank) */
+  uint64_t private_launches; /* launches on the private shared-memory path (GCB_KERNEL_PRIVATE) ... */
+  uint64_t private_redone;   /* ... in which some CTA overflowed a lane and binned its tiles again directly (this rank) */
 } gcb_stats;
 
 int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex, int gnx,
@@ -181,8 +191,9 @@ int gcb_counter_profile(gcb_counter *c, int enable);
 int gcb_counter_profile_read(gcb_counter *c, double *k1_ms, long *k1_launches, double *k1_atom_frames);
 /* The same split by what the launch was: [0] the direct uint32 kernel, [1] the packed-counter pass of a round,
  * [2] the guarded uint32 pass behind it (returns at once unless the round failed verification or was skipped),
- * [3] everything else K1 queued for those frames (verify/apply passes, gather tails). */
-enum { GCB_PROF_DIRECT = 0, GCB_PROF_PACKED = 1, GCB_PROF_REDO = 2, GCB_PROF_OTHER = 3, GCB_PROF_KINDS = 4 };
+ * [3] everything else K1 queued for those frames (verify/apply passes, gather tails, the fused xtc kernel),
+ * [4] the streaming kernel with per-CTA private shared-memory grids. */
+enum { GCB_PROF_DIRECT = 0, GCB_PROF_PACKED = 1, GCB_PROF_REDO = 2, GCB_PROF_OTHER = 3, GCB_PROF_PRIVATE = 4, GCB_PROF_KINDS = 5 };
 int gcb_counter_profile_kinds(gcb_counter *c, double ms[GCB_PROF_KINDS], long launches[GCB_PROF_KINDS], double atom_frames[GCB_PROF_KINDS]);
 
 /* Frame-sharded multi-GPU: one counter per rank; integer sum of the private

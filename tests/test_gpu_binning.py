@@ -13,7 +13,7 @@ from gridcount_b200 import _cabi as K
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [K.KERNEL_GATHER, K.KERNEL_STREAM, K.KERNEL_STREAM_INDEXED, K.KERNEL_PACKED]
+KERNELS = [K.KERNEL_GATHER, K.KERNEL_STREAM, K.KERNEL_STREAM_INDEXED, K.KERNEL_PACKED, K.KERNEL_PRIVATE]
 
 
 def to_ogeom(geom):
@@ -601,3 +601,111 @@ def test_saturation_guard_with_lowered_thresholds(monkeypatch):
         np.testing.assert_array_equal(ctr.hits_per_frame(), oh)      # per-frame statistics are 64-bit and unaffected
         assert ctr.stats().saturated == 1
         ctr.close()
+
+
+# ----------------------------------------------------------------------------- private shared-memory grids
+@pytest.mark.parametrize("bits", [8, 4])
+@pytest.mark.parametrize("kind", ["uniform", "one cell", "64 sites", "warm + background"])
+def test_private_grids_stay_exact_through_overflow_flushes_and_reset(kind, bits, monkeypatch):
+    """GCB_KERNEL_PRIVATE: every CTA bins with shared-memory atomics into its own 8- or 4-bit copy of the grid; the
+    copies rest in global memory between launches and are folded into the uint32 grid lazily.  A CTA whose digit sum
+    does not equal the hits it holds (a lane overflowed) bins its tiles again directly and the next launches back
+    off.  Counts and per-frame hits must equal the oracle whichever way every launch went, over several launches,
+    with forced flushes in between, after a reset, and for frames whose tiles straddle frame boundaries."""
+    monkeypatch.setenv("GCB_PRIVATE_BITS", str(bits))
+    L, delta = (4.0, 4.0, 4.0), 0.1
+    geom = g.setup_geometry(L, delta)                # 40^3 = 64 000 cells
+    natoms, nframes = 8190, 40                       # 8190 atoms: tiles of 3072 atoms straddle frames
+    rng = np.random.default_rng(13)
+    x = (rng.random((nframes, natoms, 3)) * np.asarray(L)).astype(np.float32)
+    if kind == "one cell":                           # every CTA gets thousands of hits on one lane: must fail and redo
+        x[:] = np.asarray([1.234, 2.345, 3.456], np.float32)
+    elif kind == "64 sites":
+        sites = (rng.random((64, 3)) * np.asarray(L)).astype(np.float32)
+        x[:] = sites[rng.integers(0, 64, (nframes, natoms))]
+    elif kind == "warm + background":
+        sites = (rng.random((64, 3)) * np.asarray(L)).astype(np.float32)
+        x[:, ::16] = sites[rng.integers(0, 64, (nframes, x[:, ::16].shape[1]))]
+    gindex = np.arange(0, natoms, 3, dtype=np.int32)
+    ocounts, ohits, _ = oracle_counts(geom, x, gindex)
+    dev = g.DeviceFrames(nframes, natoms)
+    dev.upload(x)
+    for limit in (None, "3000"):                     # default flush threshold / a flush every launch or two
+        monkeypatch.delenv("GCB_PRIVATE_LIMIT", raising=False)
+        if limit:
+            monkeypatch.setenv("GCB_PRIVATE_LIMIT", limit)
+        ctr = g.GridCounter(geom, gindex, natoms, kernel=K.KERNEL_PRIVATE)
+        for first in range(0, nframes, 10):          # four launches, nothing read in between
+            ctr.add_device_frames(dev, first, 10)
+        np.testing.assert_array_equal(ctr.counts(), ocounts)
+        np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
+        st = ctr.stats()
+        assert st.hits == int(ohits.sum()) and st.private_launches == 4
+        if kind == "one cell":
+            assert st.private_redone >= 1, "overflowing lanes were not caught by the digit-sum check"
+        if kind == "uniform":
+            assert st.private_redone == 0
+        # more frames on top of a grid that has been read (the copies were folded in and cleared)
+        ctr.add_device_frames(dev, 0, 7)
+        o2, h2, _ = oracle_counts(geom, x[:7], gindex)
+        np.testing.assert_array_equal(ctr.counts(), ocounts + o2)
+        # density (K2) straight after binning: the lazy flush must come first
+        ctr.reset()
+        ctr.add_device_frames(dev, 3, 9)
+        o3, _, _ = oracle_counts(geom, x[3:12], gindex)
+        occ = ctr.occupancy()
+        np.testing.assert_array_equal(occ, o3.astype(np.float32))
+        # and a reset drops what the copies hold
+        ctr.add_device_frames(dev, 0, 5)
+        ctr.reset()
+        ctr.add_device_frames(dev, 20, 4)
+        o4, _, _ = oracle_counts(geom, x[20:24], gindex)
+        np.testing.assert_array_equal(ctr.counts(), o4)
+        ctr.close()
+    dev.free()
+
+
+def test_private_backoff_recovers():
+    """after a launch that overflowed, the next launches go to the uint32 grid; a spread-out input later returns to
+    the private grids (the back-off halves while launches pass)"""
+    L, delta = (4.0, 4.0, 4.0), 0.1
+    geom = g.setup_geometry(L, delta)
+    natoms = 8192
+    rng = np.random.default_rng(3)
+    spread = (rng.random((12, natoms, 3)) * np.asarray(L)).astype(np.float32)
+    piled = np.broadcast_to(np.asarray([1.234, 2.345, 3.456], np.float32), (12, natoms, 3)).copy()
+    gindex = np.arange(natoms, dtype=np.int32)
+    ctr = g.GridCounter(geom, gindex, natoms, kernel=K.KERNEL_PRIVATE)
+    total = np.zeros(geom.shape, np.uint32)
+    for batch in (spread, piled, spread, spread, spread, spread, spread):
+        ctr.add_frames(batch)
+        total += oracle_counts(geom, batch, gindex)[0]
+    np.testing.assert_array_equal(ctr.counts(), total)
+    st = ctr.stats()
+    assert st.private_redone >= 1 and st.private_launches == 7
+    ctr.close()
+
+
+def test_auto_takes_the_private_path_on_the_c1_shape():
+    """BASELINE config 1 (2700 atoms, 900 OW, 60^3 cells as 4-bit private counters): AUTO bins a large batch through
+    the private grids, a small one straight into the uint32 grid, and mixing both is exact"""
+    L = (3.0, 3.0, 3.0)
+    natoms = 2700
+    geom = g.setup_geometry(L, 0.05)
+    assert geom.shape == (60, 60, 60)
+    gindex = np.arange(0, natoms, 3, dtype=np.int32)
+    big, small = 16384, 64
+    dev = g.DeviceFrames(big, natoms).generate(g.make_gen(77, L))
+    ctr = g.GridCounter(geom, gindex, natoms)
+    ctr.add_device_frames(dev)                      # 14.7 M atom-frames: private
+    ctr.add_device_frames(dev, 0, small)            # 57 600: direct
+    st = ctr.stats()
+    assert st.private_launches == 1 and st.private_redone == 0
+    assert st.hits == (big + small) * len(gindex)
+    c = ctr.counts()
+    assert int(c.sum(dtype=np.uint64)) == st.hits
+    want, _, _ = oracle_counts(geom, dev.download(0, small), gindex)
+    ref = g.GridCounter(geom, gindex, natoms, kernel=K.KERNEL_STREAM)
+    ref.add_device_frames(dev)
+    np.testing.assert_array_equal(c, ref.counts() + want)
+    ref.close(); ctr.close(); dev.free()

@@ -12,6 +12,8 @@ from gridcount_b200 import _cabi as K  # noqa: E402
 
 SHAPES = {
     "c1": ((3.0, 3.0, 3.0), 0.05, 2700, 3, 20000),
+    "c1long": ((3.0, 3.0, 3.0), 0.05, 2700, 3, 200000),
+    "pore": ((4.0, 4.0, 6.0), 0.1, 30000, 3, 20000),          # a typical pore analysis: 96 000 cells, 10 000 OW
     "c2": ((8.0, 8.0, 13.4), 0.1, 60000, 3, 4000),
     "c2all": ((8.0, 8.0, 13.4), 0.1, 60000, 1, 2000),
     "c3": ((20.0, 20.0, 20.0), 0.05, 1000000, 3, 1152),
@@ -30,7 +32,8 @@ def main():
     gindex = np.arange(0, natoms, stride, dtype=np.int32)
     gen = g.make_gen(1, L, K.GEN_CLUSTER, nsites=256, sigma=0.1) if name.endswith("k") else g.make_gen(1, L)
     dev = g.DeviceFrames(nframes, natoms).generate(gen)
-    kernels = (("gather", K.KERNEL_GATHER), ("stream", K.KERNEL_STREAM), ("packed", K.KERNEL_PACKED), ("auto", K.KERNEL_AUTO))
+    kernels = (("gather", K.KERNEL_GATHER), ("stream", K.KERNEL_STREAM), ("packed", K.KERNEL_PACKED), ("private", K.KERNEL_PRIVATE),
+               ("auto", K.KERNEL_AUTO))
     only = os.environ.get("PERF_KERNELS")
     for kname, kernel in kernels:
         if only and kname not in only.split(","):
@@ -52,6 +55,8 @@ def main():
         st = ctr.stats()
         if st.packed_rounds:
             print("    packed rounds %d, redone %d" % (st.packed_rounds, st.packed_redone))
+        if st.private_launches:
+            print("    private launches %d, redone %d" % (st.private_launches, st.private_redone))
         ctr.close()
     dev.free()
 
