@@ -47,9 +47,13 @@ SEED = 20261019
 CONFIGS = {
     "C1": dict(title="C1 SPC water box 3 nm: 2700 atoms, 900 OW counted, 0.05 nm grid 60x60x60",
                L=(3.0, 3.0, 3.0), delta=0.05, natoms=2700, stride=3, named_frames=1000, resident=20000, gen="uniform",
-               grid=(60, 60, 60), seed=SEED + 1, prefix=64,
+               grid=(60, 60, 60), seed=SEED + 1, prefix=64, reset_each_pass=True,
                note="the named job (1000 frames, 32 MB) would be L2-resident and launch-bound; measured over 20000 "
                     "distinct frames (648 MB)"),
+    "P1": dict(title="P1 (not a BASELINE config) pore region 4 x 4 x 6 nm: 30000 atoms, 10000 OW counted, 0.1 nm grid "
+                     "40x40x60 = 96000 cells, which fit one CTA's shared memory as 8-bit private counters",
+               L=(4.0, 4.0, 6.0), delta=0.1, natoms=30000, stride=3, named_frames=20000, resident=20000, gen="uniform",
+               grid=(40, 40, 60), seed=SEED + 6, prefix=64, reset_each_pass=True),
     "C2": dict(title="C2 nanopore: 60000 atoms, 20000 OW counted, 10000 frames, 0.1 nm grid 80x80x134",
                L=(8.0, 8.0, 13.4), delta=0.1, natoms=60000, stride=3, named_frames=10000, resident=10000, gen="pore",
                slab=(4.7, 8.7), pore_r=0.8, grid=(80, 80, 134), seed=SEED + 2, prefix=64),
@@ -292,7 +296,13 @@ def xtc_section(g, ctr, dev, wl, geom, gindex):
         step()
         ts.append(time.perf_counter() - t0)
     e2e_s = float(np.median(ts))
-    st = ctr.stats()
+    # parity inside the bench: the fused decode-and-bin path against decode-to-x + the binning kernels
+    got = ctr.counts()
+    d2 = xb.decode_to_device()
+    c2 = g.GridCounter(geom, gindex, natoms, device=ctr.device, kernel=g._cabi.KERNEL_STREAM)
+    c2.add_device_frames(d2, weights=w)
+    same = bool(np.array_equal(got, c2.counts()))
+    c2.close(); d2.free()
     res = {"frames": xb.nframes, "compressed_bytes_per_atom": len(data) / (NF * natoms),
            "host_decode_atoms_per_s": NF * natoms / host_s, "host_decode_threads": 1,
            "gpu_decode_atoms_per_s": xb.nframes * natoms / gpu_decode_s,
@@ -301,7 +311,7 @@ def xtc_section(g, ctr, dev, wl, geom, gindex):
                        "d2h_bytes_per_step": int(geom.cells * 4), "ms_per_step": e2e_s * 1e3,
                        "atoms_decoded_per_s": xb.nframes * natoms / e2e_s,
                        "pcie_bound_at_55GBs": 55e9 / (len(data) / (NF * natoms)) / (natoms / len(gindex)) * 1e-9,
-                       "all_hits_binned": bool(st.hits == xb.nframes * len(gindex)),
+                       "counts_equal_two_step_path": same,
                        "path": "gcb_counter_add_xtc(pinned xtc bytes): the frames are binned straight out of the GPU "
                                "decoder, no coordinates stored -> gcb_counter_density(host grid)"},
            "data": "synthetic positions of this workload, precision 1000: ~5 B/atom compressed; real water compresses further"}
@@ -389,8 +399,10 @@ def l2_ceilings(g, window_bytes, stride, device):
     """the memory system's ceilings for K1's traffic on this shape, measured now (gcb_selftest_l2)"""
     red_peak, _ = g.selftest_l2(window_bytes, 0, device)
     mix, rd = g.selftest_l2(window_bytes, 1 if stride == 3 else 2, device)
+    _, alone = g.selftest_l2(window_bytes, 3, device)
     return {"window_mb": window_bytes / 2.0 ** 20, "red_peak_gops": red_peak,
-            "stream_plus_red_gops": mix, "stream_plus_red_read_gbs": rd,
+            "stream_plus_red_gops": mix, "stream_plus_red_read_gbs": rd, "stream_alone_read_gbs": alone,
+            "stream_alone_gops": alone / (12.0 * stride),
             "mix": "one random RED per %d streamed bytes" % (36 if stride == 3 else 12)}
 
 
@@ -444,11 +456,15 @@ def measure_config(g, name, cfg, device, peak, peak_src, reps=10, extra=None):
     ctr = g.GridCounter(geom, gindex, cfg["natoms"], device=device)
     w = np.ones(F, np.float32)
     for _ in range(max(3, reps)):                 # also sizes the counter's per-call buffers for `reps` calls in flight
+        if cfg.get("reset_each_pass"):
+            ctr.reset_grid()
         ctr.add_device_frames(dev, weights=w)
     ctr.sync()
     ctr.reset_grid()
     ctr.event_record(0)
     for _ in range(reps):
+        if cfg.get("reset_each_pass"):            # (private counters accumulate over launches: identical frames binned again
+            ctr.reset_grid()                      #  and again would pile up as no trajectory does)
         ctr.add_device_frames(dev, weights=w)
     ctr.event_record(1)
     ms = ctr.event_elapsed(0, 1)
@@ -456,6 +472,8 @@ def measure_config(g, name, cfg, device, peak, peak_src, reps=10, extra=None):
     lost = st.hits != st.atom_frames
     ctr.profile(True)
     for _ in range(2):
+        if cfg.get("reset_each_pass"):
+            ctr.reset_grid()
         ctr.add_device_frames(dev, weights=w)
     packed_bytes = geom.cells if geom.cells <= (80 << 20) else geom.cells // 2
     rl = roofline_of(g, ctr, cfg["stride"], geom.cells, peak, peak_src, device, name)
@@ -465,7 +483,10 @@ def measure_config(g, name, cfg, device, peak, peak_src, reps=10, extra=None):
            "frames_resident_gb": F * cfg["natoms"] * 12 / 1e9, "passes_timed": reps,
            "value": float(gnx) * F * reps / (ms * 1e-3) * 1e-9, "unit": UNIT,
            "ms_per_pass": ms / reps, "all_hits_in_grid": not lost,
-           "packed_rounds": int(st.packed_rounds), "packed_redone": int(st.packed_redone)}
+           "packed_rounds": int(st.packed_rounds), "packed_redone": int(st.packed_redone),
+           "private_launches": int(st.private_launches), "private_redone": int(st.private_redone)}
+    if cfg.get("reset_each_pass"):
+        res["pass"] = "zero the grid + bin the resident frames"
     if cfg.get("note"):
         res["note"] = cfg["note"]
     if extra:
@@ -480,6 +501,7 @@ def measure_config(g, name, cfg, device, peak, peak_src, reps=10, extra=None):
     rl["l2"] = dict(l2)
     rl["l2"]["frac_of_red_peak"] = rl["kernel_g_atom_frames_per_s"] / l2["red_peak_gops"]
     rl["l2"]["frac_of_stream_plus_red"] = rl["kernel_g_atom_frames_per_s"] / l2["stream_plus_red_gops"]
+    rl["l2"]["frac_of_stream_alone"] = rl["kernel_g_atom_frames_per_s"] / l2["stream_alone_gops"]
     res["roofline"] = rl
     res["parity_checked"] = par["ok"]
     res["parity"] = par
@@ -689,7 +711,7 @@ def run_gpu_arm(args, rank, local_rank, world):
     k3_c2 = None
     if rank == 0 and world == 1:
         per_config = {}
-        for name in ("C1", "C2", "C4", "C4K"):
+        for name in ("C1", "P1", "C2", "C4", "C4K"):
             c = CONFIGS[name]
             extra = None
             if name == "C2":
