@@ -309,7 +309,11 @@ size_t gh_xtc_decode_frame(const uint8_t *in, size_t len, gh_frame_info *info, f
   if (!x) return off + padded;                       /* header only: skip the frame */
   unsigned sizeint[3], bitsizeint[3] = {0, 0, 0};
   int bitsize;
-  for (d = 0; d < 3; d++) sizeint[d] = (unsigned)(maxint[d] - minint[d]) + 1u;
+  for (d = 0; d < 3; d++) {
+    if (maxint[d] < minint[d] || !(prec > 0)) return 0;     /* damaged header: sizeint would wrap to 0 (division by zero below) */
+    sizeint[d] = (unsigned)(maxint[d] - minint[d]) + 1u;
+    if (sizeint[d] == 0u) return 0;
+  }
   if ((sizeint[0] | sizeint[1] | sizeint[2]) > 0xffffffu) {
     for (d = 0; d < 3; d++) bitsizeint[d] = (unsigned)bits_for(sizeint[d]);
     bitsize = 0;

@@ -210,3 +210,33 @@ def test_device_resident_grid_with_crop_equals_host_path(name, run):
     for k in ARRAYS:
         u.assert_bits_equal(rd[k], r[k], k)
     assert bytes(rd["tg"]) == bytes(r["tg"])
+
+
+def test_c3_sized_grid_bit_exact_against_the_oracle():
+    """BASELINE config 3's grid (400^3 = 64 M cells, 256 MB): every output of the analysis equals the oracle's
+    sequential chains bit for bit (the f32 `average` over 64 M cells saturates in the reference; so must ours), from
+    a host grid and from the same grid already in device memory."""
+    L, delta = (20.0, 20.0, 20.0), 0.05
+    geom = g.setup_geometry(L, delta)
+    assert geom.shape == (400, 400, 400)
+    rng = np.random.default_rng(400)
+    dens = (rng.poisson(2.0, geom.shape) * np.float32(0.41)).astype(np.float32)
+    tg = geom.tg
+    og = u.Geom.from_buffer_copy(bytes(tg))
+    u.oracle().gco_update_b(C.byref(og))
+    an = u.Analysis()
+    an.unit = u.UNITS["SPC"]; an.rad_ba_step = 1
+    u.oracle().gco_analyse(C.byref(og), u.fptr(dens), C.byref(an))
+    want = u.analysis_arrays(an, og)
+    scal = (np.float32(an.average), an.sumP, an.sumH, np.float32(an.volume), np.float32(an.reff), an.ivol)
+    u.oracle().gco_analysis_free(C.byref(an))
+    dev = g.DeviceFrames(1, dens.size // 3 + 1)
+    g._cabi.check(g._cabi.lib.gcb_memcpy_h2d(dev.ptr, dens.ctypes.data, dens.nbytes, 0), "h2d")
+    for r in (g.analyse(tg, dens, unit="SPC"), g.analyse(tg, None, unit="SPC", grid_dev=dev.ptr)):
+        for k in ("rzp", "hrzp", "zdf", "lzdf", "profile", "rdf", "hrdf", "xyp", "hxyp", "xzp", "yzp", "rweight"):
+            p, q = np.asarray(want[k], np.float32), np.asarray(r[k], np.float32)
+            assert np.array_equal(np.isnan(p), np.isnan(q)), k
+            assert ((p.view(np.uint32) == q.view(np.uint32)) | np.isnan(p)).all(), k
+        got = (np.float32(r["average"]), r["sumP"], r["sumH"], np.float32(r["volume"]), np.float32(r["reff"]), r["ivol"])
+        assert got == scal, (got, scal)
+    dev.free()

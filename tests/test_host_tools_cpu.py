@@ -112,6 +112,12 @@ def test_xtc_rejects_damage(host):
     assert host.gh_xtc_decode_frame(bad.ctypes.data_as(u.c_u8_p), len(bad), C.byref(info), u.fptr(y), 300) == 0
     short = buf[:len(buf) - 8].copy()                                    # truncated
     assert host.gh_xtc_decode_frame(short.ctypes.data_as(u.c_u8_p), len(short), C.byref(info), u.fptr(y), 300) == 0
+    # a crafted header with maxint = minint - 1 makes the range wrap to zero: must be refused, not divide by zero
+    for d in range(3):
+        wrap = buf.copy()
+        lo = int.from_bytes(bytes(wrap[60 + 4 * d:64 + 4 * d]), "big", signed=True)
+        wrap[72 + 4 * d:76 + 4 * d] = np.frombuffer((lo - 1).to_bytes(4, "big", signed=True), np.uint8)
+        assert host.gh_xtc_decode_frame(wrap.ctypes.data_as(u.c_u8_p), len(wrap), C.byref(info), u.fptr(y), 300) == 0
 
 
 def read_all(host, path):
