@@ -241,26 +241,35 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def xtc_section(g, ctr, dev, wl, geom, gindex):
-    """256 frames of the workload written as XTC (precision 1000) by the host codec (host/libgcbhost.so):
-    single-thread host decode rate, GPU decode rate, and the binning job driven from pinned XTC bytes."""
+def xtc_encode(dev, wl, nf, build=True):
+    """`nf` frames of the resident batch written as XTC (precision 1000) by the host codec (host/libgcbhost.so)
+    -> (bytes, the codec library)"""
     import gcutil as u
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host"), "libgcbhost.so"])
+    if build:
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host"), "libgcbhost.so"])
     H = C.CDLL(os.path.join(ROOT, "host", "libgcbhost.so"))
     H.gh_xtc_encode_frame.argtypes = [C.c_int, C.c_int, C.c_float, u.c_float_p, u.c_float_p, C.c_float, u.c_u8_p, C.c_size_t]
     H.gh_xtc_encode_frame.restype = C.c_size_t
     H.gh_xtc_decode_frame.argtypes = [u.c_u8_p, C.c_size_t, C.c_void_p, u.c_float_p, C.c_int]
     H.gh_xtc_decode_frame.restype = C.c_size_t
-    natoms, NF = wl["natoms"], 256
-    x = dev.download(0, NF)
+    natoms = wl["natoms"]
+    x = dev.download(0, nf)
     b9 = u.box9(wl["L"])
     buf = np.zeros(natoms * 16 + 256, np.uint8)
     parts = []
-    for f in range(NF):
+    for f in range(nf):
         n = H.gh_xtc_encode_frame(natoms, f, float(f), u.fptr(b9), u.fptr(x[f]), 1000.0, buf.ctypes.data_as(u.c_u8_p), len(buf))
         assert n > 0
         parts.append(buf[:n].tobytes())
-    data = b"".join(parts)
+    return b"".join(parts), H
+
+
+def xtc_section(g, ctr, dev, wl, geom, gindex):
+    """256 frames of the workload written as XTC (precision 1000) by the host codec (host/libgcbhost.so):
+    single-thread host decode rate, GPU decode rate, and the binning job driven from pinned XTC bytes."""
+    import gcutil as u
+    natoms, NF = wl["natoms"], 256
+    data, H = xtc_encode(dev, wl, NF)
     raw = np.frombuffer(data, np.uint8).copy()
     info = (C.c_char * 64)()
     out = np.zeros((natoms, 3), np.float32)
@@ -671,10 +680,15 @@ def run_gpu_arm(args, rank, local_rank, world):
     # ---- parity inside the bench ---------------------------------------------------------------
     parity = None
     c5 = None
+    e2e_xtc_multi = None
     if world == 1:
         parity = prefix_parity(g, cfg, geom, gindex, dev, device)
     else:
         c5, parity = c5_section(g, u, torch, dist, ctr, dev, geom, rank, world, device, barrier, max_over_ranks)
+        try:
+            e2e_xtc_multi = xtc_multi_section(g, torch, dist, rank, world, device, barrier, max_over_ranks)
+        except Exception as e:                        # (every rank fails alike or not at all: the section is collective)
+            e2e_xtc_multi = {"error": str(e)[:200]}
 
     # ---- a_ri3Dc's reductions over the job's density (K3), on its own line -----------------------
     k3 = None
@@ -741,11 +755,60 @@ def run_gpu_arm(args, rank, local_rank, world):
                 "packed_counters": packed_info,
                 "parity_checked": bool(parity and parity["ok"]), "parity": parity,
                 "cpu_baseline": cpu, "a_ri3Dc": {"C3": k3, "C2": k3_c2} if world == 1 else None, "xtc": xtc,
-                "per_config": per_config, "c5": c5}
+                "per_config": per_config, "c5": c5, "e2e_xtc": e2e_xtc_multi if world > 1 else (xtc or {}).get("e2e_xtc")}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def xtc_multi_section(g, torch, dist, rank, world, device, barrier, max_over_ranks):
+    """N > 1: the end-to-end job from XTC bytes on every rank (C2 shape, 4096 frames per rank and step): pinned
+    compressed bytes -> H2D -> GPU decode-and-bin -> NCCL grid all-reduce -> density on the host."""
+    from gridcount_b200.api import nccl_unique_id
+    cfg = CONFIGS["C2"]
+    natoms, NF, REP = cfg["natoms"], 256, 16
+    geom = g.setup_geometry(cfg["L"], cfg["delta"])
+    gindex = cfg_gindex(cfg)
+    dev = g.DeviceFrames(NF, natoms, device).generate(cfg_gen(g, cfg), frame0=rank * NF)
+    if rank == 0:
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host"), "libgcbhost.so"])
+    barrier()
+    data, _ = xtc_encode(dev, cfg, NF, build=False)
+    dev.free()
+    xb = g.XtcBuffer(data * REP, pinned=True)
+    w = np.ones(xb.nframes, np.float32)
+    ctr = g.GridCounter(geom, gindex, natoms, device=device)
+    uid = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctr.comm_init(uid[0], rank, world)
+    dens = np.zeros(geom.shape, np.float32)
+    T = float(xb.nframes * world)
+
+    def step():
+        ctr.reset_grid()
+        ctr.add_xtc(xb, w)
+        ctr.allreduce()
+        ctr.density_into(T, dens)
+
+    step()
+    barrier()
+    STEPS = 3
+    t0 = time.perf_counter()
+    for _ in range(STEPS):
+        step()
+    barrier()
+    secs = max_over_ranks(time.perf_counter() - t0) / STEPS
+    st = ctr.stats()
+    res = None
+    if rank == 0:
+        res = {"value": xb.nframes * len(gindex) * world / secs * 1e-9, "unit": UNIT, "n_gpus": world,
+               "h2d_bytes_per_step": int(xb.nbytes) * world, "d2h_bytes_per_step": int(geom.cells * 4) * world,
+               "ms_per_step": secs * 1e3, "frames_per_step": int(st.frames), "hits": int(st.hits),
+               "workload": cfg["title"] + ", %d frames per rank and step as XTC (%.2f B/atom)" % (xb.nframes, len(data) / (NF * natoms)),
+               "path": "gcb_counter_add_xtc(pinned xtc bytes) -> gcb_counter_allreduce -> gcb_counter_density(host grid)"}
+    ctr.close(); xb.free()
+    return res
 
 
 def c5_section(g, u, torch, dist, ctr, dev, geom, rank, world, device, barrier, max_over_ranks):

@@ -256,6 +256,7 @@ struct StreamSmem {
   float tile[NST][TCAP_ATOMS * 3];
   unsigned long long full[NST], empty[NST];
   TileMeta meta[NST];
+  unsigned hc[NST][2], hdone[NST];     // per stage: hits in frame f0 / f0+1 summed over the consumer warps; warps done
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -549,7 +550,7 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
   const int tid = threadIdx.x;
 
   if (tid == 0) {
-    for (int s = 0; s < NST; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], SINK::CWARPS); }
+    for (int s = 0; s < NST; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], SINK::CWARPS); S.hc[s][0] = S.hc[s][1] = S.hdone[s] = 0u; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -668,12 +669,23 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
         }
       }
     }
-    c0 = __reduce_add_sync(0xffffffffu, c0);
-    c1 = __reduce_add_sync(0xffffffffu, c1);
+    // Per-frame hit counters: the tiles of a large frame are in flight on many CTAs at once and all of them land on
+    // the same one or two counters, so the warps of a CTA first add up in shared memory and the last warp to finish
+    // the tile sends ONE global atomic per frame (a hot address costs its L2 slice the same whatever else it serves).
+    c0 = __reduce_add_sync(0xffffffffu, (c0 & 0xffffu) | (c1 << 16));          // both sums in one reduction (<= 32 * UNR each)
     if (lane == 0) {
-      if (c0) atomicAdd(hits + m.f0, (unsigned long long)c0);
-      if (c1) atomicAdd(hits + m.f0 + 1, (unsigned long long)c1);
+      c1 = c0 >> 16; c0 &= 0xffffu;
+      if (c0) atomicAdd(&S.hc[stage][0], c0);
+      if (c1) atomicAdd(&S.hc[stage][1], c1);
       sink.tile_hits(sink_smem, c0 + c1);
+      __threadfence_block();
+      if (atomicAdd(&S.hdone[stage], 1u) == (unsigned)SINK::CWARPS - 1u) {      // the last warp of this tile
+        const unsigned t0 = atomicExch(&S.hc[stage][0], 0u), t1 = atomicExch(&S.hc[stage][1], 0u);
+        S.hdone[stage] = 0u;
+        if (t0) atomicAdd(hits + m.f0, (unsigned long long)t0);
+        if (t1) atomicAdd(hits + m.f0 + 1, (unsigned long long)t1);
+        __threadfence_block();
+      }
       mbar_arrive(&S.empty[stage]);     // this warp is done with the stage (its LDS results are in registers)
     }
   }

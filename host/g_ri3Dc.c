@@ -122,40 +122,64 @@ int main(int argc, char **argv)
   float tlast = fr.time - dt0;                 /* g_ri3Dc.c:394 */
   const size_t tl = strlen(trxname);
   if (!bHostDecode && tl > 4 && !strcmp(trxname + tl - 4, ".xtc")) {
-    /* ---- .xtc: the file goes to the GPU as it is; only the frame headers are read here ---- */
+    /* ---- .xtc: the file goes to the GPU as it is; only the frame headers are read here.  It is read in bounded
+     * chunks through one pinned buffer (a trajectory need not fit into pinnable memory); a frame cut by the end of
+     * a chunk is carried over to the next one. ---- */
     gh_traj_close(trj);
     FILE *f = fopen(trxname, "rb");
     if (!f) gh_fatal("Cannot read trajectory %s", trxname);
-    fseek(f, 0, SEEK_END);
-    const size_t len = (size_t)ftell(f);
-    rewind(f);
-    void *pin = NULL;
-    CHECK(gcb_host_alloc_pinned(&pin, len + 16));
-    if (fread(pin, 1, len, f) != len) gh_fatal("Cannot read trajectory %s", trxname);
-    fclose(f);
-    long nall = 0, i;
-    CHECK(gcb_xtc_scan((const uint8_t *)pin, len, NULL, 0, &nall, NULL));
-    gcb_xtc_frame *frames = (gcb_xtc_frame *)malloc(sizeof(gcb_xtc_frame) * (size_t)(nall > 0 ? nall : 1));
-    CHECK(gcb_xtc_scan((const uint8_t *)pin, len, frames, nall, &nall, NULL));
-    /* -b / -e / -dt as read_next_x applies them */
+    size_t chunk = (size_t)512 << 20;
+    if (getenv("GCB_XTC_CHUNK_BYTES")) chunk = (size_t)strtoull(getenv("GCB_XTC_CHUNK_BYTES"), NULL, 10);
+    if (chunk < ((size_t)natoms * 16 + 4096) * 2) chunk = ((size_t)natoms * 16 + 4096) * 2;     /* at least two frames */
+    uint8_t *pin = NULL;
+    CHECK(gcb_host_alloc_pinned((void **)&pin, chunk + 16));
+    gcb_xtc_frame *frames = NULL;
+    float *tt = NULL, *w = NULL;
+    long cap = 0, i;
+    size_t have = 0;                           /* bytes in the buffer: a carried partial frame + what was read */
     double t0sel = 0;
-    int have0 = 0;
-    for (i = 0; i < nall; i++) {
-      const double t = frames[i].time;
-      if (ts.have_b && t < ts.b) continue;
-      if (ts.have_e && t > ts.e) break;
-      if (ts.have_dt && ts.dt > 0) {
-        if (!have0) { have0 = 1; t0sel = t; }
-        const double r = fmod(t - t0sel, ts.dt);
-        if (fabs(r) > 1e-4 * ts.dt && fabs(r - ts.dt) > 1e-4 * ts.dt) continue;
+    int have0 = 0, done = 0, eof = 0;
+    while (!done) {
+      const size_t got = eof ? 0 : fread(pin + have, 1, chunk - have, f);
+      if (got < chunk - have) eof = 1;
+      have += got;
+      long nall = 0;
+      size_t used = 0;
+      CHECK(gcb_xtc_scan(pin, have, NULL, 0, &nall, &used));
+      if (nall == 0) {
+        if (have > 0 && eof) gh_msg("WARNING: %zu trailing bytes of %s are not a whole frame\n", have, trxname);
+        if (have >= chunk) gh_fatal("A frame of %s does not fit the %zu-byte read buffer (GCB_XTC_CHUNK_BYTES)", trxname, chunk);
+        break;
       }
-      frames[nframes++] = frames[i];
+      if (nall > cap) {
+        cap = nall;
+        frames = (gcb_xtc_frame *)realloc(frames, sizeof(gcb_xtc_frame) * (size_t)cap);
+        tt = (float *)realloc(tt, sizeof(float) * (size_t)cap);
+        w = (float *)realloc(w, sizeof(float) * (size_t)cap);
+      }
+      CHECK(gcb_xtc_scan(pin, have, frames, nall, &nall, &used));
+      /* -b / -e / -dt as read_next_x applies them */
+      long nsel = 0;
+      for (i = 0; i < nall; i++) {
+        const double t = frames[i].time;
+        if (ts.have_b && t < ts.b) continue;
+        if (ts.have_e && t > ts.e) { done = 1; break; }
+        if (ts.have_dt && ts.dt > 0) {
+          if (!have0) { have0 = 1; t0sel = t; }
+          const double r = fmod(t - t0sel, ts.dt);
+          if (fabs(r) > 1e-4 * ts.dt && fabs(r - ts.dt) > 1e-4 * ts.dt) continue;
+        }
+        frames[nsel++] = frames[i];
+      }
+      for (i = 0; i < nsel; i++) tt[i] = frames[i].time;
+      CHECK(gcb_frame_weights(tt, nsel, bdtWeight, &tlast, w, &T_tot));          /* g_ri3Dc.c:413-416; tlast, T_tot carry over */
+      CHECK(gcb_counter_add_xtc(ctr, pin, have, frames, nsel, w));               /* returns when the bytes have been consumed */
+      nframes += nsel;
+      memmove(pin, pin + used, have - used);                                     /* the partial frame behind the last whole one */
+      have -= used;
+      if (eof && have == 0) break;
     }
-    float *tt = (float *)malloc(sizeof(float) * (size_t)(nframes > 0 ? nframes : 1));
-    float *w = (float *)malloc(sizeof(float) * (size_t)(nframes > 0 ? nframes : 1));
-    for (i = 0; i < nframes; i++) tt[i] = frames[i].time;
-    CHECK(gcb_frame_weights(tt, nframes, bdtWeight, &tlast, w, &T_tot));        /* g_ri3Dc.c:413-416 */
-    CHECK(gcb_counter_add_xtc(ctr, (const uint8_t *)pin, len, frames, nframes, w));
+    fclose(f);
     free(tt); free(w); free(frames);
     gcb_host_free_pinned(pin);
   } else {

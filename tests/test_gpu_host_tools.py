@@ -22,9 +22,10 @@ def tools():
     subprocess.check_call(["make", "-s", "-C", HOST])
 
 
-def run_tool(name, args, cwd, stdin=None):
+def run_tool(name, args, cwd, stdin=None, env=None):
     p = subprocess.run([os.path.join(HOST, name)] + [str(a) for a in args], cwd=cwd, input=stdin,
-                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600,
+                       env=dict(os.environ, **env) if env else None)
     assert p.returncode == 0, "%s failed:\n%s" % (name, p.stderr.decode(errors="replace")[-2000:])
     return p.stdout.decode(errors="replace"), p.stderr.decode(errors="replace")
 
@@ -105,6 +106,12 @@ def test_g_ri3Dc_from_xtc_counts_decoded_coordinates(tmp_path):
     run_tool("g_ri3Dc", ["-f", "traj.xtc", "-n", "grp.ndx", "-grid", "grid_host.dat", "-delta", "0.2", "-R", "1.5", "-z1", "1.0",
                          "-z2", "5.5", "-cpoint", "2.05", "1.95", "3.0", "-hostdecode"], tmp, stdin=b"OW\n")
     assert open(os.path.join(tmp, "grid.dat"), "rb").read() == open(os.path.join(tmp, "grid_host.dat"), "rb").read()
+    # the file read in small chunks (a frame cut by a chunk's end is carried over; weights and T_tot carry across calls)
+    fsize = os.path.getsize(os.path.join(tmp, "traj.xtc"))
+    run_tool("g_ri3Dc", ["-f", "traj.xtc", "-n", "grp.ndx", "-grid", "grid_chunks.dat", "-delta", "0.2", "-R", "1.5", "-z1", "1.0",
+                         "-z2", "5.5", "-cpoint", "2.05", "1.95", "3.0"], tmp, stdin=b"1\n",
+             env={"GCB_XTC_CHUNK_BYTES": str(max(1, fsize // 7))})
+    assert open(os.path.join(tmp, "grid.dat"), "rb").read() == open(os.path.join(tmp, "grid_chunks.dat"), "rb").read()
     # -b/-e select the same frames on both paths
     for extra, out in ((["-b", "10", "-e", "30"], "sel_gpu.dat"), (["-b", "10", "-e", "30", "-hostdecode"], "sel_host.dat")):
         run_tool("g_ri3Dc", ["-f", "traj.xtc", "-n", "grp.ndx", "-grid", out, "-delta", "0.2"] + extra, tmp, stdin=b"1\n")
