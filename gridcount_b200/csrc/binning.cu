@@ -256,7 +256,6 @@ struct StreamSmem {
   float tile[NST][TCAP_ATOMS * 3];
   unsigned long long full[NST], empty[NST];
   TileMeta meta[NST];
-  unsigned hc[NST][2], hdone[NST];     // per stage: hits in frame f0 / f0+1 summed over the consumer warps; warps done
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -550,7 +549,7 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
   const int tid = threadIdx.x;
 
   if (tid == 0) {
-    for (int s = 0; s < NST; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], SINK::CWARPS); S.hc[s][0] = S.hc[s][1] = S.hdone[s] = 0u; }
+    for (int s = 0; s < NST; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], SINK::CWARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -669,23 +668,16 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
         }
       }
     }
-    // Per-frame hit counters: the tiles of a large frame are in flight on many CTAs at once and all of them land on
-    // the same one or two counters, so the warps of a CTA first add up in shared memory and the last warp to finish
-    // the tile sends ONE global atomic per frame (a hot address costs its L2 slice the same whatever else it serves).
+    // Per-frame hit counters: one fire-and-forget global atomic per (warp, frame).  (Adding the warps of a CTA up in
+    // shared memory first, so that a large frame's counter sees one atomic per tile instead of eight, was measured:
+    // the returning shared-memory atomic and fence it needs sit on every tile's critical path and HALVE the kernel,
+    // 52.7 vs 101 G/s on C3.)
     c0 = __reduce_add_sync(0xffffffffu, (c0 & 0xffffu) | (c1 << 16));          // both sums in one reduction (<= 32 * UNR each)
     if (lane == 0) {
       c1 = c0 >> 16; c0 &= 0xffffu;
-      if (c0) atomicAdd(&S.hc[stage][0], c0);
-      if (c1) atomicAdd(&S.hc[stage][1], c1);
+      if (c0) atomicAdd(hits + m.f0, (unsigned long long)c0);
+      if (c1) atomicAdd(hits + m.f0 + 1, (unsigned long long)c1);
       sink.tile_hits(sink_smem, c0 + c1);
-      __threadfence_block();
-      if (atomicAdd(&S.hdone[stage], 1u) == (unsigned)SINK::CWARPS - 1u) {      // the last warp of this tile
-        const unsigned t0 = atomicExch(&S.hc[stage][0], 0u), t1 = atomicExch(&S.hc[stage][1], 0u);
-        S.hdone[stage] = 0u;
-        if (t0) atomicAdd(hits + m.f0, (unsigned long long)t0);
-        if (t1) atomicAdd(hits + m.f0 + 1, (unsigned long long)t1);
-        __threadfence_block();
-      }
       mbar_arrive(&S.empty[stage]);     // this warp is done with the stage (its LDS results are in registers)
     }
   }
@@ -722,6 +714,14 @@ bin_stream_kernel(const float *__restrict__ x, int natoms, const int *__restrict
 // ---------------------------------------------------------------------------
 __device__ float seq_add_dev(float v, float w, unsigned long long n)
 {
+  // From zero, with a weight whose significand is short (1, 2, 0.5, 0.25 ...: m * 2^e with n * m < 2^24), every
+  // partial sum j * w is exactly representable, so the chain is the exact product (the common weight-1 case).
+  if (v == 0.0f && w > 0.0f && n > 0 && n < (1ull << 24) && (__float_as_uint(w) >> 23) != 0u) {
+    unsigned m = (__float_as_uint(w) & 0x7fffffu) | 0x800000u;
+    m >>= __ffs((int)m) - 1;
+    const float p = __fmul_rn((float)n, w);
+    if (n * (unsigned long long)m < (1ull << 24) && p < 3.0e38f) return p;
+  }
   while (n > 0) {
     const float v1 = __fadd_rn(v, w);
     --n;

@@ -238,6 +238,8 @@ def test_pbc_rect_wrap(kernel):
 def _weights(kind, n, rng):
     if kind == "const01":
         return np.full(n, 0.1, np.float32)
+    if kind in ("const1", "const075", "const2p-100"):     # short significands: the exact-product shortcut of seq_add_dev
+        return np.full(n, {"const1": 1.0, "const075": 0.75, "const2p-100": 2.0 ** -100}[kind], np.float32)
     if kind == "jitter":              # dt = t_f - t_{f-1} of f32 times f*0.1: varies in the last bits
         t = (np.arange(n + 1, dtype=np.float32) * np.float32(0.1)).astype(np.float32)
         return (t[1:] - t[:-1]).astype(np.float32)
@@ -251,7 +253,7 @@ def _weights(kind, n, rng):
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
-@pytest.mark.parametrize("kind", ["const01", "jitter", "blocks", "mixed"])
+@pytest.mark.parametrize("kind", ["const01", "const1", "const075", "const2p-100", "jitter", "blocks", "mixed"])
 def test_occupancy_reproduces_reference_f32_accumulation(kind, kernel):
     """`grid[i][j][k] += weight` in f32, frame after frame (g_ri3Dc.c:149): bit-exact for any weights"""
     rng = np.random.default_rng(5)
@@ -270,7 +272,7 @@ def test_occupancy_reproduces_reference_f32_accumulation(kind, kernel):
     np.testing.assert_array_equal(ctr.counts(), ocounts)
     st = ctr.stats()
     assert st.sumP == osumP
-    assert bool(st.uniform_weight) == (kind == "const01")
+    assert bool(st.uniform_weight) == kind.startswith("const")
     # density = occupancy / ((double)(float)dV * T)
     T = float(np.sum(w.astype(np.float64)))
     og = to_ogeom(geom)
