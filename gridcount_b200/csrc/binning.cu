@@ -217,13 +217,19 @@ xtc_bin_kernel(const uint8_t *__restrict__ buf, const xtcdev::FrameDev *__restri
 // straddle tiles and every tile starts 16-byte aligned.
 // ---------------------------------------------------------------------------
 #ifndef GCB_CONSUMER_WARPS
-#define GCB_CONSUMER_WARPS 8
+#define GCB_CONSUMER_WARPS 4
 #endif
 #ifndef GCB_STAGES
 #define GCB_STAGES 3
 #endif
 #ifndef GCB_UNROLL
-#define GCB_UNROLL 4
+#define GCB_UNROLL 8
+#endif
+#ifndef GCB_PRIV_WARPS
+#define GCB_PRIV_WARPS 16
+#endif
+#ifndef GCB_PRIV_UNROLL
+#define GCB_PRIV_UNROLL 2
 #endif
 constexpr int CONSUMER_WARPS = GCB_CONSUMER_WARPS;
 constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
@@ -455,7 +461,7 @@ struct PrivState {
 template <int W>
 struct PrivateSink {
   // full-size tiles (1024 selected atoms of 3-site water per tile, two per thread of 16 consumer warps), 110 KB of ring
-  static constexpr int NSTAGES = 3, CWARPS = 16, UNROLL_ = 2, TILE_CAP = TILE_ATOMS;
+  static constexpr int NSTAGES = 3, CWARPS = GCB_PRIV_WARPS, UNROLL_ = GCB_PRIV_UNROLL, TILE_CAP = TILE_ATOMS;
   static constexpr bool PRIVATE = true;
   static constexpr unsigned PER = 32u / W, SH = W == 8 ? 2u : 3u;
   uint32_t *counts;                        // the uint32 grid (direct mode, redo)
