@@ -207,7 +207,7 @@ xtc_bin_kernel(const uint8_t *__restrict__ buf, const xtcdev::FrameDev *__restri
 // K1b  streaming kernel.  Persistent, warp-specialised CTAs: one producer warp
 // pulls fixed-size tiles of the raw frame array into a shared-memory ring with
 // TMA bulk copies (cp.async.bulk + mbarrier, full/empty barrier pairs, no
-// __syncthreads in the loop); eight consumer warps pick their selected atoms
+// __syncthreads in the loop); the consumer warps (four, eight atoms per thread) pick their selected atoms
 // out of the tile through the sorted index group, convert to bins and fire
 // one RED per hit.  HBM sees only full-line streaming reads (evict-first);
 // the gather happens in shared memory (stride 3 or 9 words: conflict free).
@@ -852,6 +852,54 @@ packed_apply_kernel(uint32_t *__restrict__ pk, size_t nwords, uint32_t *__restri
   }
 }
 
+// The 4-bit rounds of a grid like 500^3 (125 M cells) would each read and write the whole 500 MB uint32 grid to add
+// at most 15 per cell.  They go through a BYTE grid instead (a quarter of the traffic): verified nibbles are added
+// to bytes for up to 16 rounds (16 x 15 <= 255: no byte can overflow), then the bytes are folded into the uint32
+// grid in one pass (flush_mid; also before anything reads the grid).  Same contract as packed_apply_kernel otherwise.
+__global__ void __launch_bounds__(256)
+packed_apply_mid_kernel(uint32_t *__restrict__ pk, size_t nwords, uint2 *__restrict__ mid, const PackedState *__restrict__ st,
+                        unsigned long long *__restrict__ hits, long nhits, unsigned long long *__restrict__ diag)
+{
+  const bool bad = st->alarm != 0;
+  if (bad && !st->dirty) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t w = pk[i];
+    if (!w) continue;
+    pk[i] = 0u;
+    if (bad) continue;
+    // nibbles 0..3 -> the four bytes of .x, nibbles 4..7 -> .y (cells 8i .. 8i+7 are bytes 8i .. 8i+7, little endian)
+    const uint32_t lo = w & 0xffffu, hi = w >> 16;
+    uint2 m = mid[i];
+    m.x += (lo & 0xfu) | ((lo & 0xf0u) << 4) | ((lo & 0xf00u) << 8) | ((lo & 0xf000u) << 12);
+    m.y += (hi & 0xfu) | ((hi & 0xf0u) << 4) | ((hi & 0xf00u) << 8) | ((hi & 0xf000u) << 12);
+    mid[i] = m;
+  }
+  if (bad) {
+    for (long f = (long)blockIdx.x * blockDim.x + threadIdx.x; f < nhits; f += (long)gridDim.x * blockDim.x) hits[f] = 0;
+    if (blockIdx.x == 0 && threadIdx.x < 2) diag[threadIdx.x] = st->diag_snap[threadIdx.x];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mid_flush_kernel(uint2 *__restrict__ mid, size_t nwords, uint32_t *__restrict__ counts, size_t ncells)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
+    const uint2 m = mid[i];
+    if (!(m.x | m.y)) continue;
+    mid[i] = make_uint2(0u, 0u);
+    const size_t c0 = i * 8;
+    if (c0 + 8 <= ncells) {
+      uint4 *dst = reinterpret_cast<uint4 *>(counts + c0);
+      uint4 a = dst[0], b = dst[1];
+      a.x += m.x & 0xffu; a.y += (m.x >> 8) & 0xffu; a.z += (m.x >> 16) & 0xffu; a.w += m.x >> 24;
+      b.x += m.y & 0xffu; b.y += (m.y >> 8) & 0xffu; b.z += (m.y >> 16) & 0xffu; b.w += m.y >> 24;
+      dst[0] = a; dst[1] = b;
+    } else {
+      for (int l = 0; l < 8; l++) if (c0 + l < ncells) counts[c0 + l] += ((l < 4 ? m.x : m.y) >> (8 * (l & 3))) & 0xffu;
+    }
+  }
+}
+
 // In front of every private launch: turn the verdicts of the launches before into this launch's mode.
 __global__ void private_begin_kernel(PrivState *__restrict__ st)
 {
@@ -1111,6 +1159,8 @@ struct gcb_counter {
   long long priv_min_units = 0;       // AUTO takes the private path for launches of at least this many atom-frames
   uint64_t priv_launches = 0, priv_redone = 0;
   ApGroup ap_priv{0, 1, TILE_ATOMS};
+  uint2 *d_mid = nullptr;             // 4-bit packed path: byte grid between the packed rounds and the uint32 grid
+  int mid_rounds = 0;                 // rounds folded into d_mid since it was last flushed (<= 16)
   bool l2_window = false;             // persisting-L2 window over d_pk set on the compute stream
   bool saturated = false;             // some cell was clamped (diag[3])
   // xtc path: GCB_XTC_SETS sets of {compressed bytes, frame table, status, decoded frames}, copy stream + events
@@ -1336,6 +1386,10 @@ int launch_packed(gcb_counter *c, const float *d_x, long nframes, const float *d
     GCB_CUDA(cudaMemsetAsync(c->d_pk, 0, nquads * 16, c->compute));
     GCB_CUDA(cudaMalloc(&c->d_pstate, sizeof(PackedState)));
     GCB_CUDA(cudaMemsetAsync(c->d_pstate, 0, sizeof(PackedState), c->compute));
+    if (W == 4 && !getenv("GCB_NO_MID")) {
+      GCB_CUDA(cudaMalloc(&c->d_mid, nwords * sizeof(uint2)));
+      GCB_CUDA(cudaMemsetAsync(c->d_mid, 0, nwords * sizeof(uint2), c->compute));
+    }
     GCB_CUDA(cudaHostAlloc((void **)&c->h_pstate, sizeof(PackedState), cudaHostAllocDefault));
     memset(c->h_pstate, 0, sizeof(PackedState));
     // Keep the packed counters L2-resident next to the coordinate stream: a persisting-L2 set-aside with an
@@ -1378,7 +1432,13 @@ int launch_packed(gcb_counter *c, const float *d_x, long nframes, const float *d
       rc = prof_begin(c);
       if (rc) return rc;
       packed_verify_kernel<W><<<aux_grid, 256, 0, c->compute>>>(reinterpret_cast<const uint4 *>(c->d_pk), nquads, d_hits + f0, n, st);
-      packed_apply_kernel<W><<<apply_grid, 256, 0, c->compute>>>(c->d_pk, nwords, c->d_runcnt, c->ncells, st, d_hits + f0, n, c->d_diag);
+      if (W == 4 && c->d_mid) {
+        if (c->mid_rounds >= 16) { rc = flush_private(c); if (rc) return rc; }
+        packed_apply_mid_kernel<<<apply_grid, 256, 0, c->compute>>>(c->d_pk, nwords, c->d_mid, st, d_hits + f0, n, c->d_diag);
+        c->mid_rounds++;
+      } else {
+        packed_apply_kernel<W><<<apply_grid, 256, 0, c->compute>>>(c->d_pk, nwords, c->d_runcnt, c->ncells, st, d_hits + f0, n, c->d_diag);
+      }
       c->launches += 3;
       GCB_CUDA(cudaGetLastError());
       rc = prof_end(c, GCB_PROF_OTHER, 0.0);
@@ -1419,6 +1479,14 @@ bool packed_paused(gcb_counter *c)
 // reads or rescales d_runcnt (density, counts, fold, clamp, all-reduce) and before a lane could fill up.
 int flush_private(gcb_counter *c)
 {
+  if (c->mid_rounds > 0) {                       // the byte grid of the 4-bit packed rounds
+    const size_t nwords = (c->ncells + 7) / 8;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((nwords + 255) / 256, (size_t)c->sm_count * 16));
+    mid_flush_kernel<<<grid, 256, 0, c->compute>>>(c->d_mid, nwords, c->d_runcnt, c->ncells);
+    c->launches++;
+    GCB_CUDA(cudaGetLastError());
+    c->mid_rounds = 0;
+  }
   if (!c->priv_dirty) return GCB_OK;
   const int grid = (int)std::max<unsigned>(1u, std::min<unsigned>((c->priv_words + 255u) / 256u, (unsigned)c->sm_count * 8u));
   if (c->priv_bits == 8)
@@ -1671,7 +1739,7 @@ void free_counter(gcb_counter *c)
   for (auto &a : c->hit_arenas) cudaFree(a.d);
   cudaFree(c->d_gindex); cudaFree(c->d_rank); cudaFree(c->d_runcnt); cudaFree(c->d_total); cudaFree(c->d_acc);
   cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2);
-  cudaFree(c->d_pk); cudaFree(c->d_pstate); cudaFreeHost(c->h_pstate);
+  cudaFree(c->d_pk); cudaFree(c->d_pstate); cudaFreeHost(c->h_pstate); cudaFree(c->d_mid);
   cudaFree(c->d_priv); cudaFree(c->d_priv_hits); cudaFree(c->d_privstate);
   for (auto &x : c->xtc) {
     cudaFree(x.d_buf); cudaFree(x.d_meta); cudaFree(x.d_status); cudaFree(x.d_x); cudaFree(x.d_work); cudaFreeHost(x.h_meta); cudaFreeHost(x.h_status);
@@ -1866,6 +1934,10 @@ int gcb_counter_reset(gcb_counter *c)
     GCB_CUDA(cudaMemsetAsync(&c->d_privstate->launches, 0, 2 * sizeof(unsigned long long), c->compute));
   }
   c->priv_dirty = false; c->priv_bound = 0; c->priv_launches = 0; c->priv_redone = 0;
+  if (c->mid_rounds > 0) {
+    GCB_CUDA(cudaMemsetAsync(c->d_mid, 0, ((c->ncells + 7) / 8) * sizeof(uint2), c->compute));
+    c->mid_rounds = 0;
+  }
   c->bound_run = 0; c->bound_total = 0;
   c->reduced = false; c->global_frames = 0;
   c->have_run = false; c->any = false; c->uniform = true; c->w_cur = 0; c->w_first = 0;

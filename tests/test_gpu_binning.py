@@ -711,3 +711,34 @@ def test_auto_takes_the_private_path_on_the_c1_shape():
     ref.add_device_frames(dev)
     np.testing.assert_array_equal(c, ref.counts() + want)
     ref.close(); ctr.close(); dev.free()
+
+
+def test_nibble_rounds_through_the_byte_grid_stay_exact(monkeypatch):
+    """4-bit packed rounds are added to a byte grid for up to 16 rounds and folded into the uint32 grid lazily:
+    40 rounds with a read in the middle, a reset, and GCB_NO_MID as the cross-check"""
+    monkeypatch.setenv("GCB_PACKED_BITS", "4")
+    monkeypatch.setenv("GCB_PACKED_UNITS", str(8192 * 4))            # 4 frames per round
+    L, delta = (4.0, 4.0, 4.0), 0.1
+    geom = g.setup_geometry(L, delta)
+    natoms, nframes = 8192, 160
+    x = u.gen_frames(u.make_gen(77, L), 0, nframes, natoms)
+    gindex = np.arange(natoms, dtype=np.int32)
+    ocounts, ohits, _ = oracle_counts(geom, x, gindex)
+    o_half, _, _ = oracle_counts(geom, x[:100], gindex)
+    for nomid in (False, True):
+        if nomid:
+            monkeypatch.setenv("GCB_NO_MID", "1")
+        ctr = g.GridCounter(geom, gindex, natoms, kernel=K.KERNEL_PACKED)
+        ctr.add_frames(x[:100], np.ones(100, np.float32))            # 25 rounds: the byte grid is folded in once on the way
+        np.testing.assert_array_equal(ctr.counts(), o_half)          # ... and again by this read
+        ctr.add_frames(x[100:], np.ones(60, np.float32))
+        np.testing.assert_array_equal(ctr.occupancy(), ocounts.astype(np.float32))
+        np.testing.assert_array_equal(ctr.counts(), ocounts)
+        st = ctr.stats()
+        assert st.packed_rounds == 40 and st.packed_redone == 0 and st.hits == int(ohits.sum())
+        ctr.reset()
+        ctr.add_frames(x[:8], np.ones(8, np.float32))
+        ctr.reset()                                                  # drops what the byte grid holds
+        ctr.add_frames(x[8:20], np.ones(12, np.float32))
+        np.testing.assert_array_equal(ctr.counts(), oracle_counts(geom, x[8:20], gindex)[0])
+        ctr.close()
