@@ -112,6 +112,19 @@ def test_g_ri3Dc_from_xtc_counts_decoded_coordinates(tmp_path):
                          "-z2", "5.5", "-cpoint", "2.05", "1.95", "3.0"], tmp, stdin=b"1\n",
              env={"GCB_XTC_CHUNK_BYTES": str(max(1, fsize // 7))})
     assert open(os.path.join(tmp, "grid.dat"), "rb").read() == open(os.path.join(tmp, "grid_chunks.dat"), "rb").read()
+    # the frames sharded over "two GPUs" (twice this one: the in-process reduce accepts that), each shard read by its
+    # own thread in small chunks.  Without -dtweight every frame weighs 1: bit-identical to the single-GPU file.
+    run_tool("g_ri3Dc", ["-f", "traj.xtc", "-n", "grp.ndx", "-grid", "one.dat", "-delta", "0.2", "-nodtweight"], tmp, stdin=b"1\n")
+    for gpus, out in (("0,0", "two.dat"), ("0,0,0", "three.dat")):
+        so, se = run_tool("g_ri3Dc", ["-f", "traj.xtc", "-n", "grp.ndx", "-grid", out, "-delta", "0.2", "-nodtweight", "-gpus", gpus],
+                          tmp, stdin=b"1\n", env={"GCB_XTC_CHUNK_BYTES": str(max(1, fsize // 5))})
+        assert "Sharding" in se
+        assert open(os.path.join(tmp, "one.dat"), "rb").read() == open(os.path.join(tmp, out), "rb").read()
+    # with the time step as weight (f32-jittered dt) the shards' f32 accumulators are summed: equal to 1e-6
+    run_tool("g_ri3Dc", ["-f", "traj.xtc", "-n", "grp.ndx", "-grid", "two_dt.dat", "-delta", "0.2", "-R", "1.5", "-z1", "1.0",
+                         "-z2", "5.5", "-cpoint", "2.05", "1.95", "3.0", "-gpus", "0,0"], tmp, stdin=b"1\n")
+    tg2, hdr2, dens2 = g.grid_read(os.path.join(tmp, "two_dt.dat"))
+    np.testing.assert_allclose(dens2, dens, rtol=1e-6, atol=0)
     # -b/-e select the same frames on both paths
     for extra, out in ((["-b", "10", "-e", "30"], "sel_gpu.dat"), (["-b", "10", "-e", "30", "-hostdecode"], "sel_host.dat")):
         run_tool("g_ri3Dc", ["-f", "traj.xtc", "-n", "grp.ndx", "-grid", out, "-delta", "0.2"] + extra, tmp, stdin=b"1\n")
