@@ -115,7 +115,9 @@ def test_g_ri3Dc_from_xtc_counts_decoded_coordinates(tmp_path):
     # the frames sharded over "two GPUs" (twice this one: the in-process reduce accepts that), each shard read by its
     # own thread in small chunks.  Without -dtweight every frame weighs 1: bit-identical to the single-GPU file.
     run_tool("g_ri3Dc", ["-f", "traj.xtc", "-n", "grp.ndx", "-grid", "one.dat", "-delta", "0.2", "-nodtweight"], tmp, stdin=b"1\n")
-    for gpus, out in (("0,0", "two.dat"), ("0,0,0", "three.dat")):
+    import gridcount_b200 as g2
+    real = [("0,1", "two_real.dat")] if g2.device_count() >= 2 else []          # two different devices where the box has them
+    for gpus, out in [("0,0", "two.dat"), ("0,0,0", "three.dat")] + real:
         so, se = run_tool("g_ri3Dc", ["-f", "traj.xtc", "-n", "grp.ndx", "-grid", out, "-delta", "0.2", "-nodtweight", "-gpus", gpus],
                           tmp, stdin=b"1\n", env={"GCB_XTC_CHUNK_BYTES": str(max(1, fsize // 5))})
         assert "Sharding" in se

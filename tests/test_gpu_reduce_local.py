@@ -82,9 +82,11 @@ def test_uniform_weight_reduce_is_bit_exact(world):
     want, hits, occ, _, dens, sumP = oracle_all(geom, x, gindex, wall, 0.1 * F * world)
     assert 0 < int(hits.sum()) < F * world * len(gindex)
 
+    ndev = g.device_count()                      # the ranks spread over the box's GPUs (all on one where there is one)
+
     def body(rank, attach):
-        dev = g.DeviceFrames(F, NATOMS).generate(gen, frame0=rank * F)
-        ctr = attach(g.GridCounter(geom, gindex, NATOMS))
+        dev = g.DeviceFrames(F, NATOMS, rank % ndev).generate(gen, frame0=rank * F)
+        ctr = attach(g.GridCounter(geom, gindex, NATOMS, device=rank % ndev))
         res = []
         for job in range(2):
             ctr.reset()
