@@ -30,7 +30,10 @@
 
 namespace seqsum {
 
-struct alignas(16) Fn { unsigned long long a0, a1; };  // M -> M + (M & 1 ? a1 : a0); {0,0} is the identity
+// M -> M + (M & 1 ? a1 : a0); {0,0} is the identity.  The f32 chains work on 32-bit maps (every entry is capped at
+// 2^25), the f64 chain on 64-bit ones; buffers in shared and global memory hold the 64-bit form (Fn).
+template <class U> struct alignas(2 * sizeof(U)) FnT { U a0, a1; };
+using Fn = FnT<unsigned long long>;
 
 SEQSUM_HD int high_bit(uint32_t v)                      // v != 0
 {
@@ -43,6 +46,7 @@ SEQSUM_HD int high_bit(uint32_t v)                      // v != 0
 
 template <class R> struct Tr;
 template <> struct Tr<float> {
+  using U = uint32_t;                                   // map entries: <= 2^25
   static constexpr int MBITS = 24;                      // significand bits incl. the implicit one
   static constexpr int EOFF = 0;                        // a term's shift against the ulp: sh = E - ex - EOFF
   SEQSUM_HD static void unpack(float s, int &E, unsigned long long &M)
@@ -77,6 +81,7 @@ template <> struct Tr<float> {
   }
 };
 template <> struct Tr<double> {
+  using U = unsigned long long;                         // map entries: <= 2^54
   static constexpr int MBITS = 53;
   static constexpr int EOFF = 925;                      // 1075 - 150
   SEQSUM_HD static void unpack(double s, int &E, unsigned long long &M)
@@ -114,19 +119,28 @@ template <> struct Tr<double> {
 // a finite, non-negative f32 term?  (-0 is accepted: s + -0 == s for every s >= +0)
 SEQSUM_HD bool term_ok(uint32_t xb) { return ((xb >> 23) & 0xffu) != 255u && (!(xb >> 31) || (xb << 1) == 0u); }
 
+template <class R> using Map = FnT<typename Tr<R>::U>;
+
+template <class U> SEQSUM_HD Fn widen(const FnT<U> &f) { Fn o; o.a0 = f.a0; o.a1 = f.a1; return o; }
+template <class R> SEQSUM_HD Map<R> narrow(const Fn &f)          // (entries of an R-chain's map fit Tr<R>::U by construction)
+{
+  Map<R> o; o.a0 = (typename Tr<R>::U)f.a0; o.a1 = (typename Tr<R>::U)f.a1; return o;
+}
+
 // the map of one f32 term (bit pattern xb, sign ignored) while the accumulator's exponent field is E
 template <class R>
-SEQSUM_HD Fn term(uint32_t xb, int E)
+SEQSUM_HD Map<R> term(uint32_t xb, int E)
 {
-  constexpr unsigned long long CAP = 1ull << (Tr<R>::MBITS + 1);      // "reaches the next exponent for sure"
+  using U = typename Tr<R>::U;
+  constexpr U CAP = (U)1 << (Tr<R>::MBITS + 1);                        // "reaches the next exponent for sure"
   int ex = (int)((xb >> 23) & 0xffu);
   uint32_t mx = xb & 0x7fffffu;
   if (ex) mx |= 0x800000u; else ex = 1;
-  Fn f; f.a0 = 0; f.a1 = 0;
+  Map<R> f; f.a0 = 0; f.a1 = 0;
   if (mx == 0u) return f;
   const int sh = E - ex - Tr<R>::EOFF;                                 // x / u = mx / 2^sh
   if (sh <= 0) {
-    const unsigned long long k = (high_bit(mx) - sh >= Tr<R>::MBITS + 1) ? CAP : ((unsigned long long)mx << (-sh));
+    const U k = (high_bit(mx) - sh >= Tr<R>::MBITS + 1) ? CAP : ((U)mx << (-sh));
     f.a0 = k; f.a1 = k;
     return f;
   }
@@ -140,18 +154,19 @@ SEQSUM_HD Fn term(uint32_t xb, int E)
 
 // g after f, saturating at CAP (a saturated map only ever says "crossed"; its parity is not used)
 template <class R>
-SEQSUM_HD Fn then(const Fn &f, const Fn &g)
+SEQSUM_HD Map<R> then(const Map<R> &f, const Map<R> &g)
 {
-  constexpr unsigned long long CAP = 1ull << (Tr<R>::MBITS + 1);
-  Fn h;
-  h.a0 = f.a0 + ((f.a0 & 1ull) ? g.a1 : g.a0);
-  h.a1 = f.a1 + ((f.a1 & 1ull) ? g.a0 : g.a1);
+  using U = typename Tr<R>::U;
+  constexpr U CAP = (U)1 << (Tr<R>::MBITS + 1);
+  Map<R> h;
+  h.a0 = f.a0 + ((f.a0 & 1u) ? g.a1 : g.a0);
+  h.a1 = f.a1 + ((f.a1 & 1u) ? g.a0 : g.a1);
   if (h.a0 > CAP) h.a0 = CAP;
   if (h.a1 > CAP) h.a1 = CAP;
   return h;
 }
 
-SEQSUM_HD unsigned long long apply(const Fn &f, unsigned long long M) { return M + ((M & 1ull) ? f.a1 : f.a0); }
+template <class U> SEQSUM_HD unsigned long long apply(const FnT<U> &f, unsigned long long M) { return M + ((M & 1ull) ? f.a1 : f.a0); }
 
 // n repetitions of  s = (float)((double)s + c)  with a constant c > 0 (a_ri3Dc.c:637, `rweight`): per exponent
 // of s the step is one fixed map, so the chain advances a whole exponent at a time.  Host code.
@@ -194,20 +209,21 @@ inline float inc_chain_f32(float s, double c, long long n)
 // Cooperative chains.  `load(i)` returns term i (f32, already masked; must return +0 for i >= n).
 // Every thread owns T consecutive terms of a chunk, so thread order == chain order.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ Fn shfl_up_fn(const Fn &f, int d)
+template <class U>
+__device__ __forceinline__ FnT<U> shfl_up_fn(const FnT<U> &f, int d)
 {
-  Fn o;
+  FnT<U> o;
   o.a0 = __shfl_up_sync(0xffffffffu, f.a0, d);
   o.a1 = __shfl_up_sync(0xffffffffu, f.a1, d);
   return o;
 }
 
 template <class R>
-__device__ __forceinline__ Fn warp_scan(Fn f, int lane)                // inclusive
+__device__ __forceinline__ Map<R> warp_scan(Map<R> f, int lane)        // inclusive
 {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    const Fn o = shfl_up_fn(f, d);
+    const Map<R> o = shfl_up_fn(f, d);
     if (lane >= d) f = then<R>(o, f);
   }
   return f;
@@ -266,7 +282,7 @@ __device__ R block_chain(size_t n, Load load, BlockScratch &sh, bool *bad)
       for (int j = 0; j < T; j++) nx[j] = load(pos + CH + (size_t)tid * T + j);
     }
     bool ok = true;
-    Fn f; f.a0 = 0; f.a1 = 0;
+    Map<R> f; f.a0 = 0; f.a1 = 0;
 #pragma unroll
     for (int j = 0; j < T; j++) {
       const uint32_t xb = __float_as_uint(x[j]);
@@ -274,21 +290,21 @@ __device__ R block_chain(size_t n, Load load, BlockScratch &sh, bool *bad)
       f = then<R>(f, term<R>(xb, E));
     }
     if (!ok) sh.bad = 1;
-    const Fn incl_w = warp_scan<R>(f, lane);
-    if (lane == 31) sh.warp_tot[warp] = incl_w;
+    const Map<R> incl_w = warp_scan<R>(f, lane);
+    if (lane == 31) sh.warp_tot[warp] = widen(incl_w);
     __syncthreads();
     if (warp == 0) {
-      Fn t; t.a0 = 0; t.a1 = 0;
-      if (lane < NT / 32) t = sh.warp_tot[lane];
+      Map<R> t; t.a0 = 0; t.a1 = 0;
+      if (lane < NT / 32) t = narrow<R>(sh.warp_tot[lane]);
       t = warp_scan<R>(t, lane);
-      sh.warp_tot[lane] = t;
+      sh.warp_tot[lane] = widen(t);
     }
     __syncthreads();
-    Fn excl = shfl_up_fn(incl_w, 1);
+    Map<R> excl = shfl_up_fn(incl_w, 1);
     if (lane == 0) { excl.a0 = 0; excl.a1 = 0; }
-    if (warp > 0) excl = then<R>(sh.warp_tot[warp - 1], excl);
-    const Fn incl = then<R>(excl, f);
-    const Fn total = sh.warp_tot[NT / 32 - 1];
+    if (warp > 0) excl = then<R>(narrow<R>(sh.warp_tot[warp - 1]), excl);
+    const Map<R> incl = then<R>(excl, f);
+    const Map<R> total = narrow<R>(sh.warp_tot[NT / 32 - 1]);
     const bool crosses = apply(incl, M) >= LIMIT;
     if (crosses) atomicMin(&sh.first_cross, tid);
     __syncthreads();
@@ -345,24 +361,24 @@ __device__ __forceinline__ Fn ldcg_fn(const Fn *p)                     // writte
 // inclusive/exclusive block scan of one map per thread; two barriers inside, and the caller must pass
 // another barrier before the next block_scan (sh.warp_tot is reused)
 template <class R, int NT>
-__device__ __forceinline__ void block_scan(const Fn &f, BlockScratch &sh, Fn &excl, Fn &incl, Fn &total)
+__device__ __forceinline__ void block_scan(const Map<R> &f, BlockScratch &sh, Map<R> &excl, Map<R> &incl, Map<R> &total)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const Fn incl_w = warp_scan<R>(f, lane);
-  if (lane == 31) sh.warp_tot[warp] = incl_w;
+  const Map<R> incl_w = warp_scan<R>(f, lane);
+  if (lane == 31) sh.warp_tot[warp] = widen(incl_w);
   __syncthreads();
   if (warp == 0) {
-    Fn t; t.a0 = 0; t.a1 = 0;
-    if (lane < NT / 32) t = sh.warp_tot[lane];
+    Map<R> t; t.a0 = 0; t.a1 = 0;
+    if (lane < NT / 32) t = narrow<R>(sh.warp_tot[lane]);
     t = warp_scan<R>(t, lane);
-    sh.warp_tot[lane] = t;
+    sh.warp_tot[lane] = widen(t);
   }
   __syncthreads();
   excl = shfl_up_fn(incl_w, 1);
   if (lane == 0) { excl.a0 = 0; excl.a1 = 0; }
-  if (warp > 0) excl = then<R>(sh.warp_tot[warp - 1], excl);
+  if (warp > 0) excl = then<R>(narrow<R>(sh.warp_tot[warp - 1]), excl);
   incl = then<R>(excl, f);
-  total = sh.warp_tot[NT / 32 - 1];
+  total = narrow<R>(sh.warp_tot[NT / 32 - 1]);
 }
 
 template <class R, int T, int NT>
@@ -393,7 +409,7 @@ struct GridChain {
       float x[T];
       load(pos + (size_t)tid * T, x);
       bool ok = true;
-      Fn f; f.a0 = 0; f.a1 = 0;
+      Map<R> f; f.a0 = 0; f.a1 = 0;
 #pragma unroll
       for (int j = 0; j < T; j++) {
         if (pos + (size_t)tid * T + j >= end) x[j] = 0.0f;             // the rounds take over at `end`
@@ -402,7 +418,7 @@ struct GridChain {
         f = then<R>(f, term<R>(xb, E));
       }
       if (!ok) sh.bad = 1;
-      Fn excl, incl, total;
+      Map<R> excl, incl, total;
       block_scan<R, NT>(f, sh, excl, incl, total);
       if (apply(incl, M) >= LIMIT) atomicMin(&sh.first_cross, tid);
       __syncthreads();
@@ -443,7 +459,7 @@ struct GridChain {
       float x[T];
       load(pos + s * CH + (size_t)tid * T, x);
       bool ok = true;
-      Fn f; f.a0 = 0; f.a1 = 0;
+      Map<R> f; f.a0 = 0; f.a1 = 0;
 #pragma unroll
       for (int j = 0; j < T; j++) {
         const uint32_t xb = __float_as_uint(x[j]);
@@ -451,14 +467,14 @@ struct GridChain {
         f = then<R>(f, term<R>(xb, E));
       }
       if (!ok) atomicExch(bad_flag, 1);
-      const Fn w = warp_scan<R>(f, lane);
-      if (lane == 31) sh.warp_tot[warp] = w;
+      const Map<R> w = warp_scan<R>(f, lane);
+      if (lane == 31) sh.warp_tot[warp] = widen(w);
       __syncthreads();
       if (warp == 0) {
-        Fn t; t.a0 = 0; t.a1 = 0;
-        if (lane < NT / 32) t = sh.warp_tot[lane];
+        Map<R> t; t.a0 = 0; t.a1 = 0;
+        if (lane < NT / 32) t = narrow<R>(sh.warp_tot[lane]);
         t = warp_scan<R>(t, lane);
-        if (lane == 31) fbuf[s] = t;                                   // lanes beyond NT/32 hold the identity
+        if (lane == 31) fbuf[s] = widen(t);                            // lanes beyond NT/32 hold the identity
       }
       __syncthreads();
     }
@@ -473,9 +489,9 @@ struct GridChain {
     const unsigned long long per = (nseg + NT - 1) / NT;
     const unsigned long long s0 = (unsigned long long)tid * per;
     const unsigned long long s1 = s0 + per < nseg ? s0 + per : nseg;
-    Fn f; f.a0 = 0; f.a1 = 0;
-    for (unsigned long long s = s0; s < s1; s++) f = then<R>(f, ldcg_fn(fbuf + s));
-    Fn excl, incl, total;
+    Map<R> f; f.a0 = 0; f.a1 = 0;
+    for (unsigned long long s = s0; s < s1; s++) f = then<R>(f, narrow<R>(ldcg_fn(fbuf + s)));
+    Map<R> excl, incl, total;
     block_scan<R, NT>(f, sh, excl, incl, total);
     if (apply(incl, M) >= LIMIT) atomicMin(&sh.first_cross, tid);
     __syncthreads();
@@ -504,7 +520,7 @@ struct GridChain {
     // replay that segment from (E, Mc); the scan must find the crossing term
     float x[T];
     load(base + (size_t)tid * T, x);
-    Fn g; g.a0 = 0; g.a1 = 0;
+    Map<R> g; g.a0 = 0; g.a1 = 0;
 #pragma unroll
     for (int j = 0; j < T; j++) g = then<R>(g, term<R>(__float_as_uint(x[j]), E));
     block_scan<R, NT>(g, sh, excl, incl, total);                       // its barriers also publish first_cross = NT
@@ -547,7 +563,7 @@ __device__ R warp_chain(size_t n, Load load, bool *bad)
 #pragma unroll
     for (int j = 0; j < T; j++) x[j] = load(pos + (size_t)lane * T + j);
     bool ok = true;
-    Fn f; f.a0 = 0; f.a1 = 0;
+    Map<R> f; f.a0 = 0; f.a1 = 0;
 #pragma unroll
     for (int j = 0; j < T; j++) {
       const uint32_t xb = __float_as_uint(x[j]);
@@ -555,12 +571,12 @@ __device__ R warp_chain(size_t n, Load load, bool *bad)
       f = then<R>(f, term<R>(xb, E));
     }
     if (!__all_sync(0xffffffffu, ok)) { *bad = true; return (R)0; }
-    const Fn incl = warp_scan<R>(f, lane);
-    Fn excl = shfl_up_fn(incl, 1);
+    const Map<R> incl = warp_scan<R>(f, lane);
+    Map<R> excl = shfl_up_fn(incl, 1);
     if (lane == 0) { excl.a0 = 0; excl.a1 = 0; }
     const unsigned cross = __ballot_sync(0xffffffffu, apply(incl, M) >= LIMIT);
     if (!cross) {
-      Fn total;
+      Map<R> total;
       total.a0 = __shfl_sync(0xffffffffu, incl.a0, 31);
       total.a1 = __shfl_sync(0xffffffffu, incl.a1, 31);
       M = apply(total, M);

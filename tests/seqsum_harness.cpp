@@ -15,10 +15,10 @@ static R chain(const float *x, size_t n, int chunk, long *crossings, int *bad)
   Tr<R>::unpack((R)0, E, M);
   size_t pos = 0;
   *crossings = 0; *bad = 0;
-  std::vector<Fn> pre((size_t)chunk);
+  std::vector<Map<R>> pre((size_t)chunk);
   while (pos < n) {
     const size_t m = n - pos < (size_t)chunk ? n - pos : (size_t)chunk;
-    Fn acc; acc.a0 = acc.a1 = 0;
+    Map<R> acc; acc.a0 = acc.a1 = 0;
     for (size_t i = 0; i < m; i++) {
       uint32_t xb; __builtin_memcpy(&xb, x + pos + i, 4);
       if (!term_ok(xb)) { *bad = 1; return (R)0; }
