@@ -2678,7 +2678,7 @@ extern "C" int gcb_counter_allreduce(gcb_counter *c)
     unsigned long long mine[TW] = {c->any ? 1ull : 0ull, wb, c->uniform ? 1ull : 0ull, c->acc_used ? 1ull : 0ull,
                                    c->hits_per_frame.size(), c->bound_run, c->bound_total, 0ull};
     if (c->ctl) {
-      rc = gcb_ctl_allgather(c->ctl, (const uint64_t *)mine, (uint64_t *)table.data(), 120000);
+      rc = gcb_ctl_allgather(c->ctl, (const uint64_t *)mine, (uint64_t *)table.data(), 0);    // no timeout: like a collective
       if (rc) return rc;
     } else {
       rc = scratch(R * TW);

@@ -149,13 +149,17 @@ int gcb_ctl_allgather(gcb_ctl *h, const uint64_t *mine, uint64_t *all, int timeo
   uint64_t *tab = h->table((int)(k & 1));
   memcpy(tab + (size_t)h->rank * h->words, mine, sizeof(uint64_t) * (size_t)h->words);
   h->seq()[h->rank].v.store(k, std::memory_order_release);
-  const double deadline = now_s() + 1e-3 * (double)timeout_ms;
+  // timeout_ms <= 0: wait as long as it takes (a rank may still be binning its shard for minutes: the same patience
+  // a collective has).  Spin briefly, then yield, then sleep: the other ranks need the cores.
+  const double t_begin = now_s(), deadline = t_begin + 1e-3 * (double)timeout_ms;
   for (int j = 0; j < h->nranks; j++) {
     unsigned spins = 0;
     while (h->seq()[j].v.load(std::memory_order_acquire) < k) {
       if ((++spins & 1023u) == 0) {
-        if (now_s() > deadline) return gcb::fail(GCB_ERR_NCCL, "control all-gather %llu: rank %d never arrived", (unsigned long long)k, j);
-        sched_yield();
+        const double t = now_s();
+        if (timeout_ms > 0 && t > deadline)
+          return gcb::fail(GCB_ERR_NCCL, "control all-gather %llu: rank %d never arrived", (unsigned long long)k, j);
+        if (t - t_begin > 0.01) usleep(50); else sched_yield();
       }
     }
   }

@@ -217,7 +217,8 @@ int gcb_counter_allreduce(gcb_counter *c);
  * all-gather between the ranks of one node, not through a second NCCL collective.  Exposed for tests: */
 typedef struct gcb_ctl gcb_ctl;
 int gcb_ctl_open(gcb_ctl **out, const char id[128], int rank, int nranks, int words, int timeout_ms);
-int gcb_ctl_allgather(gcb_ctl *h, const uint64_t *mine /* [words] */, uint64_t *all /* [nranks][words] */, int timeout_ms);
+int gcb_ctl_allgather(gcb_ctl *h, const uint64_t *mine /* [words] */, uint64_t *all /* [nranks][words] */,
+                      int timeout_ms /* <= 0: wait for the other ranks as long as it takes */);
 void gcb_ctl_close(gcb_ctl *h);
 /* The same reduce between counters of ONE process (one host thread per counter, on one GPU or several): an
  * in-process transport behind the same protocol, for host programs that drive their GPUs from threads and for
