@@ -21,6 +21,8 @@ echo "ncu launches bench rc=$?"
 export PERF_KERNELS=auto
 full c2 bin_stream 4 python tools/perf_k1.py c2
 full c3 bin_stream 4 python tools/perf_k1.py c3
+full c4 bin_stream 4 python tools/perf_k1.py c4
+full c4apply packed_apply_mid 2 python tools/perf_k1.py c4
 full p1 bin_stream 4 python tools/perf_k1.py pore
 full c1 bin_stream 4 python tools/perf_k1.py c1long
 full c3apply packed_apply 2 python tools/perf_k1.py c3
