@@ -214,10 +214,12 @@ def run_reference_arm(args, rank, world):
     gindex = cfg_gindex(cfg)
     sample = 2 * threads                           # frames held in memory (12 MB each), one or two per thread
     x = u.gen_frames(cfg_gen(u, cfg), 0, sample, cfg["natoms"])
-    # size a step to ~3 s of binning on this host
+    # size a step to ~3 s of WALL time on this host (the first call also allocates the per-thread grids)
+    cpu_reference(sample, 1, threads, x, gindex, cfg["L"], cfg["delta"], cfg["natoms"])
+    t0 = time.perf_counter()
     rate, kind = cpu_reference(sample, 1, threads, x, gindex, cfg["L"], cfg["delta"], cfg["natoms"])
-    per_rep = sample * len(gindex) / rate
-    repeats = int(max(1, min(50, round(3.0 / max(per_rep, 1e-6)))))
+    per_rep = max(time.perf_counter() - t0, 1e-3)
+    repeats = int(max(1, min(50, round(3.0 / per_rep), 120.0 / (max(args.steps, 1) * per_rep))))     # and ~2 minutes in all
     for _ in range(min(args.warmup, 2)):
         cpu_reference(sample, 1, threads, x, gindex, cfg["L"], cfg["delta"], cfg["natoms"])
     t_units = 0.0

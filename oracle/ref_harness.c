@@ -140,6 +140,7 @@ void *gcref_grid_read(const char *path, char *header256)
 typedef struct {
   gcref_grid *g;
   const float *x; long f0, f1; int natoms; const int *gindex; int gnx; float w; double sumP;
+  long cells; int id; pthread_barrier_t *bar; struct timespec *t0;
 } gcref_job;
 
 static void *gcref_worker(void *arg)
@@ -148,6 +149,10 @@ static void *gcref_worker(void *arg)
   long f;
   int i;
   double s = 0;
+  /* every thread zeroes its own grid (first touch and clearing are not timed), then all start together */
+  memset(gcref_grid_data(j->g), 0, sizeof(real) * (size_t)j->cells);
+  pthread_barrier_wait(j->bar);
+  if (j->id == 0) clock_gettime(CLOCK_MONOTONIC, j->t0);
   for (f = j->f0; f < j->f1; f++) {
     rvec *xf = (rvec *)(j->x + (size_t)f * j->natoms * 3);
     for (i = 0; i < j->gnx; i++) s += gridcount(&j->g->tg, xf[j->gindex[i]], j->w);
@@ -155,6 +160,12 @@ static void *gcref_worker(void *arg)
   j->sumP = s;
   return NULL;
 }
+
+/* the per-thread grids are kept between calls with the same geometry and thread count: allocating and
+ * page-faulting 16 x 256 MB per call costs seconds, many times the binning that is being timed */
+static gcref_grid *pool[1024];
+static int pool_n = 0;
+static float pool_key[12];
 
 /* Returns elapsed seconds for binning nframes frames with nthreads threads;
  * *sumP_out gets the merged hit weight, merged_out (optional, cells floats)
@@ -165,30 +176,39 @@ double gcref_bench(const float box9[9], const float delta[3], const float *x, lo
 {
   gcref_job *jobs = calloc((size_t)nthreads, sizeof(*jobs));
   pthread_t *th = calloc((size_t)nthreads, sizeof(*th));
+  pthread_barrier_t bar;
   struct timespec t0, t1;
+  float key[12];
   int t;
   long cells = 0, c;
   double s = 0;
+  if (nthreads > 1024) nthreads = 1024;
+  memcpy(key, box9, sizeof(float) * 9); memcpy(key + 9, delta, sizeof(float) * 3);
+  if (pool_n != nthreads || memcmp(key, pool_key, sizeof key) != 0) {
+    for (t = 0; t < pool_n; t++) gcref_grid_free(pool[t]);
+    for (t = 0; t < nthreads; t++) pool[t] = gcref_grid_create(box9, delta, 0, NULL, 0, 0, 0);
+    pool_n = nthreads;
+    memcpy(pool_key, key, sizeof key);
+  }
+  pthread_barrier_init(&bar, NULL, (unsigned)nthreads);
   for (t = 0; t < nthreads; t++) {
-    jobs[t].g = gcref_grid_create(box9, delta, 0, NULL, 0, 0, 0);
+    jobs[t].g = pool[t];
     jobs[t].x = x; jobs[t].natoms = natoms; jobs[t].gindex = gindex; jobs[t].gnx = gnx; jobs[t].w = weight;
     jobs[t].f0 = nframes * t / nthreads; jobs[t].f1 = nframes * (t + 1) / nthreads;
-    /* touch the grid so that first-touch page faults are not timed */
     cells = (long)jobs[t].g->tg.mx[0] * jobs[t].g->tg.mx[1] * jobs[t].g->tg.mx[2];
-    memset(gcref_grid_data(jobs[t].g), 0, sizeof(real) * (size_t)cells);
+    jobs[t].cells = cells; jobs[t].id = t; jobs[t].bar = &bar; jobs[t].t0 = &t0;
   }
-  clock_gettime(CLOCK_MONOTONIC, &t0);
   for (t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, gcref_worker, &jobs[t]);
   gcref_worker(&jobs[0]);
   for (t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
   clock_gettime(CLOCK_MONOTONIC, &t1);
+  pthread_barrier_destroy(&bar);
   for (t = 0; t < nthreads; t++) {
     s += jobs[t].sumP;
     if (merged_out) {
       float *gd = gcref_grid_data(jobs[t].g);
       for (c = 0; c < cells; c++) merged_out[c] = (t ? merged_out[c] : 0) + gd[c];
     }
-    gcref_grid_free(jobs[t].g);
   }
   if (sumP_out) *sumP_out = s;
   free(jobs); free(th);
