@@ -101,8 +101,9 @@ static void *xtc_worker(void *arg)
   gcb_xtc_frame *frames = NULL;
   float *wsel = NULL;
   FILE *f = NULL;
+  int attached = 0, joined = 0;
   WCHECK(gcb_counter_create(&j->ctr, j->tg, j->grp->atoms, j->grp->n, j->natoms, &copt));
-  if (j->nranks > 1) WCHECK(gcb_counter_comm_init_local(j->ctr, j->lc, j->rank));
+  if (j->nranks > 1) { WCHECK(gcb_counter_comm_init_local(j->ctr, j->lc, j->rank)); attached = 1; }
   if (j->nsel > 0) {
     f = fopen(j->path, "rb");
     if (!f) { snprintf(j->err, sizeof j->err, "Cannot read trajectory %s", j->path); goto done; }
@@ -134,9 +135,11 @@ static void *xtc_worker(void *arg)
       i = k;
     }
   }
-  if (j->nranks > 1) WCHECK(gcb_counter_allreduce(j->ctr));
+  if (j->nranks > 1) { joined = 1; WCHECK(gcb_counter_allreduce(j->ctr)); }
   j->rc = 0;
 done:
+  /* a rank that failed on its way still takes part in the reduce, or the other ranks would wait for it forever */
+  if (j->rc && attached && !joined) gcb_counter_allreduce(j->ctr);
   if (f) fclose(f);
   free(frames); free(wsel);
   if (pin) gcb_host_free_pinned(pin);
@@ -305,6 +308,7 @@ int main(int argc, char **argv)
     free(th); free(tt); free(w); free(all);
   } else {
   /* ---- main loop over frames: batches through the pinned slots ---- */
+  if (gpulist[0]) gh_msg("Note: -gpus shards .xtc trajectories decoded on the GPU; this run uses device %d only\n", device);
   CHECK(gcb_counter_create(&ctr, &tg, grp->atoms, grp->n, natoms, &copt));
   const int NSLOTS = 3;
   int slot = 0;
