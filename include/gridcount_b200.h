@@ -234,8 +234,11 @@ void gcb_local_comm_destroy(gcb_local_comm *lc);
  * XTC trajectories decoded on the GPU.  Replaces, for .xtc input, the frames that
  * read_first_x / read_next_x deliver to the frame loop (g_ri3Dc.c:392,428; the decoder
  * itself is Gromacs' xdr3dfcoord, not part of the reference tree).  The host parses the
- * frame headers only; compressed payloads cross PCIe as they are (about a third of the
- * float coordinates) and one GPU thread decodes one frame.
+ * frame headers only; compressed payloads cross PCIe as they are (about 5 bytes per atom instead of 12).
+ * On the GPU one warp per frame walks the stream's control bits and drops a checkpoint every 64 atoms; one
+ * thread per checkpoint then decodes its atoms -- and, in gcb_counter_add_xtc, bins them on the spot (no
+ * coordinates are stored) whenever a batch is one run of integer counts.  PARITY WITH GROMACS UNPINNED (the
+ * library is not in the reference tree): pinned bit for bit to the host codec of host/trajio.c.
  * ---------------------------------------------------------------------- */
 typedef struct {
   uint64_t payload_offset;  /* byte offset of the compressed coordinates in the scanned buffer */
@@ -252,7 +255,9 @@ int gcb_xtc_decode_device(const uint8_t *buf, size_t len, const gcb_xtc_frame *f
                           int natoms, float *x_dev, int device);
 /* decode + bin: the xtc counterpart of gcb_counter_add_frames.  `buf` is host memory (pinned memory is
  * copied asynchronously); weight[f] as in gcb_counter_add_frames; with GCB_PBC_RECT the boxes of the
- * frame headers are used. */
+ * frame headers are used.  The call returns when all batches have been consumed.  A frame whose compressed
+ * stream is damaged fails the call with GCB_ERR_FORMAT and bins nothing itself, but frames of the same call
+ * before it have been binned: reset the counter. */
 int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gcb_xtc_frame *frames,
                         long nframes, const float *weight);
 
