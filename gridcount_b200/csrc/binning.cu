@@ -2163,8 +2163,12 @@ int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gc
     return GCB_OK;
   };
   long nfused = 0;
-  for (long f0 = 0; f0 < nframes; f0 += per, set = (set + 1) % GCB_XTC_SETS) {
-    const long n = std::min(per, nframes - f0);
+  // the first two batches are a quarter and a half of the others: the pipeline starts working after a quarter of a
+  // batch's copy time (nothing overlaps the first copy and the first skim)
+  long f0 = 0;
+  for (long batch = 0; f0 < nframes; batch++, set = (set + 1) % GCB_XTC_SETS) {
+    const long want = batch == 0 ? std::max<long>(16, (per / 4) & ~3L) : batch == 1 ? std::max<long>(16, (per / 2) & ~3L) : per;
+    const long n = std::min(want, nframes - f0);
     gcb_counter::XtcSet &x = c->xtc[set];
     int rc = check_set(x);
     if (rc) return rc;
@@ -2226,6 +2230,7 @@ int gcb_counter_add_xtc(gcb_counter *c, const uint8_t *buf, size_t len, const gc
     // the copy stream here, it would hold back the copy of the NEXT batch, which goes into another set)
     GCB_CUDA(cudaEventRecord(x.consumed, c->compute));
     x.nframes = n; x.first = f0;
+    f0 += n;
   }
   const double t_queued = now();
   for (auto &x : c->xtc) { int rc = check_set(x); if (rc) return rc; }
