@@ -904,6 +904,8 @@ static int analyse_impl(const gcb_tgrid *tg_in, const float *grid_zfast, bool on
   sp.min_occ = min_occ; sp.d_zdf = fmx * fmy * U; sp.DeltaR = DeltaR; sp.U = U; sp.a_z = tg.a[2]; sp.delta_z = tg.delta[2];
   sp.dV = dV;
   AN_CUDA(cudaStreamWaitEvent(st[2], gx_ready, 0));
+  // (limiting how many blocks of the slice / rdf kernels an SM takes, so that they and the cooperative whole-grid kernel
+  // are resident together, was measured: 4.84 ms of kernels at C3 size without, 4.83-5.42 with -- the three are work-bound)
   an_slice_scan_kernel<<<dim3(d.mz, 3), SLICE_THREADS, 0, st[2]>>>(d_gx.as<float>(), d, d_c2.as<float>(), d_flags.as<unsigned char>(), min_occ,
                                                                    d_sraw.as<float>(), d_nocc.as<unsigned>(), d_bad);
   an_slice_finish_kernel<<<blocks_for(d.mz, 128), 128, 0, st[2]>>>(d_sraw.as<float>(), d.mz, sp, d_zdf.as<float>(), d_lzdf.as<float>(),
