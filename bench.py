@@ -18,8 +18,10 @@ Beside the contract's keys the line carries
   roofline      K1's dominant kernel: achieved = 12 B x atom-frames / summed launch durations, measured live with CUDA
                 events around every launch; the memory-system ceilings for K1's traffic mix measured in the same run
                 by gcb_selftest_l2 (random-RED peak, and a read stream with one RED per 36 bytes)
-  per_config    (N = 1) the other named shapes C1, C2, C4 (uniform and clustered), each with value, roofline, the
-                kernel that ran and a bit-exact oracle check of a prefix of its frames
+  per_config    (N = 1) the other named shapes C1, C2, C4 (uniform and clustered) and a pore-sized grid P1, each with
+                value, roofline, the kernel that ran and a bit-exact oracle check of a prefix of its frames;
+                (N > 1) C1, C2, C4 frame-sharded with the NCCL all-reduce, value only
+  e2e_xtc       the end-to-end job from XTC bytes (compressed bytes over PCIe, decoded and binned on the GPU)
   c5            (N > 1) the C5 shape: breathing box, 256 MB NCCL all-reduce, with its own oracle parity check
   parity_checked / parity   counts and per-frame hits of a frame prefix (of every rank's shard) equal the CPU oracle's
   a_ri3Dc, xtc  (N = 1) K3 over the job's density; XTC decode rates
@@ -683,10 +685,15 @@ def run_gpu_arm(args, rank, local_rank, world):
     parity = None
     c5 = None
     e2e_xtc_multi = None
+    per_config_n = None
     if world == 1:
         parity = prefix_parity(g, cfg, geom, gindex, dev, device)
     else:
         c5, parity = c5_section(g, u, torch, dist, ctr, dev, geom, rank, world, device, barrier, max_over_ranks)
+        try:
+            per_config_n = per_config_multi(g, torch, dist, rank, world, device, barrier, max_over_ranks)
+        except Exception as e:
+            per_config_n = {"error": str(e)[:200]}
         try:
             e2e_xtc_multi = xtc_multi_section(g, torch, dist, rank, world, device, barrier, max_over_ranks)
         except Exception as e:                        # (every rank fails alike or not at all: the section is collective)
@@ -757,7 +764,7 @@ def run_gpu_arm(args, rank, local_rank, world):
                 "packed_counters": packed_info,
                 "parity_checked": bool(parity and parity["ok"]), "parity": parity,
                 "cpu_baseline": cpu, "a_ri3Dc": {"C3": k3, "C2": k3_c2} if world == 1 else None, "xtc": xtc,
-                "per_config": per_config, "c5": c5, "e2e_xtc": e2e_xtc_multi if world > 1 else (xtc or {}).get("e2e_xtc")}
+                "per_config": per_config if world == 1 else per_config_n, "c5": c5, "e2e_xtc": e2e_xtc_multi if world > 1 else (xtc or {}).get("e2e_xtc")}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -811,6 +818,55 @@ def xtc_multi_section(g, torch, dist, rank, world, device, barrier, max_over_ran
                "path": "gcb_counter_add_xtc(pinned xtc bytes) -> gcb_counter_allreduce -> gcb_counter_density(host grid)"}
     ctr.close(); xb.free()
     return res
+
+
+def per_config_multi(g, torch, dist, rank, world, device, barrier, max_over_ranks):
+    """N > 1: the other named shapes, frame-sharded like the headline -- every rank bins its own resident frames
+    (10 passes = one job), the grids are combined by the NCCL all-reduce, the density is formed; `value` counts the
+    atom-frames of all ranks.  (Rooflines, oracle parity and the private/packed accounting of these shapes are in the
+    N = 1 line.)"""
+    from gridcount_b200.api import nccl_unique_id
+    out = {}
+    for name in ("C1", "C2", "C4"):
+        cfg = CONFIGS[name]
+        geom = g.setup_geometry(cfg["L"], cfg["delta"])
+        gindex = cfg_gindex(cfg)
+        F, reps = cfg["resident"], 10
+        dev = g.DeviceFrames(F, cfg["natoms"], device).generate(cfg_gen(g, cfg), frame0=rank * F)
+        ctr = g.GridCounter(geom, gindex, cfg["natoms"], device=device)
+        uid = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctr.comm_init(uid[0], rank, world)
+        w = np.ones(F, np.float32)
+        T = float(F * reps * world)
+
+        def job():
+            ctr.reset_grid()
+            for _ in range(reps):
+                if cfg.get("reset_each_pass"):
+                    ctr.reset_grid()
+                ctr.add_device_frames(dev, weights=w)
+            ctr.allreduce()
+            ctr.density_device(T)
+
+        job()
+        ctr.sync()
+        barrier()
+        ctr.event_record(0)
+        job()
+        ctr.event_record(1)
+        ctr.sync()
+        barrier()
+        ms = max_over_ranks(ctr.event_elapsed(0, 1))
+        st = ctr.stats()
+        kept = 1 if cfg.get("reset_each_pass") else reps        # passes whose hits the final grid holds
+        if rank == 0:
+            out[name] = {"workload": cfg["title"], "n_gpus": world, "value": float(len(gindex)) * F * reps * world / (ms * 1e-3) * 1e-9,
+                         "unit": UNIT, "ms_per_job": ms, "frames_per_job": F * reps * world,
+                         "all_hits_in_grid": bool(st.hits == int(len(gindex)) * F * kept * world),
+                         "job": "%d passes over %d resident frames per rank + NCCL grid all-reduce + density" % (reps, F)}
+        ctr.close(); dev.free()
+    return out if rank == 0 else None
 
 
 def c5_section(g, u, torch, dist, ctr, dev, geom, rank, world, device, barrier, max_over_ranks):

@@ -17,6 +17,9 @@ for n, c in (d.get("per_config") or {}).items():
     if "error" in c:
         print("  %s ERROR %s" % (n, c["error"]))
         continue
+    if "roofline" not in c:
+        print("  %-4s %7.1f G/s on %d GPUs, %.2f ms per job, all hits in grid: %s" % (n, c["value"], c["n_gpus"], c["ms_per_job"], c["all_hits_in_grid"]))
+        continue
     rl = c["roofline"]
     print("  %-4s %6.1f G/s  kernel %6.1f frac %.3f  [%s]  kinds %s  parity %s  packed %d/%d private %d/%d  of stream+red %.2f of stream %.2f" % (
         n, c["value"], rl["kernel_g_atom_frames_per_s"], rl["frac"], rl["kernel"][:32], rl.get("k1_launch_kinds_ms"), c["parity_checked"],
