@@ -742,3 +742,23 @@ def test_nibble_rounds_through_the_byte_grid_stay_exact(monkeypatch):
         ctr.add_frames(x[8:20], np.ones(12, np.float32))
         np.testing.assert_array_equal(ctr.counts(), oracle_counts(geom, x[8:20], gindex)[0])
         ctr.close()
+
+
+def test_pinned_source_may_be_refilled_as_soon_as_add_frames_returns():
+    """gcb_counter_add_frames DMAs pinned memory in place; its contract is that x may be refilled when the call returns
+    (the natural read loop reuses one buffer).  Frames are overwritten with rubbish right after every call."""
+    L = (4.0, 4.0, 4.0)
+    natoms, chunk, nchunks = 50000, 40, 6            # 24 MB per call: several staging batches in flight
+    geom = g.setup_geometry(L, 0.1)
+    gindex = np.arange(0, natoms, 3, dtype=np.int32)
+    x = u.gen_frames(u.make_gen(91, L), 0, chunk * nchunks, natoms)
+    ocounts, ohits, _ = oracle_counts(geom, x, gindex)
+    pin = g.PinnedFrames(chunk, natoms)
+    ctr = g.GridCounter(geom, gindex, natoms, frames_per_batch=4)
+    for c in range(nchunks):
+        pin.array[:] = x[c * chunk:(c + 1) * chunk]
+        ctr.add_host_ptr(pin.ptr, chunk)
+        pin.array[:] = -1.0e9                         # the next chunk is "read" into the same buffer at once
+    np.testing.assert_array_equal(ctr.counts(), ocounts)
+    np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
+    ctr.close(); pin.free()
