@@ -215,3 +215,30 @@ def test_a_damaged_frame_fails_the_binning_call(host):
     with pytest.raises(g._cabi.GcbError, match="damaged"):
         ctr.add_xtc(xb, np.ones(nframes, np.float32))
     ctr.close()
+
+
+def test_xtc_into_a_grid_on_the_packed_counter_path(host):
+    """a grid whose uint32 cells exceed the L2 (234^3 = 12.8 M cells): gcb_counter_add_xtc decodes to x[frame][atom][3]
+    and bins through the packed-counter rounds instead of binning out of the decoder; counts equal the oracle's on the
+    decoded coordinates"""
+    L, natoms, nframes = (5.85, 5.85, 5.85), 60000, 40
+    rng = np.random.default_rng(21)
+    x = (rng.random((nframes, natoms, 3)) * np.asarray(L)).astype(np.float32)
+    t = np.arange(nframes, dtype=np.float32)
+    data = encode_traj(host, x, t)
+    xd = host_decode(host, data, natoms, nframes)
+    geom = g.setup_geometry(L, 0.025)
+    assert geom.cells > 12_000_000
+    gindex = np.arange(natoms, dtype=np.int32)
+    og = u.Geom.from_buffer_copy(bytes(geom.tg))
+    want = np.zeros(geom.shape, np.uint32)
+    hits = np.zeros(nframes, np.uint64)
+    u.oracle().gco_count_frames(C.byref(og), want.ctypes.data_as(u.c_u32_p), u.fptr(xd), nframes, natoms, u.iptr(gindex),
+                                len(gindex), hits.ctypes.data_as(u.c_u64_p), None)
+    xb = g.XtcBuffer(data, pinned=True)
+    ctr = g.GridCounter(geom, gindex, natoms)
+    ctr.add_xtc(xb, np.ones(nframes, np.float32))
+    np.testing.assert_array_equal(ctr.counts(), want)
+    np.testing.assert_array_equal(ctr.hits_per_frame(), hits)
+    assert ctr.stats().packed_rounds >= 1
+    ctr.close(); xb.free()
