@@ -43,7 +43,13 @@ __device__ __forceinline__ unsigned peek_bits(const uint32_t *w, unsigned nwords
 // its time is (steps per frame) x (load latency) whatever the number of frames: the fewer steps, the better.
 constexpr int SKIM_WARPS = 4;
 constexpr int SKIM_DEPTH = 4;
-__device__ __forceinline__ unsigned ceil_div_groups(unsigned atoms, unsigned g) { return g == 1u ? atoms : (atoms + g - 1u) / g; }
+// ceil(atoms / g) for the group sizes that can occur (g = 1 .. 11) and small atom counts (< 4096), without a division
+// ceil(2^16 / g) for g = 1 .. 11: a 5-bit run field can name up to 10 small atoms behind the full one (the encoder stops at 8)
+__constant__ unsigned c_rcp16[12] = {0u, 65536u, 32768u, 21846u, 16384u, 13108u, 10923u, 9363u, 8192u, 7282u, 6554u, 5958u};
+__device__ __forceinline__ unsigned ceil_div_small(unsigned atoms, unsigned g)
+{
+  return ((atoms + g - 1u) * c_rcp16[g]) >> 16;
+}
 
 __global__ void __launch_bounds__(SKIM_WARPS * 32)
 xtc_skim_kernel(const uint8_t *__restrict__ buf, const FrameDev *__restrict__ meta, long nframes, int natoms,
@@ -60,16 +66,18 @@ xtc_skim_kernel(const uint8_t *__restrict__ buf, const FrameDev *__restrict__ me
   }
   const uint32_t *w = reinterpret_cast<const uint32_t *>(buf + m.offset);
   const unsigned nwords = (m.nbytes + 3) / 4;
-  const unsigned total_bits = m.nbytes * 8u;                                  // (payloads are < 2^29 bytes: gcb_xtc_scan)
+  const unsigned total_bits = m.nbytes * 8u;                 // < 2^31 (gcb_xtc_scan): every position below fits 32 bits
   const FrameCoding fc = frame_coding(m);
   const unsigned fullbits = fc.bitsize ? (unsigned)fc.bitsize : fc.bitsizeint[0] + fc.bitsizeint[1] + fc.bitsizeint[2];
   int smallidx = m.smallidx, run = 0, k = 0;
   unsigned i = 0, next_mark = 0, bp = 0;
   bool bad = false, over = false;
-  while (i < (unsigned)natoms) {                                              // all lanes carry the same state
-    const unsigned g = 1u + (unsigned)(run / 3);                              // atoms per unflagged group
+  constexpr unsigned NG = 32u * SKIM_DEPTH;                  // groups looked at per step
+  while (i < (unsigned)natoms) {                             // all lanes carry the same state
+    const unsigned g = 1u + (unsigned)(run / 3);             // atoms per unflagged group (1 .. 11)
     const unsigned glen = fullbits + 1u + (unsigned)(run / 3) * (unsigned)smallidx;
-    const unsigned nmax = min(32u * SKIM_DEPTH, ceil_div_groups((unsigned)natoms - i, g));
+    const unsigned rem = (unsigned)natoms - i;
+    const unsigned nmax = rem >= NG * g ? NG : (g == 1u ? rem : (rem + g - 1u) / g);       // a division only near the end
     // the walk only moves forward: pull the lines it is about to read (1 .. 5 KB ahead) into L1 now, so that the
     // dependent loads of the coming steps are L1 hits
     {
@@ -77,53 +85,51 @@ xtc_skim_kernel(const uint8_t *__restrict__ buf, const FrameDev *__restrict__ me
       if (ahead < m.nbytes) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t *>(w) + ahead));
     }
     // flag bit of group j sits at bp + fullbits + j * glen; a position at or past the end of the payload (a damaged
-    // stream, caught below) wraps or saturates into "flagged"
-    const unsigned long long p0 = (unsigned long long)bp + fullbits + (unsigned long long)lane * glen;
+    // stream, caught below) reads as "flagged"
+    const unsigned p0 = bp + fullbits + lane * glen;
     unsigned word[SKIM_DEPTH];
 #pragma unroll
-    for (int d = 0; d < SKIM_DEPTH; d++) {                                    // all loads first: they overlap
-      const unsigned long long p = p0 + (unsigned long long)(32u * d) * glen;
-      word[d] = (lane + 32u * d < nmax && p < total_bits) ? __ldg(w + (unsigned)(p >> 5)) : 0xffffffffu;
+    for (int d = 0; d < SKIM_DEPTH; d++) {                   // all loads first: they overlap
+      const unsigned p = p0 + 32u * d * glen;
+      word[d] = (lane + 32u * d < nmax && p < total_bits) ? __ldg(w + (p >> 5)) : 0xffffffffu;
     }
     unsigned j0 = nmax;
 #pragma unroll
     for (int d = SKIM_DEPTH - 1; d >= 0; d--) {
-      const unsigned p = (unsigned)p0 + 32u * d * glen;
+      const unsigned p = p0 + 32u * d * glen;
       const bool flag = lane + 32u * d < nmax && ((__byte_perm(word[d], 0, 0x0123) >> (31u - (p & 31u))) & 1u) != 0u;
       const unsigned flags = __ballot_sync(0xffffffffu, flag);
       if (flags) j0 = 32u * d + (unsigned)(__ffs((int)flags) - 1);
     }
     // Groups 0 .. j0-1 are unflagged and group j0 (if there is one) begins like them: all start in the state
     // (smallidx, run) at known positions.  Every group that is the first to start at or behind a segment mark gets
-    // a checkpoint.
+    // a checkpoint: the first one ceil((next_mark - i) / g) groups on (at most SEG_ATOMS atoms away), the following
+    // ones every ceil(SEG_ATOMS / g) groups.
     {
       const unsigned jend = j0 < nmax ? j0 + 1u : j0;
-      unsigned j = next_mark <= i ? 0u : ceil_div_groups(next_mark - i, g);
+      const unsigned stride = ceil_div_small(SEG_ATOMS, g);
+      unsigned j = next_mark <= i ? 0u : ceil_div_small(next_mark - i, g);
       while (j < jend) {
         if (lane == 0) out[k] = Checkpoint{bp + j * glen, i + j * g, smallidx, run};
         k++;
         next_mark = i + j * g + SEG_ATOMS;
-        j = ceil_div_groups(next_mark - i, g);
+        j += stride;
       }
     }
-    {
-      const unsigned long long nb = (unsigned long long)bp + (unsigned long long)j0 * glen;
-      if (nb > total_bits) { bad = true; break; }
-      bp = (unsigned)nb;
-    }
+    bp += j0 * glen;
+    if (bp > total_bits) { bad = true; break; }
     i += j0 * g;
     if (j0 < nmax) {                                                          // a group that changes run / smallidx
-      const unsigned long long q = (unsigned long long)bp + fullbits;
-      if (q + 6 > total_bits) { bad = true; break; }
-      const unsigned six = peek_bits(w, nwords, (unsigned)q, 6, over);
+      const unsigned q = bp + fullbits;
+      if (q + 6u > total_bits) { bad = true; break; }
+      const unsigned six = peek_bits(w, nwords, q, 6, over);
       if (!(six & 32u)) { bad = true; break; }
       run = (int)(six & 31u);
       const int is_smaller = run % 3 - 1;
       run -= run % 3;
       i += 1u + (unsigned)(run / 3);
-      const unsigned long long nb = q + 6ull + (unsigned long long)(run / 3) * (unsigned)smallidx;
-      if (nb > total_bits) { bad = true; break; }
-      bp = (unsigned)nb;
+      bp = q + 6u + (unsigned)(run / 3) * (unsigned)smallidx;
+      if (bp > total_bits) { bad = true; break; }
       smallidx += is_smaller;
     }
     if (smallidx < FIRSTIDX || smallidx > LASTIDX || i > (unsigned)natoms || over) { bad = true; break; }
@@ -198,7 +204,7 @@ int gcb_xtc_scan(const uint8_t *buf, size_t len, gcb_xtc_frame *frames, long cap
       const size_t nbytes = be32(p + 88);
       total = 92 + ((nbytes + 3) & ~(size_t)3);
       if (len - off < total) break;
-      if (fr.smallidx < FIRSTIDX || fr.smallidx > LASTIDX || !(fr.precision > 0) || nbytes >= ((size_t)1 << 29))   // (bit positions are 32-bit)
+      if (fr.smallidx < FIRSTIDX || fr.smallidx > LASTIDX || !(fr.precision > 0) || nbytes >= ((size_t)1 << 28))   // (bit positions stay below 2^31)
         return gcb::fail(GCB_ERR_FORMAT, "damaged xtc frame header at byte %zu", off);
       for (int d = 0; d < 3; d++)
         if (fr.maxint[d] < fr.minint[d]) return gcb::fail(GCB_ERR_FORMAT, "damaged xtc frame header at byte %zu", off);
