@@ -68,7 +68,11 @@ struct gcb_counter {
   uint32_t *d_pk = nullptr;           // packed counters, always all-zero between rounds
   PackedState *d_pstate = nullptr;
   PackedState *h_pstate = nullptr;    // pinned mirror, refreshed (asynchronously) behind every call's rounds
-  int packed_pause = 0;               // calls still to be binned without the packed pass (see launch_packed)
+  int packed_pause = 0;               // calls still to be binned without the packed pass (see packed_paused)
+  int packed_bits_home = 0;           // the lane width chosen at create; packed_bits may fall back from 4 to 8 (packed_paused)
+  long long packed_units_home = 0;
+  bool packed_fallback_ok = false;    // a nibble grid may retry with byte lanes and short rounds before giving up
+  int packed_mode_calls = 0, packed_cooldown = 0;
   uint64_t packed_rounds = 0, packed_redone = 0;
   // privatised path (PrivateSink): per-CTA W-bit copies of the grid, resting in d_priv between launches
   int priv_bits = 0;                  // 0: grid too large for one CTA's shared memory; 8 or 4
@@ -289,6 +293,29 @@ int launch_gather(gcb_counter *c, const float *d_x, long long e_begin, long long
   return prof_end(c, GCB_PROF_OTHER, (double)(e_end - e_begin));
 }
 
+// Keep the packed counters L2-resident next to the coordinate stream: a persisting-L2 set-aside with an access-policy
+// window over the `bytes` of them the current lane width uses, on the compute stream.  Measured (tools/l2_window.cu,
+// profiles/l2_window_r02.txt): one RED per 36 streamed bytes into a 64 MB window runs at 83 G/s without it (the stream
+// evicts the window, whatever evict-first hints the loads carry) and at 123 G/s with it -- the rate of a 4 MB window.
+void set_packed_window(gcb_counter *c, size_t bytes)
+{
+  if (getenv("GCB_NO_L2_PERSIST") || bytes <= ((size_t)32 << 20)) return;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, c->opts.device) != cudaSuccess) { cudaGetLastError(); return; }
+  const size_t win = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+  const size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, win + ((size_t)2 << 20));
+  if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+    cudaStreamAttrValue av = {};
+    av.accessPolicyWindow.base_ptr = c->d_pk;
+    av.accessPolicyWindow.num_bytes = win;
+    av.accessPolicyWindow.hitRatio = std::min(1.0f, (float)((double)want / (double)win));
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(c->compute, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess) c->l2_window = true;
+  }
+  cudaGetLastError();
+}
+
 // Packed path: rounds of ~packed_units atom-frames; per round the streaming kernel into the packed counters
 // (returns at once while backing off), verify + apply, the guarded uint32 kernel (returns at once unless the round
 // failed or is skipped), and the gather kernel for the sub-tile tail (straight into the uint32 grid).
@@ -306,8 +333,10 @@ int launch_packed(gcb_counter *c, const float *d_x, long nframes, const float *d
   }
   const size_t nwords = (c->ncells + (32 / W) - 1) / (32 / W), nquads = (nwords + 3) / 4;
   if (!c->d_pk) {
-    GCB_CUDA(cudaMalloc(&c->d_pk, nquads * 16));
-    GCB_CUDA(cudaMemsetAsync(c->d_pk, 0, nquads * 16, c->compute));
+    // (a nibble grid that may fall back to byte lanes gets room for the bytes; the window below covers what fits)
+    const size_t pk_bytes = c->packed_fallback_ok ? ((c->ncells + 15) / 16) * 16 : nquads * 16;
+    GCB_CUDA(cudaMalloc(&c->d_pk, pk_bytes));
+    GCB_CUDA(cudaMemsetAsync(c->d_pk, 0, pk_bytes, c->compute));
     GCB_CUDA(cudaMalloc(&c->d_pstate, sizeof(PackedState)));
     GCB_CUDA(cudaMemsetAsync(c->d_pstate, 0, sizeof(PackedState), c->compute));
     if (W == 4 && !getenv("GCB_NO_MID")) {
@@ -316,25 +345,7 @@ int launch_packed(gcb_counter *c, const float *d_x, long nframes, const float *d
     }
     GCB_CUDA(cudaHostAlloc((void **)&c->h_pstate, sizeof(PackedState), cudaHostAllocDefault));
     memset(c->h_pstate, 0, sizeof(PackedState));
-    // Keep the packed counters L2-resident next to the coordinate stream: a persisting-L2 set-aside with an
-    // access-policy window over them on the compute stream.  Measured (tools/l2_window.cu, profiles/l2_window_r02.txt):
-    // one RED per 36 streamed bytes into a 64 MB window runs at 83 G/s without it (the stream evicts the window,
-    // whatever evict-first hints the loads carry) and at 123 G/s with it -- the rate of a 4 MB window.
-    if (!getenv("GCB_NO_L2_PERSIST") && nquads * 16 > ((size_t)32 << 20)) {
-      cudaDeviceProp prop;
-      GCB_CUDA(cudaGetDeviceProperties(&prop, c->opts.device));
-      const size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, nquads * 16 + ((size_t)2 << 20));
-      if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
-        cudaStreamAttrValue av = {};
-        av.accessPolicyWindow.base_ptr = c->d_pk;
-        av.accessPolicyWindow.num_bytes = std::min<size_t>(nquads * 16, (size_t)prop.accessPolicyMaxWindowSize);
-        av.accessPolicyWindow.hitRatio = std::min(1.0f, (float)((double)want / (double)(nquads * 16)));
-        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        if (cudaStreamSetAttribute(c->compute, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess) c->l2_window = true;
-      }
-      cudaGetLastError();
-    }
+    set_packed_window(c, nquads * 16);
   }
   PackedState *st = c->d_pstate;
   const int aux_grid = (int)std::max<size_t>(1, std::min<size_t>((nquads + 255) / 256, (size_t)c->sm_count * 8));
@@ -384,17 +395,48 @@ int launch_packed(gcb_counter *c, const float *d_x, long nframes, const float *d
   return GCB_OK;
 }
 
-// Input that keeps overflowing the packed lanes (atoms piled onto a few cells) is binned faster by the direct
-// kernel alone -- its hot cells stay L2-resident by themselves -- than by a packed pass that is thrown away every
-// other round.  Once the device-side back-off has reached 8 rounds the host stops queueing packed passes for 32
-// calls, then probes again.
+// What to do with input that keeps overflowing the packed lanes (the device-side back-off has reached 8 rounds; the
+// host learns of it from the pinned mirror, possibly a call late):
+//  * a grid on NIBBLE lanes (its bytes would not fit the L2: 500^3) first falls back to BYTE lanes with short rounds
+//    (0.64 hits per cell): if atoms pile up on a small part of the grid, the bytes that are actually touched are
+//    L2-resident by themselves -- measured on the clustered 500^3 shape: 83.5 G/s against 57 for the direct kernel
+//    and 45 when every nibble round is thrown away; every 256 calls the nibbles are probed again;
+//  * byte lanes that overflow as well (everything on a handful of cells) leave the packed passes alone for 32 calls:
+//    the direct kernel's hot cells stay L2-resident by themselves.
+// -> true: bin this call with the direct kernel.
 bool packed_paused(gcb_counter *c)
 {
-  if (c->packed_pause > 0) { c->packed_pause--; return true; }
-  if (c->h_pstate && ((volatile PackedState *)c->h_pstate)->backoff >= 8) {
-    c->h_pstate->backoff = 0;                    // (the mirror only: the next copy brings the device's value back)
+  if (c->packed_pause > 0) {
+    if (--c->packed_pause == 0 && c->packed_bits != c->packed_bits_home) {      // after the pause: the home lanes again
+      c->packed_bits = c->packed_bits_home; c->packed_units = c->packed_units_home; c->packed_mode_calls = 0;
+      set_packed_window(c, (c->ncells + 1) / 2);
+    }
+    return true;
+  }
+  if (c->packed_cooldown > 0) { c->packed_cooldown--; return false; }          // (a mirror copy from before the switch may still land)
+  const bool failing = c->h_pstate && ((volatile PackedState *)c->h_pstate)->backoff >= 8;
+  auto restart = [&] {                                                         // a new mode starts with a clean back-off
+    c->h_pstate->backoff = 0;
+    cudaMemsetAsync(c->d_pstate, 0, offsetof(PackedState, rounds), c->compute);
+    c->packed_cooldown = 2;
+    c->packed_mode_calls = 0;
+  };
+  if (failing) {
+    if (c->packed_fallback_ok && c->packed_bits == 4) {
+      c->packed_bits = 8;
+      c->packed_units = std::max<long long>(4096, (long long)((double)c->ncells * 0.64));
+      set_packed_window(c, c->ncells);
+      restart();
+      return false;
+    }
+    restart();
     c->packed_pause = 32;
     return true;
+  }
+  if (c->packed_bits != c->packed_bits_home && ++c->packed_mode_calls >= 256) {  // probe the home lanes again
+    c->packed_bits = c->packed_bits_home; c->packed_units = c->packed_units_home;
+    set_packed_window(c, (c->ncells + 1) / 2);
+    restart();
   }
   return false;
 }
@@ -785,6 +827,8 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
       const char *uenv = getenv("GCB_PACKED_UNITS");
       c->packed_units = uenv ? atoll(uenv) : (long long)((double)c->ncells * (c->packed_bits == 8 ? 8.0 : 1.5));
       if (c->packed_units < 4096) c->packed_units = 4096;
+      c->packed_bits_home = c->packed_bits; c->packed_units_home = c->packed_units;
+      c->packed_fallback_ok = c->packed_bits == 4 && !benv && !uenv && c->packed_auto && !getenv("GCB_NO_BYTE_FALLBACK");
     }
     // Private path: the grid as 8-bit or 4-bit counters next to the 3 x 36 KB tile ring in one CTA's shared memory.
     // A private grid is flushed before its mean load could pass 32 hits per cell (8-bit lanes, range 255: densities

@@ -441,15 +441,16 @@ def test_named_large_shapes_with_the_kernel_auto_picks(name):
     assert st.packed_rounds >= 1 and st.packed_redone == 0
     dev.generate(g.make_gen(32, L, K.GEN_CLUSTER, nsites=8, sigma=0.01))
     total = want
-    for rep in range(16):                              # enough calls for the back-off to reach the host-side pause
+    NCALLS = 40                                        # enough calls for the back-off to reach the host-side pause, on the
+    for rep in range(NCALLS):                          # 500^3 grid by way of the byte-lane fallback (which overflows as well)
         ctr.add_device_frames(dev)
         ctr.sync()                                     # (the host learns of the back-off from a mirror copied behind each call)
     w2, h2, _ = oracle_counts(geom, dev.download(), gindex)
-    total = total + 16 * w2
+    total = total + NCALLS * w2
     np.testing.assert_array_equal(ctr.counts(), total)
     st2 = ctr.stats()
-    assert st2.packed_redone >= 1 and st2.hits == int(whits.sum()) + 16 * int(h2.sum())
-    assert st2.packed_rounds < st.packed_rounds + 16, "the host never paused the packed passes"
+    assert st2.packed_redone >= 1 and st2.hits == int(whits.sum()) + NCALLS * int(h2.sum())
+    assert st2.packed_rounds < st.packed_rounds + NCALLS, "the host never paused the packed passes"
     ctr.close(); dev.free()
 
 
@@ -762,3 +763,36 @@ def test_pinned_source_may_be_refilled_as_soon_as_add_frames_returns():
     np.testing.assert_array_equal(ctr.counts(), ocounts)
     np.testing.assert_array_equal(ctr.hits_per_frame(), ohits)
     ctr.close(); pin.free()
+
+
+def test_nibble_grid_falls_back_to_byte_lanes_on_clustered_input():
+    """500^3 (nibble lanes by default): atoms piled around 256 sites overflow the nibbles; AUTO then retries with byte
+    lanes and short rounds, which hold (peak density far below 255 per round), instead of giving the packed path up;
+    counts stay exact through the switch, and uniform input afterwards goes back to the nibbles"""
+    L, delta, natoms, nframes = (10.0, 10.0, 10.0), 0.02, 100000, 960
+    geom = g.setup_geometry(L, delta)
+    assert geom.shape == (500, 500, 500)
+    gindex = np.arange(0, natoms, 3, dtype=np.int32)
+    dev = g.DeviceFrames(nframes, natoms).generate(g.make_gen(41, L, K.GEN_CLUSTER, nsites=256, sigma=0.1))
+    ctr = g.GridCounter(geom, gindex, natoms)
+    NC = 14
+    for _ in range(NC):
+        ctr.add_device_frames(dev)
+        ctr.sync()
+    st = ctr.stats()
+    assert st.hits == NC * nframes * len(gindex)
+    want, whits, _ = oracle_counts(geom, dev.download(0, 64), gindex)
+    ref = g.GridCounter(geom, gindex, natoms, kernel=K.KERNEL_STREAM)
+    ref.add_device_frames(dev)
+    c1 = ref.counts()
+    np.testing.assert_array_equal(ctr.counts(), NC * c1)
+    ref.reset(); ref.add_device_frames(dev, 0, 64)
+    np.testing.assert_array_equal(ref.counts(), want)                 # the direct kernel itself against the oracle
+    redone_before = st.packed_redone
+    for _ in range(4):                                                # by now on byte lanes: rounds hold
+        ctr.add_device_frames(dev)
+        ctr.sync()
+    st2 = ctr.stats()
+    assert st2.packed_rounds > st.packed_rounds and st2.packed_redone == redone_before, (st2.packed_rounds, st2.packed_redone, redone_before)
+    np.testing.assert_array_equal(ctr.counts(), (NC + 4) * c1)
+    ref.close(); ctr.close(); dev.free()
