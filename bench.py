@@ -426,7 +426,7 @@ def roofline_of(g, ctr, stride, cells, peak, peak_src, device, kernel_key, l2=No
     kinds = ctr.profile_kinds()
     dom = max(("direct", "packed", "redo", "private"), key=lambda k: kinds[k][0])
     k1_ms, nl, units = kinds[dom]
-    bits = 8 if cells <= (80 << 20) else 4
+    bits = ctr.stats().packed_bits or (8 if cells <= (80 << 20) else 4)
     names = {"direct": "bin_stream_kernel<DirectSink> (one RED per hit into the uint32 grid)",
              "packed": "bin_stream_kernel<PackedSink<%d>> (non-returning REDs into %d-bit L2-resident counters)" % (bits, bits),
              "private": "bin_stream_kernel<PrivateSink> (shared-memory atomics into per-CTA private copies of the grid, "
@@ -468,10 +468,12 @@ def measure_config(g, name, cfg, device, peak, peak_src, reps=10, extra=None):
     dev = g.DeviceFrames(F, cfg["natoms"], device).generate(cfg_gen(g, cfg))
     ctr = g.GridCounter(geom, gindex, cfg["natoms"], device=device)
     w = np.ones(F, np.float32)
-    for _ in range(max(3, reps)):                 # also sizes the counter's per-call buffers for `reps` calls in flight
+    for i in range(max(3, reps)):                 # also sizes the counter's per-call buffers for `reps` calls in flight
         if cfg.get("reset_each_pass"):
             ctr.reset_grid()
         ctr.add_device_frames(dev, weights=w)
+        if i < 8:
+            ctr.sync()                            # (the host-side policy of the packed path learns from finished calls)
     ctr.sync()
     ctr.reset_grid()
     ctr.event_record(0)
@@ -490,13 +492,15 @@ def measure_config(g, name, cfg, device, peak, peak_src, reps=10, extra=None):
         ctr.add_device_frames(dev, weights=w)
     packed_bytes = geom.cells if geom.cells <= (80 << 20) else geom.cells // 2
     rl = roofline_of(g, ctr, cfg["stride"], geom.cells, peak, peak_src, device, name)
+    if "PackedSink<8>" in rl["kernel"]:
+        packed_bytes = geom.cells
     window = packed_bytes if "PackedSink" in rl["kernel"] else geom.cells * 4       # what the dominant kernel's REDs address
     ctr.profile(False)
     res = {"workload": cfg["title"], "grid": list(geom.shape), "frames_resident": F,
            "frames_resident_gb": F * cfg["natoms"] * 12 / 1e9, "passes_timed": reps,
            "value": float(gnx) * F * reps / (ms * 1e-3) * 1e-9, "unit": UNIT,
            "ms_per_pass": ms / reps, "all_hits_in_grid": not lost,
-           "packed_rounds": int(st.packed_rounds), "packed_redone": int(st.packed_redone),
+           "packed_rounds": int(st.packed_rounds), "packed_redone": int(st.packed_redone), "packed_bits": int(st.packed_bits),
            "private_launches": int(st.private_launches), "private_redone": int(st.private_redone)}
     if cfg.get("reset_each_pass"):
         res["pass"] = "zero the grid + bin the resident frames"

@@ -53,7 +53,7 @@ class Stats(C.Structure):
                 ("edge_overflow", C.c_uint64), ("sumP", C.c_double), ("uniform_weight", C.c_int),
                 ("weight", C.c_float), ("kernel_launches", C.c_int64), ("packed_rounds", C.c_uint64),
                 ("packed_redone", C.c_uint64), ("saturated", C.c_int),
-                ("private_launches", C.c_uint64), ("private_redone", C.c_uint64)]
+                ("private_launches", C.c_uint64), ("private_redone", C.c_uint64), ("packed_bits", C.c_int)]
 
 
 class AnalysisOpts(C.Structure):

@@ -90,6 +90,7 @@ struct gcb_counter {
   uint2 *d_mid = nullptr;             // 4-bit packed path: byte grid between the packed rounds and the uint32 grid
   int mid_rounds = 0;                 // rounds folded into d_mid since it was last flushed (<= 16)
   bool l2_window = false;             // persisting-L2 window over d_pk set on the compute stream
+  size_t l2_limit_set = 0;            // the persisting-L2 set-aside this counter asked for
   bool saturated = false;             // some cell was clamped (diag[3])
   // xtc path: GCB_XTC_SETS sets of {compressed bytes, frame table, status, decoded frames}, copy stream + events
   struct XtcSet {
@@ -303,8 +304,12 @@ void set_packed_window(gcb_counter *c, size_t bytes)
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, c->opts.device) != cudaSuccess) { cudaGetLastError(); return; }
   const size_t win = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
-  const size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, win + ((size_t)2 << 20));
-  if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+  // The set-aside only ever grows: changing cudaLimitPersistingL2CacheSize with work in flight stalls the device for
+  // tens of milliseconds (measured: ~90 ms), so a counter that once fell back to byte lanes keeps the larger set-aside
+  // when it probes the nibbles again; the window itself is cheap to move.
+  const size_t want = std::max(c->l2_limit_set, std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, win + ((size_t)2 << 20)));
+  if (want > 0 && (c->l2_limit_set == want || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)) {
+    c->l2_limit_set = want;
     cudaStreamAttrValue av = {};
     av.accessPolicyWindow.base_ptr = c->d_pk;
     av.accessPolicyWindow.num_bytes = win;
@@ -1267,6 +1272,7 @@ int gcb_counter_stats(gcb_counter *c, gcb_stats *out)
   out->packed_redone = c->packed_redone;
   out->private_launches = c->priv_launches;
   out->private_redone = c->priv_redone;
+  out->packed_bits = c->packed_bits;
   out->saturated = c->saturated ? 1 : 0;
   return GCB_OK;
 }

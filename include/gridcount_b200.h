@@ -132,6 +132,8 @@ typedef struct {
                               bits, because the reference's f32 accumulator stops moving long before (this rank) */
   uint64_t private_launches; /* launches on the private shared-memory path (GCB_KERNEL_PRIVATE) ... */
   uint64_t private_redone;   /* ... in which some CTA overflowed a lane and binned its tiles again directly (this rank) */
+  int packed_bits;           /* lane width the packed path is using now: 8 or 4 (a nibble grid may have fallen back to
+                                bytes with short rounds after its rounds kept overflowing), 0: no packed path */
 } gcb_stats;
 
 int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex, int gnx,
