@@ -669,17 +669,30 @@ def run_gpu_arm(args, rank, local_rank, world):
     e2e_steps = max(1, min(args.steps, 3))
     step_e2e()
     barrier()
+    hs0 = ctr.host_staging()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_e2e()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    hs1 = ctr.host_staging()
+    # bytes of frames that actually crossed PCIe, counted by the library where it queues the copies (this rank; the
+    # other ranks stage the same way): frames DMA-ed out of the pinned buffer carry every atom, frames packed by the
+    # host threads only the index group
+    h2d_step = (hs1.h2d_bytes - hs0.h2d_bytes) / e2e_steps
+    fr_packed = (hs1.frames_packed - hs0.frames_packed) / e2e_steps
+    fr_in_place = (hs1.frames_in_place - hs0.frames_in_place) / e2e_steps
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
         clocks["window"] = "device-timed steps + roofline step + end-to-end steps"
     e2e_units = float(gnx) * HOSTF * E2E_CALLS * world
     e2e = {"value": e2e_units * e2e_steps / e2e_s * 1e-9, "unit": UNIT,
-           "h2d_bytes_per_step": int(HOSTF * E2E_CALLS) * natoms * 12 * world,
+           "h2d_bytes_per_step": int(h2d_step) * world,
+           "host_bytes_read_per_step": int(HOSTF * E2E_CALLS) * natoms * 12 * world,
+           "staging": {"frames_dma_in_place_per_step": fr_in_place, "frames_packed_by_host_threads_per_step": fr_packed,
+                       "pack_threads": int(hs1.threads), "pack_source_gbs": hs1.pack_bytes_per_s * 1e-9,
+                       "note": "two lanes at once: batches DMA-ed out of the pinned buffer (12 B per atom) and batches whose "
+                               "index group host threads copy into pinned slots (12 B per counted atom); rank 0's split"},
            "d2h_bytes_per_step": int(geom.cells * 4 + HOSTF * E2E_CALLS * 8) * world, "steps": e2e_steps,
            "frames_per_step_per_gpu": HOSTF * E2E_CALLS, "ms_per_step": e2e_s / e2e_steps * 1e3,
            "path": "gcb_counter_add_frames(pinned host x[F][natoms][3]) -> gcb_counter_density(host grid)"}

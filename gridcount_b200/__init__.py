@@ -6,8 +6,8 @@ package is a thin ctypes mirror of that ABI used by the tests and bench.py; it
 performs no computation of its own and has no CPU fallback."""
 from . import _cabi
 from .api import (GridCounter, Geometry, analyse, gridcalc, setup_geometry, frame_weights, header_string, grid_write,
-                  grid_read, xdr_encode, DeviceFrames, PinnedFrames, XtcBuffer, make_gen, device_count, selftest_l2)
+                  grid_read, xdr_encode, DeviceFrames, PinnedFrames, XtcBuffer, make_gen, device_count, selftest_l2, pack_frames)
 
 __all__ = ["GridCounter", "Geometry", "analyse", "gridcalc", "setup_geometry", "frame_weights", "header_string",
-           "grid_write", "grid_read", "xdr_encode", "DeviceFrames", "PinnedFrames", "XtcBuffer", "make_gen", "device_count", "selftest_l2",
+           "grid_write", "grid_read", "xdr_encode", "DeviceFrames", "PinnedFrames", "XtcBuffer", "make_gen", "device_count", "selftest_l2", "pack_frames",
            "_cabi"]

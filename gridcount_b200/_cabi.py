@@ -20,6 +20,7 @@ c_long_p = C.POINTER(C.c_long)
 HEADER_MAX = 256
 SET_CPOINT, SET_R, SET_Z1, SET_Z2 = 1, 2, 4, 8
 PBC_NONE, PBC_RECT = 0, 1
+HOST_PACK_AUTO, HOST_PACK_NEVER, HOST_PACK_ALWAYS = -1, 0, 1
 KERNEL_AUTO, KERNEL_GATHER, KERNEL_STREAM, KERNEL_STREAM_INDEXED, KERNEL_PACKED, KERNEL_PRIVATE = 0, 1, 2, 3, 5, 6
 UNITS = {"unity": 0, "SPC": 1, "molar": 2, "Angstrom": 3, "Voxel": 4}
 GEN_UNIFORM, GEN_QUANTISED, GEN_PORE, GEN_CLUSTER = 0, 1, 2, 3
@@ -54,6 +55,11 @@ class Stats(C.Structure):
                 ("weight", C.c_float), ("kernel_launches", C.c_int64), ("packed_rounds", C.c_uint64),
                 ("packed_redone", C.c_uint64), ("saturated", C.c_int),
                 ("private_launches", C.c_uint64), ("private_redone", C.c_uint64), ("packed_bits", C.c_int)]
+
+
+class HostStaging(C.Structure):
+    _fields_ = [("mode", C.c_int), ("threads", C.c_int), ("h2d_bytes", C.c_uint64), ("frames_packed", C.c_uint64),
+                ("frames_in_place", C.c_uint64), ("pack_bytes_per_s", C.c_double)]
 
 
 class AnalysisOpts(C.Structure):
@@ -101,6 +107,9 @@ SIGNATURES = {
     "gcb_counter_destroy": (None, [C.c_void_p]),
     "gcb_counter_reset": (C.c_int, [C.c_void_p]),
     "gcb_counter_add_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, c_float_p, c_float_p]),
+    "gcb_counter_set_host_pack": (C.c_int, [C.c_void_p, C.c_int]),
+    "gcb_counter_host_staging": (C.c_int, [C.c_void_p, C.POINTER(HostStaging)]),
+    "gcb_pack_frames": (C.c_int, [c_float_p, C.c_long, C.c_int, c_int_p, C.c_int, c_float_p, C.c_int]),
     "gcb_counter_add_device_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, c_float_p, c_float_p]),
     "gcb_counter_slot": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(c_float_p), c_long_p]),
     "gcb_counter_submit_slot": (C.c_int, [C.c_void_p, C.c_int, C.c_long, c_float_p, c_float_p]),

@@ -309,6 +309,15 @@ class GridCounter:
     def sync(self):
         check(lib.gcb_counter_sync(self.h), "gcb_counter_sync")
 
+    def set_host_pack(self, mode):
+        """K.HOST_PACK_AUTO / _NEVER / _ALWAYS: how add_frames stages host frames (see the header)"""
+        check(lib.gcb_counter_set_host_pack(self.h, mode), "gcb_counter_set_host_pack")
+
+    def host_staging(self):
+        s = K.HostStaging()
+        check(lib.gcb_counter_host_staging(self.h, C.byref(s)), "gcb_counter_host_staging")
+        return s
+
     def stats(self):
         s = K.Stats()
         check(lib.gcb_counter_stats(self.h, C.byref(s)), "gcb_counter_stats")
@@ -401,6 +410,16 @@ class GridCounter:
 
     def allreduce(self):
         check(lib.gcb_counter_allreduce(self.h), "gcb_counter_allreduce")
+
+
+def pack_frames(x, gindex, threads=0):
+    """out[f][i] = x[f][gindex[i]] by the library's host thread pool (the packing step of add_frames by itself)"""
+    x = np.ascontiguousarray(x, np.float32)
+    gi = np.ascontiguousarray(gindex, np.int32)
+    out = np.empty((x.shape[0], len(gi), 3), np.float32)
+    check(lib.gcb_pack_frames(_fptr(x), x.shape[0], x.shape[1], gi.ctypes.data_as(K.c_int_p), len(gi), _fptr(out), threads),
+          "gcb_pack_frames")
+    return out
 
 
 def selftest_l2(window_bytes, mix, device=0, stream_bytes=0):

@@ -35,6 +35,8 @@ struct Slot {
   unsigned long long *d_hits = nullptr, *h_hits = nullptr;
   float *d_box3 = nullptr, *h_box3 = nullptr;
   long cap = 0;                       // frames
+  long cap_pack = 0;                  // frames when the batch is staged packed (index group only), >= cap
+  bool dma_in_place = false;          // the last copy queued on this slot reads the caller's pinned memory
   long pending = 0;                   // frames whose hit counts have not been collected yet
   size_t frame0 = 0;                  // global index of the first pending frame
 };
@@ -128,6 +130,25 @@ struct gcb_counter {
   float w_cur = 0;
   bool uniform = true, any = false;
   float w_first = 0;
+
+  // Host frames may be staged PACKED: host threads copy the index group's atoms of a batch into the pinned slot
+  // (host_pack.cpp), 12 B per counted atom cross PCIe instead of 12 B per atom, and the kernels see frames of gnx
+  // atoms that are all counted (`pk`: the layout fields for that view, swapped in around the launches).
+  struct Layout {
+    int natoms = 0;
+    bool stream_ok = false, ap_ok = false;
+    ApGroup ap{0, 1, TILE_ATOMS}, ap_priv{0, 1, TILE_ATOMS};
+    int *d_gindex = nullptr;
+    unsigned *d_rank = nullptr;
+    std::vector<int> h_gindex;
+    int priv_bits = 0;
+  } pk;
+  bool pk_ready = false;
+  int host_pack = -1;                 // GCB_HOST_PACK_*: -1 auto, 0 never, 1 always
+  double pack_rate = 0;               // measured: source bytes per second the host threads pack (moving average)
+  uint64_t h2d_bytes = 0;             // bytes of frames queued host -> device by add_frames / submit_slot
+  uint64_t frames_packed = 0;         // frames that were staged packed
+  uint64_t frames_in_place = 0;       // frames DMA-ed straight out of the caller's pinned memory
 
   cudaStream_t compute = nullptr;
   std::vector<Slot> slots;
@@ -631,39 +652,108 @@ int collect_slot(gcb_counter *c, Slot &s)
   return GCB_OK;
 }
 
-int alloc_slots(gcb_counter *c)
+// `want` > 0: at least that many slots (the two-lane staging of pinned frames grows the default 3 to 6)
+int alloc_slots(gcb_counter *c, int want = 0)
 {
-  if (!c->slots.empty()) return GCB_OK;
+  const size_t have = c->slots.size();
+  const int ns = std::max<int>(want, have ? (int)have : (c->opts.nslots > 0 ? c->opts.nslots : 3));
+  if ((size_t)ns <= have) return GCB_OK;
   const size_t frame_bytes = (size_t)c->natoms * 12;
   long fpb = c->opts.frames_per_batch;
   if (fpb <= 0) fpb = (long)std::max<size_t>(1, ((size_t)32 << 20) / std::max<size_t>(frame_bytes, 1));
-  const int ns = c->opts.nslots > 0 ? c->opts.nslots : 3;
-  c->slots.resize(ns);
-  for (auto &s : c->slots) {
+  c->slots.resize((size_t)ns);
+  // a packed batch holds as many frames as fit the same bytes (at most 16 x: per-frame counters are sized by it)
+  const long fpb_pack = c->gnx > 0 ? (long)std::min<long long>((long long)fpb * 16, std::max<long long>(fpb, (long long)fpb * c->natoms / c->gnx)) : fpb;
+  for (size_t k = have; k < c->slots.size(); k++) {
+    Slot &s = c->slots[k];
     s.cap = fpb;
+    s.cap_pack = fpb_pack;
     GCB_CUDA(cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking));
     GCB_CUDA(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
     GCB_CUDA(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
     GCB_CUDA(cudaHostAlloc(&s.h_x, frame_bytes * fpb, cudaHostAllocDefault));
     GCB_CUDA(cudaMalloc(&s.d_x, frame_bytes * fpb + 16));
-    GCB_CUDA(cudaMalloc(&s.d_hits, sizeof(unsigned long long) * (fpb + 2)));
-    GCB_CUDA(cudaHostAlloc(&s.h_hits, sizeof(unsigned long long) * (fpb + 2), cudaHostAllocDefault));
-    GCB_CUDA(cudaMalloc(&s.d_box3, sizeof(float) * 3 * fpb));
-    GCB_CUDA(cudaHostAlloc(&s.h_box3, sizeof(float) * 3 * fpb, cudaHostAllocDefault));
+    GCB_CUDA(cudaMalloc(&s.d_hits, sizeof(unsigned long long) * (fpb_pack + 2)));
+    GCB_CUDA(cudaHostAlloc(&s.h_hits, sizeof(unsigned long long) * (fpb_pack + 2), cudaHostAllocDefault));
+    GCB_CUDA(cudaMalloc(&s.d_box3, sizeof(float) * 3 * fpb_pack));
+    GCB_CUDA(cudaHostAlloc(&s.h_box3, sizeof(float) * 3 * fpb_pack, cudaHostAllocDefault));
   }
   return GCB_OK;
 }
 
-// stage `n` frames that already sit in slot.h_x (or are copied there from `src`)
-int submit_slot(gcb_counter *c, Slot &s, const float *src, bool src_pinned, long n, const float *w,
-                const float *box)
+// The layout the kernels see while a packed batch is binned: frames of gnx atoms, every one of them counted.
+int ensure_pack_layout(gcb_counter *c)
 {
-  const size_t bytes = (size_t)n * c->natoms * 12;
+  if (c->pk_ready) return GCB_OK;
+  auto &L = c->pk;
+  const int n = c->gnx;
+  L.natoms = n;
+  L.stream_ok = true;
+  L.ap_ok = n >= 256;                           // (as in gcb_counter_create; smaller frames take the indexed kernels)
+  L.ap = ApGroup{0, 1, std::min(TILE_ATOMS, n & ~3)};
+  L.ap_priv = ApGroup{0, 1, std::min(PrivateSink<8>::TILE_CAP, n & ~3)};
+  L.priv_bits = n >= 256 ? c->priv_bits : 0;
+  L.h_gindex.resize((size_t)n);
+  for (int i = 0; i < n; i++) L.h_gindex[(size_t)i] = i;
+  std::vector<unsigned> rank((size_t)n + 1);
+  for (int r = 0; r <= n; r++) rank[(size_t)r] = (unsigned)r;
+  GCB_CUDA(cudaMalloc(&L.d_gindex, sizeof(int) * std::max(n, 1)));
+  GCB_CUDA(cudaMalloc(&L.d_rank, sizeof(unsigned) * rank.size()));
+  if (n) GCB_CUDA(cudaMemcpy(L.d_gindex, L.h_gindex.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+  GCB_CUDA(cudaMemcpy(L.d_rank, rank.data(), sizeof(unsigned) * rank.size(), cudaMemcpyHostToDevice));
+  c->pk_ready = true;
+  return GCB_OK;
+}
+
+void swap_layout(gcb_counter *c)
+{
+  auto &L = c->pk;
+  std::swap(c->natoms, L.natoms);
+  std::swap(c->stream_ok, L.stream_ok);
+  std::swap(c->ap_ok, L.ap_ok);
+  std::swap(c->ap, L.ap);
+  std::swap(c->ap_priv, L.ap_priv);
+  std::swap(c->d_gindex, L.d_gindex);
+  std::swap(c->d_rank, L.d_rank);
+  std::swap(c->priv_bits, L.priv_bits);
+  c->h_gindex.swap(L.h_gindex);
+}
+
+// host threads one packing job of this counter uses: ranks of a multi-GPU job share the node's cores
+int pack_threads(const gcb_counter *c)
+{
+  const int t = gcb::pack_threads_default();
+  if (c->nranks <= 1 || getenv("GCB_PACK_THREADS")) return t;
+  return std::max(1, std::min(t, 2 * t / c->nranks));
+}
+
+// stage `n` frames that already sit in slot.h_x (or are copied there from `src`; `pack`: only the index group's
+// atoms are, and the kernels run on the packed layout)
+int submit_slot(gcb_counter *c, Slot &s, const float *src, bool src_pinned, long n, const float *w,
+                const float *box, bool pack = false)
+{
+  size_t bytes = (size_t)n * c->natoms * 12;
   const float *from = s.h_x;
-  if (src) {
-    if (src_pinned) from = src;                 // DMA straight out of the caller's pinned memory
+  if (src && pack) {
+    int rc = ensure_pack_layout(c);
+    if (rc) return rc;
+    timespec t0{}, t1{};
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    gcb::pack_frames(src, n, c->natoms, c->h_gindex.data(), c->gnx, c->ap.g0, c->ap_ok ? c->ap.step : 0, s.h_x, pack_threads(c));
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    if (dt > 0 && bytes >= ((size_t)1 << 20)) {
+      const double r = (double)bytes / dt;
+      c->pack_rate = c->pack_rate > 0 ? 0.7 * c->pack_rate + 0.3 * r : r;
+    }
+    bytes = (size_t)n * c->gnx * 12;
+    c->frames_packed += (uint64_t)n;
+  } else if (src) {
+    if (src_pinned) { from = src; c->frames_in_place += (uint64_t)n; }   // DMA straight out of the caller's pinned memory
     else memcpy(s.h_x, src, bytes);
   }
+  s.dma_in_place = from != s.h_x;
+  c->h2d_bytes += bytes;
   GCB_CUDA(cudaMemcpyAsync(s.d_x, from, bytes, cudaMemcpyHostToDevice, s.copy));
   if (c->opts.pbc == GCB_PBC_RECT) {
     if (!box) return gcb::fail(GCB_ERR_ARG, "GCB_PBC_RECT needs the per-frame box");
@@ -673,7 +763,9 @@ int submit_slot(gcb_counter *c, Slot &s, const float *src, bool src_pinned, long
   GCB_CUDA(cudaEventRecord(s.copied, s.copy));
   GCB_CUDA(cudaStreamWaitEvent(c->compute, s.copied, 0));
   GCB_CUDA(cudaMemsetAsync(s.d_hits, 0, sizeof(unsigned long long) * (n + 2), c->compute));
+  if (pack) swap_layout(c);
   int rc = bin_device_batch(c, s.d_x, n, w, c->opts.pbc == GCB_PBC_RECT ? s.d_box3 : nullptr, s.d_hits);
+  if (pack) swap_layout(c);
   if (rc) return rc;
   GCB_CUDA(cudaMemcpyAsync(s.h_hits, s.d_hits, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, c->compute));
   GCB_CUDA(cudaEventRecord(s.consumed, c->compute));
@@ -708,6 +800,7 @@ void free_counter(gcb_counter *c)
   }
   for (auto &d : c->devhits) cudaFree(d.d_box3);           // (d.d lives in a hit arena)
   for (auto &a : c->hit_arenas) cudaFree(a.d);
+  cudaFree(c->pk.d_gindex); cudaFree(c->pk.d_rank);
   cudaFree(c->d_gindex); cudaFree(c->d_rank); cudaFree(c->d_runcnt); cudaFree(c->d_total); cudaFree(c->d_acc);
   cudaFree(c->d_diag); cudaFree(c->d_out); cudaFree(c->d_out2);
   cudaFree(c->d_pk); cudaFree(c->d_pstate); cudaFreeHost(c->h_pstate); cudaFree(c->d_mid);
@@ -813,6 +906,7 @@ int gcb_counter_create(gcb_counter **out, const gcb_tgrid *tg, const int *gindex
   }
 
   {
+    if (const char *e = getenv("GCB_HOST_PACK")) c->host_pack = e[0] == '0' ? 0 : e[0] == '1' ? 1 : -1;
     if (const char *e = getenv("GCB_CLAMP_AT")) c->clamp_at = strtoull(e, nullptr, 10);
     if (const char *e = getenv("GCB_CLAMP_CEILING")) c->clamp_ceiling = strtoull(e, nullptr, 10);
     if (c->clamp_at < 1 || c->clamp_ceiling > 0xffffffffull || c->clamp_at * 2 > c->clamp_ceiling) {
@@ -959,23 +1053,77 @@ int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes, const f
   if (cudaPointerGetAttributes(&attr, x) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
   else cudaGetLastError();
   const size_t frame_floats = (size_t)c->natoms * 3;
+  // How the frames reach the device (header: gcb_host_staging).  Pageable x has to pass through a pinned slot anyway:
+  // host threads copy the index group into it (packed staging).  Pinned x is staged on TWO LANES at once: batches
+  // are DMA-ed in place, and while at least `depth` of those copies are queued -- enough to keep the link busy for
+  // as long as the next packing job is expected to take -- the host threads pack the next frames instead, which
+  // then cross PCIe at 12 B per counted atom.  Whichever lane is free takes the next frames, so the split follows
+  // the host's packing rate against the link by itself; a host that packs slowly just packs little.
+  const bool can_pack = c->gnx > 0 && nframes > 0 && c->host_pack != GCB_HOST_PACK_NEVER;
+  const bool all_pack = can_pack && (c->host_pack == GCB_HOST_PACK_ALWAYS || !pinned);
+  bool two_lanes = can_pack && !all_pack && c->gnx < c->natoms && c->opts.nslots <= 0;
+  if (two_lanes && nframes > c->slots[0].cap) {
+    rc = alloc_slots(c, 6);
+    if (rc) return rc;
+  } else {
+    two_lanes = false;
+  }
+  const double frame_bytes = (double)frame_floats * 4.0, link_rate = 55e9;     // (PCIe 5 x16; a slower link only adds slack)
   long done = 0;
   while (done < nframes) {
+    bool pack = all_pack;
+    long n_pack = 0;
+    if (two_lanes) {
+      // in-place copies still queued, and the batch the host threads can pack in about the time one of them takes
+      int queued = 0;
+      for (auto &q : c->slots)
+        if (q.dma_in_place) {
+          if (cudaEventQuery(q.copied) == cudaErrorNotReady) queued++;
+          else q.dma_in_place = false;
+        }
+      cudaGetLastError();
+      const long cap = c->slots[0].cap;
+      const double rate = c->pack_rate > 0 ? c->pack_rate : 4e9 * (double)pack_threads(c);
+      n_pack = std::max<long>(1, std::min<long>(c->slots[0].cap_pack, (long)((double)cap * rate / link_rate)));
+      const double t_pack = (double)n_pack * frame_bytes / rate, t_copy = (double)cap * frame_bytes / link_rate;
+      const int depth = 1 + (int)std::ceil(t_pack / t_copy);
+      pack = depth <= (int)c->slots.size() - 2 && queued >= depth;
+    }
     Slot &s = c->slots[c->next_slot];
     c->next_slot = (c->next_slot + 1) % (int)c->slots.size();
     rc = collect_slot(c, s);
     if (rc) return rc;
-    if (!pinned) GCB_CUDA(cudaStreamSynchronize(s.copy));   // staging buffer free to overwrite
-    const long n = std::min(s.cap, nframes - done);
+    if (!pinned || pack) GCB_CUDA(cudaStreamSynchronize(s.copy));   // staging buffer free to overwrite
+    const long n = std::min(pack ? (two_lanes ? n_pack : s.cap_pack) : s.cap, nframes - done);
     rc = submit_slot(c, s, x + (size_t)done * frame_floats, pinned, n, weight ? weight + done : nullptr,
-                     box ? box + 9 * (size_t)done : nullptr);
+                     box ? box + 9 * (size_t)done : nullptr, pack);
     if (rc) return rc;
     done += n;
   }
-  // Pinned x is DMA-ed straight out of the caller's memory: the call returns when the last of those copies has
+  // Pinned x that was DMA-ed straight out of the caller's memory: the call returns when the last of those copies has
   // left it (the kernels behind them keep running), so the caller may refill x at once, as with pageable memory.
-  if (pinned)
+  if (pinned && !all_pack)
     for (auto &s : c->slots) GCB_CUDA(cudaEventSynchronize(s.copied));
+  return GCB_OK;
+}
+
+int gcb_counter_set_host_pack(gcb_counter *c, int mode)
+{
+  if (!c || mode < GCB_HOST_PACK_AUTO || mode > GCB_HOST_PACK_ALWAYS) return gcb::fail(GCB_ERR_ARG, "gcb_counter_set_host_pack: bad argument");
+  c->host_pack = mode;
+  return GCB_OK;
+}
+
+int gcb_counter_host_staging(gcb_counter *c, gcb_host_staging *out)
+{
+  if (!c || !out) return gcb::fail(GCB_ERR_ARG, "gcb_counter_host_staging: null argument");
+  memset(out, 0, sizeof *out);
+  out->mode = c->host_pack;
+  out->threads = pack_threads(c);
+  out->h2d_bytes = c->h2d_bytes;
+  out->frames_packed = c->frames_packed;
+  out->frames_in_place = c->frames_in_place;
+  out->pack_bytes_per_s = c->pack_rate;
   return GCB_OK;
 }
 

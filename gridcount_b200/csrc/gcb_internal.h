@@ -18,6 +18,12 @@ inline size_t cells(const gcb_tgrid &tg) { return (size_t)tg.mx[0] * tg.mx[1] * 
 float seq_add_f32(float v, float w, uint64_t n);
 double seq_add_f64(double v, double w, uint64_t n);
 
+// host_pack.cpp: x[frame][natoms][3] -> out[frame][gnx][3] on a pool of host threads (step > 0: the group is
+// g0 + i*step and gindex is not read; threads <= 0: pack_threads_default())
+int pack_threads_default();
+void pack_frames(const float *x, long nframes, int natoms, const int *gindex, int gnx, int g0, int step, float *out,
+                 int threads);
+
 }  // namespace gcb
 
 // The collective operations gcb_counter_allreduce needs, stream-ordered like NCCL's (dtype: ncclUint32 = 3,

@@ -151,6 +151,33 @@ int gcb_counter_reset(gcb_counter *c);
  * magnitude above 1e-38, so this never shows. */
 int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes,
                            const float *weight, const float *box);
+/* How host frames reach the device.  PACKED staging: a pool of host threads copies the index group's atoms of a
+ * batch -- what the reference's loop reads, x[index[i]] (g_ri3Dc.c:425-426) -- into a pinned slot, so that 12 B per
+ * counted atom cross PCIe instead of 12 B per atom of the frame (a third of the bytes for water oxygens), and the
+ * kernels bin frames in which every atom counts.  Counts, per-frame hits and everything derived from them are the
+ * same bits either way.  AUTO (the default; environment GCB_HOST_PACK=0/1 overrides it at create):
+ *   - pageable x is always packed (it has to be copied into a slot anyway);
+ *   - pinned x goes down TWO LANES at once: batches are DMA-ed in place, and while enough of those copies are
+ *     queued to keep the link busy, the host threads pack the next frames, which then cost a third of the link
+ *     time.  The lanes take frames as they become free, so the split follows the host's packing rate against the
+ *     link by itself (throughput ~ (link + 2/3 packing rate) / 36 B for water oxygens); a slow host packs little.
+ * NEVER is the staging of round 1 (memcpy of pageable x into the slot, pinned x DMA-ed in place).
+ * GCB_PACK_THREADS sets the pool's size (default: the CPUs the process may run on, at most 16; the ranks of a
+ * multi-GPU job share them). */
+enum { GCB_HOST_PACK_AUTO = -1, GCB_HOST_PACK_NEVER = 0, GCB_HOST_PACK_ALWAYS = 1 };
+typedef struct {
+  int mode;                 /* GCB_HOST_PACK_* */
+  int threads;              /* host threads a packing job uses */
+  uint64_t h2d_bytes;       /* bytes of frames queued host -> device so far (not cleared by gcb_counter_reset) */
+  uint64_t frames_packed;   /* frames that were staged packed so far ... */
+  uint64_t frames_in_place; /* ... and frames DMA-ed straight out of the caller's pinned memory */
+  double pack_bytes_per_s;  /* measured packing rate in bytes of source frames (moving average; 0: nothing packed yet) */
+} gcb_host_staging;
+int gcb_counter_set_host_pack(gcb_counter *c, int mode);
+int gcb_counter_host_staging(gcb_counter *c, gcb_host_staging *out);
+/* The packing step by itself (pure host code, no device needed): out[f][i][:] = x[f][gindex[i]][:].
+ * threads <= 0: the default above. */
+int gcb_pack_frames(const float *x, long nframes, int natoms, const int *gindex, int gnx, float *out, int threads);
 /* Same for frames already resident in device memory (16-byte aligned). */
 int gcb_counter_add_device_frames(gcb_counter *c, const float *x_dev, long nframes,
                                   const float *weight, const float *box);

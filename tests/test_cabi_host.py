@@ -150,3 +150,43 @@ def test_dens_units():
     tg = g.setup_geometry((3, 3, 3), 0.25).tg
     assert [K.lib.gcb_dens_unit(i, C.byref(tg)) for i in range(4)] == [1.0, np.float32(32.3227), np.float32(0.602214), 1000.0]
     assert K.lib.gcb_dens_unit(4, C.byref(tg)) == np.float32(0.25 ** 3)
+
+
+@pytest.mark.parametrize("threads", [0, 1, 3, 16])
+def test_pack_frames_copies_the_index_group(threads):
+    """gcb_pack_frames: out[f][i] = x[f][gindex[i]], the reference loop's reads (g_ri3Dc.c:425-426) laid out densely;
+    pure host code, the packing step of gcb_counter_add_frames by itself"""
+    import gridcount_b200 as g
+    rng = np.random.default_rng(3)
+    cases = [(2700, np.arange(0, 2700, 3)), (2700, np.arange(2700)), (1000, np.sort(rng.choice(1000, 137, replace=False))),
+             (5, np.array([4, 0, 0, 2])), (60000, np.arange(1, 60000, 3)), (300, np.array([], np.int64)), (7, np.array([6]))]
+    for natoms, gi in cases:
+        for nframes in (0, 1, 7, 130):
+            x = rng.random((nframes, natoms, 3), dtype=np.float32)
+            out = g.pack_frames(x, gi.astype(np.int32), threads)
+            assert out.shape == (nframes, len(gi), 3)
+            assert np.array_equal(out.view(np.uint32), x[:, gi.astype(np.int64), :].view(np.uint32)), (natoms, nframes)
+    x = np.zeros((2, 10, 3), np.float32)
+    with pytest.raises(Exception):
+        g.pack_frames(x, np.array([3, 10], np.int32), threads)       # entry outside [0, natoms)
+
+
+def test_pack_frames_from_many_threads_at_once():
+    """the pool takes one job at a time: callers on several threads (one counter per GPU in host/g_ri3Dc -gpus) queue up"""
+    import threading
+    import gridcount_b200 as g
+    rng = np.random.default_rng(4)
+    x = rng.random((40, 30000, 3), dtype=np.float32)
+    gi = np.arange(0, 30000, 3, dtype=np.int32)
+    want = x[:, gi, :]
+    bad = []
+
+    def work():
+        for _ in range(20):
+            if not np.array_equal(g.pack_frames(x, gi, 4), want):
+                bad.append(1)
+
+    ts = [threading.Thread(target=work) for _ in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not bad
