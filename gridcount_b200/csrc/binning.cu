@@ -35,7 +35,7 @@ struct Slot {
   unsigned long long *d_hits = nullptr, *h_hits = nullptr;
   float *d_box3 = nullptr, *h_box3 = nullptr;
   long cap = 0;                       // frames
-  long cap_pack = 0;                  // frames when the batch is staged packed (index group only), >= cap
+  long cap_pack = 0;                  // frames when the batch is staged packed (index group only; 0: does not fit)
   bool dma_in_place = false;          // the last copy queued on this slot reads the caller's pinned memory
   long pending = 0;                   // frames whose hit counts have not been collected yet
   size_t frame0 = 0;                  // global index of the first pending frame
@@ -662,8 +662,10 @@ int alloc_slots(gcb_counter *c, int want = 0)
   long fpb = c->opts.frames_per_batch;
   if (fpb <= 0) fpb = (long)std::max<size_t>(1, ((size_t)32 << 20) / std::max<size_t>(frame_bytes, 1));
   c->slots.resize((size_t)ns);
-  // a packed batch holds as many frames as fit the same bytes (at most 16 x: per-frame counters are sized by it)
-  const long fpb_pack = c->gnx > 0 ? (long)std::min<long long>((long long)fpb * 16, std::max<long long>(fpb, (long long)fpb * c->natoms / c->gnx)) : fpb;
+  // a packed batch holds as many frames as fit the same bytes (at most 16 x: per-frame counters are sized by it;
+  // fewer than `fpb`, possibly none, for an index group with more entries than the frame has atoms)
+  const long fpb_pack = c->gnx > 0 ? (long)std::min<long long>((long long)fpb * 16, (long long)fpb * c->natoms / c->gnx) : 0;
+  const long fpb_max = std::max(fpb, fpb_pack);
   for (size_t k = have; k < c->slots.size(); k++) {
     Slot &s = c->slots[k];
     s.cap = fpb;
@@ -673,10 +675,10 @@ int alloc_slots(gcb_counter *c, int want = 0)
     GCB_CUDA(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
     GCB_CUDA(cudaHostAlloc(&s.h_x, frame_bytes * fpb, cudaHostAllocDefault));
     GCB_CUDA(cudaMalloc(&s.d_x, frame_bytes * fpb + 16));
-    GCB_CUDA(cudaMalloc(&s.d_hits, sizeof(unsigned long long) * (fpb_pack + 2)));
-    GCB_CUDA(cudaHostAlloc(&s.h_hits, sizeof(unsigned long long) * (fpb_pack + 2), cudaHostAllocDefault));
-    GCB_CUDA(cudaMalloc(&s.d_box3, sizeof(float) * 3 * fpb_pack));
-    GCB_CUDA(cudaHostAlloc(&s.h_box3, sizeof(float) * 3 * fpb_pack, cudaHostAllocDefault));
+    GCB_CUDA(cudaMalloc(&s.d_hits, sizeof(unsigned long long) * (fpb_max + 2)));
+    GCB_CUDA(cudaHostAlloc(&s.h_hits, sizeof(unsigned long long) * (fpb_max + 2), cudaHostAllocDefault));
+    GCB_CUDA(cudaMalloc(&s.d_box3, sizeof(float) * 3 * fpb_max));
+    GCB_CUDA(cudaHostAlloc(&s.h_box3, sizeof(float) * 3 * fpb_max, cudaHostAllocDefault));
   }
   return GCB_OK;
 }
@@ -1059,7 +1061,7 @@ int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes, const f
   // as long as the next packing job is expected to take -- the host threads pack the next frames instead, which
   // then cross PCIe at 12 B per counted atom.  Whichever lane is free takes the next frames, so the split follows
   // the host's packing rate against the link by itself; a host that packs slowly just packs little.
-  const bool can_pack = c->gnx > 0 && nframes > 0 && c->host_pack != GCB_HOST_PACK_NEVER;
+  const bool can_pack = c->gnx > 0 && nframes > 0 && c->host_pack != GCB_HOST_PACK_NEVER && c->slots[0].cap_pack > 0;
   const bool all_pack = can_pack && (c->host_pack == GCB_HOST_PACK_ALWAYS || !pinned);
   bool two_lanes = can_pack && !all_pack && c->gnx < c->natoms && c->opts.nslots <= 0;
   if (two_lanes && nframes > c->slots[0].cap) {

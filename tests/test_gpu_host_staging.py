@@ -23,13 +23,15 @@ def jittered_weights(nframes, seed):
 @pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("kernel", [K.KERNEL_AUTO, K.KERNEL_GATHER, K.KERNEL_STREAM_INDEXED])
-@pytest.mark.parametrize("shape", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [0, 1, 2, 3, 4, 5])
 def test_every_staging_mode_equals_the_oracle(shape, kernel, mode, pinned):
     natoms, gindex, nframes, L, delta = [
         (3000, np.arange(0, 3000, 3), 61, (3.0, 3.0, 3.0), 0.1),                     # water oxygens
         (1500, np.arange(1, 1500, 7), 90, (2.5, 3.0, 3.5), (0.1, 0.125, 0.07)),      # g0 = 1, fewer than 256 selected
         (4099, np.random.default_rng(5).integers(0, 4099, 1500), 23, (4.0, 4.0, 4.0), 0.08),   # unsorted, duplicates
         (9000, np.array([17, 4242, 8999]), 40, (5.0, 5.0, 5.0), 0.25),               # three ions
+        (100, np.random.default_rng(6).integers(0, 100, 250), 50, (2.0, 2.0, 2.0), 0.2),       # more entries than atoms
+        (10, np.random.default_rng(7).integers(0, 10, 100), 30, (2.0, 2.0, 2.0), 0.2),         # ... so many that no packed frame fits a slot
     ][shape]
     gindex = gindex.astype(np.int32)
     x = u.gen_frames(u.make_gen(900 + shape, tuple(1.1 * v for v in L)), 0, nframes, natoms)
@@ -55,7 +57,10 @@ def test_every_staging_mode_equals_the_oracle(shape, kernel, mode, pinned):
     assert st.sumP == osumP and st.edge_overflow == oovf and st.frames == nframes
     hs = ctr.host_staging()
     assert hs.mode == mode
-    if mode == K.HOST_PACK_ALWAYS or (mode == K.HOST_PACK_AUTO and not pinned):
+    fits = (8 * natoms) // len(gindex) > 0                # packed frames per slot (frames_per_batch = 8)
+    if not fits:
+        assert hs.frames_packed == 0
+    elif mode == K.HOST_PACK_ALWAYS or (mode == K.HOST_PACK_AUTO and not pinned):
         assert hs.frames_packed == nframes and hs.h2d_bytes == nframes * len(gindex) * 12
     if mode == K.HOST_PACK_NEVER:
         assert hs.frames_packed == 0 and hs.h2d_bytes == nframes * natoms * 12
