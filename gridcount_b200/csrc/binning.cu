@@ -37,6 +37,8 @@ struct Slot {
   long cap = 0;                       // frames
   long cap_pack = 0;                  // frames when the batch is staged packed (index group only; 0: does not fit)
   bool dma_in_place = false;          // the last copy queued on this slot reads the caller's pinned memory
+  bool copy_queued = false;           // ... and has not been seen complete yet (two-lane staging)
+  size_t copy_bytes = 0;
   long pending = 0;                   // frames whose hit counts have not been collected yet
   size_t frame0 = 0;                  // global index of the first pending frame
 };
@@ -729,25 +731,16 @@ int pack_threads(const gcb_counter *c)
   return std::max(1, std::min(t, 2 * t / c->nranks));
 }
 
-// stage `n` frames that already sit in slot.h_x (or are copied there from `src`; `pack`: only the index group's
-// atoms are, and the kernels run on the packed layout)
+// stage `n` frames that already sit in slot.h_x (or are copied there from `src`; `pack`: slot.h_x holds only the
+// index group's atoms, x'[n][gnx][3], and the kernels run on the packed layout)
 int submit_slot(gcb_counter *c, Slot &s, const float *src, bool src_pinned, long n, const float *w,
                 const float *box, bool pack = false)
 {
   size_t bytes = (size_t)n * c->natoms * 12;
   const float *from = s.h_x;
-  if (src && pack) {
+  if (pack) {
     int rc = ensure_pack_layout(c);
     if (rc) return rc;
-    timespec t0{}, t1{};
-    clock_gettime(CLOCK_MONOTONIC, &t0);
-    gcb::pack_frames(src, n, c->natoms, c->h_gindex.data(), c->gnx, c->ap.g0, c->ap_ok ? c->ap.step : 0, s.h_x, pack_threads(c));
-    clock_gettime(CLOCK_MONOTONIC, &t1);
-    const double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
-    if (dt > 0 && bytes >= ((size_t)1 << 20)) {
-      const double r = (double)bytes / dt;
-      c->pack_rate = c->pack_rate > 0 ? 0.7 * c->pack_rate + 0.3 * r : r;
-    }
     bytes = (size_t)n * c->gnx * 12;
     c->frames_packed += (uint64_t)n;
   } else if (src) {
@@ -755,6 +748,8 @@ int submit_slot(gcb_counter *c, Slot &s, const float *src, bool src_pinned, long
     else memcpy(s.h_x, src, bytes);
   }
   s.dma_in_place = from != s.h_x;
+  s.copy_bytes = bytes;
+  s.copy_queued = true;
   c->h2d_bytes += bytes;
   GCB_CUDA(cudaMemcpyAsync(s.d_x, from, bytes, cudaMemcpyHostToDevice, s.copy));
   if (c->opts.pbc == GCB_PBC_RECT) {
@@ -1056,11 +1051,12 @@ int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes, const f
   else cudaGetLastError();
   const size_t frame_floats = (size_t)c->natoms * 3;
   // How the frames reach the device (header: gcb_host_staging).  Pageable x has to pass through a pinned slot anyway:
-  // host threads copy the index group into it (packed staging).  Pinned x is staged on TWO LANES at once: batches
-  // are DMA-ed in place, and while at least `depth` of those copies are queued -- enough to keep the link busy for
-  // as long as the next packing job is expected to take -- the host threads pack the next frames instead, which
-  // then cross PCIe at 12 B per counted atom.  Whichever lane is free takes the next frames, so the split follows
-  // the host's packing rate against the link by itself; a host that packs slowly just packs little.
+  // host threads copy the index group into it (packed staging).  Pinned x is staged on TWO LANES: the host threads
+  // pack batch after batch -- those cross PCIe at 12 B per counted atom -- and whenever the copies already queued
+  // would not keep the link busy until the next packed batch is ready, a batch is DMA-ed straight out of the caller's
+  // memory to fill the gap.  The host threads and the link are then both busy all the time, whatever their speeds
+  // (throughput ~ (link + 2/3 packing rate) / 36 B for water oxygens); a host that packs slowly mostly DMAs in place.
+  // A packed batch is queued (copy + kernels) while the pool's threads are already packing the next one.
   const bool can_pack = c->gnx > 0 && nframes > 0 && c->host_pack != GCB_HOST_PACK_NEVER && c->slots[0].cap_pack > 0;
   const bool all_pack = can_pack && (c->host_pack == GCB_HOST_PACK_ALWAYS || !pinned);
   bool two_lanes = can_pack && !all_pack && c->gnx < c->natoms && c->opts.nslots <= 0;
@@ -1071,36 +1067,93 @@ int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes, const f
     two_lanes = false;
   }
   const double frame_bytes = (double)frame_floats * 4.0, link_rate = 55e9;     // (PCIe 5 x16; a slower link only adds slack)
+  const int threads = pack_threads(c);
+  const int *gi = c->h_gindex.data();
+  const int g0 = c->ap.g0, gstep = c->ap_ok ? c->ap.step : 0;
+
+  struct InFlight {                   // the packed batch whose packing was started last and which is not queued yet
+    Slot *s = nullptr; long n = 0, first = 0; void *job = nullptr; timespec t0{};
+  } fly;
+  auto pack_done = [&]() {            // join the packing of `fly`, note its rate
+    gcb::pack_end(fly.job);
+    fly.job = nullptr;
+    timespec t1{};
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double dt = (double)(t1.tv_sec - fly.t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - fly.t0.tv_nsec);
+    const double bytes = (double)fly.n * frame_bytes;
+    if (dt > 0 && bytes >= (double)(1 << 20)) {
+      const double r = bytes / dt;
+      c->pack_rate = c->pack_rate > 0 ? 0.7 * c->pack_rate + 0.3 * r : r;
+    }
+  };
+  auto queue_fly = [&]() -> int {     // copy + kernels of `fly` (its packing is complete)
+    if (!fly.s) return GCB_OK;
+    Slot *s = fly.s;
+    fly.s = nullptr;
+    return submit_slot(c, *s, nullptr, false, fly.n, weight ? weight + fly.first : nullptr,
+                       box ? box + 9 * (size_t)fly.first : nullptr, true);
+  };
+  auto bail = [&](int code) { if (fly.job) { gcb::pack_end(fly.job); fly.job = nullptr; } return code; };
+
   long done = 0;
   while (done < nframes) {
     bool pack = all_pack;
-    long n_pack = 0;
+    long n_pack = c->slots[0].cap_pack;
     if (two_lanes) {
-      // in-place copies still queued, and the batch the host threads can pack in about the time one of them takes
-      int queued = 0;
+      // bytes the link still has to move, and the batch the host threads pack in about the time one in-place copy takes
+      double queued = 0;
       for (auto &q : c->slots)
-        if (q.dma_in_place) {
-          if (cudaEventQuery(q.copied) == cudaErrorNotReady) queued++;
-          else q.dma_in_place = false;
+        if (q.copy_queued) {
+          if (cudaEventQuery(q.copied) == cudaErrorNotReady) queued += (double)q.copy_bytes;
+          else q.copy_queued = false;
         }
       cudaGetLastError();
+      if (fly.s) queued += (double)fly.n * (double)c->gnx * 12.0;          // (about to be queued)
       const long cap = c->slots[0].cap;
-      const double rate = c->pack_rate > 0 ? c->pack_rate : 4e9 * (double)pack_threads(c);
+      const double rate = c->pack_rate > 0 ? c->pack_rate : 4e9 * (double)threads;
       n_pack = std::max<long>(1, std::min<long>(c->slots[0].cap_pack, (long)((double)cap * rate / link_rate)));
-      const double t_pack = (double)n_pack * frame_bytes / rate, t_copy = (double)cap * frame_bytes / link_rate;
-      const int depth = 1 + (int)std::ceil(t_pack / t_copy);
-      pack = depth <= (int)c->slots.size() - 2 && queued >= depth;
+      const double t_pack = (double)n_pack * frame_bytes / rate + 100e-6;
+      pack = queued >= t_pack * link_rate;                                  // the link has enough to do meanwhile
     }
     Slot &s = c->slots[c->next_slot];
     c->next_slot = (c->next_slot + 1) % (int)c->slots.size();
+    if (fly.s == &s) {                // (a single slot) nothing to overlap with
+      pack_done();
+      rc = queue_fly();
+      if (rc) return bail(rc);
+    }
     rc = collect_slot(c, s);
-    if (rc) return rc;
-    if (!pinned || pack) GCB_CUDA(cudaStreamSynchronize(s.copy));   // staging buffer free to overwrite
-    const long n = std::min(pack ? (two_lanes ? n_pack : s.cap_pack) : s.cap, nframes - done);
-    rc = submit_slot(c, s, x + (size_t)done * frame_floats, pinned, n, weight ? weight + done : nullptr,
-                     box ? box + 9 * (size_t)done : nullptr, pack);
-    if (rc) return rc;
+    if (rc) return bail(rc);
+    if (!pinned || pack) {            // staging buffer free to overwrite
+      const cudaError_t err = cudaStreamSynchronize(s.copy);
+      if (err != cudaSuccess) return bail(gcb::fail(GCB_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(err)));
+    }
+    const long n = std::min(pack ? n_pack : s.cap, nframes - done);
+    if (pack) {
+      if (fly.s) pack_done();         // (one packing job at a time; it has normally finished by now)
+      InFlight next;
+      next.s = &s; next.n = n; next.first = done;
+      clock_gettime(CLOCK_MONOTONIC, &next.t0);
+      next.job = gcb::pack_begin(x + (size_t)done * frame_floats, n, c->natoms, gi, c->gnx, g0, gstep, s.h_x, threads);
+      rc = queue_fly();               // the previous packed batch: copy + kernels, while the pool packs this one
+      fly = next;
+      if (rc) return bail(rc);
+    } else {
+      if (fly.s) {                    // frames are queued in the order of x
+        pack_done();
+        rc = queue_fly();
+        if (rc) return bail(rc);
+      }
+      rc = submit_slot(c, s, x + (size_t)done * frame_floats, pinned, n, weight ? weight + done : nullptr,
+                       box ? box + 9 * (size_t)done : nullptr, false);
+      if (rc) return bail(rc);
+    }
     done += n;
+  }
+  if (fly.s) {
+    pack_done();
+    rc = queue_fly();
+    if (rc) return rc;
   }
   // Pinned x that was DMA-ed straight out of the caller's memory: the call returns when the last of those copies has
   // left it (the kernels behind them keep running), so the caller may refill x at once, as with pageable memory.

@@ -23,6 +23,11 @@ double seq_add_f64(double v, double w, uint64_t n);
 int pack_threads_default();
 void pack_frames(const float *x, long nframes, int natoms, const int *gindex, int gnx, int g0, int step, float *out,
                  int threads);
+// the same in two halves: pack_begin returns while the pool's threads work (NULL: a small job, already done);
+// pack_end lets the caller join in, waits, and releases the pool.  One job at a time, both calls from one thread.
+void *pack_begin(const float *x, long nframes, int natoms, const int *gindex, int gnx, int g0, int step, float *out,
+                 int threads);
+void pack_end(void *handle);
 
 }  // namespace gcb
 

@@ -55,15 +55,12 @@ class Pool {
     return *p;
   }
 
-  void run(int threads, long nchunks, void (*fn)(void *, long), void *ctx)
+  // begin() publishes the job to `threads - 1` workers and returns at once (the number of helpers); end() lets the
+  // caller join the work, waits for the helpers and releases the pool.  Same thread for both; `job` lives in between.
+  int begin(Job &job, int threads)
   {
-    if (nchunks <= 0) return;
-    threads = (int)std::min<long>(std::min(threads, MAX_THREADS), nchunks);
-    Job job;
-    job.fn = fn; job.ctx = ctx; job.nchunks = nchunks;
-    if (threads <= 1) { job.work(); return; }
-    std::lock_guard<std::mutex> one_job(run_mutex_);
-    const int helpers = threads - 1;
+    run_mutex_.lock();
+    const int helpers = std::max(0, std::min(threads, MAX_THREADS) - 1);
     {
       std::lock_guard<std::mutex> lk(m_);
       if (pid_ != getpid()) { pid_ = getpid(); nworkers_ = 0; }      // a forked child starts without workers
@@ -77,11 +74,17 @@ class Pool {
       gen_.fetch_add(1, std::memory_order_release);
     }
     cv_.notify_all();
+    return helpers;
+  }
+
+  void end(Job &job, int helpers)
+  {
     job.work();
     for (long spin = 0; job.done.load(std::memory_order_acquire) < helpers; spin++) {
       if (spin < 20000) cpu_relax();
       else std::this_thread::yield();
     }
+    run_mutex_.unlock();
   }
 
   static constexpr int MAX_THREADS = 64;
@@ -208,18 +211,48 @@ int pack_threads_default()
   return n;
 }
 
-void pack_frames(const float *x, long nframes, int natoms, const int *gindex, int gnx, int g0, int step, float *out,
+struct PackHandle {
+  PackJob p;
+  Job job;
+  int helpers = 0;
+};
+
+// Starts packing on the pool's threads and returns a handle for pack_end (NULL: the job was small and is done).
+void *pack_begin(const float *x, long nframes, int natoms, const int *gindex, int gnx, int g0, int step, float *out,
                  int threads)
 {
-  if (nframes <= 0 || gnx <= 0) return;
-  PackJob p;
+  if (nframes <= 0 || gnx <= 0) return nullptr;
+  PackHandle *h = new PackHandle;
+  PackJob &p = h->p;
   p.x = x; p.out = out; p.nsel = (long long)nframes * gnx;
   p.natoms = natoms; p.gnx = gnx; p.g0 = g0; p.step = step; p.gindex = gindex;
   p.per_chunk = 8192;                                  // 96 KB of output per chunk
-  const long nchunks = (long)((p.nsel + p.per_chunk - 1) / p.per_chunk);
+  h->job.fn = pack_chunk; h->job.ctx = &h->p;
+  h->job.nchunks = (long)((p.nsel + p.per_chunk - 1) / p.per_chunk);
   if (threads <= 0) threads = pack_threads_default();
-  if (p.nsel < 32768) threads = 1;                     // not worth waking anybody
-  Pool::get().run(threads, nchunks, pack_chunk, &p);
+  threads = (int)std::min<long>(threads, h->job.nchunks);
+  if (threads <= 1 || p.nsel < 32768) {                // not worth waking anybody
+    h->job.work();
+    delete h;
+    return nullptr;
+  }
+  h->helpers = Pool::get().begin(h->job, threads);
+  return h;
+}
+
+// The caller joins the packing, waits for the other threads and releases the pool.
+void pack_end(void *handle)
+{
+  if (!handle) return;
+  PackHandle *h = static_cast<PackHandle *>(handle);
+  Pool::get().end(h->job, h->helpers);
+  delete h;
+}
+
+void pack_frames(const float *x, long nframes, int natoms, const int *gindex, int gnx, int g0, int step, float *out,
+                 int threads)
+{
+  pack_end(pack_begin(x, nframes, natoms, gindex, gnx, g0, step, out, threads));
 }
 
 }  // namespace gcb

@@ -157,10 +157,11 @@ int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes,
  * kernels bin frames in which every atom counts.  Counts, per-frame hits and everything derived from them are the
  * same bits either way.  AUTO (the default; environment GCB_HOST_PACK=0/1 overrides it at create):
  *   - pageable x is always packed (it has to be copied into a slot anyway);
- *   - pinned x goes down TWO LANES at once: batches are DMA-ed in place, and while enough of those copies are
- *     queued to keep the link busy, the host threads pack the next frames, which then cost a third of the link
- *     time.  The lanes take frames as they become free, so the split follows the host's packing rate against the
- *     link by itself (throughput ~ (link + 2/3 packing rate) / 36 B for water oxygens); a slow host packs little.
+ *   - pinned x goes down TWO LANES at once: the host threads pack batch after batch, and whenever the copies already
+ *     queued would not keep the link busy until the next packed batch is ready, a batch is DMA-ed straight out of the
+ *     caller's memory to fill the gap.  Host threads and link are then both busy all the time, whatever their speeds
+ *     (throughput ~ (link + 2/3 packing rate) / 36 B for water oxygens); a host that packs slowly mostly DMAs in place.
+ *     Only calls of more than one batch, and only counters created with nslots = 0 (the pipeline is then 6 slots deep).
  * NEVER is the staging of round 1 (memcpy of pageable x into the slot, pinned x DMA-ed in place).
  * GCB_PACK_THREADS sets the pool's size (default: the CPUs the process may run on, at most 16; the ranks of a
  * multi-GPU job share them). */
