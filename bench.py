@@ -549,6 +549,7 @@ def bind_to_gpu_numa_node(device):
         if not cpus:
             return None
         os.sched_setaffinity(0, cpus)
+        bind_to_gpu_numa_node.node, bind_to_gpu_numa_node.ncpus = node, len(cpus)
         return "numa node %d (%d cpus)" % (node, len(cpus))
     except Exception:
         return None
@@ -574,6 +575,17 @@ def run_gpu_arm(args, rank, local_rank, world):
     device = local_rank
     torch.cuda.set_device(device)
     numa = bind_to_gpu_numa_node(device) if world > 1 else None
+    if world > 1 and "GCB_PACK_THREADS" not in os.environ:
+        # host threads that pack frames for this rank (gcb_host_staging): the CPUs this rank may run on, shared
+        # with the other ranks bound to the same NUMA node (the library's own default cannot know those)
+        try:
+            mine = (getattr(bind_to_gpu_numa_node, "node", -1), getattr(bind_to_gpu_numa_node, "ncpus", len(os.sched_getaffinity(0))))
+            every = [None] * world
+            dist.all_gather_object(every, mine)
+            sharing = sum(1 for e in every if e[0] == mine[0]) if mine[0] >= 0 else world
+            os.environ["GCB_PACK_THREADS"] = str(max(1, min(16, mine[1] // max(1, sharing))))
+        except Exception:
+            pass
 
     def barrier():
         if dist is not None:

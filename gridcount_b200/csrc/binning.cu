@@ -728,7 +728,7 @@ int pack_threads(const gcb_counter *c)
 {
   const int t = gcb::pack_threads_default();
   if (c->nranks <= 1 || getenv("GCB_PACK_THREADS")) return t;
-  return std::max(1, std::min(t, 2 * t / c->nranks));
+  return std::min(t, std::max(2, gcb::pack_cpus() / c->nranks));
 }
 
 // stage `n` frames that already sit in slot.h_x (or are copied there from `src`; `pack`: slot.h_x holds only the
@@ -1113,7 +1113,9 @@ int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes, const f
       const double rate = c->pack_rate > 0 ? c->pack_rate : 4e9 * (double)threads;
       n_pack = std::max<long>(1, std::min<long>(c->slots[0].cap_pack, (long)((double)cap * rate / link_rate)));
       const double t_pack = (double)n_pack * frame_bytes / rate + 100e-6;
-      pack = queued >= t_pack * link_rate;                                  // the link has enough to do meanwhile
+      // pack while the link has enough to do meanwhile; the last frames of a call are packed in any case, so that
+      // the call does not end with a long copy out of the caller's memory to wait for
+      pack = queued >= t_pack * link_rate || nframes - done <= 2 * n_pack;
     }
     Slot &s = c->slots[c->next_slot];
     c->next_slot = (c->next_slot + 1) % (int)c->slots.size();
@@ -1158,7 +1160,8 @@ int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes, const f
   // Pinned x that was DMA-ed straight out of the caller's memory: the call returns when the last of those copies has
   // left it (the kernels behind them keep running), so the caller may refill x at once, as with pageable memory.
   if (pinned && !all_pack)
-    for (auto &s : c->slots) GCB_CUDA(cudaEventSynchronize(s.copied));
+    for (auto &s : c->slots)
+      if (s.dma_in_place || !two_lanes) GCB_CUDA(cudaEventSynchronize(s.copied));
   return GCB_OK;
 }
 

@@ -21,6 +21,7 @@ double seq_add_f64(double v, double w, uint64_t n);
 // host_pack.cpp: x[frame][natoms][3] -> out[frame][gnx][3] on a pool of host threads (step > 0: the group is
 // g0 + i*step and gindex is not read; threads <= 0: pack_threads_default())
 int pack_threads_default();
+int pack_cpus();
 void pack_frames(const float *x, long nframes, int natoms, const int *gindex, int gnx, int g0, int step, float *out,
                  int threads);
 // the same in two halves: pack_begin returns while the pool's threads work (NULL: a small job, already done);

@@ -197,16 +197,25 @@ void pack_chunk(void *ctx, long chunk)
 
 namespace gcb {
 
+// CPUs this process may run on
+int pack_cpus()
+{
+  static const int n = [] {
+    int cpus = 0;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) cpus = CPU_COUNT(&set);
+    if (cpus <= 0) cpus = (int)sysconf(_SC_NPROCESSORS_ONLN);
+    return std::max(1, cpus);
+  }();
+  return n;
+}
+
 // host threads a packing job may use: GCB_PACK_THREADS, else the CPUs this process may run on, at most 16
 int pack_threads_default()
 {
   static const int n = [] {
     if (const char *e = getenv("GCB_PACK_THREADS")) { const int v = atoi(e); if (v >= 1) return std::min(v, Pool::MAX_THREADS); }
-    int cpus = 0;
-    cpu_set_t set;
-    if (sched_getaffinity(0, sizeof set, &set) == 0) cpus = CPU_COUNT(&set);
-    if (cpus <= 0) cpus = (int)sysconf(_SC_NPROCESSORS_ONLN);
-    return std::max(1, std::min(cpus, 16));
+    return std::min(pack_cpus(), 16);
   }();
   return n;
 }
