@@ -703,6 +703,9 @@ def run_gpu_arm(args, rank, local_rank, world):
            "host_bytes_read_per_step": int(HOSTF * E2E_CALLS) * natoms * 12 * world,
            "staging": {"frames_dma_in_place_per_step": fr_in_place, "frames_packed_by_host_threads_per_step": fr_packed,
                        "pack_threads": int(hs1.threads), "pack_source_gbs": hs1.pack_bytes_per_s * 1e-9,
+                       "trial": {"two_lanes_kept": int(hs1.lanes), "two_lane_frames_per_s": hs1.two_lane_frames_per_s,
+                                 "dma_in_place_frames_per_s": hs1.in_place_frames_per_s,
+                                 "note": "the counter's first calls (warm-up step) time both ways and keep the faster"},
                        "note": "two lanes at once: batches DMA-ed out of the pinned buffer (12 B per atom) and batches whose "
                                "index group host threads copy into pinned slots (12 B per counted atom); rank 0's split"},
            "d2h_bytes_per_step": int(geom.cells * 4 + HOSTF * E2E_CALLS * 8) * world, "steps": e2e_steps,

@@ -59,7 +59,8 @@ class Stats(C.Structure):
 
 class HostStaging(C.Structure):
     _fields_ = [("mode", C.c_int), ("threads", C.c_int), ("h2d_bytes", C.c_uint64), ("frames_packed", C.c_uint64),
-                ("frames_in_place", C.c_uint64), ("pack_bytes_per_s", C.c_double)]
+                ("frames_in_place", C.c_uint64), ("pack_bytes_per_s", C.c_double), ("lanes", C.c_int),
+                ("two_lane_frames_per_s", C.c_double), ("in_place_frames_per_s", C.c_double)]
 
 
 class AnalysisOpts(C.Structure):

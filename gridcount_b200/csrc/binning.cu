@@ -148,6 +148,13 @@ struct gcb_counter {
   bool pk_ready = false;
   int host_pack = -1;                 // GCB_HOST_PACK_*: -1 auto, 0 never, 1 always
   double pack_rate = 0;               // measured: source bytes per second the host threads pack (moving average)
+  // AUTO, pinned frames: do the two lanes beat plain DMA out of the caller's memory ON THIS HOST?  (They may not
+  // where many ranks share the host's memory bandwidth: a packed atom costs the host 36 B read + 12 B written +
+  // 12 B read by the DMA engine, an atom DMA-ed in place 36 B.)  The first calls time both, ~40 ms of calls each.
+  int lanes_choice = -1;              // -1: still measuring, 0: DMA in place only, 1: two lanes
+  int trial_phase = 0;                // 0: timing the two lanes, 1: timing DMA in place
+  int trial_calls[2] = {0, 0};
+  double trial_s[2] = {0, 0}, trial_frames[2] = {0, 0};
   uint64_t h2d_bytes = 0;             // bytes of frames queued host -> device by add_frames / submit_slot
   uint64_t frames_packed = 0;         // frames that were staged packed
   uint64_t frames_in_place = 0;       // frames DMA-ed straight out of the caller's pinned memory
@@ -1060,12 +1067,19 @@ int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes, const f
   const bool can_pack = c->gnx > 0 && nframes > 0 && c->host_pack != GCB_HOST_PACK_NEVER && c->slots[0].cap_pack > 0;
   const bool all_pack = can_pack && (c->host_pack == GCB_HOST_PACK_ALWAYS || !pinned);
   bool two_lanes = can_pack && !all_pack && c->gnx < c->natoms && c->opts.nslots <= 0;
+  int measuring = -1;                 // the phase of the trial this call belongs to
   if (two_lanes && nframes > c->slots[0].cap) {
     rc = alloc_slots(c, 6);
     if (rc) return rc;
+    if (c->host_pack == GCB_HOST_PACK_AUTO) {
+      if (c->lanes_choice < 0) { measuring = c->trial_phase; two_lanes = measuring == 0; }
+      else two_lanes = c->lanes_choice == 1;
+    }
   } else {
     two_lanes = false;
   }
+  timespec call_t0{};
+  if (measuring >= 0) clock_gettime(CLOCK_MONOTONIC, &call_t0);
   const double frame_bytes = (double)frame_floats * 4.0, link_rate = 55e9;     // (PCIe 5 x16; a slower link only adds slack)
   const int threads = pack_threads(c);
   const int *gi = c->h_gindex.data();
@@ -1162,6 +1176,16 @@ int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes, const f
   if (pinned && !all_pack)
     for (auto &s : c->slots)
       if (s.dma_in_place || !two_lanes) GCB_CUDA(cudaEventSynchronize(s.copied));
+  if (measuring >= 0 && c->trial_calls[measuring]++ > 0) {        // (a phase's first call carries the other phase's tail)
+    timespec t1{};
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    c->trial_s[measuring] += (double)(t1.tv_sec - call_t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - call_t0.tv_nsec);
+    c->trial_frames[measuring] += (double)nframes;
+    if (c->trial_s[measuring] >= 0.04) {
+      if (measuring == 0) c->trial_phase = 1;
+      else c->lanes_choice = c->trial_frames[0] / c->trial_s[0] > 1.05 * c->trial_frames[1] / c->trial_s[1] ? 1 : 0;
+    }
+  }
   return GCB_OK;
 }
 
@@ -1182,6 +1206,9 @@ int gcb_counter_host_staging(gcb_counter *c, gcb_host_staging *out)
   out->frames_packed = c->frames_packed;
   out->frames_in_place = c->frames_in_place;
   out->pack_bytes_per_s = c->pack_rate;
+  out->lanes = c->lanes_choice;
+  out->two_lane_frames_per_s = c->trial_s[0] > 0 ? c->trial_frames[0] / c->trial_s[0] : 0.0;
+  out->in_place_frames_per_s = c->trial_s[1] > 0 ? c->trial_frames[1] / c->trial_s[1] : 0.0;
   return GCB_OK;
 }
 

@@ -162,6 +162,10 @@ int gcb_counter_add_frames(gcb_counter *c, const float *x, long nframes,
  *     caller's memory to fill the gap.  Host threads and link are then both busy all the time, whatever their speeds
  *     (throughput ~ (link + 2/3 packing rate) / 36 B for water oxygens); a host that packs slowly mostly DMAs in place.
  *     Only calls of more than one batch, and only counters created with nslots = 0 (the pipeline is then 6 slots deep).
+ *     Whether the two lanes beat plain DMA depends on the host as well (a packed atom costs its memory system
+ *     36 B read + 12 B written + 12 B read by the DMA engine, an atom DMA-ed in place 36 B; many ranks may share
+ *     it), so the first calls time both ways, about 40 ms of calls each, and the counter keeps the two lanes only
+ *     if they moved frames at least 5 % faster.
  * NEVER is the staging of round 1 (memcpy of pageable x into the slot, pinned x DMA-ed in place).
  * GCB_PACK_THREADS sets the pool's size (default: the CPUs the process may run on, at most 16; the ranks of a
  * multi-GPU job share them). */
@@ -173,6 +177,8 @@ typedef struct {
   uint64_t frames_packed;   /* frames that were staged packed so far ... */
   uint64_t frames_in_place; /* ... and frames DMA-ed straight out of the caller's pinned memory */
   double pack_bytes_per_s;  /* measured packing rate in bytes of source frames (moving average; 0: nothing packed yet) */
+  int lanes;                /* AUTO with pinned x: 1 the two lanes won the trial, 0 DMA in place did, -1 still measuring */
+  double two_lane_frames_per_s, in_place_frames_per_s;   /* what the trial measured (0: not measured yet) */
 } gcb_host_staging;
 int gcb_counter_set_host_pack(gcb_counter *c, int mode);
 int gcb_counter_host_staging(gcb_counter *c, gcb_host_staging *out);

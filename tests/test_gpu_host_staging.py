@@ -114,6 +114,23 @@ def test_both_lanes_carry_pinned_frames():
     assert hs.frames_in_place > 0 and hs.frames_packed > 0, (hs.frames_in_place, hs.frames_packed)
     assert hs.h2d_bytes == hs.frames_in_place * natoms * 12 + hs.frames_packed * len(gindex) * 12
     assert hs.pack_bytes_per_s > 0 and hs.threads >= 1
+    # the counter's trial: after ~40 ms of calls on the two lanes and ~40 ms of plain DMA it settles on the faster way
+    assert hs.lanes == -1
+    more = 0
+    while ctr.host_staging().lanes < 0 and more < 200:
+        ctr.add_host_ptr(pin.ptr, nframes)
+        more += 1
+    hs = ctr.host_staging()
+    assert hs.lanes in (0, 1) and hs.two_lane_frames_per_s > 0 and hs.in_place_frames_per_s > 0, (more, hs.lanes)
+    assert (hs.two_lane_frames_per_s > 1.05 * hs.in_place_frames_per_s) == (hs.lanes == 1)
+    before = (hs.frames_packed, hs.frames_in_place)
+    ctr.add_host_ptr(pin.ptr, nframes)
+    hs = ctr.host_staging()
+    assert hs.frames_packed + hs.frames_in_place == before[0] + before[1] + nframes
+    if hs.lanes == 0:
+        assert hs.frames_packed == before[0]
+    np.testing.assert_array_equal(ctr.counts(), (3 + more + 1) * ocounts)
+    assert ctr.stats().frames == (3 + more + 1) * nframes
     # an explicit slot count keeps the round-1 staging (the caller sized the pipeline)
     ctr2 = g.GridCounter(geom, gindex, natoms, frames_per_batch=4, nslots=2)
     ctr2.add_host_ptr(pin.ptr, nframes)

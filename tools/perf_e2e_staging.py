@@ -54,10 +54,12 @@ def main():
         st = ctr.stats()
         assert st.hits == st.atom_frames == int(units), (st.hits, st.atom_frames, units)
         crc[mname] = zlib.crc32(dens.tobytes())
-        print("%s %-6s %.1f ms/step  %.3f G atom-frames/s  h2d %.2f GB/step  packed %d in-place %d frames/step  pack %.1f GB/s on %d threads  crc %08x"
+        print("%s %-6s %.1f ms/step  %.3f G atom-frames/s  h2d %.2f GB/step  packed %d in-place %d frames/step  pack %.1f GB/s on %d threads  "
+              "trial: lanes=%d two-lane %.0f in-place %.0f frames/s  crc %08x"
               % (name, mname, dt * 1e3, units / dt * 1e-9, (h1.h2d_bytes - h0.h2d_bytes) / steps * 1e-9,
                  (h1.frames_packed - h0.frames_packed) // steps, (h1.frames_in_place - h0.frames_in_place) // steps,
-                 h1.pack_bytes_per_s * 1e-9, h1.threads, crc[mname]), flush=True)
+                 h1.pack_bytes_per_s * 1e-9, h1.threads, h1.lanes, h1.two_lane_frames_per_s, h1.in_place_frames_per_s,
+                 crc[mname]), flush=True)
         ctr.close()
     assert len(set(crc.values())) == 1, "density differs between staging modes"
     pin.free()
