@@ -5,7 +5,9 @@
 // gridcount() (g_ri3Dc.c:139-152) inside it.  The device code lives in k1_kernels.cuh and k1_passes.cuh.
 //
 // Data layout in HBM
-//   frames   x[frame][atom][3] f32, exactly the host rvec layout (12 B/atom)
+//   frames   x[frame][atom][3] f32, exactly the host rvec layout (12 B/atom); host frames may arrive PACKED,
+//            x'[frame][gnx][3] (the index group only, copied by host threads: host_pack.cpp), and are then binned
+//            as frames of gnx atoms that all count
 //   counts   u32 [mx][my][mz], z fastest (the reference's contiguous block)
 //   acc      f32 same shape, only materialised when frame weights change
 //   gindex   i32 sorted copy of the index group, rank[] = prefix count per atom

@@ -144,8 +144,9 @@ int gcb_counter_reset(gcb_counter *c);
 /* Host frames x[nframes][natoms][3]; weight[f] is the reference's per-frame
  * `weight` (NULL: 1); box[f][9] is only read with GCB_PBC_RECT.  Frames are
  * staged through pinned buffers in batches on CUDA streams and binned
- * asynchronously; the call returns when all of x has been consumed: pageable x has been copied to the staging
- * buffers, pinned x (which is DMA-ed in place) has been read by the last copy, so the caller may refill x at once.
+ * asynchronously; the call returns when all of x has been consumed: the host threads have copied what they pack into
+ * the staging buffers (gcb_host_staging below), and the last DMA that reads pinned x in place has finished, so the
+ * caller may refill x at once.
  * Frames whose weight differs from frame to frame in short runs are accumulated with global f32 atomics
  * (RED.ADD.F32), which flush subnormal sums to zero whatever -ftz says; weights are time steps, many orders of
  * magnitude above 1e-38, so this never shows. */
