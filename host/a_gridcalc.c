@@ -24,8 +24,8 @@ int main(int argc, char **argv)
   gh_parse_args(argc, argv, synopsis, fnm, 2, pa, 1, NULL);
   const int nfile = fnm[0].nnames;
   if (!nfile) gh_fatal("No input files!");
-  float **grids = (float **)calloc((size_t)nfile, sizeof(float *));
-  float *tw = (float *)calloc((size_t)nfile, sizeof(float));
+  float **grids = (float **)gh_zalloc((size_t)nfile, sizeof(float *));
+  float *tw = (float *)gh_zalloc((size_t)nfile, sizeof(float));
   gcb_tgrid tg0, tg;
   char header[GCB_HEADER_MAX + 1];
   double sumT = 0;
@@ -44,7 +44,7 @@ int main(int argc, char **argv)
   }
   gh_msg("No sanity checks... proceeding with the above %d grids.\n", nfile);
   const size_t cells = (size_t)tg0.mx[0] * tg0.mx[1] * tg0.mx[2];
-  float *avg = (float *)malloc(sizeof(float) * cells);
+  float *avg = (float *)gh_alloc(sizeof(float) * cells);
   float tweight = 0;
   CHECK(gcb_gridcalc(nfile, (const float *const *)grids, tw, &tg0, avg, &tweight, device));
   tg0.tweight = tweight;

@@ -34,6 +34,27 @@ void gh_fatal(const char *fmt, ...)
   exit(1);
 }
 
+void *gh_alloc(size_t bytes)
+{
+  void *p = malloc(bytes ? bytes : 1);
+  if (!p) gh_fatal("Out of memory (%zu bytes)", bytes);
+  return p;
+}
+
+void *gh_zalloc(size_t count, size_t size)
+{
+  void *p = calloc(count ? count : 1, size ? size : 1);
+  if (!p) gh_fatal("Out of memory (%zu x %zu bytes)", count, size);
+  return p;
+}
+
+void *gh_realloc(void *old, size_t bytes)
+{
+  void *p = realloc(old, bytes ? bytes : 1);
+  if (!p) gh_fatal("Out of memory (%zu bytes)", bytes);
+  return p;
+}
+
 /* ------------------------------------------------------------------ options */
 static int looks_like_option(const char *s)
 {
@@ -46,7 +67,7 @@ static char *dup_with_ext(const char *name, const char *ext)
   const char *slash = strrchr(name, '/');
   const char *dot = strrchr(slash ? slash : name, '.');
   size_t n = strlen(name) + strlen(ext) + 1;
-  char *out = (char *)malloc(n);
+  char *out = (char *)gh_alloc(n);
   snprintf(out, n, "%s%s", name, dot ? "" : ext);
   return out;
 }
@@ -113,7 +134,7 @@ void gh_parse_args(int argc, char **argv, const char *synopsis, gh_file *files, 
       done = 1;
       if (files[j].mode == GH_F_READ_MULT) {
         while (i + 1 < argc && !looks_like_option(argv[i + 1])) {
-          files[j].names = (char **)realloc(files[j].names, sizeof(char *) * (size_t)(files[j].nnames + 1));
+          files[j].names = (char **)gh_realloc(files[j].names, sizeof(char *) * (size_t)(files[j].nnames + 1));
           files[j].names[files[j].nnames++] = dup_with_ext(argv[++i], files[j].ext);
         }
       } else if (i + 1 < argc && !looks_like_option(argv[i + 1])) {
@@ -164,7 +185,7 @@ void gh_parse_args(int argc, char **argv, const char *synopsis, gh_file *files, 
   for (j = 0; j < nfiles; j++) {
     if (files[j].mode == GH_F_READ_MULT) {
       if (files[j].nnames == 0) {
-        files[j].names = (char **)malloc(sizeof(char *));
+        files[j].names = (char **)gh_alloc(sizeof(char *));
         files[j].names[0] = dup_with_ext(files[j].defname, files[j].ext);
         files[j].nnames = 1;
       }
@@ -211,7 +232,7 @@ int gh_ndx_read(const char *path, gh_group **groups, int *ngroups)
       p++;
       while (isspace((unsigned char)*p)) p++;
       while (q > p && isspace((unsigned char)q[-1])) *--q = 0;
-      g = (gh_group *)realloc(g, sizeof(gh_group) * (size_t)(ng + 1));
+      g = (gh_group *)gh_realloc(g, sizeof(gh_group) * (size_t)(ng + 1));
       g[ng].name = strdup(p); g[ng].n = 0; g[ng].atoms = NULL;
       ng++;
       cap = 0;
@@ -222,7 +243,7 @@ int gh_ndx_read(const char *path, gh_group **groups, int *ngroups)
       char *end;
       long v = strtol(p, &end, 10);
       if (end == p) break;
-      if (g[ng - 1].n == cap) { cap = cap ? 2 * cap : 256; g[ng - 1].atoms = (int *)realloc(g[ng - 1].atoms, sizeof(int) * (size_t)cap); }
+      if (g[ng - 1].n == cap) { cap = cap ? 2 * cap : 256; g[ng - 1].atoms = (int *)gh_realloc(g[ng - 1].atoms, sizeof(int) * (size_t)cap); }
       g[ng - 1].atoms[g[ng - 1].n++] = (int)v - 1;          /* 1-based on disk (count.c:173-174) */
       p = end;
     }

@@ -54,7 +54,7 @@ static long xtc_index(const char *path, int natoms, xtc_entry **out)
     uint64_t size;
     if (natoms <= 9) size = 56 + (uint64_t)natoms * 12;
     else { if (got < 92) break; size = 92 + (((uint64_t)rd_be32(h + 88) + 3) & ~(uint64_t)3); }
-    if (n == cap) { cap = cap ? 2 * cap : 1024; e = (xtc_entry *)realloc(e, sizeof(xtc_entry) * (size_t)cap); }
+    if (n == cap) { cap = cap ? 2 * cap : 1024; e = (xtc_entry *)gh_realloc(e, sizeof(xtc_entry) * (size_t)cap); }
     uint32_t tb = rd_be32(h + 12);
     e[n].off = off; e[n].size = size; memcpy(&e[n].time, &tb, 4);
     n++;
@@ -121,8 +121,8 @@ static void *xtc_worker(void *arg)
       WCHECK(gcb_xtc_scan(pin, len, NULL, 0, &nall, NULL));
       if (nall > cap) {
         cap = nall;
-        frames = (gcb_xtc_frame *)realloc(frames, sizeof(gcb_xtc_frame) * (size_t)cap);
-        wsel = (float *)realloc(wsel, sizeof(float) * (size_t)cap);
+        frames = (gcb_xtc_frame *)gh_realloc(frames, sizeof(gcb_xtc_frame) * (size_t)cap);
+        wsel = (float *)gh_realloc(wsel, sizeof(float) * (size_t)cap);
       }
       WCHECK(gcb_xtc_scan(pin, len, frames, nall, &nall, NULL));
       /* keep the selected ones: a frame's payload starts 92 (or 56) bytes behind its header */
@@ -203,14 +203,14 @@ int main(int argc, char **argv)
     grp = gh_ndx_select(groups, ng);
   } else {                                  /* get_index without a file: the default group of all atoms */
     int i;
-    whole.name = (char *)"System"; whole.n = natoms; whole.atoms = (int *)malloc(sizeof(int) * (size_t)natoms);
+    whole.name = (char *)"System"; whole.n = natoms; whole.atoms = (int *)gh_alloc(sizeof(int) * (size_t)natoms);
     for (i = 0; i < natoms; i++) whole.atoms[i] = i;
     grp = &whole;
     gh_msg("Selected %d: '%s'\n", 0, whole.name);
   }
 
   /* get_timestep (g_ri3Dc.c:155-177): the time between the first two frames */
-  float *x = (float *)malloc(sizeof(float) * 3 * (size_t)natoms);
+  float *x = (float *)gh_alloc(sizeof(float) * 3 * (size_t)natoms);
   gh_frame_info fr, fr2;
   float dt0;
   {
@@ -280,8 +280,8 @@ int main(int argc, char **argv)
       }
       all[nframes++] = all[i];
     }
-    float *tt = (float *)malloc(sizeof(float) * (size_t)(nframes > 0 ? nframes : 1));
-    float *w = (float *)malloc(sizeof(float) * (size_t)(nframes > 0 ? nframes : 1));
+    float *tt = (float *)gh_alloc(sizeof(float) * (size_t)(nframes > 0 ? nframes : 1));
+    float *w = (float *)gh_alloc(sizeof(float) * (size_t)(nframes > 0 ? nframes : 1));
     for (i = 0; i < nframes; i++) tt[i] = all[i].time;
     CHECK(gcb_frame_weights(tt, nframes, bdtWeight, &tlast, w, &T_tot));        /* g_ri3Dc.c:413-416 */
     /* pass 2: one contiguous shard of the selected frames per device, one thread per device */
@@ -289,9 +289,9 @@ int main(int argc, char **argv)
     if (getenv("GCB_XTC_CHUNK_BYTES")) chunk = (size_t)strtoull(getenv("GCB_XTC_CHUNK_BYTES"), NULL, 10);
     if (chunk < ((size_t)natoms * 16 + 4096) * 2) chunk = ((size_t)natoms * 16 + 4096) * 2;     /* at least two frames */
     njobs = ndev;
-    jobs = (xtc_job *)calloc((size_t)njobs, sizeof(xtc_job));
+    jobs = (xtc_job *)gh_zalloc((size_t)njobs, sizeof(xtc_job));
     if (njobs > 1) CHECK(gcb_local_comm_create(&lc, njobs));
-    pthread_t *th = (pthread_t *)calloc((size_t)njobs, sizeof(pthread_t));
+    pthread_t *th = (pthread_t *)gh_zalloc((size_t)njobs, sizeof(pthread_t));
     int r;
     for (r = 0; r < njobs; r++) {
       const long f0 = nframes * r / njobs, f1 = nframes * (r + 1) / njobs;
@@ -315,9 +315,9 @@ int main(int argc, char **argv)
   long cap = 0, n = 0;
   float *xs = NULL, *w, *boxes, *tbuf;
   CHECK(gcb_counter_slot(ctr, slot, &xs, &cap));
-  w = (float *)malloc(sizeof(float) * (size_t)cap);
-  tbuf = (float *)malloc(sizeof(float) * (size_t)cap);
-  boxes = (float *)malloc(sizeof(float) * 9 * (size_t)cap);
+  w = (float *)gh_alloc(sizeof(float) * (size_t)cap);
+  tbuf = (float *)gh_alloc(sizeof(float) * (size_t)cap);
+  boxes = (float *)gh_alloc(sizeof(float) * 9 * (size_t)cap);
   int more = 1;
   while (more) {
     memcpy(xs + (size_t)n * natoms * 3, x, sizeof(float) * 3 * (size_t)natoms);

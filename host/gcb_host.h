@@ -25,6 +25,11 @@ void gh_set_program(const char *argv0);
 const char *gh_program(void);
 void gh_msg(const char *fmt, ...);
 void gh_fatal(const char *fmt, ...);
+/* checked allocation: like Gromacs' snew/srenew (smalloc.h) these end the program with a message instead of
+ * returning NULL */
+void *gh_alloc(size_t bytes);
+void *gh_zalloc(size_t count, size_t size);
+void *gh_realloc(void *p, size_t bytes);
 
 /* ---- options ---------------------------------------------------------------- */
 typedef enum { GH_BOOL, GH_INT, GH_REAL, GH_RVEC, GH_STR, GH_ENUM } gh_opt_type;

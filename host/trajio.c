@@ -378,6 +378,7 @@ struct gh_xtc_writer { FILE *f; uint8_t *buf; size_t cap; };
 gh_xtc_writer *gh_xtc_create(const char *path)
 {
   gh_xtc_writer *w = (gh_xtc_writer *)calloc(1, sizeof *w);
+  if (!w) return NULL;
   w->f = fopen(path, "wb");
   if (!w->f) { free(w); return NULL; }
   return w;
@@ -386,7 +387,11 @@ gh_xtc_writer *gh_xtc_create(const char *path)
 int gh_xtc_write(gh_xtc_writer *w, int natoms, int step, float time, const float box9[9], const float *x, float prec)
 {
   const size_t need = (size_t)natoms * 16 + 256;
-  if (need > w->cap) { w->buf = (uint8_t *)realloc(w->buf, need); w->cap = need; }
+  if (need > w->cap) {
+    uint8_t *nb = (uint8_t *)realloc(w->buf, need);
+    if (!nb) return -1;
+    w->buf = nb; w->cap = need;
+  }
   const size_t n = gh_xtc_encode_frame(natoms, step, time, box9, x, prec, w->buf, w->cap);
   if (!n) return -1;
   return fwrite(w->buf, 1, n, w->f) == n ? 0 : -1;
@@ -427,6 +432,7 @@ static int xtc_peek_natoms(FILE *f)
 gh_traj *gh_traj_open(const char *path)
 {
   gh_traj *t = (gh_traj *)calloc(1, sizeof *t);
+  if (!t) return NULL;
   t->f = fopen(path, "rb");
   if (!t->f) { free(t); return NULL; }
   if (has_ext(path, ".xtc")) {
@@ -468,7 +474,11 @@ static int next_xtc(gh_traj *t, gh_frame_info *info, float *x)
     const size_t nbytes = be_get32(head + XTC_HEADER_BYTES + 32);
     total = XTC_HEADER_BYTES + 36 + ((nbytes + 3) & ~(size_t)3);
   }
-  if (total > t->cap) { t->buf = (uint8_t *)realloc(t->buf, total); t->cap = total; }
+  if (total > t->cap) {                     /* (a damaged header may ask for gigabytes: that is a bad file, not a crash) */
+    uint8_t *nb = (uint8_t *)realloc(t->buf, total);
+    if (!nb) return -1;
+    t->buf = nb; t->cap = total;
+  }
   const size_t have = natoms <= 9 ? XTC_HEADER_BYTES : XTC_HEADER_BYTES + 36;
   memcpy(t->buf, head, have);
   if (fread(t->buf + have, 1, total - have, t->f) != total - have) return -1;

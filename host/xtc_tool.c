@@ -18,7 +18,7 @@ int main(int argc, char **argv)
   gh_traj *t = gh_traj_open(argv[2]);
   if (!t) gh_fatal("Cannot read trajectory %s", argv[2]);
   const int natoms = gh_traj_natoms(t);
-  float *x = (float *)malloc(sizeof(float) * 3 * (size_t)natoms);
+  float *x = (float *)gh_alloc(sizeof(float) * 3 * (size_t)natoms);
   gh_frame_info fr;
   if (!strcmp(argv[1], "convert")) {
     if (argc < 4) gh_fatal("convert needs an output name");
